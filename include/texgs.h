@@ -1,0 +1,171 @@
+/*
+ * texgs.h — C-ABI of the B200-native Texture-GS rasterizer (libtexgs.so).
+ *
+ * This is the drop-in boundary for the one hot path of slothfulxtx/Texture-GS: what the reference
+ * reaches through the (un-vendored) pybind module ``diff_gauss_uv_tex._C``
+ *   - ``_C.rasterize_gaussians``           <- called by GaussianRasterizer.forward, which the
+ *                                              reference invokes at render/uv_tex_render.py:56-66
+ *   - ``_C.rasterize_gaussians_backward``  <- autograd backward of the same call
+ *                                              (loss.backward(), models/texture_gaussian3d.py:410)
+ * and through ``diff_gauss._C`` for the texture-less variant (render/render.py:75-84).
+ *
+ * Conventions
+ *   * every pointer named ``d_*`` or living in an args struct is a DEVICE pointer to contiguous
+ *     fp32 / int32 memory owned by the caller (PyTorch); the library never allocates persistent
+ *     memory and keeps no global mutable state (re-entrant; last error is thread-local);
+ *   * ``stream`` is a ``cudaStream_t`` passed as ``void*``; all work is enqueued on it;
+ *   * return value 0 = success, otherwise a non-zero code (cudaError_t value or TEXGS_E_*);
+ *     ``texgs_last_error()`` returns the message for the calling thread;
+ *   * no host synchronisation happens inside any call unless ``TEXGS_FLAG_DEBUG`` is set
+ *     (mirrors ``raster_settings.debug``, render/uv_tex_render.py:37).
+ */
+#ifndef TEXGS_H_
+#define TEXGS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TEXGS_ABI_VERSION 1
+
+#define TEXGS_E_INVALID   1001   /* bad argument */
+#define TEXGS_E_WORKSPACE 1002   /* workspace too small */
+
+#define TEXGS_FLAG_PREFILTERED 1u   /* GaussianRasterizationSettings.prefiltered (uv_tex_render.py:36) */
+#define TEXGS_FLAG_DEBUG       2u   /* GaussianRasterizationSettings.debug       (uv_tex_render.py:37) */
+
+/* colour source of a splat */
+#define TEXGS_MODE_TEXTURE 0   /* diff_gauss_uv_tex: C0*cube(uv + J*delta) + SH_rest + 0.5, clamped at 0 */
+#define TEXGS_MODE_SH      1   /* diff_gauss:        SH(full, incl. DC) + 0.5, clamped at 0              */
+#define TEXGS_MODE_PRECOMP 2   /* diff_gauss:        colors_precomp used as given                        */
+
+/* Problem description = GaussianRasterizationSettings (render/uv_tex_render.py:25-38) + tensor
+ * shapes + the kwargs of GaussianRasterizer.__call__ (render/uv_tex_render.py:56-66). */
+typedef struct TexgsFwdArgs {
+    int32_t P;              /* number of Gaussians                                                  */
+    int32_t M;              /* SH coefficients per Gaussian in ``shs`` (row length / 3); 0 if none  */
+    int32_t sh_degree;      /* active degree (raster_settings.sh_degree)                            */
+    int32_t E;              /* channels of extra_attrs (0 if None)                                  */
+    int32_t H, W;           /* image_height, image_width                                            */
+    int32_t R;              /* cube face resolution of ``texture`` (6,R,R,3); 0 if no texture       */
+    int32_t mode;           /* TEXGS_MODE_*                                                         */
+    uint32_t flags;         /* TEXGS_FLAG_*                                                         */
+    float tanfovx, tanfovy, scale_modifier;
+    float viewmatrix[16];   /* raster_settings.viewmatrix, row-major as torch stores it (= W2C^T)   */
+    float projmatrix[16];   /* raster_settings.projmatrix (= viewmatrix @ P^T)                      */
+    float campos[3];
+    float bg[3];
+    /* inputs (device) */
+    const float* means3D;        /* (P,3)                                        */
+    const float* shs;            /* (P,M,3) or NULL                              */
+    const float* colors_precomp; /* (P,3) or NULL (TEXGS_MODE_PRECOMP)           */
+    const float* opacities;      /* (P,1)                                        */
+    const float* scales;         /* (P,3)                                        */
+    const float* rotations;      /* (P,4) quaternion (r,x,y,z)                   */
+    const float* uvs;            /* (P,3)   or NULL                              */
+    const float* gradient_uvs;   /* (P,9) row-major d uv_i / d x_j, or NULL      */
+    const float* texture;        /* (6,R,R,3) or NULL                            */
+    const float* extra_attrs;    /* (P,E) or NULL                                */
+} TexgsFwdArgs;
+
+/* Device-written run statistics, copied to ``counters_host`` (pinned) when that pointer is given. */
+typedef struct TexgsCounters {
+    uint32_t num_pairs;      /* K: (tile, Gaussian) pairs this view needs                         */
+    uint32_t num_visible;    /* V: Gaussians with radius > 0                                      */
+    uint32_t overflow;       /* 1 if K > pair_capacity: outputs are NOT valid, retry with >= K    */
+    uint32_t max_tile_len;   /* longest per-tile list                                             */
+    uint32_t num_blend_lo;   /* (pixel, Gaussian) contributions blended, low / high 32 bits       */
+    uint32_t num_blend_hi;   /*   (only counted when TEXGS_FLAG_DEBUG is set)                     */
+    uint32_t reserved[2];
+} TexgsCounters;
+
+/* Sizes (bytes) of the three caller-owned workspaces for a given problem and pair capacity.
+ *   geom : per-Gaussian projected records (kept for backward)
+ *   bin  : tile counts/offsets, unsorted + sorted (tile, Gaussian) pair lists (kept for backward)
+ *   img  : per-pixel final transmittance + contributor count (kept for backward) */
+int texgs_workspace_sizes(const TexgsFwdArgs* a, uint64_t pair_capacity,
+                          size_t* geom_bytes, size_t* bin_bytes, size_t* img_bytes);
+
+/* Forward: preprocess -> per-tile binning -> per-tile sort -> render.  Replaces
+ * ``_C.rasterize_gaussians`` [EXT] as reached from render/uv_tex_render.py:56.
+ * Outputs: image (3,H,W), depth (1,H,W), norm (3,H,W), alpha (1,H,W), radii (P,) int32,
+ * extra (E,H,W) or NULL.  ``counters_host`` may be NULL; if given it must be pinned host memory and
+ * is filled by an async copy on ``stream`` issued right after the tile scan, i.e. BEFORE the
+ * expensive kernels; ``counters_ready_event`` (a cudaEvent_t, may be NULL) is recorded right after
+ * that copy so the host can learn K / overflow without draining the stream. */
+int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t pair_capacity,
+                  void* img_ws, float* out_image, float* out_depth, float* out_norm,
+                  float* out_alpha, int32_t* out_radii, float* out_extra,
+                  TexgsCounters* counters_host, void* counters_ready_event, void* stream);
+
+typedef struct TexgsBwdArgs {
+    TexgsFwdArgs fwd;            /* the same args the forward ran with                          */
+    const void* geom_ws;         /* workspaces as left by texgs_forward                         */
+    const void* bin_ws;
+    const void* img_ws;
+    uint64_t pair_capacity;
+    /* incoming cotangents (device); any may be NULL (= zero) */
+    const float* dL_dimage;      /* (3,H,W) */
+    const float* dL_ddepth;      /* (1,H,W) */
+    const float* dL_dnorm;       /* (3,H,W) */
+    const float* dL_dalpha;      /* (1,H,W) */
+    const float* dL_dextra;      /* (E,H,W) */
+    /* scratch (device): P*TEXGS_BWD_ACC_FLOATS floats, zeroed by the library */
+    float* acc_ws;
+    /* gradient outputs (device). Per-Gaussian ones are fully written by the library (no
+     * pre-zeroing needed); dL_dtexture is ACCUMULATED into (atomics) unless
+     * ``zero_texture_grad`` is non-zero, in which case the library clears it first. NULL = skip. */
+    float* dL_dmeans3D;          /* (P,3)   */
+    float* dL_dmeans2D;          /* (P,3)  xy slots written in NDC units, z = 0                 */
+    float* dL_dopacity;          /* (P,1)   */
+    float* dL_dscales;           /* (P,3)   */
+    float* dL_drotations;        /* (P,4)   */
+    float* dL_dshs;              /* (P,M,3) */
+    float* dL_dcolors_precomp;   /* (P,3)   */
+    float* dL_duvs;              /* (P,3)   */
+    float* dL_dtexture;          /* (6,R,R,3) */
+    float* dL_dextra_attrs;      /* (P,E)   */
+    int32_t zero_texture_grad;
+    int32_t reserved;
+} TexgsBwdArgs;
+
+#define TEXGS_BWD_ACC_FLOATS 24
+
+/* Backward: per-tile back-to-front render backward -> per-Gaussian preprocess backward.  Replaces
+ * ``_C.rasterize_gaussians_backward`` [EXT]. */
+int texgs_backward(const TexgsBwdArgs* b, void* stream);
+
+/* Frustum test only (upstream ``GaussianRasterizer.markVisible`` [EXT]; unused in the reference
+ * tree). present (P,) int32: 1 if the Gaussian passes the near-plane cull. */
+int texgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix16_host,
+                       const float* projmatrix16_host, int32_t* present, void* stream);
+
+/* Debug / test introspection: byte offsets of the sub-buffers inside the workspaces. */
+typedef struct TexgsLayout {
+    uint64_t geom_records;     /* P x 128 B projected records                                  */
+    uint64_t geom_rects;       /* P x 8 B  (4 x uint16: x0,y0,x1,y1 tile rect)                 */
+    uint64_t bin_counters;     /* TexgsCounters                                                */
+    uint64_t bin_tile_count;   /* T x uint32                                                   */
+    uint64_t bin_tile_offset;  /* (T+1) x uint32                                               */
+    uint64_t bin_tile_cursor;  /* T x uint32                                                   */
+    uint64_t bin_pairs;        /* capacity x 8 B  {gaussian id, depth bits} unsorted->sorted   */
+    uint64_t bin_sorted_ids;   /* capacity x uint32 gaussian ids in (tile, depth, id) order    */
+    uint64_t img_final_T;      /* H*W floats                                                   */
+    uint64_t img_n_contrib;    /* H*W uint32                                                   */
+    uint64_t num_tiles;
+    uint64_t record_bytes;
+} TexgsLayout;
+int texgs_workspace_layout(const TexgsFwdArgs* a, uint64_t pair_capacity, TexgsLayout* out);
+
+int texgs_abi_version(void);
+const char* texgs_last_error(void);
+/* Comma-separated list of the __global__ kernels this library launches (evidence for tests). */
+const char* texgs_kernel_names(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEXGS_H_ */

@@ -1,0 +1,296 @@
+"""GPU parity tests proper: the CUDA path (through uv_tex_render -> autograd.Function -> C-ABI)
+against the oracle on the same seeded inputs.
+
+Tolerances are BASELINE.json's: 1e-4 abs per pixel on outputs, 1e-3 rel (max-norm) on gradients.
+Pixels where the oracle itself flags a blend decision as being within a few ulp of its threshold
+(alpha ~ 1/255, T ~ 1e-4) are compared separately: a 1-ulp difference in exp() legitimately flips
+such a contribution (SURVEY §7 'threshold discontinuities'); their fraction is asserted tiny.
+"""
+import ctypes as C
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from util import ABS_TOL, GRAD_RTOL, compare_images, rel_err, run_cuda, run_oracle
+from texture_gs_b200.scene import (C0, SyntheticGaussians, orbit_cameras, output_cotangents, sphere_shell_scene)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests selected (-m gpu) but no CUDA device is visible")
+    from texture_gs_b200 import _lib
+    _lib.load()   # fail loudly if the extension is missing
+
+
+def _check_forward(g, cam, bg=(0.0, 0.0, 0.0), max_amb=5e-3):
+    ref, aux, _ = run_oracle(g, cam, bg=bg)
+    got, stats, _ = run_cuda(g, cam, bg=bg)
+    rep = compare_images(got[:4], ref[:4], aux["ambiguous"])
+    print(rep, stats)
+    assert stats.num_pairs == aux["num_pairs"], (stats, aux["num_pairs"])
+    assert stats.num_visible == aux["num_visible"]
+    assert (got[4] != ref[4]).sum() == 0, "radii differ"
+    assert rep["ambiguous_frac"] <= max_amb
+    for n in ("image", "depth", "norm", "alpha"):
+        assert rep[n]["max_clear"] <= ABS_TOL * (3.0 if n == "depth" else 1.0), (n, rep[n])   # depth is O(2.5)-scaled
+        assert rep[n]["frac_over"] <= 1e-3, (n, rep[n])
+    return rep
+
+
+def _check_backward(g, cam, bg=(0.0, 0.0, 0.0), seed=3):
+    cot = output_cotangents(cam.image_height, cam.image_width, seed=seed)
+    _, _, gref = run_oracle(g, cam, bg=bg, cot=cot)
+    _, _, ggot = run_cuda(g, cam, bg=bg, cot=cot)
+    errs = {}
+    for k, r in gref.items():
+        if r is None:
+            continue
+        assert ggot[k] is not None, k
+        c = ggot[k]
+        if k == "means2D":
+            c, r = c[:, :2], r[:, :2]
+        errs[k] = rel_err(c.reshape(r.shape), r)
+    print(errs)
+    for k, e in errs.items():
+        assert e <= GRAD_RTOL, (k, e, errs)
+    return errs
+
+
+def test_golden_tiny_scene():
+    z = np.load(Path(__file__).resolve().parent / "golden" / "tiny_scene.npz")
+    g = sphere_shell_scene(int(z["N"]), int(z["R"]), sh_degree=3, seed=int(z["scene_seed"]), tex_seed=int(z["tex_seed"]))
+    cam = orbit_cameras(1, int(z["W"]), int(z["H"]), seed=int(z["cam_seed"]))[0]
+    got, stats, _ = run_cuda(g, cam, bg=tuple(float(v) for v in z["bg"]))
+    _, aux, _ = run_oracle(g, cam, bg=tuple(float(v) for v in z["bg"]))
+    clear = ~aux["ambiguous"].numpy()
+    assert np.abs(got[0].numpy() - z["image"])[:, clear].max() <= ABS_TOL
+    assert np.abs(got[1][0].numpy() - z["depth"])[clear].max() <= 3 * ABS_TOL
+    assert np.abs(got[2].numpy() - z["norm"])[:, clear].max() <= ABS_TOL
+    assert np.abs(got[3][0].numpy() - z["alpha"])[clear].max() <= ABS_TOL
+    assert (got[4].numpy() == z["radii"]).all()
+
+
+@pytest.mark.parametrize("n,w,h,r,deg,seed", [(2000, 128, 96, 64, 3, 0), (500, 70, 50, 16, 0, 4), (3000, 96, 160, 32, 2, 7)])
+def test_forward_parity_small(n, w, h, r, deg, seed):
+    g = sphere_shell_scene(n, r, sh_degree=deg, seed=seed, tex_seed=seed + 1)
+    cam = orbit_cameras(1, w, h, seed=seed + 2)[0]
+    _check_forward(g, cam, bg=(0.2, 0.4, 0.6))
+
+
+@pytest.mark.parametrize("n,w,h,r,deg,seed", [(2000, 128, 96, 64, 3, 0), (500, 70, 50, 16, 0, 4)])
+def test_backward_parity_small(n, w, h, r, deg, seed):
+    g = sphere_shell_scene(n, r, sh_degree=deg, seed=seed, tex_seed=seed + 1)
+    cam = orbit_cameras(1, w, h, seed=seed + 2)[0]
+    _check_backward(g, cam, bg=(0.2, 0.4, 0.6))
+
+
+def test_config0_10k_256_forward_and_backward():
+    """BASELINE.json configs[0]: 10k Gaussians, 256x256, 512^2 cube texture, 1 camera."""
+    g = sphere_shell_scene(10_000, 512, sh_degree=3, seed=0)
+    cam = orbit_cameras(1, 256, 256, seed=1)[0]
+    _check_forward(g, cam)
+    _check_backward(g, cam)
+
+
+def test_binning_order_matches_oracle():
+    """Sorted per-tile lists == (tile, depth, index) order of the oracle (spec E4), read back through
+    the workspace layout the C-ABI publishes."""
+    from texture_gs_b200 import _lib as L
+    from texture_gs_b200.rasterizer import _RasterizeGaussians, GaussianRasterizationSettings
+    g = sphere_shell_scene(4000, 16, sh_degree=0, seed=2).to("cuda", requires_grad=True)
+    cam = orbit_cameras(1, 160, 112, seed=5)[0].to("cuda")
+    st = GaussianRasterizationSettings(112, 160, math.tan(cam.FoVx / 2), math.tan(cam.FoVy / 2), torch.zeros(3, device="cuda"), 1.0,
+                                       cam.world_view_transform, cam.full_proj_transform, 0, cam.camera_center, False, False)
+    t = g.tensors()
+    m2 = torch.zeros_like(t["xyz"], requires_grad=True)
+    out = _RasterizeGaussians.apply(t["xyz"], m2, t["shs"], None, t["opacity"], t["scaling"], t["rotation"], t["uvs"],
+                                    t["grad_uvs"], t["texture"], st, L.MODE_TEXTURE)
+    saved = out[0].grad_fn.saved_tensors
+    binw = saved[-2]
+    cap = out[0].grad_fn.cap if hasattr(out[0].grad_fn, "cap") else None
+    from texture_gs_b200.rasterizer import last_stats
+    stats = last_stats()
+    lib = L.load()
+    a = L.TexgsFwdArgs(); a.P, a.H, a.W, a.R = 4000, 112, 160, 16
+    lay = L.TexgsLayout()
+    assert lib.texgs_workspace_layout(C.byref(a), stats.pair_capacity, C.byref(lay)) == 0
+    K = stats.num_pairs
+    T = lay.num_tiles
+    raw = binw.cpu().numpy()
+    offs = raw[lay.bin_tile_offset: lay.bin_tile_offset + 4 * (T + 1)].view(np.uint32)
+    ids = raw[lay.bin_sorted_ids: lay.bin_sorted_ids + 4 * K].view(np.uint32)
+    _, aux, _ = run_oracle(g, cam.to("cpu"))
+    assert K == aux["num_pairs"] and offs[-1] == K
+    tile_of = np.repeat(np.arange(T), np.diff(offs.astype(np.int64)))
+    assert (tile_of == aux["tile_of"]).all()
+    assert (ids.astype(np.int64) == aux["gid_of"]).all()
+
+
+def test_plain_3dgs_modes_match_oracle():
+    """texture=None: colour from colors_precomp or full SH (the diff_gauss surface, render/render.py:75-84)."""
+    from oracle import raster_ref as RR
+    from util import oracle_settings
+    from texture_gs_b200 import GaussianRasterizationSettings, GaussianRasterizer
+    N, W, H = 1500, 96, 80
+    g = sphere_shell_scene(N, 4, sh_degree=3, seed=8)
+    cam = orbit_cameras(1, W, H, seed=9)[0]
+    gen = torch.Generator().manual_seed(1)
+    cols = torch.rand(N, 3, generator=gen)
+    shs_full = torch.cat([torch.randn(N, 1, 3, generator=gen), 0.1 * torch.randn(N, 15, 3, generator=gen)], dim=1)
+    cot = output_cotangents(H, W, seed=2)
+    for kind in ("precomp", "sh"):
+        # oracle
+        t = g.to(dtype=torch.float32, requires_grad=True).tensors()
+        c_ref = cols.clone().requires_grad_(True)
+        s_ref = shs_full.clone().requires_grad_(True)
+        st = oracle_settings(cam, 3, bg=(0.1, 0.1, 0.3))
+        o = RR.rasterize(t["xyz"], None, s_ref if kind == "sh" else None, t["opacity"], t["scaling"], t["rotation"], None, None, None, st,
+                         colors_precomp=c_ref if kind == "precomp" else None, return_aux=True)
+        Lr = sum((a * b).sum() for a, b in zip(o[:4], cot))
+        Lr.backward()
+        # cuda
+        tc = g.to("cuda", requires_grad=True).tensors()
+        c_cu = cols.clone().cuda().requires_grad_(True)
+        s_cu = shs_full.clone().cuda().requires_grad_(True)
+        camd = orbit_cameras(1, W, H, seed=9)[0].to("cuda")
+        stc = GaussianRasterizationSettings(H, W, math.tan(camd.FoVx / 2), math.tan(camd.FoVy / 2), torch.tensor([0.1, 0.1, 0.3], device="cuda"),
+                                            1.0, camd.world_view_transform, camd.full_proj_transform, 3, camd.camera_center, False, False)
+        m2 = torch.zeros(N, 3, device="cuda", requires_grad=True)
+        oc = GaussianRasterizer(stc)(means3D=tc["xyz"], means2D=m2, opacities=tc["opacity"], shs=s_cu if kind == "sh" else None,
+                                     colors_precomp=c_cu if kind == "precomp" else None, scales=tc["scaling"], rotations=tc["rotation"])
+        Lc = sum((a * b.cuda()).sum() for a, b in zip(oc[:4], cot))
+        Lc.backward()
+        rep = compare_images([x.detach().cpu() for x in oc[:4]], [x.detach() for x in o[:4]], o[-1]["ambiguous"])
+        print(kind, rep)
+        for n in ("image", "depth", "norm", "alpha"):
+            assert rep[n]["max_clear"] <= ABS_TOL * (3.0 if n == "depth" else 1.0), (kind, n, rep[n])
+        pairs = [("xyz", tc["xyz"].grad, t["xyz"].grad), ("opacity", tc["opacity"].grad, t["opacity"].grad),
+                 ("scaling", tc["scaling"].grad, t["scaling"].grad), ("rotation", tc["rotation"].grad, t["rotation"].grad)]
+        pairs.append(("color", c_cu.grad, c_ref.grad) if kind == "precomp" else ("shs", s_cu.grad, s_ref.grad))
+        for name, a, b in pairs:
+            e = rel_err(a.cpu(), b)
+            assert e <= GRAD_RTOL, (kind, name, e)
+
+
+def test_edge_cases_empty_culled_single_and_ragged_sizes():
+    from texture_gs_b200 import uv_tex_render
+    bg = torch.tensor([0.3, 0.5, 0.7], device="cuda")
+    # (a) zero Gaussians
+    g0 = sphere_shell_scene(4, 4, sh_degree=0)
+    t = {k: (v[:0] if (v is not None and k != "texture") else v) for k, v in g0.tensors().items()}
+    ge = SyntheticGaussians(active_sh_degree=0, **{k: (v.detach() if v is not None else None) for k, v in t.items()}).to("cuda", requires_grad=True)
+    cam = orbit_cameras(1, 33, 17, seed=3)[0].to("cuda")
+    pkg = uv_tex_render(cam, ge, None, bg)
+    assert pkg["render"].shape == (3, 17, 33)
+    assert torch.allclose(pkg["render"], bg[:, None, None].expand(3, 17, 33))
+    assert float(pkg["alpha"].abs().max()) == 0.0 and pkg["radii"].numel() == 0
+    pkg["render"].sum().backward()
+    # (b) everything behind the camera -> culled, radii == 0
+    gb = sphere_shell_scene(64, 4, sh_degree=0)
+    tb = gb.tensors()
+    far = SyntheticGaussians(active_sh_degree=0, **{**{k: (v.detach() if v is not None else None) for k, v in tb.items()},
+                                                      "xyz": tb["xyz"].detach() * 0 + cam.camera_center.cpu() * 2.0}).to("cuda", requires_grad=True)
+    pkg = uv_tex_render(cam, far, None, bg)
+    assert int(pkg["radii"].max()) == 0 and float(pkg["alpha"].abs().max()) == 0.0
+    assert not bool(pkg["visibility_filter"].any())
+    pkg["render"].sum().backward()
+    assert float(far.get_xyz.grad.abs().max()) == 0.0
+    # (c) ragged image sizes (not multiples of 16) and a single Gaussian, against the oracle
+    for (w, h, n, seed) in [(17, 33, 1, 1), (31, 15, 40, 2), (130, 70, 700, 3)]:
+        g = sphere_shell_scene(n, 8, sh_degree=1, seed=seed, coverage=8.0)
+        c = orbit_cameras(1, w, h, seed=seed)[0]
+        _check_forward(g, c, bg=(0.3, 0.5, 0.7))
+        _check_backward(g, c, bg=(0.3, 0.5, 0.7))
+
+
+def test_long_tile_lists_take_the_global_sort_path():
+    """> 4096 Gaussians in one tile exceeds the shared-memory sort capacity (global-memory network)."""
+    n = 6000
+    g = sphere_shell_scene(n, 8, sh_degree=0, seed=5, coverage=4.0)
+    t = g.tensors()
+    # squeeze all centres into a small patch facing the camera so that one tile sees > 4096 of them
+    cam = orbit_cameras(1, 48, 48, seed=6)[0]
+    c = cam.camera_center / cam.camera_center.norm()
+    gen = torch.Generator().manual_seed(0)
+    xyz = c[None, :] * 1.0 + 0.01 * torch.randn(n, 3, generator=gen)
+    uv = xyz / xyz.norm(dim=1, keepdim=True)
+    gg = SyntheticGaussians(active_sh_degree=0, **{**{k: (v.detach() if v is not None else None) for k, v in t.items()},
+                                                    "xyz": xyz, "uvs": uv, "opacity": torch.full((n, 1), 0.02)})
+    ref, aux, _ = run_oracle(gg, cam)
+    got, stats, _ = run_cuda(gg, cam)
+    assert stats.max_tile_len > 4096
+    rep = compare_images(got[:4], ref[:4], aux["ambiguous"])
+    print(rep, stats)
+    for nme in ("image", "alpha"):
+        assert rep[nme]["max_clear"] <= 2 * ABS_TOL, rep
+
+
+def test_capacity_overflow_retry_is_transparent():
+    from texture_gs_b200 import rasterizer as RZ
+    g = sphere_shell_scene(3000, 16, sh_degree=0, seed=1)
+    cam = orbit_cameras(1, 128, 128, seed=2)[0]
+    got1, s1, _ = run_cuda(g, cam)
+    RZ._capacity_hint[(0, 3000, 128, 128)] = 64          # force an overflow on the first attempt
+    got2, s2, _ = run_cuda(g, cam)
+    assert s2.num_pairs == s1.num_pairs and s2.pair_capacity >= s2.num_pairs
+    for a, b in zip(got1, got2):
+        assert torch.equal(a, b)
+
+
+def test_forward_is_deterministic_and_backward_linear_in_cotangent():
+    g = sphere_shell_scene(5000, 64, sh_degree=3, seed=3)
+    cam = orbit_cameras(1, 200, 120, seed=4)[0]
+    cot = output_cotangents(120, 200, seed=5)
+    o1, _, g1 = run_cuda(g, cam, cot=cot)
+    o2, _, g2 = run_cuda(g, cam, cot=[2.0 * c for c in cot])
+    for a, b in zip(o1, o2):
+        assert torch.equal(a, b)                                  # bitwise reproducible forward
+    for k in g1:
+        if g1[k] is not None:
+            assert rel_err(g2[k], 2.0 * g1[k]) < 1e-4, k         # atomics reorder float sums only
+
+
+@pytest.mark.parametrize("n,w,h,r", [(500_000, 1920, 1080, 2048)])
+def test_full_size_properties(n, w, h, r):
+    """BASELINE.json configs[2] at full size, checked through size-independent properties:
+    (1) constant texture => image == plain-3DGS render with that colour (two different kernel
+        instantiations must agree to 1e-4);
+    (2) with g_image = 1 and no active clamp, sum(dL/dtexture) per channel == C0 * sum(alpha):
+        the bilinear weights of every contribution sum to one (checksum of the scatter);
+    (3) alpha in [0, 1], all outputs finite, radii >= 0, image == accumulated + T*bg."""
+    from texture_gs_b200 import GaussianRasterizationSettings, GaussianRasterizer, uv_tex_render
+    g = sphere_shell_scene(n, r, sh_degree=0, seed=0, device="cuda", requires_grad=False)
+    t = g.tensors()
+    tex = torch.full_like(t["texture"], (0.6 - 0.5) / C0)
+    gc = SyntheticGaussians(active_sh_degree=0, **{**{k: (v.detach() if v is not None else None) for k, v in t.items()},
+                                                    "texture": tex.requires_grad_(True), "shs": None})
+    cam = orbit_cameras(1, w, h, seed=1)[0].to("cuda")
+    bg = torch.tensor([0.1, 0.2, 0.3], device="cuda")
+    pkg = uv_tex_render(cam, gc, None, bg)
+    img, alpha = pkg["render"], pkg["alpha"]
+    assert torch.isfinite(img).all() and torch.isfinite(pkg["depth"]).all() and torch.isfinite(pkg["norm"]).all()
+    assert float(alpha.min()) >= 0.0 and float(alpha.max()) <= 1.0 + 1e-5
+    assert int(pkg["radii"].min()) >= 0
+    img.sum().backward()
+    dtex = gc.get_texture.grad
+    for ch in range(3):
+        s = float(dtex[..., ch].double().sum())
+        e = C0 * float(alpha.double().sum())
+        assert abs(s - e) <= 1e-3 * e, (ch, s, e)
+    st = GaussianRasterizationSettings(h, w, math.tan(cam.FoVx / 2), math.tan(cam.FoVy / 2), bg, 1.0, cam.world_view_transform,
+                                       cam.full_proj_transform, 0, cam.camera_center, False, False)
+    plain = GaussianRasterizer(st)(means3D=t["xyz"].detach(), means2D=torch.zeros_like(t["xyz"]), opacities=t["opacity"].detach(),
+                                   colors_precomp=torch.full((n, 3), 0.6, device="cuda"), scales=t["scaling"].detach(),
+                                   rotations=t["rotation"].detach())
+    assert float((plain[0] - img.detach()).abs().max()) <= ABS_TOL
+    assert torch.equal(plain[3], alpha.detach())
+    # background identity: image - bg*(1 - alpha_sum) == colour * alpha for a constant colour  (T_final = 1 - alpha here
+    # only approximately, so check the weaker bound image <= 0.6*alpha + bg*(1-alpha) + tol)
+    bound = 0.6 * alpha + bg[:, None, None] * (1 - alpha) + 1e-3
+    assert bool((img.detach() <= bound + 1e-3).all())

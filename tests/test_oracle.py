@@ -1,0 +1,207 @@
+"""CPU tests of the oracle itself (SURVEY §8c self-tests): golden vectors, independent loop
+restatement, analytic cases, conventions pinned by the reference tree, autograd gradcheck."""
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import raster_ref as RR
+from oracle.raster_loop import rasterize_loop
+from texture_gs_b200.scene import (C0, SyntheticGaussians, band_limited_texture, orbit_cameras,
+                                   sphere_shell_scene)
+from util import oracle_settings, run_oracle
+
+GOLDEN = Path(__file__).resolve().parent / "golden" / "tiny_scene.npz"
+
+
+def _golden_scene():
+    z = np.load(GOLDEN)
+    g = sphere_shell_scene(int(z["N"]), int(z["R"]), sh_degree=3, seed=int(z["scene_seed"]), tex_seed=int(z["tex_seed"]))
+    cam = orbit_cameras(1, int(z["W"]), int(z["H"]), seed=int(z["cam_seed"]))[0]
+    return z, g, cam
+
+
+def test_oracle_matches_golden_fp64():
+    z, g, cam = _golden_scene()
+    (img, dep, nrm, alp, radii), aux, _ = run_oracle(g, cam, bg=tuple(z["bg"]), dtype=torch.float64)
+    assert np.abs(img.numpy() - z["image"]).max() < 1e-6
+    assert np.abs(dep[0].numpy() - z["depth"]).max() < 1e-6
+    assert np.abs(nrm.numpy() - z["norm"]).max() < 1e-6
+    assert np.abs(alp[0].numpy() - z["alpha"]).max() < 1e-6
+    assert (radii.numpy() == z["radii"]).all()
+
+
+def test_oracle_fp32_matches_golden_within_tolerance():
+    z, g, cam = _golden_scene()
+    (img, dep, nrm, alp, radii), aux, _ = run_oracle(g, cam, bg=tuple(z["bg"]), dtype=torch.float32)
+    clear = ~aux["ambiguous"].numpy()
+    assert np.abs(img.numpy() - z["image"])[:, clear].max() < 1e-4
+    assert np.abs(alp[0].numpy() - z["alpha"])[clear].max() < 1e-4
+
+
+@pytest.mark.parametrize("seed,deg", [(0, 3), (5, 0), (9, 2)])
+def test_vectorised_oracle_equals_loop_oracle(seed, deg):
+    g = sphere_shell_scene(150, 16, sh_degree=deg, seed=seed, tex_seed=seed + 1)
+    cam = orbit_cameras(1, 40, 24, seed=seed + 2)[0]
+    (img, dep, nrm, alp, radii), aux, _ = run_oracle(g, cam, bg=(0.3, 0.1, 0.2), dtype=torch.float64)
+    t = {k: (None if v is None else v.detach().double().numpy()) for k, v in g.tensors().items()}
+    ref = rasterize_loop(t["xyz"], t["shs"], t["opacity"], t["scaling"], t["rotation"], t["uvs"], t["grad_uvs"], t["texture"],
+                         H=24, W=40, tanfovx=math.tan(cam.FoVx / 2), tanfovy=math.tan(cam.FoVy / 2), bg=np.array([0.3, 0.1, 0.2]),
+                         scale_modifier=1.0, viewmatrix=cam.world_view_transform.double().numpy(),
+                         projmatrix=cam.full_proj_transform.double().numpy(), sh_degree=deg, campos=cam.camera_center.double().numpy())
+    assert np.abs(img.numpy() - ref[0]).max() < 1e-10
+    assert np.abs(dep[0].numpy() - ref[1]).max() < 1e-10
+    assert np.abs(nrm.numpy() - ref[2]).max() < 1e-10
+    assert np.abs(alp[0].numpy() - ref[3]).max() < 1e-10
+    assert (radii.numpy() == ref[4]).all()
+
+
+def test_cube_face_roundtrip_matches_reference_layout():
+    """dir -> (face, sx, sy) inverts the reference's cube_to_dir (NVDIFFREC/util.py:94-101)."""
+    def cube_to_dir(s, x, y):   # restated from the reference table
+        one = torch.ones_like(x)
+        return [torch.stack(v, -1) for v in ([one, -y, -x], [-one, -y, x], [x, one, y], [x, -one, -y], [x, -y, one], [-x, -y, -one])][s]
+    gen = torch.Generator().manual_seed(0)
+    x = torch.rand(1000, generator=gen, dtype=torch.float64) * 1.98 - 0.99
+    y = torch.rand(1000, generator=gen, dtype=torch.float64) * 1.98 - 0.99
+    for s in range(6):
+        d = cube_to_dir(s, x, y) * (0.5 + torch.rand(1000, 1, generator=gen, dtype=torch.float64))
+        face, sx, sy = RR.cube_face_coords(d)
+        assert (face == s).all()
+        assert (sx - x).abs().max() < 1e-12 and (sy - y).abs().max() < 1e-12
+
+
+def test_cube_sample_texel_centres_and_index_order():
+    """Sampling at a texel centre returns that texel: tensor index order [face,row(y),col(x)]
+    (NVDIFFREC/util.py:104-116, cubemap.cu:34-35)."""
+    R = 8
+    tex = torch.arange(6 * R * R * 3, dtype=torch.float64).reshape(6, R, R, 3)
+    for s, (ix, iy) in [(0, (1, 6)), (3, (7, 0)), (5, (4, 4))]:
+        x = 2 * (ix + 0.5) / R - 1
+        y = 2 * (iy + 0.5) / R - 1
+        d = [(1, -y, -x), (-1, -y, x), (x, 1, y), (x, -1, -y), (x, -y, 1), (-x, -y, -1)][s]
+        got = RR.cube_sample(tex, torch.tensor([d], dtype=torch.float64))[0]
+        assert torch.allclose(got, tex[s, iy, ix])
+
+
+def test_camera_conventions_match_reference_formulas():
+    """world_view_transform = W2C^T, full_proj = view @ P^T, w_clip = z_view, pixel centres."""
+    cam = orbit_cameras(1, 64, 48, seed=4)[0]
+    V, PM = cam.world_view_transform.double(), cam.full_proj_transform.double()
+    p = torch.tensor([[0.1, -0.2, 0.3]], dtype=torch.float64)
+    pv = p @ V[:3, :3] + V[3, :3]
+    ph = p @ PM[:3, :] + PM[3, :]
+    assert abs(float(ph[0, 3] - pv[0, 2])) < 1e-6                      # w_clip == z_view
+    assert abs(float(ph[0, 0] / ph[0, 3] - pv[0, 0] / pv[0, 2] / math.tan(cam.FoVx / 2))) < 1e-6
+    cc = torch.inverse(V)[3, :3]
+    assert torch.allclose(cc, cam.camera_center.double(), atol=1e-6)
+    assert abs(float(cc.norm()) - 2.5) < 1e-5
+    o = torch.zeros(1, 3, dtype=torch.float64)                          # camera looks at the origin
+    ov = o @ V[:3, :3] + V[3, :3]
+    assert abs(float(ov[0, 0])) < 1e-6 and abs(float(ov[0, 1])) < 1e-6 and abs(float(ov[0, 2]) - 2.5) < 1e-5
+
+
+def _single_disc(opacity=0.8, scale=0.05, tex_val=1.0, R=8):
+    """One fronto-parallel disc at the origin, camera on +z... built via look_at."""
+    cam = orbit_cameras(1, 32, 32, seed=2)[0]
+    n = cam.camera_center.double() / cam.camera_center.double().norm()      # disc normal towards camera
+    # quaternion taking z -> n
+    q = torch.tensor([1 + n[2], -n[1], n[0], 0.0], dtype=torch.float64)
+    q = q / q.norm()
+    tex = torch.full((6, R, R, 3), (tex_val - 0.5) / C0, dtype=torch.float32)
+    g = SyntheticGaussians(
+        xyz=torch.zeros(1, 3), opacity=torch.tensor([[opacity]]), scaling=torch.tensor([[scale, scale, math.exp(-20.0)]]),
+        rotation=q.float()[None], shs=None, texture=tex, uvs=torch.tensor([[0.0, 0.0, 1.0]]),
+        grad_uvs=torch.zeros(1, 9), active_sh_degree=0)
+    return g, cam
+
+
+def test_single_frontoparallel_disc_closed_form():
+    """alpha(pixel) = o * exp(-r^2 / (2 (sigma_px^2 + 0.3))) for an isotropic fronto-parallel disc."""
+    g, cam = _single_disc()
+    (img, dep, nrm, alp, radii), aux, _ = run_oracle(g, cam, dtype=torch.float64)
+    f = cam.image_height / (2 * math.tan(cam.FoVy / 2))
+    sig2 = (0.05 * f / 2.5) ** 2 + 0.3
+    ys, xs = torch.meshgrid(torch.arange(32, dtype=torch.float64), torch.arange(32, dtype=torch.float64), indexing="ij")
+    r2 = (xs - 15.5) ** 2 + (ys - 15.5) ** 2
+    a = 0.8 * torch.exp(-0.5 * r2 / sig2)
+    a = torch.where(a >= 1 / 255, a, torch.zeros_like(a))
+    inside = r2.sqrt() < float(radii[0]) - 16   # only compare well inside the tile rect
+    assert (alp[0] - a).abs()[r2 < 36].max() < 2e-3       # EWA is first order: small perspective error allowed
+    assert (dep[0] - 2.5 * alp[0]).abs().max() < 1e-4
+    n = cam.camera_center.double() / cam.camera_center.double().norm()
+    assert (nrm - n[:, None, None] * alp).abs().max() < 1e-6   # quaternion stored in fp32
+    assert (img - 1.0 * alp).abs().max() < 1e-6                # constant texture rgb = 1
+
+
+def test_constant_texture_equals_plain_3dgs_with_that_colour():
+    g = sphere_shell_scene(300, 8, sh_degree=0, seed=3)
+    t = g.tensors()
+    const = torch.full_like(t["texture"], (0.7 - 0.5) / C0)
+    g2 = SyntheticGaussians(**{**{k: (v.detach() if v is not None else None) for k, v in t.items()}, "texture": const, "shs": None},
+                            active_sh_degree=0)
+    cam = orbit_cameras(1, 48, 32, seed=1)[0]
+    (img, dep, nrm, alp, _), _, _ = run_oracle(g2, cam, dtype=torch.float64)
+    st = oracle_settings(cam, 0, dtype=torch.float64)
+    tt = g2.to(dtype=torch.float64).tensors()
+    out = RR.rasterize(tt["xyz"], None, None, tt["opacity"], tt["scaling"], tt["rotation"], None, None, None, st,
+                       colors_precomp=torch.full((300, 3), 0.7, dtype=torch.float64))
+    assert (out[0] - img).abs().max() < 1e-6   # texture constant stored in fp32
+    assert (out[3] - alp).abs().max() < 1e-12
+
+
+def test_identity_uv_on_sphere_is_second_order_accurate():
+    """uv=normalize(x), J=(I-uu^T)/|x|: the first-order UV at the intersection equals
+    normalize(intersection) up to O(|delta|^2)."""
+    n = torch.tensor([0.0, 0.0, 1.0], dtype=torch.float64)
+    mu = n.clone()
+    uv = mu / mu.norm()
+    J = (torch.eye(3, dtype=torch.float64) - uv[:, None] * uv[None, :]) / mu.norm()
+    for eps in (1e-2, 1e-3):
+        x = mu + torch.tensor([eps, -0.5 * eps, 0.0], dtype=torch.float64)     # point on the disc plane
+        approx = uv + J @ (x - mu)
+        exact = x / x.norm()
+        err = (approx / approx.norm() - exact).norm()
+        assert err < 2 * eps * eps
+
+
+def test_gradcheck_fp64_small_scene():
+    """Analytic autograd of the oracle vs central differences (fp64, all differentiable inputs)."""
+    g = sphere_shell_scene(12, 4, sh_degree=3, seed=21, coverage=30.0).to(dtype=torch.float64)
+    cam = orbit_cameras(1, 16, 16, seed=22)[0]
+    st = oracle_settings(cam, 3, dtype=torch.float64, bg=(0.2, 0.3, 0.4))
+    t = g.tensors()
+    gen = torch.Generator().manual_seed(5)
+    cot = [torch.randn(c, 16, 16, generator=gen, dtype=torch.float64) for c in (3, 1, 3, 1)]
+
+    def f(xyz, opacity, scaling, rotation, shs, texture, uvs):
+        o = RR.rasterize(xyz, None, shs, opacity, scaling, rotation, uvs, t["grad_uvs"], texture, st)
+        return sum((a * b).sum() for a, b in zip(o[:4], cot))
+
+    names = ["xyz", "opacity", "scaling", "rotation", "shs", "texture", "uvs"]
+    inputs = [t[k].detach().clone().requires_grad_(True) for k in names]
+    L = f(*inputs)
+    grads = torch.autograd.grad(L, inputs)
+    gen = torch.Generator().manual_seed(6)
+    for name, x, gx in zip(names, inputs, grads):
+        for _ in range(3):
+            d = torch.randn(x.shape, generator=gen, dtype=torch.float64)
+            if name == "scaling":
+                d[:, 2] = 0           # the flat axis (exp(-20)) is below finite-difference resolution
+            d = d / d.norm()
+            h = 1e-6 * max(1.0, float(x.abs().max())) if name != "scaling" else 1e-8
+            args_p = [a if a is not x else (x + h * d) for a in inputs]
+            args_m = [a if a is not x else (x - h * d) for a in inputs]
+            with torch.no_grad():
+                fd = (f(*args_p) - f(*args_m)) / (2 * h)
+            an = (gx * d).sum()
+            assert abs(float(fd - an)) <= 1e-4 * max(1.0, abs(float(an))), (name, float(fd), float(an))
+
+
+def test_band_limited_texture_is_smooth_and_in_range():
+    t = band_limited_texture(64, seed=2)
+    rgb = C0 * t + 0.5
+    assert float(rgb.min()) >= -1e-6 and float(rgb.max()) <= 1 + 1e-6
+    assert float((rgb[:, :, 1:] - rgb[:, :, :-1]).abs().max()) < 0.35

@@ -1,0 +1,255 @@
+// texgs_api.cu — extern "C" boundary of libtexgs.so (declared in include/texgs.h).
+// Host side only validates arguments, carves the caller-owned workspaces and enqueues kernels on
+// the caller's stream. No allocation, no global mutable state, no host sync (unless DEBUG).
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "texgs_binning.cuh"
+#include "texgs_common.cuh"
+#include "texgs_preprocess.cuh"
+#include "texgs_render.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define TEXGS_CUDA_TRY(expr)                                                                             \
+    do {                                                                                                 \
+        cudaError_t err__ = (expr);                                                                      \
+        if (err__ != cudaSuccess)                                                                        \
+            return fail((int)err__, std::string(#expr) + ": " + cudaGetErrorString(err__));              \
+    } while (0)
+
+#define TEXGS_KERNEL_CHECK(name, debug, stream)                                                          \
+    do {                                                                                                 \
+        cudaError_t err__ = cudaGetLastError();                                                          \
+        if (err__ == cudaSuccess && (debug)) err__ = cudaStreamSynchronize(stream);                      \
+        if (err__ != cudaSuccess) return fail((int)err__, std::string(name) + ": " + cudaGetErrorString(err__)); \
+    } while (0)
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+struct Layout {
+    TexgsLayout l;
+    uint64_t geom_bytes, bin_bytes, img_bytes, bin_zero_bytes;
+};
+
+int make_layout(const TexgsFwdArgs* a, uint64_t cap, Layout& L) {
+    if (!a) return fail(TEXGS_E_INVALID, "args is NULL");
+    if (a->P < 0 || a->H <= 0 || a->W <= 0) return fail(TEXGS_E_INVALID, "bad P/H/W");
+    const uint64_t gx = (a->W + TEXGS_TILE - 1) / TEXGS_TILE, gy = (a->H + TEXGS_TILE - 1) / TEXGS_TILE;
+    if (gx > 65535 || gy > 65535) return fail(TEXGS_E_INVALID, "image too large for 16-bit tile coordinates");
+    const uint64_t T = gx * gy, P = (uint64_t)a->P, HW = (uint64_t)a->H * a->W;
+    memset(&L, 0, sizeof(L));
+    L.l.num_tiles = T;
+    L.l.record_bytes = sizeof(GaussRec);
+    uint64_t o = 0;
+    L.l.geom_records = o; o = align_up(o + P * sizeof(GaussRec), 256);
+    L.l.geom_rects = o;   o = align_up(o + P * sizeof(uint2), 256);
+    L.geom_bytes = o;
+    o = 0;
+    L.l.bin_counters = o;    o = align_up(o + sizeof(TexgsCounters), 256);
+    L.l.bin_tile_count = o;  o = align_up(o + T * 4, 256);
+    L.l.bin_tile_cursor = o; o = align_up(o + T * 4, 256);
+    L.bin_zero_bytes = o;    // [counters | tile_count | tile_cursor] are cleared together
+    L.l.bin_tile_offset = o; o = align_up(o + (T + 1) * 4, 256);
+    L.l.bin_pairs = o;       o = align_up(o + cap * 8, 256);
+    L.l.bin_sorted_ids = o;  o = align_up(o + cap * 4, 256);
+    L.bin_bytes = o;
+    o = 0;
+    L.l.img_final_T = o;   o = align_up(o + HW * 4, 256);
+    L.l.img_n_contrib = o; o = align_up(o + HW * 4, 256);
+    L.img_bytes = o;
+    return 0;
+}
+
+int max_degree_for(int M_rest) {
+    int d = 0;
+    while (d < 3 && (d + 2) * (d + 2) - 1 <= M_rest) ++d;
+    return d;
+}
+
+int fill_params(const TexgsFwdArgs* a, void* geom, void* bin, uint64_t cap, void* img, const Layout& L, RasterParams& p) {
+    if (a->mode != TEXGS_MODE_TEXTURE && a->mode != TEXGS_MODE_SH && a->mode != TEXGS_MODE_PRECOMP)
+        return fail(TEXGS_E_INVALID, "unknown mode");
+    if (a->E != 0 || a->extra_attrs) return fail(TEXGS_E_INVALID, "extra_attrs is not supported yet (the reference never passes it)");
+    if (a->P > 0 && (!a->means3D || !a->opacities || !a->scales || !a->rotations))
+        return fail(TEXGS_E_INVALID, "means3D/opacities/scales/rotations must be given");
+    if (((uintptr_t)a->rotations & 15) != 0) return fail(TEXGS_E_INVALID, "rotations must be 16-byte aligned");
+    if (a->mode == TEXGS_MODE_TEXTURE) {
+        if (!a->uvs || !a->gradient_uvs || !a->texture || a->R <= 0)
+            return fail(TEXGS_E_INVALID, "texture mode needs uvs, gradient_uvs, texture and R > 0");
+        if ((uint64_t)a->R * a->R * 18 >= (1ull << 31)) return fail(TEXGS_E_INVALID, "texture too large for 32-bit texel offsets");
+    } else if (a->mode == TEXGS_MODE_SH) {
+        if (!a->shs || a->M < 1) return fail(TEXGS_E_INVALID, "SH mode needs shs with M >= 1");
+    } else if (!a->colors_precomp) {
+        return fail(TEXGS_E_INVALID, "precomp mode needs colors_precomp");
+    }
+    if ((!geom || !bin || !img)) return fail(TEXGS_E_WORKSPACE, "workspace pointer is NULL");
+    if (((uintptr_t)geom & 127) || ((uintptr_t)bin & 127) || ((uintptr_t)img & 127))
+        return fail(TEXGS_E_WORKSPACE, "workspaces must be 128-byte aligned");
+    memset(&p, 0, sizeof(p));
+    p.P = a->P; p.M = a->shs ? a->M : 0; p.E = 0; p.H = a->H; p.W = a->W; p.R = a->R; p.mode = a->mode;
+    const int m_rest = (a->mode == TEXGS_MODE_SH) ? p.M - 1 : p.M;
+    int deg = a->sh_degree < 0 ? 0 : a->sh_degree;
+    const int dmax = max_degree_for(m_rest);
+    p.sh_degree = deg < dmax ? deg : dmax;
+    p.flags = a->flags;
+    p.grid_x = (a->W + TEXGS_TILE - 1) / TEXGS_TILE;
+    p.grid_y = (a->H + TEXGS_TILE - 1) / TEXGS_TILE;
+    p.num_tiles = p.grid_x * p.grid_y;
+    p.tanfovx = a->tanfovx; p.tanfovy = a->tanfovy; p.scale_modifier = a->scale_modifier;
+    p.focal_x = (float)a->W / (2.0f * a->tanfovx);
+    p.focal_y = (float)a->H / (2.0f * a->tanfovy);
+    memcpy(p.view.m, a->viewmatrix, sizeof(float) * 16);
+    memcpy(p.proj.m, a->projmatrix, sizeof(float) * 16);
+    memcpy(p.campos, a->campos, sizeof(float) * 3);
+    memcpy(p.bg, a->bg, sizeof(float) * 3);
+    p.means3D = a->means3D; p.shs = a->shs; p.colors_precomp = a->colors_precomp; p.opacities = a->opacities;
+    p.scales = a->scales; p.rotations = a->rotations; p.uvs = a->uvs; p.gradient_uvs = a->gradient_uvs;
+    p.texture = a->texture; p.extra_attrs = nullptr;
+    char* g = (char*)geom; char* b = (char*)bin; char* im = (char*)img;
+    p.recs = (GaussRec*)(g + L.l.geom_records);
+    p.rects = (uint2*)(g + L.l.geom_rects);
+    p.counters = (TexgsCounters*)(b + L.l.bin_counters);
+    p.tile_count = (unsigned*)(b + L.l.bin_tile_count);
+    p.tile_cursor = (unsigned*)(b + L.l.bin_tile_cursor);
+    p.tile_offset = (unsigned*)(b + L.l.bin_tile_offset);
+    p.pairs = (uint2*)(b + L.l.bin_pairs);
+    p.sorted_ids = (unsigned*)(b + L.l.bin_sorted_ids);
+    p.pair_capacity = cap;
+    p.final_T = (float*)(im + L.l.img_final_T);
+    p.n_contrib = (unsigned*)(im + L.l.img_n_contrib);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int texgs_abi_version(void) { return TEXGS_ABI_VERSION; }
+
+const char* texgs_last_error(void) { return g_last_error.c_str(); }
+
+const char* texgs_kernel_names(void) {
+    return "texgs_preprocess_fwd,texgs_scan_tiles,texgs_scatter_pairs,texgs_sort_tiles,texgs_render_fwd,"
+           "texgs_render_bwd,texgs_preprocess_bwd,texgs_mark_visible_kernel";
+}
+
+int texgs_workspace_sizes(const TexgsFwdArgs* a, uint64_t pair_capacity, size_t* geom_bytes, size_t* bin_bytes,
+                          size_t* img_bytes) {
+    Layout L;
+    if (int rc = make_layout(a, pair_capacity, L)) return rc;
+    if (geom_bytes) *geom_bytes = (size_t)L.geom_bytes;
+    if (bin_bytes) *bin_bytes = (size_t)L.bin_bytes;
+    if (img_bytes) *img_bytes = (size_t)L.img_bytes;
+    return 0;
+}
+
+int texgs_workspace_layout(const TexgsFwdArgs* a, uint64_t pair_capacity, TexgsLayout* out) {
+    Layout L;
+    if (int rc = make_layout(a, pair_capacity, L)) return rc;
+    if (!out) return fail(TEXGS_E_INVALID, "out is NULL");
+    *out = L.l;
+    return 0;
+}
+
+int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t pair_capacity, void* img_ws,
+                  float* out_image, float* out_depth, float* out_norm, float* out_alpha, int32_t* out_radii,
+                  float* out_extra, TexgsCounters* counters_host, void* counters_ready_event, void* stream_) {
+    (void)out_extra;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    Layout L;
+    if (int rc = make_layout(a, pair_capacity, L)) return rc;
+    RasterParams p;
+    if (int rc = fill_params(a, geom_ws, bin_ws, pair_capacity, img_ws, L, p)) return rc;
+    if (!out_image || !out_depth || !out_norm || !out_alpha || !out_radii) return fail(TEXGS_E_INVALID, "output pointer is NULL");
+    const bool debug = (a->flags & TEXGS_FLAG_DEBUG) != 0;
+
+    TEXGS_CUDA_TRY(cudaMemsetAsync((char*)bin_ws + L.l.bin_counters, 0, L.bin_zero_bytes, stream));
+    const int gblocks = (p.P + 255) / 256;
+    if (p.P > 0) {
+        texgs_preprocess_fwd<<<gblocks, 256, 0, stream>>>(p, out_radii);
+        TEXGS_KERNEL_CHECK("texgs_preprocess_fwd", debug, stream);
+    }
+    texgs_scan_tiles<<<1, TEXGS_SCAN_THREADS, 0, stream>>>(p);
+    TEXGS_KERNEL_CHECK("texgs_scan_tiles", debug, stream);
+    if (counters_host && !debug) {
+        TEXGS_CUDA_TRY(cudaMemcpyAsync(counters_host, p.counters, sizeof(TexgsCounters), cudaMemcpyDeviceToHost, stream));
+        if (counters_ready_event) TEXGS_CUDA_TRY(cudaEventRecord((cudaEvent_t)counters_ready_event, stream));
+    }
+    if (p.P > 0) {
+        texgs_scatter_pairs<<<gblocks, 256, 0, stream>>>(p);
+        TEXGS_KERNEL_CHECK("texgs_scatter_pairs", debug, stream);
+    }
+    texgs_sort_tiles<<<p.num_tiles, TEXGS_SORT_THREADS, 0, stream>>>(p);
+    TEXGS_KERNEL_CHECK("texgs_sort_tiles", debug, stream);
+    if (p.mode == TEXGS_MODE_TEXTURE)
+        texgs_render_fwd<TEXGS_MODE_TEXTURE><<<p.num_tiles, 256, 0, stream>>>(p, out_image, out_depth, out_norm, out_alpha);
+    else
+        texgs_render_fwd<TEXGS_MODE_SH><<<p.num_tiles, 256, 0, stream>>>(p, out_image, out_depth, out_norm, out_alpha);
+    TEXGS_KERNEL_CHECK("texgs_render_fwd", debug, stream);
+    if (counters_host && debug) {   // debug: counters include the blend count, copied after the render
+        TEXGS_CUDA_TRY(cudaMemcpyAsync(counters_host, p.counters, sizeof(TexgsCounters), cudaMemcpyDeviceToHost, stream));
+        if (counters_ready_event) TEXGS_CUDA_TRY(cudaEventRecord((cudaEvent_t)counters_ready_event, stream));
+        TEXGS_CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    return 0;
+}
+
+int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!b) return fail(TEXGS_E_INVALID, "args is NULL");
+    const TexgsFwdArgs* a = &b->fwd;
+    Layout L;
+    if (int rc = make_layout(a, b->pair_capacity, L)) return rc;
+    RasterParams p;
+    if (int rc = fill_params(a, (void*)b->geom_ws, (void*)b->bin_ws, b->pair_capacity, (void*)b->img_ws, L, p)) return rc;
+    if (!b->acc_ws) return fail(TEXGS_E_WORKSPACE, "acc_ws is NULL");
+    const bool debug = (a->flags & TEXGS_FLAG_DEBUG) != 0;
+
+    TEXGS_CUDA_TRY(cudaMemsetAsync(b->acc_ws, 0, (size_t)p.P * TEXGS_BWD_ACC_FLOATS * sizeof(float), stream));
+    if (b->dL_dtexture && b->zero_texture_grad && p.mode == TEXGS_MODE_TEXTURE)
+        TEXGS_CUDA_TRY(cudaMemsetAsync(b->dL_dtexture, 0, (size_t)6 * p.R * p.R * 3 * sizeof(float), stream));
+    BwdIn in{b->dL_dimage, b->dL_ddepth, b->dL_dnorm, b->dL_dalpha};
+    if (p.mode == TEXGS_MODE_TEXTURE)
+        texgs_render_bwd<TEXGS_MODE_TEXTURE><<<p.num_tiles, 256, 0, stream>>>(p, in, b->acc_ws, b->dL_dtexture);
+    else
+        texgs_render_bwd<TEXGS_MODE_SH><<<p.num_tiles, 256, 0, stream>>>(p, in, b->acc_ws, nullptr);
+    TEXGS_KERNEL_CHECK("texgs_render_bwd", debug, stream);
+    if (p.P > 0) {
+        BwdOut g{b->dL_dmeans3D, b->dL_dmeans2D, b->dL_dopacity, b->dL_dscales, b->dL_drotations,
+                 b->dL_dshs, b->dL_dcolors_precomp, b->dL_duvs, b->dL_dextra_attrs};
+        texgs_preprocess_bwd<<<(p.P + 255) / 256, 256, 0, stream>>>(p, nullptr, b->acc_ws, g);
+        TEXGS_KERNEL_CHECK("texgs_preprocess_bwd", debug, stream);
+    }
+    return 0;
+}
+
+__global__ void texgs_mark_visible_kernel(int P, const float* __restrict__ means3D, Mat4 view, int* __restrict__ present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float3 pv = xform43(view, f3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]));
+    present[idx] = (pv.z > TEXGS_NEAR) ? 1 : 0;
+}
+
+int texgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix16_host, const float* projmatrix16_host,
+                       int32_t* present, void* stream_) {
+    (void)projmatrix16_host;
+    if (P < 0 || (P > 0 && (!means3D || !present)) || !viewmatrix16_host) return fail(TEXGS_E_INVALID, "bad arguments");
+    Mat4 v;
+    memcpy(v.m, viewmatrix16_host, sizeof(float) * 16);
+    if (P > 0) {
+        texgs_mark_visible_kernel<<<(P + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(P, means3D, v, present);
+        TEXGS_KERNEL_CHECK("texgs_mark_visible_kernel", false, (cudaStream_t)stream_);
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,164 @@
+// texgs_binning.cuh — tile binning without a global sort (spec E4).
+//
+// The reference lineage sorts all K (tile | depth) 64-bit keys with one device-wide radix sort
+// (6-8 passes over 12 B*K). Here tiles are bins from the start:
+//   1. preprocess counts pairs per tile (atomics on tile_count[T])
+//   2. one CTA scans tile_count -> tile_offset (T ~ 8k..32k: one block is enough), publishes K
+//   3. scatter: every visible Gaussian claims a slot in each of its tiles' segments and writes
+//      {id, depth bits} there (unordered inside the segment)
+//   4. one CTA per tile sorts its segment by the 64-bit key (depth bits << 32 | id) in shared
+//      memory (bitonic network) and emits the sorted id list.
+// Total traffic: 8 B*K written + read once, 4 B*K written — vs ~150 B*K for the radix sort.
+// Order is exactly (tile, depth, Gaussian index) ascending, i.e. what a stable radix sort of
+// index-ordered duplicates produces.
+#pragma once
+#include "texgs_common.cuh"
+
+#define TEXGS_SCAN_THREADS 1024
+
+__global__ void __launch_bounds__(TEXGS_SCAN_THREADS) texgs_scan_tiles(const RasterParams p) {
+    __shared__ unsigned warp_tot[32];
+    __shared__ unsigned carry;
+    __shared__ unsigned smax[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    unsigned vmax = 0;
+    __syncthreads();
+    for (int base = 0; base < p.num_tiles; base += TEXGS_SCAN_THREADS) {
+        const int i = base + tid;
+        const unsigned v = (i < p.num_tiles) ? p.tile_count[i] : 0u;
+        vmax = max(vmax, v);
+        unsigned x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_tot[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_tot[lane] = w;   // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned warp_excl = (wid == 0) ? 0u : warp_tot[wid - 1];
+        const unsigned incl = carry + warp_excl + x;
+        if (i < p.num_tiles) p.tile_offset[i] = incl - v;
+        __syncthreads();
+        if (tid == TEXGS_SCAN_THREADS - 1) carry = incl;
+        __syncthreads();
+    }
+    // max tile length (statistics only)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0) smax[wid] = vmax;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned mm = 0;
+        for (int w = 0; w < TEXGS_SCAN_THREADS / 32; ++w) mm = max(mm, smax[w]);
+        const unsigned K = carry;
+        p.tile_offset[p.num_tiles] = K;
+        p.counters->num_pairs = K;
+        p.counters->max_tile_len = mm;
+        p.counters->overflow = ((unsigned long long)K > p.pair_capacity) ? 1u : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256) texgs_scatter_pairs(const RasterParams p) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.P) return;
+    if (p.counters->overflow) return;
+    const uint2 rc = p.rects[idx];
+    const int x0 = rc.x & 0xffff, x1 = rc.x >> 16, y0 = rc.y & 0xffff, y1 = rc.y >> 16;
+    if (x1 <= x0 || y1 <= y0) return;
+    const unsigned depth_bits = __float_as_uint(p.recs[idx].q[1].z);
+    for (int ty = y0; ty < y1; ++ty)
+        for (int tx = x0; tx < x1; ++tx) {
+            const int t = ty * p.grid_x + tx;
+            const unsigned slot = p.tile_offset[t] + atomicAdd(&p.tile_cursor[t], 1u);
+            p.pairs[slot] = make_uint2((unsigned)idx, depth_bits);
+        }
+}
+
+// Per-tile sort. Keys are 64-bit (depth bits << 32 | id); +inf padding = all ones.
+#define TEXGS_SORT_THREADS 256
+#define TEXGS_SORT_SMEM_ELEMS 4096   // 32 KB of u64
+
+__device__ __forceinline__ void cmpxchg(unsigned long long& a, unsigned long long& b) {
+    if (a > b) { const unsigned long long t = a; a = b; b = t; }
+}
+
+__global__ void __launch_bounds__(TEXGS_SORT_THREADS) texgs_sort_tiles(const RasterParams p) {
+    __shared__ unsigned long long keys[TEXGS_SORT_SMEM_ELEMS];
+    if (p.counters->overflow) return;
+    const int tile = blockIdx.x;
+    const unsigned start = p.tile_offset[tile];
+    const unsigned n = p.tile_offset[tile + 1] - start;
+    if (n == 0) return;
+    unsigned long long* seg = reinterpret_cast<unsigned long long*>(p.pairs + start);
+    const int tid = threadIdx.x;
+    if (n == 1) {
+        if (tid == 0) p.sorted_ids[start] = (unsigned)(seg[0] & 0xffffffffull);
+        return;
+    }
+    unsigned npad = 2;
+    while (npad < n) npad <<= 1;
+    if (npad <= TEXGS_SORT_SMEM_ELEMS) {
+        for (unsigned i = tid; i < npad; i += TEXGS_SORT_THREADS) keys[i] = (i < n) ? seg[i] : ~0ull;
+        __syncthreads();
+        // bitonic network, all compare-exchanges ascending (flip-merge formulation)
+        for (unsigned k = 2; k <= npad; k <<= 1) {
+            // first step of the merge: partner = i ^ (k - 1)
+            for (unsigned i = tid; i < npad / 2; i += TEXGS_SORT_THREADS) {
+                const unsigned blk = i / (k / 2), off = i % (k / 2);
+                const unsigned lo = blk * k + off, hi = blk * k + (k - 1 - off);
+                unsigned long long a = keys[lo], b = keys[hi];
+                if (a > b) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncthreads();
+            for (unsigned j = k / 4; j > 0; j >>= 1) {
+                for (unsigned i = tid; i < npad / 2; i += TEXGS_SORT_THREADS) {
+                    const unsigned lo = 2 * j * (i / j) + (i % j), hi = lo + j;
+                    unsigned long long a = keys[lo], b = keys[hi];
+                    if (a > b) { keys[lo] = b; keys[hi] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        for (unsigned i = tid; i < n; i += TEXGS_SORT_THREADS) {
+            const unsigned long long kv = keys[i];
+            seg[i] = kv;
+            p.sorted_ids[start + i] = (unsigned)(kv & 0xffffffffull);
+        }
+    } else {
+        // rare: list longer than the shared-memory capacity -> same network on global memory with
+        // virtual +inf padding (exchanges touching an index >= n are no-ops)
+        for (unsigned k = 2; k <= npad; k <<= 1) {
+            for (unsigned i = tid; i < npad / 2; i += TEXGS_SORT_THREADS) {
+                const unsigned blk = i / (k / 2), off = i % (k / 2);
+                const unsigned lo = blk * k + off, hi = blk * k + (k - 1 - off);
+                if (hi < n) {
+                    unsigned long long a = seg[lo], b = seg[hi];
+                    if (a > b) { seg[lo] = b; seg[hi] = a; }
+                }
+            }
+            __syncthreads();
+            for (unsigned j = k / 4; j > 0; j >>= 1) {
+                for (unsigned i = tid; i < npad / 2; i += TEXGS_SORT_THREADS) {
+                    const unsigned lo = 2 * j * (i / j) + (i % j), hi = lo + j;
+                    if (hi < n) {
+                        unsigned long long a = seg[lo], b = seg[hi];
+                        if (a > b) { seg[lo] = b; seg[hi] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (unsigned i = tid; i < n; i += TEXGS_SORT_THREADS) p.sorted_ids[start + i] = (unsigned)(seg[i] & 0xffffffffull);
+    }
+}

@@ -1,0 +1,223 @@
+// texgs_common.cuh — shared device helpers for the sm_100a Texture-GS rasterizer.
+//
+// Data layout in HBM:
+//   * GaussRec: one 128-byte, 128-byte-aligned projected record per Gaussian (indexed by Gaussian
+//     id, only written for visible Gaussians). One record = one L2 line = one cp.async.bulk.
+//   * pairs / sorted ids: per-tile contiguous segments (tile_offset[t] .. tile_offset[t+1]).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/texgs.h"
+
+#define TEXGS_TILE 16
+#define TEXGS_TILE_PIX 256
+#define TEXGS_ALPHA_MIN (1.0f / 255.0f)
+#define TEXGS_ALPHA_MAX 0.99f
+#define TEXGS_T_STOP 1e-4f
+#define TEXGS_NEAR 0.2f
+#define TEXGS_ND_EPS 1e-8f
+
+#define SH_C0 0.28209479177387814f
+#define SH_C1 0.4886025119029199f
+__device__ __constant__ float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                          -1.0925484305920792f, 0.5462742152960396f};
+__device__ __constant__ float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                          0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                          -0.5900435899266435f};
+
+// 128-byte projected record (8 x float4). Field map (f = float index):
+//   f0  x        f1  y        f2  conic_a  f3  conic_b      | q0  \ everything the alpha test needs
+//   f4  conic_c  f5  opacity  f6  depth    f7  nm = n_v.p_v | q1  / lives in the first 32-byte sector
+//   f8  nv.x     f9  nv.y     f10 nv.z     f11 pv.x         | q2   view-space disc normal / centre
+//   f12 pv.y     f13 col.r    f14 col.g    f15 col.b        | q3   col = SH_rest + 0.5 (pre-clamp)
+//   f16 uv.x     f17 uv.y     f18 uv.z     f19 J'00         | q4   J' = J * (view->world rot)
+//   f20 J'01     f21 J'02     f22 J'10     f23 J'11         | q5
+//   f24 J'12     f25 J'20     f26 J'21     f27 J'22         | q6
+//   f28 id(bits) f29..31 spare                              | q7
+struct __align__(128) GaussRec { float4 q[8]; };
+static_assert(sizeof(GaussRec) == 128, "record must be one 128 B line");
+
+struct Mat4 { float m[16]; };   // row-major as torch stores it: element (r,c) = m[4*r+c]
+
+// Kernel parameter block (passed by value).
+struct RasterParams {
+    int P, M, sh_degree, E, H, W, R, mode;
+    unsigned flags;
+    int grid_x, grid_y, num_tiles;
+    float tanfovx, tanfovy, scale_modifier;
+    float focal_x, focal_y;
+    Mat4 view, proj;
+    float campos[3];
+    float bg[3];
+    const float *means3D, *shs, *colors_precomp, *opacities, *scales, *rotations, *uvs,
+        *gradient_uvs, *texture, *extra_attrs;
+    // workspaces
+    GaussRec* recs;
+    uint2* rects;            // 4 x uint16 packed: .x = x0 | x1<<16, .y = y0 | y1<<16
+    TexgsCounters* counters;
+    unsigned* tile_count;
+    unsigned* tile_offset;
+    unsigned* tile_cursor;
+    uint2* pairs;            // .x = gaussian id, .y = depth bits  (as u64: depth in the high word)
+    unsigned* sorted_ids;
+    unsigned long long pair_capacity;
+    float* final_T;
+    unsigned* n_contrib;
+};
+
+// ---------------------------------------------------------------------------------------------
+// small math helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// p_view / p_hom with the reference's row-vector convention: out[c] = sum_r p[r] M[r][c] + M[3][c]
+__device__ __forceinline__ float3 xform43(const Mat4& M, float3 p) {
+    return f3(M.m[0] * p.x + M.m[4] * p.y + M.m[8] * p.z + M.m[12],
+              M.m[1] * p.x + M.m[5] * p.y + M.m[9] * p.z + M.m[13],
+              M.m[2] * p.x + M.m[6] * p.y + M.m[10] * p.z + M.m[14]);
+}
+__device__ __forceinline__ float4 xform44(const Mat4& M, float3 p) {
+    return make_float4(M.m[0] * p.x + M.m[4] * p.y + M.m[8] * p.z + M.m[12],
+                       M.m[1] * p.x + M.m[5] * p.y + M.m[9] * p.z + M.m[13],
+                       M.m[2] * p.x + M.m[6] * p.y + M.m[10] * p.z + M.m[14],
+                       M.m[3] * p.x + M.m[7] * p.y + M.m[11] * p.z + M.m[15]);
+}
+// world -> view rotation of a direction: out[c] = sum_r d[r] V[r][c]
+__device__ __forceinline__ float3 rot_w2v(const Mat4& V, float3 d) {
+    return f3(V.m[0] * d.x + V.m[4] * d.y + V.m[8] * d.z,
+              V.m[1] * d.x + V.m[5] * d.y + V.m[9] * d.z,
+              V.m[2] * d.x + V.m[6] * d.y + V.m[10] * d.z);
+}
+// view -> world rotation of a direction: out[r] = sum_c V[r][c] d[c]
+__device__ __forceinline__ float3 rot_v2w(const Mat4& V, float3 d) {
+    return f3(V.m[0] * d.x + V.m[1] * d.y + V.m[2] * d.z,
+              V.m[4] * d.x + V.m[5] * d.y + V.m[6] * d.z,
+              V.m[8] * d.x + V.m[9] * d.y + V.m[10] * d.z);
+}
+
+// quaternion (r,x,y,z) -> rotation, row-major R[3*r+c]  (reference utils/general.py:87-108)
+__device__ __forceinline__ void quat_to_rot(float4 q, float* R) {
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - r * z);       R[2] = 2.f * (x * z + r * y);
+    R[3] = 2.f * (x * y + r * z);       R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - r * x);
+    R[6] = 2.f * (x * z - r * y);       R[7] = 2.f * (y * z + r * x);       R[8] = 1.f - 2.f * (x * x + y * y);
+}
+
+// argmin of the three scales, first index wins ties (torch.argmin semantics on ties are
+// "first occurrence")
+__device__ __forceinline__ int argmin3(float a, float b, float c) {
+    int k = 0; float m = a;
+    if (b < m) { m = b; k = 1; }
+    if (c < m) { k = 2; }
+    return k;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cube map lookup (E11). Face layout = reference NVDIFFREC/util.py:94-101 / cubemap.cu:32-61.
+// ---------------------------------------------------------------------------------------------
+struct CubeCoord {
+    int face;        // 0..5
+    int axis;        // major axis 0/1/2
+    float inv_m;     // 1/|u_major|
+    float sx, sy;    // face coordinates in [-1,1]
+    // sx = sgx * u[ix] * inv_m ; sy = sgy * u[iy] * inv_m ; m = sgm * u[axis]
+    int ix, iy;
+    float sgx, sgy, sgm;
+};
+
+__device__ __forceinline__ CubeCoord cube_coord(float ux, float uy, float uz) {
+    CubeCoord c;
+    const float ax = fabsf(ux), ay = fabsf(uy), az = fabsf(uz);
+    float m;
+    if (ax >= ay && ax >= az) {
+        c.axis = 0; m = ax;
+        if (ux < 0.f) { c.face = 1; c.ix = 2; c.sgx = 1.f;  c.iy = 1; c.sgy = -1.f; c.sgm = -1.f; }
+        else          { c.face = 0; c.ix = 2; c.sgx = -1.f; c.iy = 1; c.sgy = -1.f; c.sgm = 1.f; }
+    } else if (ay >= az) {
+        c.axis = 1; m = ay;
+        if (uy < 0.f) { c.face = 3; c.ix = 0; c.sgx = 1.f; c.iy = 2; c.sgy = -1.f; c.sgm = -1.f; }
+        else          { c.face = 2; c.ix = 0; c.sgx = 1.f; c.iy = 2; c.sgy = 1.f;  c.sgm = 1.f; }
+    } else {
+        c.axis = 2; m = az;
+        if (uz < 0.f) { c.face = 5; c.ix = 0; c.sgx = -1.f; c.iy = 1; c.sgy = -1.f; c.sgm = -1.f; }
+        else          { c.face = 4; c.ix = 0; c.sgx = 1.f;  c.iy = 1; c.sgy = -1.f; c.sgm = 1.f; }
+    }
+    c.inv_m = 1.0f / fmaxf(m, 1e-20f);
+    const float vx = (c.ix == 0) ? ux : ((c.ix == 1) ? uy : uz);
+    const float vy = (c.iy == 0) ? ux : ((c.iy == 1) ? uy : uz);
+    c.sx = c.sgx * vx * c.inv_m;
+    c.sy = c.sgy * vy * c.inv_m;
+    return c;
+}
+
+struct Bilerp {
+    int i00, i01, i10, i11;   // float offsets of the four texels' red channel
+    float wx, wy;
+};
+
+__device__ __forceinline__ Bilerp cube_bilerp(const CubeCoord& c, int R) {
+    Bilerp b;
+    const float halfR = 0.5f * (float)R;
+    const float fx = (c.sx + 1.0f) * halfR - 0.5f;
+    const float fy = (c.sy + 1.0f) * halfR - 0.5f;
+    const float x0f = floorf(fx), y0f = floorf(fy);
+    b.wx = fx - x0f;
+    b.wy = fy - y0f;
+    // clamp in float first: u' may be garbage (inf/nan) for degenerate inputs
+    const int x0 = (int)fminf(fmaxf(x0f, -1.0f), (float)R);
+    const int y0 = (int)fminf(fmaxf(y0f, -1.0f), (float)R);
+    const int x0c = min(max(x0, 0), R - 1), x1c = min(max(x0 + 1, 0), R - 1);
+    const int y0c = min(max(y0, 0), R - 1), y1c = min(max(y0 + 1, 0), R - 1);
+    const int base = c.face * R;
+    b.i00 = ((base + y0c) * R + x0c) * 3;
+    b.i01 = ((base + y0c) * R + x1c) * 3;
+    b.i10 = ((base + y1c) * R + x0c) * 3;
+    b.i11 = ((base + y1c) * R + x1c) * 3;
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + bulk async copy (TMA 1-D) — sm_90+/sm_100a PTX
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (bytes multiple of 16, both 16-B aligned), completes on ``bar``
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}

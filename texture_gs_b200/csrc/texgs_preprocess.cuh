@@ -1,0 +1,405 @@
+// texgs_preprocess.cuh — per-Gaussian forward projection and its backward (a9).
+// Spec items E1-E3, E8, E12(SH part) of SURVEY §8c; maths conventions cited in oracle/raster_ref.py.
+#pragma once
+#include "texgs_common.cuh"
+
+// SH bands l>=1 evaluated at unit direction d. ``sh`` points at the first REST coefficient of this
+// Gaussian (3 floats per coefficient). Sign pattern: reference utils/sh.py:69-112.
+__device__ __forceinline__ float3 sh_rest_eval(int deg, const float* __restrict__ sh, float3 d) {
+    float3 r = f3(0.f, 0.f, 0.f);
+    if (deg <= 0) return r;
+    const float x = d.x, y = d.y, z = d.z;
+#define SH_ACC(k, w) { const float ww = (w); r.x += ww * sh[3 * (k)]; r.y += ww * sh[3 * (k) + 1]; r.z += ww * sh[3 * (k) + 2]; }
+    SH_ACC(0, -SH_C1 * y) SH_ACC(1, SH_C1 * z) SH_ACC(2, -SH_C1 * x)
+    if (deg > 1) {
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+        SH_ACC(3, SH_C2[0] * xy) SH_ACC(4, SH_C2[1] * yz) SH_ACC(5, SH_C2[2] * (2.f * zz - xx - yy))
+        SH_ACC(6, SH_C2[3] * xz) SH_ACC(7, SH_C2[4] * (xx - yy))
+        if (deg > 2) {
+            SH_ACC(8, SH_C3[0] * y * (3.f * xx - yy)) SH_ACC(9, SH_C3[1] * xy * z)
+            SH_ACC(10, SH_C3[2] * y * (4.f * zz - xx - yy))
+            SH_ACC(11, SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy))
+            SH_ACC(12, SH_C3[4] * x * (4.f * zz - xx - yy)) SH_ACC(13, SH_C3[5] * z * (xx - yy))
+            SH_ACC(14, SH_C3[6] * x * (xx - 3.f * yy))
+        }
+    }
+#undef SH_ACC
+    return r;
+}
+
+// Everything the forward projection of one Gaussian produces (shared by fwd and bwd kernels so
+// that the backward recomputes exactly what the forward saw).
+struct Proj {
+    bool visible;
+    float3 pv;          // view-space centre
+    float4 ph;          // clip-space
+    float pw;           // 1/(w+1e-7)
+    float R[9];         // rotation
+    float3 s;           // scales * modifier
+    float tx, ty;       // clamped view x,y
+    bool clampx, clampy;
+    float T[6];         // 2x3: J * W
+    float Sig[6];       // xx,xy,xz,yy,yz,zz
+    float a, b, c, det; // 2-D covariance (dilated) and determinant
+    float radius;
+    float x, y;         // pixel-space mean
+    int rx0, ry0, rx1, ry1;
+    int kmin;           // axis of the smallest scale
+    float nsign;        // +1 / -1 (flip to face the camera)
+    float3 nv;          // view-space facing normal
+    float3 m;           // centre - campos (world)
+};
+
+__device__ __forceinline__ void project_gaussian(const RasterParams& p, int idx, Proj& o) {
+    const float3 mu = f3(p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]);
+    o.visible = false;
+    o.pv = xform43(p.view, mu);
+    if (!(o.pv.z > TEXGS_NEAR)) return;                                     // E1
+    o.ph = xform44(p.proj, mu);
+    o.pw = 1.0f / (o.ph.w + 1e-7f);
+    const float4 q = *reinterpret_cast<const float4*>(p.rotations + 4 * idx);
+    quat_to_rot(q, o.R);
+    o.s = f3(p.scales[3 * idx] * p.scale_modifier, p.scales[3 * idx + 1] * p.scale_modifier,
+             p.scales[3 * idx + 2] * p.scale_modifier);
+    // L = R diag(s);  Sigma = L L^T
+    float L[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { L[3 * r] = o.R[3 * r] * o.s.x; L[3 * r + 1] = o.R[3 * r + 1] * o.s.y; L[3 * r + 2] = o.R[3 * r + 2] * o.s.z; }
+    o.Sig[0] = L[0] * L[0] + L[1] * L[1] + L[2] * L[2];
+    o.Sig[1] = L[0] * L[3] + L[1] * L[4] + L[2] * L[5];
+    o.Sig[2] = L[0] * L[6] + L[1] * L[7] + L[2] * L[8];
+    o.Sig[3] = L[3] * L[3] + L[4] * L[4] + L[5] * L[5];
+    o.Sig[4] = L[3] * L[6] + L[4] * L[7] + L[5] * L[8];
+    o.Sig[5] = L[6] * L[6] + L[7] * L[7] + L[8] * L[8];
+    // E2: EWA projection
+    const float limx = 1.3f * p.tanfovx, limy = 1.3f * p.tanfovy;
+    const float tz = o.pv.z;
+    const float qx = o.pv.x / tz, qy = o.pv.y / tz;
+    o.clampx = (qx < -limx) || (qx > limx);
+    o.clampy = (qy < -limy) || (qy > limy);
+    o.tx = fminf(limx, fmaxf(-limx, qx)) * tz;
+    o.ty = fminf(limy, fmaxf(-limy, qy)) * tz;
+    const float j00 = p.focal_x / tz, j02 = -p.focal_x * o.tx / (tz * tz);
+    const float j11 = p.focal_y / tz, j12 = -p.focal_y * o.ty / (tz * tz);
+    // W[c][r] = V[r][c]  (world -> view rotation);  T = J W
+    const float* V = p.view.m;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        o.T[r] = j00 * V[4 * r + 0] + j02 * V[4 * r + 2];
+        o.T[3 + r] = j11 * V[4 * r + 1] + j12 * V[4 * r + 2];
+    }
+    const float* S = o.Sig;
+    const float u0 = S[0] * o.T[0] + S[1] * o.T[1] + S[2] * o.T[2];
+    const float u1 = S[1] * o.T[0] + S[3] * o.T[1] + S[4] * o.T[2];
+    const float u2 = S[2] * o.T[0] + S[4] * o.T[1] + S[5] * o.T[2];
+    const float w0 = S[0] * o.T[3] + S[1] * o.T[4] + S[2] * o.T[5];
+    const float w1 = S[1] * o.T[3] + S[3] * o.T[4] + S[4] * o.T[5];
+    const float w2 = S[2] * o.T[3] + S[4] * o.T[4] + S[5] * o.T[5];
+    o.a = o.T[0] * u0 + o.T[1] * u1 + o.T[2] * u2 + 0.3f;
+    o.b = o.T[3] * u0 + o.T[4] * u1 + o.T[5] * u2;
+    o.c = o.T[3] * w0 + o.T[4] * w1 + o.T[5] * w2 + 0.3f;
+    o.det = o.a * o.c - o.b * o.b;
+    if (o.det == 0.0f) return;
+    // E3: radius, pixel mean, tile rect
+    const float mid = 0.5f * (o.a + o.c);
+    const float lam = mid + sqrtf(fmaxf(0.1f, mid * mid - o.det));
+    o.radius = ceilf(3.0f * sqrtf(lam));
+    o.x = ((o.ph.x * o.pw + 1.0f) * (float)p.W - 1.0f) * 0.5f;
+    o.y = ((o.ph.y * o.pw + 1.0f) * (float)p.H - 1.0f) * 0.5f;
+    if (!(isfinite(o.x) && isfinite(o.y) && isfinite(o.radius))) return;
+    const float gxf = (float)p.grid_x, gyf = (float)p.grid_y;
+    o.rx0 = (int)fminf(gxf, fmaxf(0.f, floorf((o.x - o.radius) * (1.0f / TEXGS_TILE))));
+    o.rx1 = (int)fminf(gxf, fmaxf(0.f, floorf((o.x + o.radius + (TEXGS_TILE - 1)) * (1.0f / TEXGS_TILE))));
+    o.ry0 = (int)fminf(gyf, fmaxf(0.f, floorf((o.y - o.radius) * (1.0f / TEXGS_TILE))));
+    o.ry1 = (int)fminf(gyf, fmaxf(0.f, floorf((o.y + o.radius + (TEXGS_TILE - 1)) * (1.0f / TEXGS_TILE))));
+    if ((o.rx1 - o.rx0) * (o.ry1 - o.ry0) <= 0) return;
+    // E8: facing disc normal
+    o.kmin = argmin3(p.scales[3 * idx], p.scales[3 * idx + 1], p.scales[3 * idx + 2]);
+    const float3 nraw = f3(o.R[o.kmin], o.R[3 + o.kmin], o.R[6 + o.kmin]);
+    o.m = f3(mu.x - p.campos[0], mu.y - p.campos[1], mu.z - p.campos[2]);
+    o.nsign = (dot3(nraw, o.m) > 0.f) ? -1.f : 1.f;
+    o.nv = rot_w2v(p.view, f3(o.nsign * nraw.x, o.nsign * nraw.y, o.nsign * nraw.z));
+    o.visible = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) texgs_preprocess_fwd(const RasterParams p, int* __restrict__ radii) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.P) return;
+    Proj o;
+    project_gaussian(p, idx, o);
+    if (!o.visible) {
+        radii[idx] = 0;
+        p.rects[idx] = make_uint2(0u, 0u);
+        return;
+    }
+    radii[idx] = (int)o.radius;
+    p.rects[idx] = make_uint2((unsigned)o.rx0 | ((unsigned)o.rx1 << 16), (unsigned)o.ry0 | ((unsigned)o.ry1 << 16));
+
+    const float inv_det = 1.0f / o.det;
+    float3 col;
+    if (p.mode == TEXGS_MODE_PRECOMP) {
+        col = f3(p.colors_precomp[3 * idx], p.colors_precomp[3 * idx + 1], p.colors_precomp[3 * idx + 2]);
+    } else {
+        const float inv_len = rsqrtf(dot3(o.m, o.m));
+        const float3 dir = f3(o.m.x * inv_len, o.m.y * inv_len, o.m.z * inv_len);
+        if (p.mode == TEXGS_MODE_TEXTURE) {
+            col = (p.shs != nullptr) ? sh_rest_eval(min(p.sh_degree, 3), p.shs + (size_t)idx * p.M * 3, dir)
+                                     : f3(0.f, 0.f, 0.f);
+        } else {  // full SH: DC + rest
+            const float* sh = p.shs + (size_t)idx * p.M * 3;
+            col = sh_rest_eval(min(p.sh_degree, 3), sh + 3, dir);
+            col.x += SH_C0 * sh[0]; col.y += SH_C0 * sh[1]; col.z += SH_C0 * sh[2];
+        }
+        col.x += 0.5f; col.y += 0.5f; col.z += 0.5f;
+        if (p.mode == TEXGS_MODE_SH) { col.x = fmaxf(col.x, 0.f); col.y = fmaxf(col.y, 0.f); col.z = fmaxf(col.z, 0.f); }
+    }
+    float uv[3] = {0.f, 0.f, 0.f};
+    float Jp[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (p.mode == TEXGS_MODE_TEXTURE) {
+        uv[0] = p.uvs[3 * idx]; uv[1] = p.uvs[3 * idx + 1]; uv[2] = p.uvs[3 * idx + 2];
+        // J' = J * Wm^T : J'[i][c] = sum_r J[i][r] * V[r][c]   (delta_world = Wm^T delta_view)
+        const float* J = p.gradient_uvs + (size_t)9 * idx;
+        const float* V = p.view.m;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                Jp[3 * i + c] = J[3 * i] * V[c] + J[3 * i + 1] * V[4 + c] + J[3 * i + 2] * V[8 + c];
+    }
+    GaussRec* r = p.recs + idx;
+    r->q[0] = make_float4(o.x, o.y, o.c * inv_det, -o.b * inv_det);
+    r->q[1] = make_float4(o.a * inv_det, p.opacities[idx], o.pv.z, dot3(o.nv, o.pv));
+    r->q[2] = make_float4(o.nv.x, o.nv.y, o.nv.z, o.pv.x);
+    r->q[3] = make_float4(o.pv.y, col.x, col.y, col.z);
+    r->q[4] = make_float4(uv[0], uv[1], uv[2], Jp[0]);
+    r->q[5] = make_float4(Jp[1], Jp[2], Jp[3], Jp[4]);
+    r->q[6] = make_float4(Jp[5], Jp[6], Jp[7], Jp[8]);
+    r->q[7] = make_float4(__int_as_float(idx), 0.f, 0.f, 0.f);
+
+    for (int ty = o.ry0; ty < o.ry1; ++ty)
+        for (int tx = o.rx0; tx < o.rx1; ++tx) atomicAdd(&p.tile_count[ty * p.grid_x + tx], 1u);
+    atomicAdd(&p.counters->num_visible, 1u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: accumulators (TEXGS_BWD_ACC_FLOATS per Gaussian, written by the render backward) ->
+// gradients of the operator inputs.
+//   acc[0..1]  dL/d(x,y) pixel units      acc[2..4]  dL/d conic (a,b,c)     acc[5] dL/d opacity
+//   acc[6..8]  dL/d col                   acc[9]     dL/d depth             acc[10..12] dL/d n_v
+//   acc[13..15] dL/d uv                   acc[16..19] S0, S1, S2, S3 (intersection path)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sh_rest_bwd(int deg, const float* __restrict__ sh, float3 d, float3 g,
+                                            float* __restrict__ dsh, float3& ddir) {
+    // dsh_k = basis_k * g ;  ddir = sum_k dbasis_k/dd * (sh_k . g)
+    ddir = f3(0.f, 0.f, 0.f);
+    if (deg <= 0) return;
+    const float x = d.x, y = d.y, z = d.z;
+#define SH_B(k, w, dwx, dwy, dwz) { const float ww = (w); const float sg = sh[3 * (k)] * g.x + sh[3 * (k) + 1] * g.y + sh[3 * (k) + 2] * g.z; \
+        if (dsh) { dsh[3 * (k)] = ww * g.x; dsh[3 * (k) + 1] = ww * g.y; dsh[3 * (k) + 2] = ww * g.z; } \
+        ddir.x += (dwx) * sg; ddir.y += (dwy) * sg; ddir.z += (dwz) * sg; }
+    SH_B(0, -SH_C1 * y, 0.f, -SH_C1, 0.f)
+    SH_B(1, SH_C1 * z, 0.f, 0.f, SH_C1)
+    SH_B(2, -SH_C1 * x, -SH_C1, 0.f, 0.f)
+    if (deg > 1) {
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+        SH_B(3, SH_C2[0] * xy, SH_C2[0] * y, SH_C2[0] * x, 0.f)
+        SH_B(4, SH_C2[1] * yz, 0.f, SH_C2[1] * z, SH_C2[1] * y)
+        SH_B(5, SH_C2[2] * (2.f * zz - xx - yy), SH_C2[2] * -2.f * x, SH_C2[2] * -2.f * y, SH_C2[2] * 4.f * z)
+        SH_B(6, SH_C2[3] * xz, SH_C2[3] * z, 0.f, SH_C2[3] * x)
+        SH_B(7, SH_C2[4] * (xx - yy), SH_C2[4] * 2.f * x, SH_C2[4] * -2.f * y, 0.f)
+        if (deg > 2) {
+            SH_B(8, SH_C3[0] * y * (3.f * xx - yy), SH_C3[0] * 6.f * xy, SH_C3[0] * (3.f * xx - 3.f * yy), 0.f)
+            SH_B(9, SH_C3[1] * xy * z, SH_C3[1] * yz, SH_C3[1] * xz, SH_C3[1] * xy)
+            SH_B(10, SH_C3[2] * y * (4.f * zz - xx - yy), SH_C3[2] * -2.f * xy, SH_C3[2] * (4.f * zz - xx - 3.f * yy), SH_C3[2] * 8.f * yz)
+            SH_B(11, SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy), SH_C3[3] * -6.f * xz, SH_C3[3] * -6.f * yz, SH_C3[3] * (6.f * zz - 3.f * xx - 3.f * yy))
+            SH_B(12, SH_C3[4] * x * (4.f * zz - xx - yy), SH_C3[4] * (4.f * zz - 3.f * xx - yy), SH_C3[4] * -2.f * xy, SH_C3[4] * 8.f * xz)
+            SH_B(13, SH_C3[5] * z * (xx - yy), SH_C3[5] * 2.f * xz, SH_C3[5] * -2.f * yz, SH_C3[5] * (xx - yy))
+            SH_B(14, SH_C3[6] * x * (xx - 3.f * yy), SH_C3[6] * (3.f * xx - 3.f * yy), SH_C3[6] * -6.f * xy, 0.f)
+        }
+    }
+#undef SH_B
+}
+
+struct BwdOut {
+    float *dmeans3D, *dmeans2D, *dopacity, *dscales, *drotations, *dshs, *dcolors_precomp, *duvs, *dextra_attrs;
+};
+
+__global__ void __launch_bounds__(256) texgs_preprocess_bwd(const RasterParams p, const int* __restrict__ radii_unused,
+                                                          const float* __restrict__ acc_all, const BwdOut g) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.P) return;
+    const int nsh = p.M * 3;
+    Proj o;
+    project_gaussian(p, idx, o);
+    float dmu[3] = {0.f, 0.f, 0.f};
+    if (!o.visible) {
+        if (g.dmeans3D) { g.dmeans3D[3 * idx] = 0.f; g.dmeans3D[3 * idx + 1] = 0.f; g.dmeans3D[3 * idx + 2] = 0.f; }
+        if (g.dmeans2D) { g.dmeans2D[3 * idx] = 0.f; g.dmeans2D[3 * idx + 1] = 0.f; g.dmeans2D[3 * idx + 2] = 0.f; }
+        if (g.dopacity) g.dopacity[idx] = 0.f;
+        if (g.dscales) { g.dscales[3 * idx] = 0.f; g.dscales[3 * idx + 1] = 0.f; g.dscales[3 * idx + 2] = 0.f; }
+        if (g.drotations) *reinterpret_cast<float4*>(g.drotations + 4 * idx) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.dshs) for (int k = 0; k < nsh; ++k) g.dshs[(size_t)idx * nsh + k] = 0.f;
+        if (g.dcolors_precomp) { g.dcolors_precomp[3 * idx] = 0.f; g.dcolors_precomp[3 * idx + 1] = 0.f; g.dcolors_precomp[3 * idx + 2] = 0.f; }
+        if (g.duvs) { g.duvs[3 * idx] = 0.f; g.duvs[3 * idx + 1] = 0.f; g.duvs[3 * idx + 2] = 0.f; }
+        return;
+    }
+    const float* acc = acc_all + (size_t)idx * TEXGS_BWD_ACC_FLOATS;
+    const float* V = p.view.m;
+
+    // ---- colour -> SH / precomp --------------------------------------------------------------
+    float3 gcol = f3(acc[6], acc[7], acc[8]);
+    if (p.mode == TEXGS_MODE_PRECOMP) {
+        if (g.dcolors_precomp) { g.dcolors_precomp[3 * idx] = gcol.x; g.dcolors_precomp[3 * idx + 1] = gcol.y; g.dcolors_precomp[3 * idx + 2] = gcol.z; }
+    } else if (p.shs != nullptr) {
+        const float len2 = dot3(o.m, o.m);
+        const float inv_len = rsqrtf(len2);
+        const float3 dir = f3(o.m.x * inv_len, o.m.y * inv_len, o.m.z * inv_len);
+        const float* sh = p.shs + (size_t)idx * nsh;
+        float* dsh = g.dshs ? g.dshs + (size_t)idx * nsh : nullptr;
+        const int deg = min(p.sh_degree, 3);
+        const int nrest_active = (deg + 1) * (deg + 1) - 1;
+        int first_rest = 0;
+        if (p.mode == TEXGS_MODE_SH) {
+            // clamp mask of the per-Gaussian colour
+            float3 col = sh_rest_eval(deg, sh + 3, dir);
+            col.x += SH_C0 * sh[0] + 0.5f; col.y += SH_C0 * sh[1] + 0.5f; col.z += SH_C0 * sh[2] + 0.5f;
+            if (col.x < 0.f) gcol.x = 0.f;
+            if (col.y < 0.f) gcol.y = 0.f;
+            if (col.z < 0.f) gcol.z = 0.f;
+            if (dsh) { dsh[0] = SH_C0 * gcol.x; dsh[1] = SH_C0 * gcol.y; dsh[2] = SH_C0 * gcol.z; }
+            first_rest = 1;
+        }
+        float3 ddir;
+        sh_rest_bwd(deg, sh + 3 * first_rest, dir, gcol, dsh ? dsh + 3 * first_rest : nullptr, ddir);
+        if (dsh) for (int k = 3 * (first_rest + nrest_active); k < nsh; ++k) dsh[k] = 0.f;
+        // dir = m/|m|
+        const float dd = dot3(dir, ddir);
+        dmu[0] += (ddir.x - dir.x * dd) * inv_len;
+        dmu[1] += (ddir.y - dir.y * dd) * inv_len;
+        dmu[2] += (ddir.z - dir.z * dd) * inv_len;
+    } else if (g.dshs) {
+        for (int k = 0; k < nsh; ++k) g.dshs[(size_t)idx * nsh + k] = 0.f;
+    }
+
+    // ---- intersection path + normal + depth: view-space grads --------------------------------
+    float3 dpv = f3(0.f, 0.f, acc[9]);                    // depth = pv.z
+    float3 dnv = f3(acc[10], acc[11], acc[12]);
+    if (p.mode == TEXGS_MODE_TEXTURE) {
+        const float3 duv = f3(acc[13], acc[14], acc[15]);
+        if (g.duvs) { g.duvs[3 * idx] = duv.x; g.duvs[3 * idx + 1] = duv.y; g.duvs[3 * idx + 2] = duv.z; }
+        const float S0 = acc[16], S1 = acc[17], S2 = acc[18], S3 = acc[19];
+        // J'^T duv, J'[i][c] = sum_r J[i][r] V[r][c]
+        const float* J = p.gradient_uvs + (size_t)9 * idx;
+        float jtw[3];  // world: J^T duv
+#pragma unroll
+        for (int r = 0; r < 3; ++r) jtw[r] = J[r] * duv.x + J[3 + r] * duv.y + J[6 + r] * duv.z;
+        const float3 jtv = rot_w2v(p.view, f3(jtw[0], jtw[1], jtw[2]));   // view: J'^T duv
+        dpv.x += o.nv.x * S0 - jtv.x; dpv.y += o.nv.y * S0 - jtv.y; dpv.z += o.nv.z * S0 - jtv.z;
+        dnv.x += o.pv.x * S0 - S1;    dnv.y += o.pv.y * S0 - S2;    dnv.z += o.pv.z * S0 - S3;
+    }
+
+    // ---- 2-D mean -> clip -> world -----------------------------------------------------------
+    const float dndx = acc[0] * 0.5f * (float)p.W, dndy = acc[1] * 0.5f * (float)p.H;   // NDC units
+    if (g.dmeans2D) { g.dmeans2D[3 * idx] = dndx; g.dmeans2D[3 * idx + 1] = dndy; g.dmeans2D[3 * idx + 2] = 0.f; }
+    {
+        const float dphx = dndx * o.pw, dphy = dndy * o.pw;
+        const float dphw = -(dndx * o.ph.x + dndy * o.ph.y) * o.pw * o.pw;
+        const float* PM = p.proj.m;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) dmu[r] += dphx * PM[4 * r + 0] + dphy * PM[4 * r + 1] + dphw * PM[4 * r + 3];
+    }
+
+    // ---- conic -> cov2D ----------------------------------------------------------------------
+    const float dA = acc[2], dB = acc[3], dC = acc[4];
+    const float a = o.a, b = o.b, c = o.c;
+    const float id2 = 1.0f / (o.det * o.det);
+    const float dLda = (-c * c * dA + b * c * dB - b * b * dC) * id2;
+    const float dLdc = (-b * b * dA + a * b * dB - a * a * dC) * id2;
+    const float dLdb = (2.f * b * c * dA - (a * c + b * b) * dB + 2.f * a * b * dC) * id2;
+    // symmetric G_cov = [[dLda, dLdb/2],[dLdb/2, dLdc]]
+    const float g00 = dLda, g01 = 0.5f * dLdb, g11 = dLdc;
+    const float* T = o.T;
+    const float* S = o.Sig;
+    // dL/dSigma (full symmetric matrix) = T^T G T
+    float GM[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            GM[3 * i + j] = T[i] * (g00 * T[j] + g01 * T[3 + j]) + T[3 + i] * (g01 * T[j] + g11 * T[3 + j]);
+    // dL/dL = 2 GM L,  L = R diag(s)
+    float dR[9];
+    float ds[3] = {0.f, 0.f, 0.f};
+    const float sarr[3] = {o.s.x, o.s.y, o.s.z};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float dL = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) dL += GM[3 * r + j] * o.R[3 * j + k] * sarr[k];
+            dL *= 2.f;
+            dR[3 * r + k] = dL * sarr[k];
+            ds[k] += dL * o.R[3 * r + k];
+        }
+    // dL/dT = 2 G T Sigma
+    float TS[6];
+    TS[0] = T[0] * S[0] + T[1] * S[1] + T[2] * S[2];
+    TS[1] = T[0] * S[1] + T[1] * S[3] + T[2] * S[4];
+    TS[2] = T[0] * S[2] + T[1] * S[4] + T[2] * S[5];
+    TS[3] = T[3] * S[0] + T[4] * S[1] + T[5] * S[2];
+    TS[4] = T[3] * S[1] + T[4] * S[3] + T[5] * S[4];
+    TS[5] = T[3] * S[2] + T[4] * S[4] + T[5] * S[5];
+    float dT[6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        dT[j] = 2.f * (g00 * TS[j] + g01 * TS[3 + j]);
+        dT[3 + j] = 2.f * (g01 * TS[j] + g11 * TS[3 + j]);
+    }
+    // T = Jm W, W[c][r] = V[r][c]  ->  dJm[i][c] = sum_r dT[i][r] V[r][c]
+    const float dJ00 = dT[0] * V[0] + dT[1] * V[4] + dT[2] * V[8];
+    const float dJ02 = dT[0] * V[2] + dT[1] * V[6] + dT[2] * V[10];
+    const float dJ11 = dT[3] * V[1] + dT[4] * V[5] + dT[5] * V[9];
+    const float dJ12 = dT[3] * V[2] + dT[4] * V[6] + dT[5] * V[10];
+    const float tz = o.pv.z, itz = 1.0f / tz, itz2 = itz * itz, itz3 = itz2 * itz;
+    const float dtx = -p.focal_x * itz2 * dJ02;
+    const float dty = -p.focal_y * itz2 * dJ12;
+    const float dtz = -p.focal_x * itz2 * dJ00 - p.focal_y * itz2 * dJ11 + 2.f * p.focal_x * o.tx * itz3 * dJ02 +
+                      2.f * p.focal_y * o.ty * itz3 * dJ12;
+    // tx = clamp(x/z) * z : unclamped -> tx = x ; clamped -> tx = lim * z
+    if (!o.clampx) dpv.x += dtx; else dpv.z += dtx * (o.tx * itz);
+    if (!o.clampy) dpv.y += dty; else dpv.z += dty * (o.ty * itz);
+    dpv.z += dtz;
+
+    // ---- view -> world -----------------------------------------------------------------------
+    {
+        const float3 w = rot_v2w(p.view, dpv);
+        dmu[0] += w.x; dmu[1] += w.y; dmu[2] += w.z;
+        const float3 dn = rot_v2w(p.view, dnv);     // dL/d n (world, facing)
+        dR[0 + o.kmin] += o.nsign * dn.x;
+        dR[3 + o.kmin] += o.nsign * dn.y;
+        dR[6 + o.kmin] += o.nsign * dn.z;
+    }
+
+    // ---- outputs -----------------------------------------------------------------------------
+    if (g.dmeans3D) { g.dmeans3D[3 * idx] = dmu[0]; g.dmeans3D[3 * idx + 1] = dmu[1]; g.dmeans3D[3 * idx + 2] = dmu[2]; }
+    if (g.dopacity) g.dopacity[idx] = acc[5];
+    if (g.dscales) {
+        g.dscales[3 * idx] = ds[0] * p.scale_modifier;
+        g.dscales[3 * idx + 1] = ds[1] * p.scale_modifier;
+        g.dscales[3 * idx + 2] = ds[2] * p.scale_modifier;
+    }
+    if (g.drotations) {
+        const float4 q = *reinterpret_cast<const float4*>(p.rotations + 4 * idx);
+        const float r = q.x, x = q.y, y = q.z, z = q.w;
+        float4 dq;
+        dq.x = 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]);
+        dq.y = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]);
+        dq.z = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]);
+        dq.w = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]);
+        *reinterpret_cast<float4*>(g.drotations + 4 * idx) = dq;
+    }
+}

@@ -1,0 +1,306 @@
+"""Host side of the drop-in boundary: the Python surface of ``diff_gauss_uv_tex`` / ``diff_gauss``.
+
+Mirrors what the reference imports at ``render/uv_tex_render.py:4`` and ``render/render.py:4``:
+
+* ``GaussianRasterizationSettings`` — the 12 fields built at ``render/uv_tex_render.py:25-38``;
+* ``GaussianRasterizer(raster_settings=...)`` — an ``nn.Module`` called with the kwargs of
+  ``render/uv_tex_render.py:56-66`` (textured) or ``render/render.py:75-84`` (plain 3DGS) and
+  returning ``(image, depth, norm, alpha, radii, extra)``.
+
+Underneath: one ``torch.autograd.Function`` whose forward/backward each make ONE call into the
+C-ABI library (``include/texgs.h``) with raw device pointers on the current CUDA stream.
+PyTorch owns every buffer. There is no CPU / eager fallback: without libtexgs.so or without a CUDA
+device every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+import weakref
+from typing import NamedTuple, Optional
+
+import torch
+from torch import nn
+
+from . import _lib as L
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool = False
+    debug: bool = False
+
+
+# ---------------------------------------------------------------------------------------------
+# small host-side caches (no device state)
+# ---------------------------------------------------------------------------------------------
+
+_host_cache: dict = {}
+_host_cache_lock = threading.Lock()
+
+
+def _host_floats(t: torch.Tensor, n: int):
+    """Host copy of a small settings tensor (view/proj matrices, campos, bg).
+
+    The reference keeps these on the GPU (``utils/cameras.py:62-65``); reading them costs one
+    device->host sync the first time a given tensor object is seen, afterwards the copy is served
+    from a cache keyed on object identity + in-place version counter."""
+    if not isinstance(t, torch.Tensor):
+        vals = [float(v) for v in t]
+        assert len(vals) == n
+        return vals
+    if t.device.type == "cpu":
+        vals = t.detach().reshape(-1).to(torch.float32).tolist()
+        assert len(vals) == n, f"expected {n} values, got {len(vals)}"
+        return vals
+    key = id(t)
+    with _host_cache_lock:
+        hit = _host_cache.get(key)
+        if hit is not None and hit[0]() is t and hit[1] == t._version:
+            return hit[2]
+    vals = t.detach().reshape(-1).to(torch.float32).cpu().tolist()
+    assert len(vals) == n, f"expected {n} values, got {len(vals)}"
+    with _host_cache_lock:
+        if len(_host_cache) > 4096:
+            _host_cache.clear()
+        try:
+            ref = weakref.ref(t, lambda _r, k=key: _host_cache.pop(k, None))
+        except TypeError:
+            return vals
+        _host_cache[key] = (ref, t._version, vals)
+    return vals
+
+
+_capacity_hint: dict = {}          # (device index, P, H, W) -> pair capacity that last sufficed
+_pinned: dict = {}                 # device index -> (pinned int32[8], cuda event)
+_pinned_lock = threading.Lock()
+
+
+def _pinned_counters(dev_index: int):
+    with _pinned_lock:
+        ent = _pinned.get(dev_index)
+        if ent is None:
+            buf = torch.zeros(8, dtype=torch.int32).pin_memory()
+            ev = torch.cuda.Event(enable_timing=False, blocking=False)
+            with torch.cuda.device(dev_index):
+                ev.record()          # torch creates the cudaEvent_t lazily; force it so .cuda_event is valid
+                ev.synchronize()
+            ent = (buf, ev)
+            _pinned[dev_index] = ent
+        return ent
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _prep(t: Optional[torch.Tensor], device) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.device != device:
+        raise L.TexgsError(f"tensor on {t.device}, expected {device}")
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class RasterStats(NamedTuple):
+    num_pairs: int
+    num_visible: int
+    max_tile_len: int
+    num_blend: int
+    pair_capacity: int
+
+
+_last_stats = threading.local()
+
+
+def last_stats() -> Optional[RasterStats]:
+    """Counters (V, K, longest tile list, [debug] blended contributions) of the calling thread's
+    most recent forward — what bench.py needs for the algorithmic-byte count."""
+    return getattr(_last_stats, "v", None)
+
+
+def _build_args(st: GaussianRasterizationSettings, mode: int, means3D, shs, colors_precomp, opacities, scales,
+                rotations, uvs, gradient_uvs, texture) -> L.TexgsFwdArgs:
+    a = L.TexgsFwdArgs()
+    a.P = means3D.shape[0]
+    a.M = 0 if shs is None else shs.shape[1]
+    a.sh_degree = int(st.sh_degree)
+    a.E = 0
+    a.H, a.W = int(st.image_height), int(st.image_width)
+    a.R = 0 if texture is None else texture.shape[1]
+    a.mode = mode
+    a.flags = (L.FLAG_PREFILTERED if st.prefiltered else 0) | (L.FLAG_DEBUG if st.debug else 0)
+    a.tanfovx, a.tanfovy, a.scale_modifier = float(st.tanfovx), float(st.tanfovy), float(st.scale_modifier)
+    a.viewmatrix = (C.c_float * 16)(*_host_floats(st.viewmatrix, 16))
+    a.projmatrix = (C.c_float * 16)(*_host_floats(st.projmatrix, 16))
+    a.campos = (C.c_float * 3)(*_host_floats(st.campos, 3))
+    a.bg = (C.c_float * 3)(*_host_floats(st.bg, 3))
+    a.means3D = _ptr(means3D)
+    a.shs = _ptr(shs)
+    a.colors_precomp = _ptr(colors_precomp)
+    a.opacities = _ptr(opacities)
+    a.scales = _ptr(scales)
+    a.rotations = _ptr(rotations)
+    a.uvs = _ptr(uvs)
+    a.gradient_uvs = _ptr(gradient_uvs)
+    a.texture = _ptr(texture)
+    a.extra_attrs = None
+    return a
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, shs, colors_precomp, opacities, scales, rotations, uvs, gradient_uvs,
+                texture, st: GaussianRasterizationSettings, mode: int):
+        lib = L.load()
+        if not means3D.is_cuda:
+            raise L.TexgsError("the rasterizer runs on CUDA tensors only (no CPU fallback); got " + str(means3D.device))
+        dev = means3D.device
+        m3, sh, cp, op = _prep(means3D, dev), _prep(shs, dev), _prep(colors_precomp, dev), _prep(opacities, dev)
+        sc, ro, uv, guv, tex = _prep(scales, dev), _prep(rotations, dev), _prep(uvs, dev), _prep(gradient_uvs, dev), _prep(texture, dev)
+        P, H, W = m3.shape[0], int(st.image_height), int(st.image_width)
+        if mode == L.MODE_TEXTURE:
+            if tex is None or uv is None or guv is None:
+                raise L.TexgsError("textured rasterization needs uvs, gradient_uvs and texture")
+            if tex.dim() != 4 or tex.shape[0] != 6 or tex.shape[1] != tex.shape[2] or tex.shape[3] != 3:
+                raise L.TexgsError(f"texture must be (6,R,R,3), got {tuple(tex.shape)}")
+            if guv.shape != (P, 9) or uv.shape != (P, 3):
+                raise L.TexgsError("uvs must be (P,3) and gradient_uvs (P,9)")
+        if sh is not None and (sh.dim() != 3 or sh.shape[0] != P or sh.shape[2] != 3):
+            raise L.TexgsError(f"shs must be (P,M,3), got {tuple(sh.shape)}")
+        if op.numel() != P or sc.shape != (P, 3) or ro.shape != (P, 4):
+            raise L.TexgsError("opacities (P,1), scales (P,3), rotations (P,4) expected")
+
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            a = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex)
+            image = torch.empty(3, H, W, device=dev, dtype=torch.float32)
+            depth = torch.empty(1, H, W, device=dev, dtype=torch.float32)
+            norm = torch.empty(3, H, W, device=dev, dtype=torch.float32)
+            alpha = torch.empty(1, H, W, device=dev, dtype=torch.float32)
+            radii = torch.empty(P, device=dev, dtype=torch.int32)
+            key = (dev.index, P, H, W)
+            cap = _capacity_hint.get(key, max(1 << 16, 8 * P))
+            pinned, event = _pinned_counters(dev.index)
+            gs, bs, is_ = C.c_size_t(), C.c_size_t(), C.c_size_t()
+            for _attempt in range(8):
+                L.check(lib.texgs_workspace_sizes(C.byref(a), cap, C.byref(gs), C.byref(bs), C.byref(is_)), "texgs_workspace_sizes")
+                geom = torch.empty(max(gs.value, 256), device=dev, dtype=torch.uint8)
+                binw = torch.empty(max(bs.value, 256), device=dev, dtype=torch.uint8)
+                imgw = torch.empty(max(is_.value, 256), device=dev, dtype=torch.uint8)
+                with _pinned_lock:
+                    L.check(lib.texgs_forward(C.byref(a), _ptr(geom), _ptr(binw), cap, _ptr(imgw), _ptr(image), _ptr(depth),
+                                              _ptr(norm), _ptr(alpha), _ptr(radii), None,
+                                              C.c_void_p(pinned.data_ptr()), C.c_void_p(event.cuda_event), C.c_void_p(stream)),
+                            "texgs_forward")
+                    # waits only until the tile scan is done (early in the stream), not for the render
+                    event.synchronize()
+                    K, V, overflow, maxlen, blo, bhi = (int(x) & 0xFFFFFFFF for x in pinned[:6].tolist())
+                if not overflow:
+                    break
+                cap = int(K * 1.25) + 4096
+            else:
+                raise L.TexgsError("pair capacity kept overflowing")
+            _capacity_hint[key] = max(cap, _capacity_hint.get(key, 0)) if not overflow else cap
+            _last_stats.v = RasterStats(K, V, maxlen, blo | (bhi << 32), cap)
+
+        ctx.st, ctx.mode, ctx.cap = st, mode, cap
+        ctx.dev = dev
+        ctx.has = (shs is not None, colors_precomp is not None, uvs is not None, texture is not None)
+        ctx.save_for_backward(m3, sh, cp, op, sc, ro, uv, guv, tex, geom, binw, imgw)
+        ctx.mark_non_differentiable(radii)
+        return image, depth, norm, alpha, radii
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_image, g_depth, g_norm, g_alpha, _g_radii):
+        lib = L.load()
+        m3, sh, cp, op, sc, ro, uv, guv, tex, geom, binw, imgw = ctx.saved_tensors
+        st, mode, dev = ctx.st, ctx.mode, ctx.dev
+        P = m3.shape[0]
+        need = ctx.needs_input_grad   # means3D, means2D, shs, colors_precomp, opacities, scales, rotations, uvs, gradient_uvs, texture
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            b = L.TexgsBwdArgs()
+            b.fwd = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex)
+            b.geom_ws, b.bin_ws, b.img_ws, b.pair_capacity = _ptr(geom), _ptr(binw), _ptr(imgw), ctx.cap
+            keep = [_prep(g, dev) for g in (g_image, g_depth, g_norm, g_alpha)]
+            b.dL_dimage, b.dL_ddepth, b.dL_dnorm, b.dL_dalpha = (_ptr(k) for k in keep)
+            acc = torch.empty(max(P, 1) * L.BWD_ACC_FLOATS, device=dev, dtype=torch.float32)
+            b.acc_ws = _ptr(acc)
+
+            def out(flag, *shape):
+                return torch.empty(*shape, device=dev, dtype=torch.float32) if flag else None
+
+            d_m3 = out(need[0], P, 3)
+            d_m2 = out(need[1], P, 3)
+            d_sh = out(need[2] and sh is not None, *(sh.shape if sh is not None else (0,)))
+            d_cp = out(need[3] and cp is not None, P, 3)
+            d_op = out(need[4], P, 1)
+            d_sc = out(need[5], P, 3)
+            d_ro = out(need[6], P, 4)
+            d_uv = out(need[7] and uv is not None, P, 3)
+            d_tex = out(need[9] and tex is not None, *(tex.shape if tex is not None else (0,)))
+            b.dL_dmeans3D, b.dL_dmeans2D, b.dL_dshs, b.dL_dcolors_precomp = _ptr(d_m3), _ptr(d_m2), _ptr(d_sh), _ptr(d_cp)
+            b.dL_dopacity, b.dL_dscales, b.dL_drotations, b.dL_duvs = _ptr(d_op), _ptr(d_sc), _ptr(d_ro), _ptr(d_uv)
+            b.dL_dtexture = _ptr(d_tex)
+            b.zero_texture_grad = 1
+            L.check(lib.texgs_backward(C.byref(b), C.c_void_p(stream)), "texgs_backward")
+        return d_m3, d_m2, d_sh, d_cp, d_op, d_sc, d_ro, d_uv, None, d_tex, None, None
+
+
+class GaussianRasterizer(nn.Module):
+    """Callable with the kwargs of reference ``render/uv_tex_render.py:56-66`` (``uvs``,
+    ``gradient_uvs``, ``texture`` given -> textured mode) or ``render/render.py:75-84``
+    (``colors_precomp`` / full ``shs`` -> plain 3DGS mode)."""
+
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions: torch.Tensor) -> torch.Tensor:
+        lib = L.load()
+        st = self.raster_settings
+        pos = _prep(positions, positions.device)
+        if not pos.is_cuda:
+            raise L.TexgsError("markVisible needs CUDA tensors")
+        present = torch.empty(pos.shape[0], device=pos.device, dtype=torch.int32)
+        with torch.cuda.device(pos.device):
+            vm = (C.c_float * 16)(*_host_floats(st.viewmatrix, 16))
+            pm = (C.c_float * 16)(*_host_floats(st.projmatrix, 16))
+            L.check(lib.texgs_mark_visible(pos.shape[0], _ptr(pos), vm, pm, _ptr(present),
+                                           C.c_void_p(torch.cuda.current_stream(pos.device).cuda_stream)), "texgs_mark_visible")
+        return present.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3Ds_precomp=None, uvs=None, gradient_uvs=None, texture=None, extra_attrs=None):
+        st = self.raster_settings
+        if extra_attrs is not None:
+            raise NotImplementedError("extra_attrs is always None in the reference tree (render/uv_tex_render.py:7); not built yet")
+        if cov3Ds_precomp is not None:
+            raise NotImplementedError("cov3Ds_precomp: the disc normal / intersection need scales + rotations")
+        if scales is None or rotations is None:
+            raise ValueError("Please provide scales and rotations")
+        if texture is not None:
+            mode = L.MODE_TEXTURE
+            if colors_precomp is not None:
+                raise ValueError("texture and colors_precomp are mutually exclusive")
+        else:
+            if (shs is None) == (colors_precomp is None):
+                raise ValueError("Please provide exactly one of either SHs or precomputed colors!")
+            mode = L.MODE_SH if shs is not None else L.MODE_PRECOMP
+        image, depth, norm, alpha, radii = _RasterizeGaussians.apply(
+            means3D, means2D, shs, colors_precomp, opacities, scales, rotations, uvs, gradient_uvs, texture, st, mode)
+        return image, depth, norm, alpha, radii, None
