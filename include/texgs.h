@@ -69,7 +69,23 @@ typedef struct TexgsFwdArgs {
     const float* gradient_uvs;   /* (P,9) row-major d uv_i / d x_j, or NULL      */
     const float* texture;        /* (6,R,R,3) or NULL                            */
     const float* extra_attrs;    /* (P,E) or NULL                                */
+    /* optional per-kernel timing: HOST array of TEXGS_EV_COUNT cudaEvent_t (as void*), recorded on
+     * the stream at the stage boundaries below; NULL = off. Forward fills slots 0..5, backward
+     * (through TexgsBwdArgs.fwd) slots 6..9. */
+    void* const* profile_events;
 } TexgsFwdArgs;
+
+#define TEXGS_EV_FWD_START      0
+#define TEXGS_EV_FWD_PREPROCESS 1   /* after texgs_preprocess_fwd (+ workspace clear) */
+#define TEXGS_EV_FWD_SCAN       2   /* after texgs_scan_tiles                          */
+#define TEXGS_EV_FWD_SCATTER    3   /* after texgs_scatter_pairs                       */
+#define TEXGS_EV_FWD_SORT       4   /* after texgs_sort_tiles                          */
+#define TEXGS_EV_FWD_RENDER     5   /* after texgs_render_fwd                          */
+#define TEXGS_EV_BWD_START      6
+#define TEXGS_EV_BWD_CLEAR      7   /* after the accumulator / texture-grad clears     */
+#define TEXGS_EV_BWD_RENDER     8   /* after texgs_render_bwd                          */
+#define TEXGS_EV_BWD_PREPROCESS 9   /* after texgs_preprocess_bwd                      */
+#define TEXGS_EV_COUNT          10
 
 /* Device-written run statistics, copied to ``counters_host`` (pinned) when that pointer is given. */
 typedef struct TexgsCounters {

@@ -54,6 +54,7 @@ ALPHA_MAX = 0.99
 T_STOP = 1e-4
 NEAR_CULL = 0.2
 ND_EPS = 1e-8
+GRAZING_COS = 0.1     # test-side conditioning flag only (never changes the rendered values)
 
 
 class RasterSettings(NamedTuple):
@@ -327,6 +328,7 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
     final_T = torch.ones(npix_pad, dtype=dt, device=dev)
     n_contrib = torch.zeros(npix_pad, dtype=torch.int64, device=dev)
     ambiguous = torch.zeros(npix_pad, dtype=torch.bool, device=dev)
+    grazing = torch.zeros(npix_pad, dtype=torch.bool, device=dev)
     n_blend = 0
 
     # tile segments
@@ -420,6 +422,11 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
                 nd = (nrm * d_w).sum(-1)
                 nm = (nrm * mvec).sum(-1)
                 safe = nd.abs() >= ND_EPS                                     # E9
+                with torch.no_grad():
+                    # conditioning flag: t = n.m / n.d amplifies rounding by 1/cos(angle(n, d));
+                    # below GRAZING_COS fp32 cannot hold 1e-4 / 1e-3 (fp32 vs fp64 oracle differ too)
+                    cosang = nd.abs() / (d_w.norm(dim=-1) * nrm.norm(dim=-1).clamp_min(1e-30))
+                    grazing[pix[cosang < GRAZING_COS]] = True
                 nd_s = torch.where(safe, nd, torch.ones_like(nd))
                 tpar = torch.where(safe, nm / nd_s, torch.zeros_like(nd))
                 delta = torch.where(safe[:, None], tpar[:, None] * d_w - mvec, torch.zeros_like(mvec))
@@ -457,7 +464,9 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
     out = (image, depth, norm, alpha_img, pre["radii"], extra)
     if return_aux:
         aux = dict(final_T=Tf[0].detach(), n_contrib=unpad(n_contrib.reshape(-1, 1), 1)[0],
-                   ambiguous=unpad(ambiguous.reshape(-1, 1), 1)[0], num_pairs=int(tile_of.shape[0]),
+                   ambiguous=unpad(ambiguous.reshape(-1, 1), 1)[0] | unpad(grazing.reshape(-1, 1), 1)[0],
+                   threshold_ambiguous=unpad(ambiguous.reshape(-1, 1), 1)[0],
+                   grazing=unpad(grazing.reshape(-1, 1), 1)[0], num_pairs=int(tile_of.shape[0]),
                    num_visible=int(pre["visible"].sum()), num_blend=n_blend, pre=pre,
                    tile_of=tile_of, gid_of=gid_of)
         return out + (aux,)

@@ -1,0 +1,69 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: view sharding and the flat
+gradient bucket whose slices are the leaves' .grad, summed with one all-reduce."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from texture_gs_b200.dist import GradBucket, shard_views
+
+
+def test_shard_views_partitions_exactly():
+    for n in (32, 7, 1, 0):
+        for w in (1, 2, 3, 8):
+            parts = [shard_views(n, w, r) for r in range(w)]
+            flat = [v for p in parts for v in p]
+            assert flat == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_bucket_slices_are_the_grads_and_accumulate_in_place():
+    a = torch.randn(5, 3, requires_grad=True)
+    b = torch.randn(7, requires_grad=True)
+    c = torch.randn(2, 2)                       # no grad: not in the bucket
+    bk = GradBucket({"a": a, "b": b, "c": c, "none": None})
+    assert set(bk.params) == {"a", "b"}
+    ptr_a = a.grad.data_ptr()
+    for _ in range(3):                            # three "views" accumulate into the same storage
+        ((a * 2).sum() + (b * 3).sum()).backward()
+    assert a.grad.data_ptr() == ptr_a == bk.flat.data_ptr()
+    assert torch.allclose(bk.grads()["a"], torch.full((5, 3), 6.0))
+    assert torch.allclose(bk.grads()["b"], torch.full((7,), 9.0))
+    bk.zero()
+    assert float(bk.flat.abs().sum()) == 0 and a.grad.data_ptr() == ptr_a
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    w = torch.randn(6, 4)                        # replicated "texture"
+    x = torch.randn(3)                           # replicated "gaussian parameter"
+    w.requires_grad_(True); x.requires_grad_(True)
+    bk = GradBucket({"w": w, "x": x})
+    views = shard_views(10, world, rank)
+    for v in views:                              # a view's loss depends on its index
+        ((w * (v + 1)).sum() + (x * x).sum() * (v + 1)).backward()
+    bk.all_reduce()
+    # expected: sum over all 10 views
+    s = sum(v + 1 for v in range(10))
+    ok = torch.allclose(bk.grads()["w"], torch.full((6, 4), float(s))) and \
+        torch.allclose(bk.grads()["x"], 2 * x.detach() * s)
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_allreduce_matches_single_process_sum():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}

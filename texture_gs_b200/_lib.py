@@ -17,6 +17,9 @@ FLAG_PREFILTERED = 1
 FLAG_DEBUG = 2
 MODE_TEXTURE, MODE_SH, MODE_PRECOMP = 0, 1, 2
 BWD_ACC_FLOATS = 24
+EV_COUNT = 10
+EV_NAMES = ("fwd_start", "preprocess_fwd", "scan_tiles", "scatter_pairs", "sort_tiles", "render_fwd",
+            "bwd_start", "bwd_clear", "render_bwd", "preprocess_bwd")
 
 _fp = C.c_void_p   # device pointers travel as void*
 
@@ -31,6 +34,7 @@ class TexgsFwdArgs(C.Structure):
         ("campos", C.c_float * 3), ("bg", C.c_float * 3),
         ("means3D", _fp), ("shs", _fp), ("colors_precomp", _fp), ("opacities", _fp), ("scales", _fp),
         ("rotations", _fp), ("uvs", _fp), ("gradient_uvs", _fp), ("texture", _fp), ("extra_attrs", _fp),
+        ("profile_events", C.POINTER(C.c_void_p)),
     ]
 
 

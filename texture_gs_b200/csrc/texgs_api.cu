@@ -33,6 +33,12 @@ int fail(int code, const std::string& msg) {
         if (err__ != cudaSuccess) return fail((int)err__, std::string(name) + ": " + cudaGetErrorString(err__)); \
     } while (0)
 
+#define TEXGS_EV(a, slot, stream)                                                                        \
+    do {                                                                                                 \
+        if ((a)->profile_events && (a)->profile_events[slot])                                            \
+            TEXGS_CUDA_TRY(cudaEventRecord((cudaEvent_t)(a)->profile_events[slot], stream));             \
+    } while (0)
+
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
@@ -83,12 +89,12 @@ int fill_params(const TexgsFwdArgs* a, void* geom, void* bin, uint64_t cap, void
         return fail(TEXGS_E_INVALID, "means3D/opacities/scales/rotations must be given");
     if (((uintptr_t)a->rotations & 15) != 0) return fail(TEXGS_E_INVALID, "rotations must be 16-byte aligned");
     if (a->mode == TEXGS_MODE_TEXTURE) {
-        if (!a->uvs || !a->gradient_uvs || !a->texture || a->R <= 0)
+        if ((a->P > 0 && (!a->uvs || !a->gradient_uvs)) || !a->texture || a->R <= 0)
             return fail(TEXGS_E_INVALID, "texture mode needs uvs, gradient_uvs, texture and R > 0");
         if ((uint64_t)a->R * a->R * 18 >= (1ull << 31)) return fail(TEXGS_E_INVALID, "texture too large for 32-bit texel offsets");
     } else if (a->mode == TEXGS_MODE_SH) {
-        if (!a->shs || a->M < 1) return fail(TEXGS_E_INVALID, "SH mode needs shs with M >= 1");
-    } else if (!a->colors_precomp) {
+        if ((a->P > 0 && !a->shs) || a->M < 1) return fail(TEXGS_E_INVALID, "SH mode needs shs with M >= 1");
+    } else if (a->P > 0 && !a->colors_precomp) {
         return fail(TEXGS_E_INVALID, "precomp mode needs colors_precomp");
     }
     if ((!geom || !bin || !img)) return fail(TEXGS_E_WORKSPACE, "workspace pointer is NULL");
@@ -172,14 +178,17 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
     if (!out_image || !out_depth || !out_norm || !out_alpha || !out_radii) return fail(TEXGS_E_INVALID, "output pointer is NULL");
     const bool debug = (a->flags & TEXGS_FLAG_DEBUG) != 0;
 
+    TEXGS_EV(a, TEXGS_EV_FWD_START, stream);
     TEXGS_CUDA_TRY(cudaMemsetAsync((char*)bin_ws + L.l.bin_counters, 0, L.bin_zero_bytes, stream));
     const int gblocks = (p.P + 255) / 256;
     if (p.P > 0) {
         texgs_preprocess_fwd<<<gblocks, 256, 0, stream>>>(p, out_radii);
         TEXGS_KERNEL_CHECK("texgs_preprocess_fwd", debug, stream);
     }
+    TEXGS_EV(a, TEXGS_EV_FWD_PREPROCESS, stream);
     texgs_scan_tiles<<<1, TEXGS_SCAN_THREADS, 0, stream>>>(p);
     TEXGS_KERNEL_CHECK("texgs_scan_tiles", debug, stream);
+    TEXGS_EV(a, TEXGS_EV_FWD_SCAN, stream);
     if (counters_host && !debug) {
         TEXGS_CUDA_TRY(cudaMemcpyAsync(counters_host, p.counters, sizeof(TexgsCounters), cudaMemcpyDeviceToHost, stream));
         if (counters_ready_event) TEXGS_CUDA_TRY(cudaEventRecord((cudaEvent_t)counters_ready_event, stream));
@@ -188,13 +197,16 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
         texgs_scatter_pairs<<<gblocks, 256, 0, stream>>>(p);
         TEXGS_KERNEL_CHECK("texgs_scatter_pairs", debug, stream);
     }
+    TEXGS_EV(a, TEXGS_EV_FWD_SCATTER, stream);
     texgs_sort_tiles<<<p.num_tiles, TEXGS_SORT_THREADS, 0, stream>>>(p);
     TEXGS_KERNEL_CHECK("texgs_sort_tiles", debug, stream);
+    TEXGS_EV(a, TEXGS_EV_FWD_SORT, stream);
     if (p.mode == TEXGS_MODE_TEXTURE)
         texgs_render_fwd<TEXGS_MODE_TEXTURE><<<p.num_tiles, 256, 0, stream>>>(p, out_image, out_depth, out_norm, out_alpha);
     else
         texgs_render_fwd<TEXGS_MODE_SH><<<p.num_tiles, 256, 0, stream>>>(p, out_image, out_depth, out_norm, out_alpha);
     TEXGS_KERNEL_CHECK("texgs_render_fwd", debug, stream);
+    TEXGS_EV(a, TEXGS_EV_FWD_RENDER, stream);
     if (counters_host && debug) {   // debug: counters include the blend count, copied after the render
         TEXGS_CUDA_TRY(cudaMemcpyAsync(counters_host, p.counters, sizeof(TexgsCounters), cudaMemcpyDeviceToHost, stream));
         if (counters_ready_event) TEXGS_CUDA_TRY(cudaEventRecord((cudaEvent_t)counters_ready_event, stream));
@@ -214,21 +226,25 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
     if (!b->acc_ws) return fail(TEXGS_E_WORKSPACE, "acc_ws is NULL");
     const bool debug = (a->flags & TEXGS_FLAG_DEBUG) != 0;
 
+    TEXGS_EV(a, TEXGS_EV_BWD_START, stream);
     TEXGS_CUDA_TRY(cudaMemsetAsync(b->acc_ws, 0, (size_t)p.P * TEXGS_BWD_ACC_FLOATS * sizeof(float), stream));
     if (b->dL_dtexture && b->zero_texture_grad && p.mode == TEXGS_MODE_TEXTURE)
         TEXGS_CUDA_TRY(cudaMemsetAsync(b->dL_dtexture, 0, (size_t)6 * p.R * p.R * 3 * sizeof(float), stream));
+    TEXGS_EV(a, TEXGS_EV_BWD_CLEAR, stream);
     BwdIn in{b->dL_dimage, b->dL_ddepth, b->dL_dnorm, b->dL_dalpha};
     if (p.mode == TEXGS_MODE_TEXTURE)
         texgs_render_bwd<TEXGS_MODE_TEXTURE><<<p.num_tiles, 256, 0, stream>>>(p, in, b->acc_ws, b->dL_dtexture);
     else
         texgs_render_bwd<TEXGS_MODE_SH><<<p.num_tiles, 256, 0, stream>>>(p, in, b->acc_ws, nullptr);
     TEXGS_KERNEL_CHECK("texgs_render_bwd", debug, stream);
+    TEXGS_EV(a, TEXGS_EV_BWD_RENDER, stream);
     if (p.P > 0) {
         BwdOut g{b->dL_dmeans3D, b->dL_dmeans2D, b->dL_dopacity, b->dL_dscales, b->dL_drotations,
                  b->dL_dshs, b->dL_dcolors_precomp, b->dL_duvs, b->dL_dextra_attrs};
         texgs_preprocess_bwd<<<(p.P + 255) / 256, 256, 0, stream>>>(p, nullptr, b->acc_ws, g);
         TEXGS_KERNEL_CHECK("texgs_preprocess_bwd", debug, stream);
     }
+    TEXGS_EV(a, TEXGS_EV_BWD_PREPROCESS, stream);
     return 0;
 }
 

@@ -221,3 +221,49 @@ __device__ __forceinline__ float warp_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     return v;
 }
+
+// Transposing warp reduction of 20 per-lane values: instead of 5 shuffles per value (100), every
+// step halves the number of values a lane still owns (16 -> 8 -> 4 -> 2 -> 1, then 4 -> 2 -> 1),
+// 22 shuffles in total. On return
+//   outA on lane l holds the warp total of value ((l >> 1) & 15)            (values 0..15)
+//   outB on lane l holds the warp total of value 16 + 2*bit4(l) + bit3(l)   (values 16..19)
+__device__ __forceinline__ void warp_reduce20(const float (&v)[20], int lane, float& outA, float& outB) {
+    const unsigned full = 0xffffffffu;
+    const bool h4 = (lane & 16) != 0, h3 = (lane & 8) != 0, h2 = (lane & 4) != 0, h1 = (lane & 2) != 0;
+    float a8[8], a4[4], a2[2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = h4 ? v[i] : v[i + 8], keep = h4 ? v[i + 8] : v[i];
+        a8[i] = keep + __shfl_xor_sync(full, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = h3 ? a8[i] : a8[i + 4], keep = h3 ? a8[i + 4] : a8[i];
+        a4[i] = keep + __shfl_xor_sync(full, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h2 ? a4[i] : a4[i + 2], keep = h2 ? a4[i + 2] : a4[i];
+        a2[i] = keep + __shfl_xor_sync(full, send, 4);
+    }
+    {
+        const float send = h1 ? a2[0] : a2[1], keep = h1 ? a2[1] : a2[0];
+        float a1 = keep + __shfl_xor_sync(full, send, 2);
+        a1 += __shfl_xor_sync(full, a1, 1);
+        outA = a1;
+    }
+    float b2[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h4 ? v[16 + i] : v[18 + i], keep = h4 ? v[18 + i] : v[16 + i];
+        b2[i] = keep + __shfl_xor_sync(full, send, 16);
+    }
+    {
+        const float send = h3 ? b2[0] : b2[1], keep = h3 ? b2[1] : b2[0];
+        float b1 = keep + __shfl_xor_sync(full, send, 8);
+        b1 += __shfl_xor_sync(full, b1, 4);
+        b1 += __shfl_xor_sync(full, b1, 2);
+        b1 += __shfl_xor_sync(full, b1, 1);
+        outB = b1;
+    }
+}

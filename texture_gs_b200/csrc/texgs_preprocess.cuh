@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(256) texgs_preprocess_fwd(const RasterParams p
 // gradients of the operator inputs.
 //   acc[0..1]  dL/d(x,y) pixel units      acc[2..4]  dL/d conic (a,b,c)     acc[5] dL/d opacity
 //   acc[6..8]  dL/d col                   acc[9]     dL/d depth             acc[10..12] dL/d n_v
-//   acc[13..15] dL/d uv                   acc[16..19] S0, S1, S2, S3 (intersection path)
+//   acc[13..15] dL/d uv                   acc[16] S0 = sum s, acc[17..19] sum s*Delta_v (intersection path,
+//                                          s = (J'^T gu . v)/(n_v . v))
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void sh_rest_bwd(int deg, const float* __restrict__ sh, float3 d, float3 g,
                                             float* __restrict__ dsh, float3& ddir) {
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(256) texgs_preprocess_bwd(const RasterParams p
         for (int r = 0; r < 3; ++r) jtw[r] = J[r] * duv.x + J[3 + r] * duv.y + J[6 + r] * duv.z;
         const float3 jtv = rot_w2v(p.view, f3(jtw[0], jtw[1], jtw[2]));   // view: J'^T duv
         dpv.x += o.nv.x * S0 - jtv.x; dpv.y += o.nv.y * S0 - jtv.y; dpv.z += o.nv.z * S0 - jtv.z;
-        dnv.x += o.pv.x * S0 - S1;    dnv.y += o.pv.y * S0 - S2;    dnv.z += o.pv.z * S0 - S3;
+        dnv.x -= S1; dnv.y -= S2; dnv.z -= S3;      // dL/dn_v = -sum s*Delta_v
     }
 
     // ---- 2-D mean -> clip -> world -----------------------------------------------------------

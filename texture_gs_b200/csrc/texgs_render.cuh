@@ -59,6 +59,7 @@ __device__ __forceinline__ void issue_batch(const RasterParams& p, GaussRec (*s_
 struct UvEval {
     float ux, uy, uz;
     float nd, t;
+    float dx, dy, dz;   // Delta in view space
     bool safe;
 };
 __device__ __forceinline__ UvEval eval_uv(const float4& g1, const float4& g2, const float4& g3, const float4& g4,
@@ -68,12 +69,13 @@ __device__ __forceinline__ UvEval eval_uv(const float4& g1, const float4& g2, co
     e.ux = g4.x; e.uy = g4.y; e.uz = g4.z;
     e.safe = fabsf(e.nd) >= TEXGS_ND_EPS;
     e.t = 0.f;
+    e.dx = e.dy = e.dz = 0.f;
     if (e.safe) {
         e.t = g1.w / e.nd;
-        const float dx = e.t * vx - g2.w, dy = e.t * vy - g3.x, dz = e.t - g1.z;
-        e.ux += g4.w * dx + g5.x * dy + g5.y * dz;
-        e.uy += g5.z * dx + g5.w * dy + g6.x * dz;
-        e.uz += g6.y * dx + g6.z * dy + g6.w * dz;
+        e.dx = e.t * vx - g2.w; e.dy = e.t * vy - g3.x; e.dz = e.t - g1.z;
+        e.ux += g4.w * e.dx + g5.x * e.dy + g5.y * e.dz;
+        e.uy += g5.z * e.dx + g5.w * e.dy + g6.x * e.dz;
+        e.uz += g6.y * e.dx + g6.z * e.dy + g6.w * e.dz;
     }
     return e;
 }
@@ -98,8 +100,9 @@ __global__ void __launch_bounds__(256) texgs_render_fwd(const RasterParams p, fl
     if (nb > 0) issue_batch(p, s_rec, s_bar, start, n, 0);
 
     float T = 1.0f, Cr = 0.f, Cg = 0.f, Cb = 0.f, D = 0.f, Nx = 0.f, Ny = 0.f, Nz = 0.f, A = 0.f;
-    unsigned contributor = 0, last = 0, nblend = 0;
+    unsigned last = 0, nblend = 0;
     bool done = !g.inside;
+    bool warp_done = false;          // uniform across the warp
     const float pxf = (float)g.px, pyf = (float)g.py;
     const float* __restrict__ tex = p.texture;
     const int R = p.R;
@@ -110,46 +113,51 @@ __global__ void __launch_bounds__(256) texgs_render_fwd(const RasterParams p, fl
         const int cnt = (int)min((unsigned)TEXGS_BATCH, n - (unsigned)b * TEXGS_BATCH);
         mbar_wait(&s_bar[s], (unsigned)(b >> 1) & 1u);
         if (b + 1 < nb) issue_batch(p, s_rec, s_bar, start, n, b + 1);
-        if (!done) {
+        if (!warp_done) {
+            // The loop is warp-synchronous: every lane walks the same j, per-lane state is a
+            // predicate. (A per-lane continue/break loop never reconverges on sm_70+ and runs the
+            // lanes one after the other.)
             for (int j = 0; j < cnt; ++j) {
-                ++contributor;
                 const GaussRec& rec = s_rec[s][j];
                 const float4 g0 = rec.q[0], g1 = rec.q[1];
                 const float dx = g0.x - pxf, dy = g0.y - pyf;
                 const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
-                if (power > 0.0f) continue;
                 const float alpha = fminf(TEXGS_ALPHA_MAX, g1.y * texgs_exp(power));
-                if (alpha < TEXGS_ALPHA_MIN) continue;
+                bool cand = !done && (power <= 0.0f) && (alpha >= TEXGS_ALPHA_MIN);
+                if (!__any_sync(0xffffffffu, cand)) continue;
                 const float test_T = T * (1.0f - alpha);
-                if (test_T < TEXGS_T_STOP) { done = true; break; }
-                const float4 g2 = rec.q[2], g3 = rec.q[3];
-                float cr = g3.y, cg = g3.z, cb = g3.w;
-                if (MODE == TEXGS_MODE_TEXTURE) {
-                    const float4 g4 = rec.q[4], g5 = rec.q[5], g6 = rec.q[6];
-                    const UvEval e = eval_uv(g1, g2, g3, g4, g5, g6, g.vx, g.vy);
-                    const CubeCoord cc = cube_coord(e.ux, e.uy, e.uz);
-                    const Bilerp bl = cube_bilerp(cc, R);
-                    float tx3[3];
+                if (cand && test_T < TEXGS_T_STOP) { done = true; cand = false; }
+                if (cand) {
+                    const float4 g2 = rec.q[2], g3 = rec.q[3];
+                    float cr = g3.y, cg = g3.z, cb = g3.w;
+                    if (MODE == TEXGS_MODE_TEXTURE) {
+                        const float4 g4 = rec.q[4], g5 = rec.q[5], g6 = rec.q[6];
+                        const UvEval e = eval_uv(g1, g2, g3, g4, g5, g6, g.vx, g.vy);
+                        const CubeCoord cc = cube_coord(e.ux, e.uy, e.uz);
+                        const Bilerp bl = cube_bilerp(cc, R);
+                        float tx3[3];
 #pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        const float t00 = __ldg(tex + bl.i00 + ch), t01 = __ldg(tex + bl.i01 + ch);
-                        const float t10 = __ldg(tex + bl.i10 + ch), t11 = __ldg(tex + bl.i11 + ch);
-                        const float top = t00 + bl.wx * (t01 - t00);
-                        const float bot = t10 + bl.wx * (t11 - t10);
-                        tx3[ch] = top + bl.wy * (bot - top);
+                        for (int ch = 0; ch < 3; ++ch) {
+                            const float t00 = __ldg(tex + bl.i00 + ch), t01 = __ldg(tex + bl.i01 + ch);
+                            const float t10 = __ldg(tex + bl.i10 + ch), t11 = __ldg(tex + bl.i11 + ch);
+                            const float top = t00 + bl.wx * (t01 - t00);
+                            const float bot = t10 + bl.wx * (t11 - t10);
+                            tx3[ch] = top + bl.wy * (bot - top);
+                        }
+                        cr = fmaxf(0.f, SH_C0 * tx3[0] + cr);
+                        cg = fmaxf(0.f, SH_C0 * tx3[1] + cg);
+                        cb = fmaxf(0.f, SH_C0 * tx3[2] + cb);
                     }
-                    cr = fmaxf(0.f, SH_C0 * tx3[0] + cr);
-                    cg = fmaxf(0.f, SH_C0 * tx3[1] + cg);
-                    cb = fmaxf(0.f, SH_C0 * tx3[2] + cb);
+                    const float w = alpha * T;
+                    Cr += w * cr; Cg += w * cg; Cb += w * cb;
+                    D += w * g1.z;
+                    Nx += w * g2.x; Ny += w * g2.y; Nz += w * g2.z;
+                    A += w;
+                    T = test_T;
+                    last = (unsigned)b * TEXGS_BATCH + (unsigned)j + 1u;
+                    ++nblend;
                 }
-                const float w = alpha * T;
-                Cr += w * cr; Cg += w * cg; Cb += w * cb;
-                D += w * g1.z;
-                Nx += w * g2.x; Ny += w * g2.y; Nz += w * g2.z;
-                A += w;
-                T = test_T;
-                last = contributor;
-                ++nblend;
+                if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
             }
         }
         if (__syncthreads_and(done ? 1 : 0)) {
@@ -357,20 +365,18 @@ __global__ void __launch_bounds__(256) texgs_render_bwd(const RasterParams p, co
                         const float gvz = g5.y * gu[0] + g6.x * gu[1] + g6.w * gu[2];
                         const float sden = (gvx * g.vx + gvy * g.vy + gvz) / e.nd;
                         v[16] = sden;
-                        v[17] = sden * e.t * g.vx;
-                        v[18] = sden * e.t * g.vy;
-                        v[19] = sden * e.t;
+                        v[17] = sden * e.dx;
+                        v[18] = sden * e.dy;
+                        v[19] = sden * e.dz;
                     }
                 }
             }
-#pragma unroll
-            for (int q = 0; q < 20; ++q) v[q] = warp_sum(v[q]);
-            if (lane < 20) {
-                float val = v[0];
-#pragma unroll
-                for (int q = 1; q < 20; ++q) if (lane == q) val = v[q];
-                const unsigned id = (unsigned)__float_as_int(rec.q[7].x);
-                if (val != 0.f) atomicAdd(acc + (size_t)id * TEXGS_BWD_ACC_FLOATS + lane, val);
+            float outA, outB;
+            warp_reduce20(v, lane, outA, outB);
+            {
+                float* dst = acc + (size_t)(unsigned)__float_as_int(rec.q[7].x) * TEXGS_BWD_ACC_FLOATS;
+                if ((lane & 1) == 0 && outA != 0.f) atomicAdd(dst + (lane >> 1), outA);
+                if ((lane & 7) == 1 && outB != 0.f) atomicAdd(dst + 16 + (lane >> 3), outB);
             }
         }
         __syncthreads();   // everybody done reading stage s before it is refilled two visits later

@@ -157,6 +157,10 @@ def _build_args(st: GaussianRasterizationSettings, mode: int, means3D, shs, colo
     a.gradient_uvs = _ptr(gradient_uvs)
     a.texture = _ptr(texture)
     a.extra_attrs = None
+    from .profiling import current_event_array
+    arr = current_event_array()
+    if arr is not None:
+        a.profile_events = C.cast(arr, C.POINTER(C.c_void_p))
     return a
 
 

@@ -163,7 +163,7 @@ class SyntheticGaussians:
 
 
 def band_limited_texture(R: int, seed: int = 2, cells: int = 0, device="cpu") -> torch.Tensor:
-    """(6,R,R,3) cube texture in SH-DC encoding, rgb = smooth noise in [0,1].
+    """(6,R,R,3) cube texture in SH-DC encoding, rgb = smooth noise in [0.1,0.9].
 
     Low-resolution uniform noise (``cells`` per face edge, default R/16 but at least 4) upsampled
     bicubically, so neighbouring texels differ by O(1/16) of the dynamic range."""
@@ -171,7 +171,9 @@ def band_limited_texture(R: int, seed: int = 2, cells: int = 0, device="cpu") ->
     g = torch.Generator().manual_seed(seed)
     low = torch.rand(6, 3, cells, cells, generator=g, dtype=torch.float32).to(device)
     up = torch.nn.functional.interpolate(low, size=(R, R), mode="bicubic", align_corners=False)
-    rgb = up.clamp_(0.0, 1.0).permute(0, 2, 3, 1).contiguous()
+    # keep rgb inside [0.1, 0.9]: a texel clamped to exactly 0 would put the colour clamp of
+    # spec E12 (max(0, .)) on a knife-edge and make its gradient mask implementation-defined
+    rgb = (0.1 + 0.8 * up.clamp_(0.0, 1.0)).permute(0, 2, 3, 1).contiguous()
     return (rgb - 0.5) / C0
 
 
