@@ -54,7 +54,8 @@ ALPHA_MAX = 0.99
 T_STOP = 1e-4
 NEAR_CULL = 0.2
 ND_EPS = 1e-8
-GRAZING_COS = 0.1     # test-side conditioning flag only (never changes the rendered values)
+GRAZING_COS = 0.05    # test-side conditioning flag only (never changes the rendered values); calibrated so that
+                      # the fp32 and fp64 oracles agree to 1e-3 on every gradient once flagged pixels carry no cotangent
 
 
 class RasterSettings(NamedTuple):
@@ -424,7 +425,7 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
                 safe = nd.abs() >= ND_EPS                                     # E9
                 with torch.no_grad():
                     # conditioning flag: t = n.m / n.d amplifies rounding by 1/cos(angle(n, d));
-                    # below GRAZING_COS fp32 cannot hold 1e-4 / 1e-3 (fp32 vs fp64 oracle differ too)
+                    # below GRAZING_COS fp32 cannot hold 1e-4 / 1e-3 (the fp32 and fp64 oracles differ by more)
                     cosang = nd.abs() / (d_w.norm(dim=-1) * nrm.norm(dim=-1).clamp_min(1e-30))
                     grazing[pix[cosang < GRAZING_COS]] = True
                 nd_s = torch.where(safe, nd, torch.ones_like(nd))

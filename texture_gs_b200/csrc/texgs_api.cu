@@ -175,7 +175,7 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
     if (int rc = make_layout(a, pair_capacity, L)) return rc;
     RasterParams p;
     if (int rc = fill_params(a, geom_ws, bin_ws, pair_capacity, img_ws, L, p)) return rc;
-    if (!out_image || !out_depth || !out_norm || !out_alpha || !out_radii) return fail(TEXGS_E_INVALID, "output pointer is NULL");
+    if (!out_image || !out_depth || !out_norm || !out_alpha || (!out_radii && a->P > 0)) return fail(TEXGS_E_INVALID, "output pointer is NULL");
     const bool debug = (a->flags & TEXGS_FLAG_DEBUG) != 0;
 
     TEXGS_EV(a, TEXGS_EV_FWD_START, stream);

@@ -132,7 +132,7 @@ def last_stats() -> Optional[RasterStats]:
 
 
 def _build_args(st: GaussianRasterizationSettings, mode: int, means3D, shs, colors_precomp, opacities, scales,
-                rotations, uvs, gradient_uvs, texture) -> L.TexgsFwdArgs:
+                rotations, uvs, gradient_uvs, texture, profile_arr=None) -> L.TexgsFwdArgs:
     a = L.TexgsFwdArgs()
     a.P = means3D.shape[0]
     a.M = 0 if shs is None else shs.shape[1]
@@ -157,10 +157,8 @@ def _build_args(st: GaussianRasterizationSettings, mode: int, means3D, shs, colo
     a.gradient_uvs = _ptr(gradient_uvs)
     a.texture = _ptr(texture)
     a.extra_attrs = None
-    from .profiling import current_event_array
-    arr = current_event_array()
-    if arr is not None:
-        a.profile_events = C.cast(arr, C.POINTER(C.c_void_p))
+    if profile_arr is not None:
+        a.profile_events = C.cast(profile_arr, C.POINTER(C.c_void_p))
     return a
 
 
@@ -189,7 +187,9 @@ class _RasterizeGaussians(torch.autograd.Function):
 
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
-            a = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex)
+            from .profiling import current_event_array
+            prof = current_event_array()      # captured here: backward runs on autograd's thread
+            a = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex, prof)
             image = torch.empty(3, H, W, device=dev, dtype=torch.float32)
             depth = torch.empty(1, H, W, device=dev, dtype=torch.float32)
             norm = torch.empty(3, H, W, device=dev, dtype=torch.float32)
@@ -220,7 +220,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             _capacity_hint[key] = max(cap, _capacity_hint.get(key, 0)) if not overflow else cap
             _last_stats.v = RasterStats(K, V, maxlen, blo | (bhi << 32), cap)
 
-        ctx.st, ctx.mode, ctx.cap = st, mode, cap
+        ctx.st, ctx.mode, ctx.cap, ctx.prof = st, mode, cap, prof
         ctx.dev = dev
         ctx.has = (shs is not None, colors_precomp is not None, uvs is not None, texture is not None)
         ctx.save_for_backward(m3, sh, cp, op, sc, ro, uv, guv, tex, geom, binw, imgw)
@@ -238,7 +238,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             b = L.TexgsBwdArgs()
-            b.fwd = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex)
+            b.fwd = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex, ctx.prof)
             b.geom_ws, b.bin_ws, b.img_ws, b.pair_capacity = _ptr(geom), _ptr(binw), _ptr(imgw), ctx.cap
             keep = [_prep(g, dev) for g in (g_image, g_depth, g_norm, g_alpha)]
             b.dL_dimage, b.dL_ddepth, b.dL_dnorm, b.dL_dalpha = (_ptr(k) for k in keep)
