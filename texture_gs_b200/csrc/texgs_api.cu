@@ -135,6 +135,22 @@ int fill_params(const TexgsFwdArgs* a, void* geom, void* bin, uint64_t cap, void
     return 0;
 }
 
+// The render kernels use 65 KB of dynamic shared memory (8 warps x 2 stages x 32 records): opt in
+// once per device context. Idempotent, so the per-thread flag is only an optimisation.
+int ensure_render_smem() {
+    static thread_local int done_for_device = -1;
+    int dev = 0;
+    TEXGS_CUDA_TRY(cudaGetDevice(&dev));
+    if (done_for_device == dev) return 0;
+    const int bytes = (int)TEXGS_RENDER_SMEM;
+    TEXGS_CUDA_TRY(cudaFuncSetAttribute(texgs_render_fwd<TEXGS_MODE_TEXTURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    TEXGS_CUDA_TRY(cudaFuncSetAttribute(texgs_render_fwd<TEXGS_MODE_SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    TEXGS_CUDA_TRY(cudaFuncSetAttribute(texgs_render_bwd<TEXGS_MODE_TEXTURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    TEXGS_CUDA_TRY(cudaFuncSetAttribute(texgs_render_bwd<TEXGS_MODE_SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done_for_device = dev;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -201,10 +217,11 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
     texgs_sort_tiles<<<p.num_tiles, TEXGS_SORT_THREADS, 0, stream>>>(p);
     TEXGS_KERNEL_CHECK("texgs_sort_tiles", debug, stream);
     TEXGS_EV(a, TEXGS_EV_FWD_SORT, stream);
+    if (int rc = ensure_render_smem()) return rc;
     if (p.mode == TEXGS_MODE_TEXTURE)
-        texgs_render_fwd<TEXGS_MODE_TEXTURE><<<p.num_tiles, 256, 0, stream>>>(p, out_image, out_depth, out_norm, out_alpha);
+        texgs_render_fwd<TEXGS_MODE_TEXTURE><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha);
     else
-        texgs_render_fwd<TEXGS_MODE_SH><<<p.num_tiles, 256, 0, stream>>>(p, out_image, out_depth, out_norm, out_alpha);
+        texgs_render_fwd<TEXGS_MODE_SH><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha);
     TEXGS_KERNEL_CHECK("texgs_render_fwd", debug, stream);
     TEXGS_EV(a, TEXGS_EV_FWD_RENDER, stream);
     if (counters_host && debug) {   // debug: counters include the blend count, copied after the render
@@ -232,10 +249,11 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
         TEXGS_CUDA_TRY(cudaMemsetAsync(b->dL_dtexture, 0, (size_t)6 * p.R * p.R * 3 * sizeof(float), stream));
     TEXGS_EV(a, TEXGS_EV_BWD_CLEAR, stream);
     BwdIn in{b->dL_dimage, b->dL_ddepth, b->dL_dnorm, b->dL_dalpha};
+    if (int rc = ensure_render_smem()) return rc;
     if (p.mode == TEXGS_MODE_TEXTURE)
-        texgs_render_bwd<TEXGS_MODE_TEXTURE><<<p.num_tiles, 256, 0, stream>>>(p, in, b->acc_ws, b->dL_dtexture);
+        texgs_render_bwd<TEXGS_MODE_TEXTURE><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, b->dL_dtexture);
     else
-        texgs_render_bwd<TEXGS_MODE_SH><<<p.num_tiles, 256, 0, stream>>>(p, in, b->acc_ws, nullptr);
+        texgs_render_bwd<TEXGS_MODE_SH><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, nullptr);
     TEXGS_KERNEL_CHECK("texgs_render_bwd", debug, stream);
     TEXGS_EV(a, TEXGS_EV_BWD_RENDER, stream);
     if (p.P > 0) {

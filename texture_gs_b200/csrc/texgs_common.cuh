@@ -143,7 +143,7 @@ __device__ __forceinline__ CubeCoord cube_coord(float ux, float uy, float uz) {
         if (uz < 0.f) { c.face = 5; c.ix = 0; c.sgx = -1.f; c.iy = 1; c.sgy = -1.f; c.sgm = -1.f; }
         else          { c.face = 4; c.ix = 0; c.sgx = 1.f;  c.iy = 1; c.sgy = -1.f; c.sgm = 1.f; }
     }
-    c.inv_m = 1.0f / fmaxf(m, 1e-20f);
+    c.inv_m = __fdividef(1.0f, fmaxf(m, 1e-20f));
     const float vx = (c.ix == 0) ? ux : ((c.ix == 1) ? uy : uz);
     const float vy = (c.iy == 0) ? ux : ((c.iy == 1) ? uy : uz);
     c.sx = c.sgx * vx * c.inv_m;

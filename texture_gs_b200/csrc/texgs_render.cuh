@@ -1,14 +1,13 @@
 // texgs_render.cuh — per-tile blend kernels (SURVEY §8a rows a7 forward, a8 backward).
 //
-// One CTA = one 16x16 tile, 256 threads, warp w owns an 8x4 pixel block (better texel / alpha-test
-// coherence than 16x2 rows). The tile's depth-sorted Gaussian list is streamed through shared
-// memory in batches of TEXGS_BATCH records: each thread issues ONE 128-byte cp.async.bulk (TMA 1-D)
-// per record, completion is tracked by an mbarrier per stage, two stages are in flight so the gather
-// of batch b+1 overlaps the blend of batch b. Spec items E5-E12.
+// One CTA = one 16x16 tile = 8 independent warps; warp w owns an 8x4 pixel block (one pixel per
+// lane). Every warp streams the tile's depth-sorted list on its own: exact splat-vs-block culling at
+// load time, one 128-byte cp.async.bulk (TMA 1-D) per surviving record into a private 2-stage ring
+// tracked by mbarriers, no block barrier in the loop (see "Per-warp streaming" below).
+// Spec items E5-E12.
 #pragma once
 #include "texgs_common.cuh"
 
-#define TEXGS_BATCH 128
 
 #ifndef TEXGS_FAST_EXP
 #define TEXGS_FAST_EXP 1
@@ -23,6 +22,7 @@ __device__ __forceinline__ float texgs_exp(float x) {
 
 struct PixelGeom {
     int tile, px, py, pix;
+    int bx, by;      // origin of this warp's 8x4 pixel block
     bool inside;
     float vx, vy;    // view ray (vx, vy, 1)
 };
@@ -32,9 +32,10 @@ __device__ __forceinline__ PixelGeom pixel_geom(const RasterParams& p) {
     g.tile = blockIdx.x;
     const int tx = g.tile % p.grid_x, ty = g.tile / p.grid_x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
-    g.px = tx * TEXGS_TILE + lx;
-    g.py = ty * TEXGS_TILE + ly;
+    g.bx = tx * TEXGS_TILE + (warp & 1) * 8;
+    g.by = ty * TEXGS_TILE + (warp >> 1) * 4;
+    g.px = g.bx + (lane & 7);
+    g.py = g.by + (lane >> 3);
     g.inside = (g.px < p.W) && (g.py < p.H);
     g.pix = g.py * p.W + g.px;
     g.vx = ((2.0f * (float)g.px + 1.0f) / (float)p.W - 1.0f) * p.tanfovx;
@@ -42,16 +43,78 @@ __device__ __forceinline__ PixelGeom pixel_geom(const RasterParams& p) {
     return g;
 }
 
-// issue the gather of batch ``b`` of this tile's list into stage b&1
-__device__ __forceinline__ void issue_batch(const RasterParams& p, GaussRec (*s_rec)[TEXGS_BATCH], uint64_t* s_bar,
-                                            unsigned start, unsigned n, int b) {
-    const int s = b & 1;
-    const unsigned cnt = min((unsigned)TEXGS_BATCH, n - (unsigned)b * TEXGS_BATCH);
-    const unsigned tid = threadIdx.x;
-    if (tid == 0) mbar_arrive_expect_tx(&s_bar[s], cnt * (unsigned)sizeof(GaussRec));
-    if (tid < cnt) {
-        const unsigned id = p.sorted_ids[start + (unsigned)b * TEXGS_BATCH + tid];
-        bulk_g2s(&s_rec[s][tid], p.recs + id, (unsigned)sizeof(GaussRec), &s_bar[s]);
+// ---------------------------------------------------------------------------------------------
+// Per-warp streaming of the tile's sorted list.
+//
+// Each warp walks the list in chunks of 32 entries (one per lane). A lane reads its entry's id,
+// then the first 32-byte sector of that Gaussian's record (centre, conic, opacity) and tests
+// EXACTLY whether the splat's alpha >= 1/255 ellipse intersects the warp's 8x4 pixel block; only
+// the survivors are gathered — one 128-byte cp.async.bulk each — compacted in list order into the
+// warp's private stage (2 stages, an mbarrier each). While chunk c is blended, the copies of
+// chunk c+1 are landing and the id / cull-sector loads of chunk c+2 are in flight. There is no
+// block-level barrier in the loop and every warp stops on its own.
+// ---------------------------------------------------------------------------------------------
+#define TEXGS_CHUNK 32
+#define TEXGS_STAGES 2
+
+struct __align__(128) WarpSmem {
+    GaussRec rec[TEXGS_STAGES][TEXGS_CHUNK];
+    uint64_t bar[TEXGS_STAGES];
+    unsigned mask[TEXGS_STAGES];
+    unsigned pad[26];
+};
+static_assert(sizeof(WarpSmem) % 128 == 0, "WarpSmem must keep the records 128-byte aligned");
+#define TEXGS_RENDER_SMEM (8 * sizeof(WarpSmem))
+
+// Can  q(d) = a dx^2 + 2 b dx dy + c dy^2  (d = p - mu) drop to <= tau somewhere on the rectangle
+// [x0,x1] x [y0,y1]?  q is convex with its minimum at mu, so the constrained minimum is either mu
+// itself (inside) or lies on an edge that FACES mu; at most two 1-D clamped minimisations.
+__device__ __forceinline__ bool splat_hits_block(float mx, float my, float a, float b, float c, float opacity,
+                                                 float x0, float x1, float y0, float y1) {
+    const bool inx = (mx >= x0) && (mx <= x1), iny = (my >= y0) && (my <= y1);
+    if (inx && iny) return true;
+    float q = 3.0e38f;
+    if (!inx) {
+        const float dx = ((mx < x0) ? x0 : x1) - mx;
+        const float dy = fminf(fmaxf(__fdividef(-b * dx, c), y0 - my), y1 - my);
+        q = a * dx * dx + 2.f * b * dx * dy + c * dy * dy;
+    }
+    if (!iny) {
+        const float dy = ((my < y0) ? y0 : y1) - my;
+        const float dx = fminf(fmaxf(__fdividef(-b * dy, a), x0 - mx), x1 - mx);
+        q = fminf(q, a * dx * dx + 2.f * b * dx * dy + c * dy * dy);
+    }
+    // alpha >= 1/255  <=>  q <= 2 ln(255 o); keep a margin far above the rounding of __expf/__logf
+    const float tau = 2.0f * __logf(255.0f * opacity);
+    return q <= tau * 1.001f + 0.02f;
+}
+
+struct ChunkLoad {       // registers carried across one blend phase
+    unsigned id;         // Gaussian id of this lane's entry (chunk c+2)
+    float4 q0, q1;       // cull sector of this lane's entry (chunk c+1 at issue time)
+    bool valid;
+};
+
+__device__ __forceinline__ unsigned stream_load_id(const RasterParams& p, unsigned start, unsigned limit, int chunk, int lane,
+                                                   bool& valid) {
+    const unsigned e = (unsigned)chunk * TEXGS_CHUNK + (unsigned)lane;
+    valid = (chunk >= 0) && (e < limit);
+    return valid ? __ldg(p.sorted_ids + start + e) : 0u;
+}
+
+// ballot the cull test of one chunk and gather the survivors into stage ``s``
+__device__ __forceinline__ void stream_issue(const RasterParams& p, WarpSmem& ws, int s, int lane, unsigned id, bool valid,
+                                             const float4& q0, const float4& q1, const PixelGeom& g) {
+    const bool pass = valid && splat_hits_block(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, (float)g.bx, (float)(g.bx + 7),
+                                                (float)g.by, (float)(g.by + 3));
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (lane == 0) {
+        ws.mask[s] = m;
+        mbar_arrive_expect_tx(&ws.bar[s], (unsigned)__popc(m) * (unsigned)sizeof(GaussRec));
+    }
+    if (pass) {
+        const int slot = __popc(m & ((1u << lane) - 1u));
+        bulk_g2s(&ws.rec[s][slot], p.recs + id, (unsigned)sizeof(GaussRec), &ws.bar[s]);
     }
 }
 
@@ -71,7 +134,7 @@ __device__ __forceinline__ UvEval eval_uv(const float4& g1, const float4& g2, co
     e.t = 0.f;
     e.dx = e.dy = e.dz = 0.f;
     if (e.safe) {
-        e.t = g1.w / e.nd;
+        e.t = __fdividef(g1.w, e.nd);
         e.dx = e.t * vx - g2.w; e.dy = e.t * vy - g3.x; e.dz = e.t - g1.z;
         e.ux += g4.w * e.dx + g5.x * e.dy + g5.y * e.dz;
         e.uy += g5.z * e.dx + g5.w * e.dy + g6.x * e.dz;
@@ -87,38 +150,68 @@ template <int MODE>
 __global__ void __launch_bounds__(256) texgs_render_fwd(const RasterParams p, float* __restrict__ out_image,
                                                       float* __restrict__ out_depth, float* __restrict__ out_norm,
                                                       float* __restrict__ out_alpha) {
-    __shared__ GaussRec s_rec[2][TEXGS_BATCH];
-    __shared__ __align__(8) uint64_t s_bar[2];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     if (p.counters->overflow) return;
     const PixelGeom g = pixel_geom(p);
+    const int lane = threadIdx.x & 31;
+    WarpSmem& ws = reinterpret_cast<WarpSmem*>(smem_raw)[threadIdx.x >> 5];
     const unsigned start = p.tile_offset[g.tile];
     const unsigned n = p.tile_offset[g.tile + 1] - start;
-    const int nb = (int)((n + TEXGS_BATCH - 1) / TEXGS_BATCH);
-
-    if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
-    __syncthreads();
-    if (nb > 0) issue_batch(p, s_rec, s_bar, start, n, 0);
+    const int nchunks = (int)((n + TEXGS_CHUNK - 1) / TEXGS_CHUNK);
 
     float T = 1.0f, Cr = 0.f, Cg = 0.f, Cb = 0.f, D = 0.f, Nx = 0.f, Ny = 0.f, Nz = 0.f, A = 0.f;
     unsigned last = 0, nblend = 0;
     bool done = !g.inside;
-    bool warp_done = false;          // uniform across the warp
     const float pxf = (float)g.px, pyf = (float)g.py;
     const float* __restrict__ tex = p.texture;
     const int R = p.R;
 
-    int pending = -1;
-    for (int b = 0; b < nb; ++b) {
-        const int s = b & 1;
-        const int cnt = (int)min((unsigned)TEXGS_BATCH, n - (unsigned)b * TEXGS_BATCH);
-        mbar_wait(&s_bar[s], (unsigned)(b >> 1) & 1u);
-        if (b + 1 < nb) issue_batch(p, s_rec, s_bar, start, n, b + 1);
-        if (!warp_done) {
-            // The loop is warp-synchronous: every lane walks the same j, per-lane state is a
-            // predicate. (A per-lane continue/break loop never reconverges on sm_70+ and runs the
-            // lanes one after the other.)
-            for (int j = 0; j < cnt; ++j) {
-                const GaussRec& rec = s_rec[s][j];
+    // a warp whose block lies completely outside the image has nothing to do
+    if (nchunks > 0 && !__all_sync(0xffffffffu, done)) {
+        if (lane == 0) {
+            mbar_init(&ws.bar[0], 1);
+            mbar_init(&ws.bar[1], 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        // prologue: chunks 0 and 1 are gathered, the id of chunk 2 is loaded
+        bool v0, v1, v2;
+        const unsigned id0 = stream_load_id(p, start, n, 0, lane, v0);
+        const unsigned id1 = stream_load_id(p, start, n, 1 < nchunks ? 1 : -1, lane, v1);
+        unsigned id2 = stream_load_id(p, start, n, 2 < nchunks ? 2 : -1, lane, v2);
+        {
+            const float4* r0 = reinterpret_cast<const float4*>(p.recs + id0);
+            const float4 a0 = v0 ? __ldg(r0) : make_float4(0.f, 0.f, 1.f, 0.f), a1 = v0 ? __ldg(r0 + 1) : make_float4(1.f, 0.f, 0.f, 0.f);
+            stream_issue(p, ws, 0, lane, id0, v0, a0, a1, g);
+            if (1 < nchunks) {
+                const float4* r1 = reinterpret_cast<const float4*>(p.recs + id1);
+                const float4 b0 = v1 ? __ldg(r1) : make_float4(0.f, 0.f, 1.f, 0.f), b1 = v1 ? __ldg(r1 + 1) : make_float4(1.f, 0.f, 0.f, 0.f);
+                stream_issue(p, ws, 1, lane, id1, v1, b0, b1, g);
+            }
+        }
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c & 1;
+            // loads for the chunks ahead: cull sector of chunk c+2 (its id arrived during the last
+            // blend phase), id of chunk c+3
+            float4 q0n = make_float4(0.f, 0.f, 1.f, 0.f), q1n = make_float4(1.f, 0.f, 0.f, 0.f);
+            const unsigned idn = id2;
+            const bool vn = v2;
+            if (vn) {
+                const float4* rn = reinterpret_cast<const float4*>(p.recs + idn);
+                q0n = __ldg(rn);
+                q1n = __ldg(rn + 1);
+            }
+            id2 = stream_load_id(p, start, n, (c + 3 < nchunks) ? c + 3 : -1, lane, v2);
+
+            mbar_wait(&ws.bar[s], (unsigned)(c >> 1) & 1u);
+            __syncwarp();
+            unsigned m = ws.mask[s];
+            int slot = 0;
+            bool warp_done = false;
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                const GaussRec& rec = ws.rec[s][slot++];
                 const float4 g0 = rec.q[0], g1 = rec.q[1];
                 const float dx = g0.x - pxf, dy = g0.y - pyf;
                 const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
@@ -154,18 +247,21 @@ __global__ void __launch_bounds__(256) texgs_render_fwd(const RasterParams p, fl
                     Nx += w * g2.x; Ny += w * g2.y; Nz += w * g2.z;
                     A += w;
                     T = test_T;
-                    last = (unsigned)b * TEXGS_BATCH + (unsigned)j + 1u;
+                    last = (unsigned)c * TEXGS_CHUNK + (unsigned)l + 1u;
                     ++nblend;
                 }
                 if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
             }
-        }
-        if (__syncthreads_and(done ? 1 : 0)) {
-            if (b + 1 < nb) pending = b + 1;
-            break;
+            __syncwarp();
+            if (warp_done) {
+                // never leave with a bulk copy in flight: chunk c+1 was issued one phase ago
+                if (c + 1 < nchunks) mbar_wait(&ws.bar[s ^ 1], (unsigned)((c + 1) >> 1) & 1u);
+                break;
+            }
+            // stage s is free again: gather chunk c+2 into it
+            if (c + 2 < nchunks) stream_issue(p, ws, s, lane, idn, vn, q0n, q1n, g);
         }
     }
-    if (pending >= 0) mbar_wait(&s_bar[pending & 1], (unsigned)(pending >> 1) & 1u);   // never exit with a copy in flight
 
     if (g.inside) {
         const int HW = p.H * p.W;
@@ -185,7 +281,7 @@ __global__ void __launch_bounds__(256) texgs_render_fwd(const RasterParams p, fl
         unsigned tot = nblend;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        if ((threadIdx.x & 31) == 0 && tot) {
+        if (lane == 0 && tot) {
             atomicAdd(reinterpret_cast<unsigned long long*>(&p.counters->num_blend_lo), (unsigned long long)tot);
         }
     }
@@ -201,30 +297,22 @@ struct BwdIn {
 template <int MODE>
 __global__ void __launch_bounds__(256) texgs_render_bwd(const RasterParams p, const BwdIn in, float* __restrict__ acc,
                                                       float* __restrict__ dtex) {
-    __shared__ GaussRec s_rec[2][TEXGS_BATCH];
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ unsigned s_max;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     if (p.counters->overflow) return;
     const PixelGeom g = pixel_geom(p);
+    const int lane = threadIdx.x & 31;
+    WarpSmem& ws = reinterpret_cast<WarpSmem*>(smem_raw)[threadIdx.x >> 5];
     const unsigned start = p.tile_offset[g.tile];
     const unsigned n = p.tile_offset[g.tile + 1] - start;
     if (n == 0) return;
-    const int lane = threadIdx.x & 31;
 
-    if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); s_max = 0; }
-    __syncthreads();
     const unsigned last = g.inside ? p.n_contrib[g.pix] : 0u;
-    {
-        unsigned m = last;
+    unsigned max_last = last;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0 && m) atomicMax(&s_max, m);
-    }
-    __syncthreads();
-    const unsigned max_last = s_max;
-    if (max_last == 0) return;
-    const int nb = (int)((max_last + TEXGS_BATCH - 1) / TEXGS_BATCH);   // batches that hold contributors
-    // batches are visited back to front: visit k = 0.. nb-1 handles batch b = nb-1-k, stage k&1
+    for (int o = 16; o > 0; o >>= 1) max_last = max(max_last, __shfl_xor_sync(0xffffffffu, max_last, o));
+    if (max_last == 0) return;                      // uniform per warp
+    // chunks are visited back to front: visit k handles chunk c = c_top - k in stage k & 1
+    const int c_top = (int)((max_last - 1) / TEXGS_CHUNK);
 
     const int HW = p.H * p.W;
     float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f;
@@ -245,32 +333,50 @@ __global__ void __launch_bounds__(256) texgs_render_bwd(const RasterParams p, co
 
     float T = T_final, acc_rec = 0.f, last_alpha = 0.f, last_X = 0.f;
 
-    // visit 0 -> batch nb-1
+    if (lane == 0) {
+        mbar_init(&ws.bar[0], 1);
+        mbar_init(&ws.bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    // prologue: visits 0 and 1 gathered, id of visit 2 loaded. Entries at or beyond max_last can
+    // not contribute to this warp and are not gathered.
+    bool v0, v1, v2;
+    const unsigned id0 = stream_load_id(p, start, max_last, c_top, lane, v0);
+    const unsigned id1 = stream_load_id(p, start, max_last, c_top - 1, lane, v1);
+    unsigned id2 = stream_load_id(p, start, max_last, c_top - 2, lane, v2);
     {
-        const int b = nb - 1;
-        const unsigned cnt = min((unsigned)TEXGS_BATCH, n - (unsigned)b * TEXGS_BATCH);
-        if (threadIdx.x == 0) mbar_arrive_expect_tx(&s_bar[0], cnt * (unsigned)sizeof(GaussRec));
-        if (threadIdx.x < cnt) {
-            const unsigned id = p.sorted_ids[start + (unsigned)b * TEXGS_BATCH + threadIdx.x];
-            bulk_g2s(&s_rec[0][threadIdx.x], p.recs + id, (unsigned)sizeof(GaussRec), &s_bar[0]);
+        const float4* r0 = reinterpret_cast<const float4*>(p.recs + id0);
+        const float4 a0 = v0 ? __ldg(r0) : make_float4(0.f, 0.f, 1.f, 0.f), a1 = v0 ? __ldg(r0 + 1) : make_float4(1.f, 0.f, 0.f, 0.f);
+        stream_issue(p, ws, 0, lane, id0, v0, a0, a1, g);
+        if (c_top >= 1) {
+            const float4* r1 = reinterpret_cast<const float4*>(p.recs + id1);
+            const float4 b0 = v1 ? __ldg(r1) : make_float4(0.f, 0.f, 1.f, 0.f), b1 = v1 ? __ldg(r1 + 1) : make_float4(1.f, 0.f, 0.f, 0.f);
+            stream_issue(p, ws, 1, lane, id1, v1, b0, b1, g);
         }
     }
-    for (int k = 0; k < nb; ++k) {
-        const int b = nb - 1 - k;
+    for (int k = 0; k <= c_top; ++k) {
+        const int c = c_top - k;
         const int s = k & 1;
-        const int cnt = (int)min((unsigned)TEXGS_BATCH, n - (unsigned)b * TEXGS_BATCH);
-        mbar_wait(&s_bar[s], (unsigned)(k >> 1) & 1u);
-        if (k + 1 < nb) {   // prefetch batch b-1 into the other stage (always a full batch)
-            const int b2 = b - 1, s2 = s ^ 1;
-            if (threadIdx.x == 0) mbar_arrive_expect_tx(&s_bar[s2], TEXGS_BATCH * (unsigned)sizeof(GaussRec));
-            if (threadIdx.x < TEXGS_BATCH) {
-                const unsigned id = p.sorted_ids[start + (unsigned)b2 * TEXGS_BATCH + threadIdx.x];
-                bulk_g2s(&s_rec[s2][threadIdx.x], p.recs + id, (unsigned)sizeof(GaussRec), &s_bar[s2]);
-            }
+        float4 q0n = make_float4(0.f, 0.f, 1.f, 0.f), q1n = make_float4(1.f, 0.f, 0.f, 0.f);
+        const unsigned idn = id2;
+        const bool vn = v2;
+        if (vn) {
+            const float4* rn = reinterpret_cast<const float4*>(p.recs + idn);
+            q0n = __ldg(rn);
+            q1n = __ldg(rn + 1);
         }
-        for (int j = cnt - 1; j >= 0; --j) {
-            const unsigned gi = (unsigned)b * TEXGS_BATCH + (unsigned)j;   // 0-based position in the list
-            const GaussRec& rec = s_rec[s][j];
+        id2 = stream_load_id(p, start, max_last, c - 3, lane, v2);
+
+        mbar_wait(&ws.bar[s], (unsigned)(k >> 1) & 1u);
+        __syncwarp();
+        unsigned m = ws.mask[s];
+        int slot = __popc(m);
+        while (m) {
+            const int l = 31 - __clz(m);
+            m &= ~(1u << l);
+            const GaussRec& rec = ws.rec[s][--slot];
+            const unsigned gi = (unsigned)c * TEXGS_CHUNK + (unsigned)l;   // 0-based position in the list
             const float4 g0 = rec.q[0], g1 = rec.q[1];
             const float dx = g0.x - pxf, dy = g0.y - pyf;
             const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
@@ -285,7 +391,8 @@ __global__ void __launch_bounds__(256) texgs_render_bwd(const RasterParams p, co
             for (int q = 0; q < 20; ++q) v[q] = 0.f;
             if (contrib) {
                 const float4 g2 = rec.q[2], g3 = rec.q[3];
-                T = T / (1.0f - alpha);
+                const float inv_1ma = __fdividef(1.0f, 1.0f - alpha);
+                T = T * inv_1ma;
                 const float w = alpha * T;
                 float cr = g3.y, cg = g3.z, cb = g3.w;
                 float mr = 1.f, mg = 1.f, mb = 1.f;
@@ -315,20 +422,19 @@ __global__ void __launch_bounds__(256) texgs_render_bwd(const RasterParams p, co
                 }
                 const float X = gr * cr + gg * cg + gb * cb + gd * g1.z + gnv.x * g2.x + gnv.y * g2.y + gnv.z * g2.z + ga;
                 acc_rec = last_alpha * last_X + (1.0f - last_alpha) * acc_rec;
-                const float dL_dalpha = (X - acc_rec) * T - (T_final / (1.0f - alpha)) * bgdot;
+                const float dL_dalpha = (X - acc_rec) * T - (T_final * inv_1ma) * bgdot;
                 last_alpha = alpha;
                 last_X = X;
                 // alpha = min(0.99, o*G): derivative of the clamp is zero when it is active
                 const float live = (aG <= TEXGS_ALPHA_MAX) ? 1.f : 0.f;
                 const float dL_dG = live * g1.y * dL_dalpha;
                 v[5] = live * G * dL_dalpha;
-                const float gdx = -G * (g0.z * dx + g0.w * dy);   // dG/d(dx)
-                const float gdy = -G * (g1.x * dy + g0.w * dx);
-                v[0] = dL_dG * gdx;
-                v[1] = dL_dG * gdy;
-                v[2] = -0.5f * G * dx * dx * dL_dG;
-                v[3] = -G * dx * dy * dL_dG;
-                v[4] = -0.5f * G * dy * dy * dL_dG;
+                const float GdG = G * dL_dG;
+                v[0] = -GdG * (g0.z * dx + g0.w * dy);
+                v[1] = -GdG * (g1.x * dy + g0.w * dx);
+                v[2] = -0.5f * GdG * dx * dx;
+                v[3] = -GdG * dx * dy;
+                v[4] = -0.5f * GdG * dy * dy;
                 const float wr = w * gr * mr, wg = w * gg * mg, wb = w * gb * mb;   // dL/d col (masked)
                 v[6] = wr; v[7] = wg; v[8] = wb;
                 v[9] = w * gd;
@@ -340,9 +446,10 @@ __global__ void __launch_bounds__(256) texgs_render_bwd(const RasterParams p, co
                     const float w10 = (1.f - bl.wx) * bl.wy, w11 = bl.wx * bl.wy;
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) {
-                        const float top = t00[ch] + bl.wx * (t01[ch] - t00[ch]);
-                        const float bot = t10[ch] + bl.wx * (t11[ch] - t10[ch]);
-                        dwx += gt[ch] * ((1.f - bl.wy) * (t01[ch] - t00[ch]) + bl.wy * (t11[ch] - t10[ch]));
+                        const float dtop = t01[ch] - t00[ch], dbot = t11[ch] - t10[ch];
+                        const float top = t00[ch] + bl.wx * dtop;
+                        const float bot = t10[ch] + bl.wx * dbot;
+                        dwx += gt[ch] * (dtop + bl.wy * (dbot - dtop));
                         dwy += gt[ch] * (bot - top);
                         if (dtex && gt[ch] != 0.f) {
                             atomicAdd(dtex + bl.i00 + ch, gt[ch] * w00);
@@ -351,10 +458,10 @@ __global__ void __launch_bounds__(256) texgs_render_bwd(const RasterParams p, co
                             atomicAdd(dtex + bl.i11 + ch, gt[ch] * w11);
                         }
                     }
-                    const float dsx = dwx * halfR, dsy = dwy * halfR;
-                    float gu[3] = {0.f, 0.f, 0.f};
-                    const float ax = cc.sgx * dsx * cc.inv_m, ay = cc.sgy * dsy * cc.inv_m;
-                    const float am = cc.sgm * (-(cc.sx * dsx + cc.sy * dsy) * cc.inv_m);
+                    const float dsx = dwx * halfR * cc.inv_m, dsy = dwy * halfR * cc.inv_m;
+                    const float ax = cc.sgx * dsx, ay = cc.sgy * dsy;
+                    const float am = -cc.sgm * (cc.sx * dsx + cc.sy * dsy);
+                    float gu[3];
 #pragma unroll
                     for (int q = 0; q < 3; ++q) gu[q] = (q == cc.ix ? ax : 0.f) + (q == cc.iy ? ay : 0.f) + (q == cc.axis ? am : 0.f);
                     v[13] = gu[0]; v[14] = gu[1]; v[15] = gu[2];
@@ -363,7 +470,7 @@ __global__ void __launch_bounds__(256) texgs_render_bwd(const RasterParams p, co
                         const float gvx = g4.w * gu[0] + g5.z * gu[1] + g6.y * gu[2];
                         const float gvy = g5.x * gu[0] + g5.w * gu[1] + g6.z * gu[2];
                         const float gvz = g5.y * gu[0] + g6.x * gu[1] + g6.w * gu[2];
-                        const float sden = (gvx * g.vx + gvy * g.vy + gvz) / e.nd;
+                        const float sden = __fdividef(gvx * g.vx + gvy * g.vy + gvz, e.nd);
                         v[16] = sden;
                         v[17] = sden * e.dx;
                         v[18] = sden * e.dy;
@@ -379,6 +486,7 @@ __global__ void __launch_bounds__(256) texgs_render_bwd(const RasterParams p, co
                 if ((lane & 7) == 1 && outB != 0.f) atomicAdd(dst + 16 + (lane >> 3), outB);
             }
         }
-        __syncthreads();   // everybody done reading stage s before it is refilled two visits later
+        __syncwarp();
+        if (k + 2 <= c_top) stream_issue(p, ws, s, lane, idn, vn, q0n, q1n, g);
     }
 }
