@@ -35,7 +35,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 VIEWS_PER_STEP = 32
-KERNELS_PER_VIEW = 7   # preprocess_fwd, scan_tiles, scatter_pairs, sort_tiles, render_fwd, render_bwd, preprocess_bwd
+KERNELS_PER_VIEW = 7   # (+1 texgs_pack_texture_kernel per step) preprocess_fwd, scan_tiles, scatter_pairs, sort_tiles, render_fwd, render_bwd, preprocess_bwd
 
 
 def parse():
@@ -262,7 +262,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    from texture_gs_b200 import invalidate_packed_cache
+
     def step(tm=None):
+        # one texture update per step: the packed (6,R,R,4) copy is rebuilt once per 32-view batch
+        invalidate_packed_cache()
         bucket.zero()
         render_views_accumulate(uv_tex_render, g, cams, cot, views, bg, timer=tm)
         bucket.all_reduce()
@@ -343,7 +347,7 @@ def main():
                        "tex_res": wl.tex_res, "views_per_step": args.views, "sh_degree": 3,
                        "parallelism": f"dp{world} (views sharded, 1 all-reduce of {bucket.nbytes / 1e6:.0f} MB/step)" if world > 1 else "single GPU",
                        "l2_policy": "inputs larger than L2 (texture 302 MB + records 64 MB, a different camera every view)"},
-            "clocks": clock_rec, "e2e": e2e, "gpu_launches": KERNELS_PER_VIEW * len(views) * args.steps,
+            "clocks": clock_rec, "e2e": e2e, "gpu_launches": (KERNELS_PER_VIEW * len(views) + 1) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -372,7 +376,10 @@ def run_e2e(args, wl, g, cams, cot_dev, bg, bucket, views, dev, world, sync_all)
                 d.copy_(h, non_blocking=True)
             ready[slot].record(copy_stream)
 
+    from texture_gs_b200 import invalidate_packed_cache
+
     def step():
+        invalidate_packed_cache()
         bucket.zero()
         total = torch.zeros((), device=dev)
         main = torch.cuda.current_stream(dev)

@@ -69,6 +69,10 @@ typedef struct TexgsFwdArgs {
     const float* gradient_uvs;   /* (P,9) row-major d uv_i / d x_j, or NULL      */
     const float* texture;        /* (6,R,R,3) or NULL                            */
     const float* extra_attrs;    /* (P,E) or NULL                                */
+    /* optional: the same texture repacked as (6,R,R,4) fp32 (rgb + one pad float) by
+     * texgs_pack_texture; when given the render kernels fetch one 128-bit texel per tap instead
+     * of three scalars. Must correspond to ``texture``. NULL = read ``texture`` directly. */
+    const float* texture_rgba;
     /* optional per-kernel timing: HOST array of TEXGS_EV_COUNT cudaEvent_t (as void*), recorded on
      * the stream at the stage boundaries below; NULL = off. Forward fills slots 0..5, backward
      * (through TexgsBwdArgs.fwd) slots 6..9. */
@@ -143,6 +147,8 @@ typedef struct TexgsBwdArgs {
     float* dL_dcolors_precomp;   /* (P,3)   */
     float* dL_duvs;              /* (P,3)   */
     float* dL_dtexture;          /* (6,R,R,3) */
+    float* dL_dtexture_rgba;     /* (6,R,R,4) alternative to dL_dtexture: accumulated with 128-bit vector
+                                    atomics (red.global.add.v4.f32), 4th float stays 0; give exactly one */
     float* dL_dextra_attrs;      /* (P,E)   */
     int32_t zero_texture_grad;
     int32_t reserved;
@@ -153,6 +159,9 @@ typedef struct TexgsBwdArgs {
 /* Backward: per-tile back-to-front render backward -> per-Gaussian preprocess backward.  Replaces
  * ``_C.rasterize_gaussians_backward`` [EXT]. */
 int texgs_backward(const TexgsBwdArgs* b, void* stream);
+
+/* (6,R,R,3) -> (6,R,R,4) repack of the cube texture (see TexgsFwdArgs.texture_rgba). */
+int texgs_pack_texture(const float* texture, int32_t R, float* texture_rgba, void* stream);
 
 /* Frustum test only (upstream ``GaussianRasterizer.markVisible`` [EXT]; unused in the reference
  * tree). present (P,) int32: 1 if the Gaussian passes the near-plane cull. */

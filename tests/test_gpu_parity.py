@@ -265,6 +265,28 @@ def test_long_tile_lists_take_the_global_sort_path():
         assert rep[nme]["max_clear"] <= 2 * ABS_TOL, rep
 
 
+def test_packed_and_plain_texture_paths_agree():
+    """The (6,R,R,4) packed-texture kernels (128-bit loads / vector atomics) and the plain (6,R,R,3)
+    kernels are two instantiations of the same code: outputs identical, gradients equal up to the
+    order of float atomics."""
+    from texture_gs_b200 import rasterizer as RZ
+    g = sphere_shell_scene(4000, 64, sh_degree=3, seed=6)
+    cam = orbit_cameras(1, 176, 112, seed=7)[0]
+    cot = output_cotangents(112, 176, seed=8)
+    try:
+        RZ.USE_PACKED_TEXTURE = True
+        o1, _, g1 = run_cuda(g, cam, cot=cot)
+        RZ.USE_PACKED_TEXTURE = False
+        o2, _, g2 = run_cuda(g, cam, cot=cot)
+    finally:
+        RZ.USE_PACKED_TEXTURE = True
+    for a, b in zip(o1, o2):
+        assert torch.equal(a, b)
+    for k in g1:
+        if g1[k] is not None:
+            assert rel_err(g1[k], g2[k]) < 1e-5, k
+
+
 def test_capacity_overflow_retry_is_transparent():
     from texture_gs_b200 import rasterizer as RZ
     g = sphere_shell_scene(3000, 16, sh_degree=0, seed=1)

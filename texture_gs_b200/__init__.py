@@ -3,7 +3,8 @@
 Public surface (mirrors what reference render/uv_tex_render.py and render/render.py use):
     GaussianRasterizationSettings, GaussianRasterizer, uv_tex_render, render
 """
-from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, last_stats  # noqa: F401
+from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, invalidate_packed_cache,  # noqa: F401
+                         last_stats)
 from .render import render, uv_tex_render, type2render_func  # noqa: F401
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "uv_tex_render", "render", "type2render_func",

@@ -10,7 +10,8 @@ import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libtexgs.so"
+# TEXGS_LIB selects an alternative build of the same ABI (kernel-tuning experiments, tools/build_variants.py)
+LIB_PATH = Path(os.environ["TEXGS_LIB"]).resolve() if os.environ.get("TEXGS_LIB") else _PKG / "libtexgs.so"
 
 TEXGS_ABI_VERSION = 1
 FLAG_PREFILTERED = 1
@@ -34,6 +35,7 @@ class TexgsFwdArgs(C.Structure):
         ("campos", C.c_float * 3), ("bg", C.c_float * 3),
         ("means3D", _fp), ("shs", _fp), ("colors_precomp", _fp), ("opacities", _fp), ("scales", _fp),
         ("rotations", _fp), ("uvs", _fp), ("gradient_uvs", _fp), ("texture", _fp), ("extra_attrs", _fp),
+        ("texture_rgba", _fp),
         ("profile_events", C.POINTER(C.c_void_p)),
     ]
 
@@ -52,7 +54,7 @@ class TexgsBwdArgs(C.Structure):
         ("acc_ws", _fp),
         ("dL_dmeans3D", _fp), ("dL_dmeans2D", _fp), ("dL_dopacity", _fp), ("dL_dscales", _fp),
         ("dL_drotations", _fp), ("dL_dshs", _fp), ("dL_dcolors_precomp", _fp), ("dL_duvs", _fp),
-        ("dL_dtexture", _fp), ("dL_dextra_attrs", _fp),
+        ("dL_dtexture", _fp), ("dL_dtexture_rgba", _fp), ("dL_dextra_attrs", _fp),
         ("zero_texture_grad", C.c_int32), ("reserved", C.c_int32),
     ]
 
@@ -74,6 +76,7 @@ SYMBOLS = {
     "texgs_forward": (C.c_int, [C.POINTER(TexgsFwdArgs), _fp, _fp, C.c_uint64, _fp, _fp, _fp, _fp, _fp, _fp, _fp,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "texgs_backward": (C.c_int, [C.POINTER(TexgsBwdArgs), C.c_void_p]),
+    "texgs_pack_texture": (C.c_int, [_fp, C.c_int32, _fp, C.c_void_p]),
     "texgs_mark_visible": (C.c_int, [C.c_int32, _fp, C.POINTER(C.c_float), C.POINTER(C.c_float), _fp, C.c_void_p]),
 }
 

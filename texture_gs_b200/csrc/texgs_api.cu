@@ -120,6 +120,8 @@ int fill_params(const TexgsFwdArgs* a, void* geom, void* bin, uint64_t cap, void
     p.means3D = a->means3D; p.shs = a->shs; p.colors_precomp = a->colors_precomp; p.opacities = a->opacities;
     p.scales = a->scales; p.rotations = a->rotations; p.uvs = a->uvs; p.gradient_uvs = a->gradient_uvs;
     p.texture = a->texture; p.extra_attrs = nullptr;
+    p.texture_rgba = (a->mode == TEXGS_MODE_TEXTURE) ? reinterpret_cast<const float4*>(a->texture_rgba) : nullptr;
+    if (((uintptr_t)a->texture_rgba & 15) != 0) return fail(TEXGS_E_INVALID, "texture_rgba must be 16-byte aligned");
     char* g = (char*)geom; char* b = (char*)bin; char* im = (char*)img;
     p.recs = (GaussRec*)(g + L.l.geom_records);
     p.rects = (uint2*)(g + L.l.geom_rects);
@@ -143,10 +145,16 @@ int ensure_render_smem() {
     TEXGS_CUDA_TRY(cudaGetDevice(&dev));
     if (done_for_device == dev) return 0;
     const int bytes = (int)TEXGS_RENDER_SMEM;
-    TEXGS_CUDA_TRY(cudaFuncSetAttribute(texgs_render_fwd<TEXGS_MODE_TEXTURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    TEXGS_CUDA_TRY(cudaFuncSetAttribute(texgs_render_fwd<TEXGS_MODE_SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    TEXGS_CUDA_TRY(cudaFuncSetAttribute(texgs_render_bwd<TEXGS_MODE_TEXTURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    TEXGS_CUDA_TRY(cudaFuncSetAttribute(texgs_render_bwd<TEXGS_MODE_SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+#define TEXGS_SET_SMEM(k) TEXGS_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
+    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, true>));
+    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, false>));
+    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_SH, false>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, true>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, false>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, true>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, false>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_SH, false, false>));
+#undef TEXGS_SET_SMEM
     done_for_device = dev;
     return 0;
 }
@@ -161,7 +169,7 @@ const char* texgs_last_error(void) { return g_last_error.c_str(); }
 
 const char* texgs_kernel_names(void) {
     return "texgs_preprocess_fwd,texgs_scan_tiles,texgs_scatter_pairs,texgs_sort_tiles,texgs_render_fwd,"
-           "texgs_render_bwd,texgs_preprocess_bwd,texgs_mark_visible_kernel";
+           "texgs_render_bwd,texgs_preprocess_bwd,texgs_mark_visible_kernel,texgs_pack_texture_kernel";
 }
 
 int texgs_workspace_sizes(const TexgsFwdArgs* a, uint64_t pair_capacity, size_t* geom_bytes, size_t* bin_bytes,
@@ -218,10 +226,12 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
     TEXGS_KERNEL_CHECK("texgs_sort_tiles", debug, stream);
     TEXGS_EV(a, TEXGS_EV_FWD_SORT, stream);
     if (int rc = ensure_render_smem()) return rc;
-    if (p.mode == TEXGS_MODE_TEXTURE)
-        texgs_render_fwd<TEXGS_MODE_TEXTURE><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha);
+    if (p.mode == TEXGS_MODE_TEXTURE && p.texture_rgba)
+        texgs_render_fwd<TEXGS_MODE_TEXTURE, true><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha);
+    else if (p.mode == TEXGS_MODE_TEXTURE)
+        texgs_render_fwd<TEXGS_MODE_TEXTURE, false><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha);
     else
-        texgs_render_fwd<TEXGS_MODE_SH><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha);
+        texgs_render_fwd<TEXGS_MODE_SH, false><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha);
     TEXGS_KERNEL_CHECK("texgs_render_fwd", debug, stream);
     TEXGS_EV(a, TEXGS_EV_FWD_RENDER, stream);
     if (counters_host && debug) {   // debug: counters include the blend count, copied after the render
@@ -245,15 +255,26 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
 
     TEXGS_EV(a, TEXGS_EV_BWD_START, stream);
     TEXGS_CUDA_TRY(cudaMemsetAsync(b->acc_ws, 0, (size_t)p.P * TEXGS_BWD_ACC_FLOATS * sizeof(float), stream));
+    if (b->dL_dtexture && b->dL_dtexture_rgba) return fail(TEXGS_E_INVALID, "give dL_dtexture or dL_dtexture_rgba, not both");
+    if (((uintptr_t)b->dL_dtexture_rgba & 15) != 0) return fail(TEXGS_E_INVALID, "dL_dtexture_rgba must be 16-byte aligned");
     if (b->dL_dtexture && b->zero_texture_grad && p.mode == TEXGS_MODE_TEXTURE)
         TEXGS_CUDA_TRY(cudaMemsetAsync(b->dL_dtexture, 0, (size_t)6 * p.R * p.R * 3 * sizeof(float), stream));
+    if (b->dL_dtexture_rgba && b->zero_texture_grad && p.mode == TEXGS_MODE_TEXTURE)
+        TEXGS_CUDA_TRY(cudaMemsetAsync(b->dL_dtexture_rgba, 0, (size_t)6 * p.R * p.R * 4 * sizeof(float), stream));
     TEXGS_EV(a, TEXGS_EV_BWD_CLEAR, stream);
     BwdIn in{b->dL_dimage, b->dL_ddepth, b->dL_dnorm, b->dL_dalpha};
     if (int rc = ensure_render_smem()) return rc;
-    if (p.mode == TEXGS_MODE_TEXTURE)
-        texgs_render_bwd<TEXGS_MODE_TEXTURE><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, b->dL_dtexture);
-    else
-        texgs_render_bwd<TEXGS_MODE_SH><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, nullptr);
+    // the four variants: texel reads packed or not  x  texel-gradient writes packed or not
+    if (p.mode == TEXGS_MODE_TEXTURE) {
+        const bool rd4 = p.texture_rgba != nullptr, wr4 = b->dL_dtexture_rgba != nullptr;
+        float* dt = wr4 ? b->dL_dtexture_rgba : b->dL_dtexture;
+        if (rd4 && wr4)       texgs_render_bwd<TEXGS_MODE_TEXTURE, true, true><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, dt);
+        else if (rd4)         texgs_render_bwd<TEXGS_MODE_TEXTURE, true, false><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, dt);
+        else if (wr4)         texgs_render_bwd<TEXGS_MODE_TEXTURE, false, true><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, dt);
+        else                  texgs_render_bwd<TEXGS_MODE_TEXTURE, false, false><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, dt);
+    } else {
+        texgs_render_bwd<TEXGS_MODE_SH, false, false><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, nullptr);
+    }
     TEXGS_KERNEL_CHECK("texgs_render_bwd", debug, stream);
     TEXGS_EV(a, TEXGS_EV_BWD_RENDER, stream);
     if (p.P > 0) {
@@ -263,6 +284,33 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
         TEXGS_KERNEL_CHECK("texgs_preprocess_bwd", debug, stream);
     }
     TEXGS_EV(a, TEXGS_EV_BWD_PREPROCESS, stream);
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) texgs_pack_texture_kernel(const float* __restrict__ tex, float4* __restrict__ out, size_t ntexel) {
+    // 4 texels (48 B in, 64 B out) per thread: three 128-bit loads, four 128-bit stores
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t t0 = q * 4;
+    if (t0 + 3 < ntexel) {
+        const float4* src = reinterpret_cast<const float4*>(tex + t0 * 3);
+        const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        out[t0] = make_float4(a.x, a.y, a.z, 0.f);
+        out[t0 + 1] = make_float4(a.w, b.x, b.y, 0.f);
+        out[t0 + 2] = make_float4(b.z, b.w, c.x, 0.f);
+        out[t0 + 3] = make_float4(c.y, c.z, c.w, 0.f);
+    } else {
+        for (size_t t = t0; t < ntexel; ++t) out[t] = make_float4(tex[3 * t], tex[3 * t + 1], tex[3 * t + 2], 0.f);
+    }
+}
+
+int texgs_pack_texture(const float* texture, int32_t R, float* texture_rgba, void* stream_) {
+    if (!texture || !texture_rgba || R <= 0) return fail(TEXGS_E_INVALID, "bad arguments");
+    if (((uintptr_t)texture & 15) || ((uintptr_t)texture_rgba & 15)) return fail(TEXGS_E_INVALID, "texture buffers must be 16-byte aligned");
+    const size_t ntexel = (size_t)6 * R * R;
+    const size_t nthreads = (ntexel + 3) / 4;
+    texgs_pack_texture_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+        texture, reinterpret_cast<float4*>(texture_rgba), ntexel);
+    TEXGS_KERNEL_CHECK("texgs_pack_texture_kernel", false, (cudaStream_t)stream_);
     return 0;
 }
 

@@ -51,6 +51,7 @@ struct RasterParams {
     float bg[3];
     const float *means3D, *shs, *colors_precomp, *opacities, *scales, *rotations, *uvs,
         *gradient_uvs, *texture, *extra_attrs;
+    const float4* texture_rgba;   // optional (6,R,R,4) copy of the texture
     // workspaces
     GaussRec* recs;
     uint2* rects;            // 4 x uint16 packed: .x = x0 | x1<<16, .y = y0 | y1<<16
@@ -152,7 +153,7 @@ __device__ __forceinline__ CubeCoord cube_coord(float ux, float uy, float uz) {
 }
 
 struct Bilerp {
-    int i00, i01, i10, i11;   // float offsets of the four texels' red channel
+    int i00, i01, i10, i11;   // TEXEL indices of the four taps (x3 = float offset in the rgb layout)
     float wx, wy;
 };
 
@@ -170,10 +171,10 @@ __device__ __forceinline__ Bilerp cube_bilerp(const CubeCoord& c, int R) {
     const int x0c = min(max(x0, 0), R - 1), x1c = min(max(x0 + 1, 0), R - 1);
     const int y0c = min(max(y0, 0), R - 1), y1c = min(max(y0 + 1, 0), R - 1);
     const int base = c.face * R;
-    b.i00 = ((base + y0c) * R + x0c) * 3;
-    b.i01 = ((base + y0c) * R + x1c) * 3;
-    b.i10 = ((base + y1c) * R + x0c) * 3;
-    b.i11 = ((base + y1c) * R + x1c) * 3;
+    b.i00 = (base + y0c) * R + x0c;
+    b.i01 = (base + y0c) * R + x1c;
+    b.i10 = (base + y1c) * R + x0c;
+    b.i11 = (base + y1c) * R + x1c;
     return b;
 }
 
@@ -266,4 +267,28 @@ __device__ __forceinline__ void warp_reduce20(const float (&v)[20], int lane, fl
         b1 += __shfl_xor_sync(full, b1, 1);
         outB = b1;
     }
+}
+
+// four bilinear taps as rgb triples, from the packed (float4) or the plain (3 floats) layout
+template <bool TEX4>
+__device__ __forceinline__ void fetch_taps(const float* __restrict__ tex, const float4* __restrict__ tex4, const Bilerp& bl,
+                                           float (&t00)[3], float (&t01)[3], float (&t10)[3], float (&t11)[3]) {
+    if (TEX4) {
+        const float4 a = __ldg(tex4 + bl.i00), b = __ldg(tex4 + bl.i01), c = __ldg(tex4 + bl.i10), d = __ldg(tex4 + bl.i11);
+        t00[0] = a.x; t00[1] = a.y; t00[2] = a.z;
+        t01[0] = b.x; t01[1] = b.y; t01[2] = b.z;
+        t10[0] = c.x; t10[1] = c.y; t10[2] = c.z;
+        t11[0] = d.x; t11[1] = d.y; t11[2] = d.z;
+    } else {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            t00[ch] = __ldg(tex + 3 * bl.i00 + ch); t01[ch] = __ldg(tex + 3 * bl.i01 + ch);
+            t10[ch] = __ldg(tex + 3 * bl.i10 + ch); t11[ch] = __ldg(tex + 3 * bl.i11 + ch);
+        }
+    }
+}
+
+// 128-bit vector reduction (sm_90+): one L2 atomic op for a whole padded texel
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }

@@ -9,6 +9,12 @@
 #include "texgs_common.cuh"
 
 
+#ifndef TEXGS_FWD_MIN_CTAS
+#define TEXGS_FWD_MIN_CTAS 3
+#endif
+#ifndef TEXGS_BWD_MIN_CTAS
+#define TEXGS_BWD_MIN_CTAS 2
+#endif
 #ifndef TEXGS_FAST_EXP
 #define TEXGS_FAST_EXP 1
 #endif
@@ -146,8 +152,8 @@ __device__ __forceinline__ UvEval eval_uv(const float4& g1, const float4& g2, co
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(256) texgs_render_fwd(const RasterParams p, float* __restrict__ out_image,
+template <int MODE, bool TEX4>
+__global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(const RasterParams p, float* __restrict__ out_image,
                                                       float* __restrict__ out_depth, float* __restrict__ out_norm,
                                                       float* __restrict__ out_alpha) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -228,13 +234,12 @@ __global__ void __launch_bounds__(256) texgs_render_fwd(const RasterParams p, fl
                         const UvEval e = eval_uv(g1, g2, g3, g4, g5, g6, g.vx, g.vy);
                         const CubeCoord cc = cube_coord(e.ux, e.uy, e.uz);
                         const Bilerp bl = cube_bilerp(cc, R);
-                        float tx3[3];
+                        float tx3[3], t00[3], t01[3], t10[3], t11[3];
+                        fetch_taps<TEX4>(tex, p.texture_rgba, bl, t00, t01, t10, t11);
 #pragma unroll
                         for (int ch = 0; ch < 3; ++ch) {
-                            const float t00 = __ldg(tex + bl.i00 + ch), t01 = __ldg(tex + bl.i01 + ch);
-                            const float t10 = __ldg(tex + bl.i10 + ch), t11 = __ldg(tex + bl.i11 + ch);
-                            const float top = t00 + bl.wx * (t01 - t00);
-                            const float bot = t10 + bl.wx * (t11 - t10);
+                            const float top = t00[ch] + bl.wx * (t01[ch] - t00[ch]);
+                            const float bot = t10[ch] + bl.wx * (t11[ch] - t10[ch]);
                             tx3[ch] = top + bl.wy * (bot - top);
                         }
                         cr = fmaxf(0.f, SH_C0 * tx3[0] + cr);
@@ -294,8 +299,8 @@ struct BwdIn {
     const float *dL_dimage, *dL_ddepth, *dL_dnorm, *dL_dalpha;
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(256) texgs_render_bwd(const RasterParams p, const BwdIn in, float* __restrict__ acc,
+template <int MODE, bool TEX4, bool GRAD4>
+__global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(const RasterParams p, const BwdIn in, float* __restrict__ acc,
                                                       float* __restrict__ dtex) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     if (p.counters->overflow) return;
@@ -407,10 +412,9 @@ __global__ void __launch_bounds__(256) texgs_render_bwd(const RasterParams p, co
                     cc = cube_coord(e.ux, e.uy, e.uz);
                     bl = cube_bilerp(cc, R);
                     float tx3[3];
+                    fetch_taps<TEX4>(tex, p.texture_rgba, bl, t00, t01, t10, t11);
 #pragma unroll
                     for (int ch = 0; ch < 3; ++ch) {
-                        t00[ch] = __ldg(tex + bl.i00 + ch); t01[ch] = __ldg(tex + bl.i01 + ch);
-                        t10[ch] = __ldg(tex + bl.i10 + ch); t11[ch] = __ldg(tex + bl.i11 + ch);
                         const float top = t00[ch] + bl.wx * (t01[ch] - t00[ch]);
                         const float bot = t10[ch] + bl.wx * (t11[ch] - t10[ch]);
                         tx3[ch] = top + bl.wy * (bot - top);
@@ -451,12 +455,18 @@ __global__ void __launch_bounds__(256) texgs_render_bwd(const RasterParams p, co
                         const float bot = t10[ch] + bl.wx * dbot;
                         dwx += gt[ch] * (dtop + bl.wy * (dbot - dtop));
                         dwy += gt[ch] * (bot - top);
-                        if (dtex && gt[ch] != 0.f) {
-                            atomicAdd(dtex + bl.i00 + ch, gt[ch] * w00);
-                            atomicAdd(dtex + bl.i01 + ch, gt[ch] * w01);
-                            atomicAdd(dtex + bl.i10 + ch, gt[ch] * w10);
-                            atomicAdd(dtex + bl.i11 + ch, gt[ch] * w11);
+                        if (!GRAD4 && dtex && gt[ch] != 0.f) {
+                            atomicAdd(dtex + 3 * bl.i00 + ch, gt[ch] * w00);
+                            atomicAdd(dtex + 3 * bl.i01 + ch, gt[ch] * w01);
+                            atomicAdd(dtex + 3 * bl.i10 + ch, gt[ch] * w10);
+                            atomicAdd(dtex + 3 * bl.i11 + ch, gt[ch] * w11);
                         }
+                    }
+                    if (GRAD4 && dtex && (gt[0] != 0.f || gt[1] != 0.f || gt[2] != 0.f)) {
+                        red_add_v4(dtex + 4 * bl.i00, gt[0] * w00, gt[1] * w00, gt[2] * w00, 0.f);
+                        red_add_v4(dtex + 4 * bl.i01, gt[0] * w01, gt[1] * w01, gt[2] * w01, 0.f);
+                        red_add_v4(dtex + 4 * bl.i10, gt[0] * w10, gt[1] * w10, gt[2] * w10, 0.f);
+                        red_add_v4(dtex + 4 * bl.i11, gt[0] * w11, gt[1] * w11, gt[2] * w11, 0.f);
                     }
                     const float dsx = dwx * halfR * cc.inv_m, dsy = dwy * halfR * cc.inv_m;
                     const float ax = cc.sgx * dsx, ay = cc.sgy * dsy;

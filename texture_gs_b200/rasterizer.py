@@ -99,6 +99,34 @@ def _pinned_counters(dev_index: int):
         return ent
 
 
+# Packed (6,R,R,4) copy of a texture, cached per texture tensor object + in-place version: the
+# optimizer step bumps ``_version`` so the copy is rebuilt exactly once per texture update (the
+# reference renders 1-2 times per update, models/texture_gaussian3d.py:318,378; a view batch more).
+USE_PACKED_TEXTURE = True
+_packed_cache: dict = {}
+
+
+def invalidate_packed_cache():
+    _packed_cache.clear()
+
+
+def _packed_texture(lib, texture_arg: torch.Tensor, tex: torch.Tensor, stream: int) -> torch.Tensor:
+    key = id(texture_arg)
+    hit = _packed_cache.get(key)
+    if hit is not None and hit[0]() is texture_arg and hit[1] == texture_arg._version and hit[2] == tex.data_ptr():
+        return hit[3]
+    tex4 = torch.empty(tex.shape[0], tex.shape[1], tex.shape[2], 4, device=tex.device, dtype=torch.float32)
+    L.check(lib.texgs_pack_texture(_ptr(tex), tex.shape[1], _ptr(tex4), C.c_void_p(stream)), "texgs_pack_texture")
+    try:
+        ref = weakref.ref(texture_arg, lambda _r, k=key: _packed_cache.pop(k, None))
+        if len(_packed_cache) > 8:
+            _packed_cache.clear()
+        _packed_cache[key] = (ref, texture_arg._version, tex.data_ptr(), tex4)
+    except TypeError:
+        pass
+    return tex4
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -190,6 +218,10 @@ class _RasterizeGaussians(torch.autograd.Function):
             from .profiling import current_event_array
             prof = current_event_array()      # captured here: backward runs on autograd's thread
             a = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex, prof)
+            tex4 = None
+            if mode == L.MODE_TEXTURE and USE_PACKED_TEXTURE:
+                tex4 = _packed_texture(lib, texture, tex, stream)
+                a.texture_rgba = _ptr(tex4)
             image = torch.empty(3, H, W, device=dev, dtype=torch.float32)
             depth = torch.empty(1, H, W, device=dev, dtype=torch.float32)
             norm = torch.empty(3, H, W, device=dev, dtype=torch.float32)
@@ -220,7 +252,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             _capacity_hint[key] = max(cap, _capacity_hint.get(key, 0)) if not overflow else cap
             _last_stats.v = RasterStats(K, V, maxlen, blo | (bhi << 32), cap)
 
-        ctx.st, ctx.mode, ctx.cap, ctx.prof = st, mode, cap, prof
+        ctx.st, ctx.mode, ctx.cap, ctx.prof, ctx.tex4 = st, mode, cap, prof, tex4
         ctx.dev = dev
         ctx.has = (shs is not None, colors_precomp is not None, uvs is not None, texture is not None)
         ctx.save_for_backward(m3, sh, cp, op, sc, ro, uv, guv, tex, geom, binw, imgw)
@@ -239,6 +271,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             stream = torch.cuda.current_stream(dev).cuda_stream
             b = L.TexgsBwdArgs()
             b.fwd = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex, ctx.prof)
+            if ctx.tex4 is not None:
+                b.fwd.texture_rgba = _ptr(ctx.tex4)
             b.geom_ws, b.bin_ws, b.img_ws, b.pair_capacity = _ptr(geom), _ptr(binw), _ptr(imgw), ctx.cap
             keep = [_prep(g, dev) for g in (g_image, g_depth, g_norm, g_alpha)]
             b.dL_dimage, b.dL_ddepth, b.dL_dnorm, b.dL_dalpha = (_ptr(k) for k in keep)
@@ -256,10 +290,21 @@ class _RasterizeGaussians(torch.autograd.Function):
             d_sc = out(need[5], P, 3)
             d_ro = out(need[6], P, 4)
             d_uv = out(need[7] and uv is not None, P, 3)
-            d_tex = out(need[9] and tex is not None, *(tex.shape if tex is not None else (0,)))
+            d_tex, d_tex4 = None, None
+            if need[9] and tex is not None:
+                if ctx.tex4 is not None:
+                    # padded gradient: 128-bit vector atomics in the kernel; the (6,R,R,3) gradient
+                    # autograd sees is a strided view of it (no unpack pass)
+                    d_tex4 = torch.empty(tex.shape[0], tex.shape[1], tex.shape[2], 4, device=dev, dtype=torch.float32)
+                    d_tex = d_tex4[..., :3]
+                else:
+                    d_tex = torch.empty(tex.shape, device=dev, dtype=torch.float32)
             b.dL_dmeans3D, b.dL_dmeans2D, b.dL_dshs, b.dL_dcolors_precomp = _ptr(d_m3), _ptr(d_m2), _ptr(d_sh), _ptr(d_cp)
             b.dL_dopacity, b.dL_dscales, b.dL_drotations, b.dL_duvs = _ptr(d_op), _ptr(d_sc), _ptr(d_ro), _ptr(d_uv)
-            b.dL_dtexture = _ptr(d_tex)
+            if d_tex4 is not None:
+                b.dL_dtexture_rgba = _ptr(d_tex4)
+            else:
+                b.dL_dtexture = _ptr(d_tex)
             b.zero_texture_grad = 1
             L.check(lib.texgs_backward(C.byref(b), C.c_void_p(stream)), "texgs_backward")
         return d_m3, d_m2, d_sh, d_cp, d_op, d_sc, d_ro, d_uv, None, d_tex, None, None
