@@ -268,7 +268,7 @@ def main():
         # one texture update per step: the packed (6,R,R,4) copy is rebuilt once per 32-view batch
         invalidate_packed_cache()
         bucket.zero()
-        render_views_accumulate(uv_tex_render, g, cams, cot, views, bg, timer=tm)
+        render_views_accumulate(uv_tex_render, g, cams, cot, views, bg, timer=tm, bucket=bucket)
         bucket.all_reduce()
 
     for _ in range(args.warmup):
@@ -302,7 +302,7 @@ def main():
 
     # ---- unique texels touched by one view (for the algorithmic byte count) ---------------------
     bucket.zero()
-    render_views_accumulate(uv_tex_render, g, cams, [torch.ones_like(c) for c in cot], views[:1] or [0], bg)
+    render_views_accumulate(uv_tex_render, g, cams, [torch.ones_like(c) for c in cot], views[:1] or [0], bg, bucket=bucket)
     U = int((bucket.grads()["texture"].abs().sum(dim=-1) > 0).sum().item())
     bucket.zero()
 
@@ -393,11 +393,12 @@ def run_e2e(args, wl, g, cams, cot_dev, bg, bucket, views, dev, world, sync_all)
                 upload((i + 1) & 1)
             main.wait_event(ready[slot])
             cam = cams[v % len(cams)]
-            pkg = uv_tex_render(cam, g, None, bg)
-            outs = [pkg["render"], pkg["depth"], pkg["norm"], pkg["alpha"]]
-            with torch.no_grad():
-                total += sum((o.detach() * c).sum() for o, c in zip(outs, bufs[slot]))
-            torch.autograd.backward(outs, list(bufs[slot]))
+            with bucket.fused():
+                pkg = uv_tex_render(cam, g, None, bg)
+                outs = [pkg["render"], pkg["depth"], pkg["norm"], pkg["alpha"]]
+                with torch.no_grad():
+                    total += sum((o.detach() * c).sum() for o, c in zip(outs, bufs[slot]))
+                torch.autograd.backward(outs, list(bufs[slot]))
             free[slot].record(main)
         bucket.all_reduce()
         result_host.copy_(total.reshape(1), non_blocking=True)

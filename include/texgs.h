@@ -151,8 +151,20 @@ typedef struct TexgsBwdArgs {
                                     atomics (red.global.add.v4.f32), 4th float stays 0; give exactly one */
     float* dL_dextra_attrs;      /* (P,E)   */
     int32_t zero_texture_grad;
-    int32_t reserved;
+    /* TEXGS_ACC_* bits: the marked per-Gaussian outputs are ADDED to (``out += grad``, rows of culled
+     * Gaussians untouched) instead of overwritten — lets the caller point them at a persistent
+     * gradient bucket (the all-reduce buffer) and skip autograd's separate accumulation pass. */
+    uint32_t accumulate_mask;
 } TexgsBwdArgs;
+
+#define TEXGS_ACC_MEANS3D   1u
+#define TEXGS_ACC_MEANS2D   2u
+#define TEXGS_ACC_OPACITY   4u
+#define TEXGS_ACC_SCALES    8u
+#define TEXGS_ACC_ROTATIONS 16u
+#define TEXGS_ACC_SHS       32u
+#define TEXGS_ACC_COLORS    64u
+#define TEXGS_ACC_UVS       128u
 
 #define TEXGS_BWD_ACC_FLOATS 24
 

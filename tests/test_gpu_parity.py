@@ -287,6 +287,27 @@ def test_packed_and_plain_texture_paths_agree():
             assert rel_err(g1[k], g2[k]) < 1e-5, k
 
 
+def test_fused_bucket_accumulation_equals_autograd_accumulation():
+    """GradBucket.fused(): the backward kernels add into the flat bucket (padded texture layout,
+    accumulate_mask for the per-Gaussian outputs); result == autograd's own .grad accumulation."""
+    from texture_gs_b200 import uv_tex_render
+    from texture_gs_b200.dist import GradBucket, render_views_accumulate
+    cams = orbit_cameras(3, 160, 96, seed=11, device="cuda")
+    cot = output_cotangents(96, 160, seed=12, device="cuda")
+    bg = torch.tensor([0.1, 0.0, 0.2], device="cuda")
+    res = []
+    for fused in (False, True):
+        g = sphere_shell_scene(3000, 32, sh_degree=3, seed=10, device="cuda")
+        bk = GradBucket(g.tensors())
+        assert bk.padded["texture"] and g.get_texture.grad.shape == g.get_texture.shape
+        render_views_accumulate(uv_tex_render, g, cams, cot, range(3), bg, bucket=bk if fused else None)
+        res.append({k: v.detach().clone() for k, v in bk.grads().items()})
+        pad = bk.flat[bk.offsets["texture"][0]: bk.offsets["texture"][0] + bk.offsets["texture"][1]].view(-1, 4)[:, 3]
+        assert float(pad.abs().max()) == 0.0            # the pad float of every texel stays zero
+    for k in res[0]:
+        assert rel_err(res[1][k], res[0][k]) < 1e-5, k
+
+
 def test_capacity_overflow_retry_is_transparent():
     from texture_gs_b200 import rasterizer as RZ
     g = sphere_shell_scene(3000, 16, sh_degree=0, seed=1)

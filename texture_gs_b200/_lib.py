@@ -18,6 +18,7 @@ FLAG_PREFILTERED = 1
 FLAG_DEBUG = 2
 MODE_TEXTURE, MODE_SH, MODE_PRECOMP = 0, 1, 2
 BWD_ACC_FLOATS = 24
+ACC_MEANS3D, ACC_MEANS2D, ACC_OPACITY, ACC_SCALES, ACC_ROTATIONS, ACC_SHS, ACC_COLORS, ACC_UVS = 1, 2, 4, 8, 16, 32, 64, 128
 EV_COUNT = 10
 EV_NAMES = ("fwd_start", "preprocess_fwd", "scan_tiles", "scatter_pairs", "sort_tiles", "render_fwd",
             "bwd_start", "bwd_clear", "render_bwd", "preprocess_bwd")
@@ -55,7 +56,7 @@ class TexgsBwdArgs(C.Structure):
         ("dL_dmeans3D", _fp), ("dL_dmeans2D", _fp), ("dL_dopacity", _fp), ("dL_dscales", _fp),
         ("dL_drotations", _fp), ("dL_dshs", _fp), ("dL_dcolors_precomp", _fp), ("dL_duvs", _fp),
         ("dL_dtexture", _fp), ("dL_dtexture_rgba", _fp), ("dL_dextra_attrs", _fp),
-        ("zero_texture_grad", C.c_int32), ("reserved", C.c_int32),
+        ("zero_texture_grad", C.c_int32), ("accumulate_mask", C.c_uint32),
     ]
 
 

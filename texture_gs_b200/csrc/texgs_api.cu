@@ -256,6 +256,7 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
     TEXGS_EV(a, TEXGS_EV_BWD_START, stream);
     TEXGS_CUDA_TRY(cudaMemsetAsync(b->acc_ws, 0, (size_t)p.P * TEXGS_BWD_ACC_FLOATS * sizeof(float), stream));
     if (b->dL_dtexture && b->dL_dtexture_rgba) return fail(TEXGS_E_INVALID, "give dL_dtexture or dL_dtexture_rgba, not both");
+    if (((uintptr_t)b->dL_drotations & 15) != 0) return fail(TEXGS_E_INVALID, "dL_drotations must be 16-byte aligned");
     if (((uintptr_t)b->dL_dtexture_rgba & 15) != 0) return fail(TEXGS_E_INVALID, "dL_dtexture_rgba must be 16-byte aligned");
     if (b->dL_dtexture && b->zero_texture_grad && p.mode == TEXGS_MODE_TEXTURE)
         TEXGS_CUDA_TRY(cudaMemsetAsync(b->dL_dtexture, 0, (size_t)6 * p.R * p.R * 3 * sizeof(float), stream));
@@ -279,7 +280,7 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
     TEXGS_EV(a, TEXGS_EV_BWD_RENDER, stream);
     if (p.P > 0) {
         BwdOut g{b->dL_dmeans3D, b->dL_dmeans2D, b->dL_dopacity, b->dL_dscales, b->dL_drotations,
-                 b->dL_dshs, b->dL_dcolors_precomp, b->dL_duvs, b->dL_dextra_attrs};
+                 b->dL_dshs, b->dL_dcolors_precomp, b->dL_duvs, b->dL_dextra_attrs, b->accumulate_mask};
         texgs_preprocess_bwd<<<(p.P + 255) / 256, 256, 0, stream>>>(p, nullptr, b->acc_ws, g);
         TEXGS_KERNEL_CHECK("texgs_preprocess_bwd", debug, stream);
     }

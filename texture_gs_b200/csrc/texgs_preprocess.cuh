@@ -192,14 +192,16 @@ __global__ void __launch_bounds__(256) texgs_preprocess_fwd(const RasterParams p
 //   acc[13..15] dL/d uv                   acc[16] S0 = sum s, acc[17..19] sum s*Delta_v (intersection path,
 //                                          s = (J'^T gu . v)/(n_v . v))
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void put(float* p, float v, bool acc) { if (acc) *p += v; else *p = v; }
+
 __device__ __forceinline__ void sh_rest_bwd(int deg, const float* __restrict__ sh, float3 d, float3 g,
-                                            float* __restrict__ dsh, float3& ddir) {
+                                            float* __restrict__ dsh, float3& ddir, bool accum) {
     // dsh_k = basis_k * g ;  ddir = sum_k dbasis_k/dd * (sh_k . g)
     ddir = f3(0.f, 0.f, 0.f);
     if (deg <= 0) return;
     const float x = d.x, y = d.y, z = d.z;
 #define SH_B(k, w, dwx, dwy, dwz) { const float ww = (w); const float sg = sh[3 * (k)] * g.x + sh[3 * (k) + 1] * g.y + sh[3 * (k) + 2] * g.z; \
-        if (dsh) { dsh[3 * (k)] = ww * g.x; dsh[3 * (k) + 1] = ww * g.y; dsh[3 * (k) + 2] = ww * g.z; } \
+        if (dsh) { put(dsh + 3 * (k), ww * g.x, accum); put(dsh + 3 * (k) + 1, ww * g.y, accum); put(dsh + 3 * (k) + 2, ww * g.z, accum); } \
         ddir.x += (dwx) * sg; ddir.y += (dwy) * sg; ddir.z += (dwz) * sg; }
     SH_B(0, -SH_C1 * y, 0.f, -SH_C1, 0.f)
     SH_B(1, SH_C1 * z, 0.f, 0.f, SH_C1)
@@ -226,6 +228,7 @@ __device__ __forceinline__ void sh_rest_bwd(int deg, const float* __restrict__ s
 
 struct BwdOut {
     float *dmeans3D, *dmeans2D, *dopacity, *dscales, *drotations, *dshs, *dcolors_precomp, *duvs, *dextra_attrs;
+    unsigned acc;   // TEXGS_ACC_* bits: add into the output instead of overwriting it
 };
 
 __global__ void __launch_bounds__(256) texgs_preprocess_bwd(const RasterParams p, const int* __restrict__ radii_unused,
@@ -236,15 +239,18 @@ __global__ void __launch_bounds__(256) texgs_preprocess_bwd(const RasterParams p
     Proj o;
     project_gaussian(p, idx, o);
     float dmu[3] = {0.f, 0.f, 0.f};
-    if (!o.visible) {
-        if (g.dmeans3D) { g.dmeans3D[3 * idx] = 0.f; g.dmeans3D[3 * idx + 1] = 0.f; g.dmeans3D[3 * idx + 2] = 0.f; }
-        if (g.dmeans2D) { g.dmeans2D[3 * idx] = 0.f; g.dmeans2D[3 * idx + 1] = 0.f; g.dmeans2D[3 * idx + 2] = 0.f; }
-        if (g.dopacity) g.dopacity[idx] = 0.f;
-        if (g.dscales) { g.dscales[3 * idx] = 0.f; g.dscales[3 * idx + 1] = 0.f; g.dscales[3 * idx + 2] = 0.f; }
-        if (g.drotations) *reinterpret_cast<float4*>(g.drotations + 4 * idx) = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g.dshs) for (int k = 0; k < nsh; ++k) g.dshs[(size_t)idx * nsh + k] = 0.f;
-        if (g.dcolors_precomp) { g.dcolors_precomp[3 * idx] = 0.f; g.dcolors_precomp[3 * idx + 1] = 0.f; g.dcolors_precomp[3 * idx + 2] = 0.f; }
-        if (g.duvs) { g.duvs[3 * idx] = 0.f; g.duvs[3 * idx + 1] = 0.f; g.duvs[3 * idx + 2] = 0.f; }
+    const bool a_m3 = g.acc & TEXGS_ACC_MEANS3D, a_m2 = g.acc & TEXGS_ACC_MEANS2D, a_op = g.acc & TEXGS_ACC_OPACITY;
+    const bool a_sc = g.acc & TEXGS_ACC_SCALES, a_ro = g.acc & TEXGS_ACC_ROTATIONS, a_sh = g.acc & TEXGS_ACC_SHS;
+    const bool a_cp = g.acc & TEXGS_ACC_COLORS, a_uv = g.acc & TEXGS_ACC_UVS;
+    if (!o.visible) {   // zero gradient: written in overwrite mode, nothing to add in accumulate mode
+        if (g.dmeans3D && !a_m3) { g.dmeans3D[3 * idx] = 0.f; g.dmeans3D[3 * idx + 1] = 0.f; g.dmeans3D[3 * idx + 2] = 0.f; }
+        if (g.dmeans2D && !a_m2) { g.dmeans2D[3 * idx] = 0.f; g.dmeans2D[3 * idx + 1] = 0.f; g.dmeans2D[3 * idx + 2] = 0.f; }
+        if (g.dopacity && !a_op) g.dopacity[idx] = 0.f;
+        if (g.dscales && !a_sc) { g.dscales[3 * idx] = 0.f; g.dscales[3 * idx + 1] = 0.f; g.dscales[3 * idx + 2] = 0.f; }
+        if (g.drotations && !a_ro) *reinterpret_cast<float4*>(g.drotations + 4 * idx) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.dshs && !a_sh) for (int k = 0; k < nsh; ++k) g.dshs[(size_t)idx * nsh + k] = 0.f;
+        if (g.dcolors_precomp && !a_cp) { g.dcolors_precomp[3 * idx] = 0.f; g.dcolors_precomp[3 * idx + 1] = 0.f; g.dcolors_precomp[3 * idx + 2] = 0.f; }
+        if (g.duvs && !a_uv) { g.duvs[3 * idx] = 0.f; g.duvs[3 * idx + 1] = 0.f; g.duvs[3 * idx + 2] = 0.f; }
         return;
     }
     const float* acc = acc_all + (size_t)idx * TEXGS_BWD_ACC_FLOATS;
@@ -253,7 +259,7 @@ __global__ void __launch_bounds__(256) texgs_preprocess_bwd(const RasterParams p
     // ---- colour -> SH / precomp --------------------------------------------------------------
     float3 gcol = f3(acc[6], acc[7], acc[8]);
     if (p.mode == TEXGS_MODE_PRECOMP) {
-        if (g.dcolors_precomp) { g.dcolors_precomp[3 * idx] = gcol.x; g.dcolors_precomp[3 * idx + 1] = gcol.y; g.dcolors_precomp[3 * idx + 2] = gcol.z; }
+        if (g.dcolors_precomp) { put(g.dcolors_precomp + 3 * idx, gcol.x, a_cp); put(g.dcolors_precomp + 3 * idx + 1, gcol.y, a_cp); put(g.dcolors_precomp + 3 * idx + 2, gcol.z, a_cp); }
     } else if (p.shs != nullptr) {
         const float len2 = dot3(o.m, o.m);
         const float inv_len = rsqrtf(len2);
@@ -270,18 +276,18 @@ __global__ void __launch_bounds__(256) texgs_preprocess_bwd(const RasterParams p
             if (col.x < 0.f) gcol.x = 0.f;
             if (col.y < 0.f) gcol.y = 0.f;
             if (col.z < 0.f) gcol.z = 0.f;
-            if (dsh) { dsh[0] = SH_C0 * gcol.x; dsh[1] = SH_C0 * gcol.y; dsh[2] = SH_C0 * gcol.z; }
+            if (dsh) { put(dsh, SH_C0 * gcol.x, a_sh); put(dsh + 1, SH_C0 * gcol.y, a_sh); put(dsh + 2, SH_C0 * gcol.z, a_sh); }
             first_rest = 1;
         }
         float3 ddir;
-        sh_rest_bwd(deg, sh + 3 * first_rest, dir, gcol, dsh ? dsh + 3 * first_rest : nullptr, ddir);
-        if (dsh) for (int k = 3 * (first_rest + nrest_active); k < nsh; ++k) dsh[k] = 0.f;
+        sh_rest_bwd(deg, sh + 3 * first_rest, dir, gcol, dsh ? dsh + 3 * first_rest : nullptr, ddir, a_sh);
+        if (dsh && !a_sh) for (int k = 3 * (first_rest + nrest_active); k < nsh; ++k) dsh[k] = 0.f;
         // dir = m/|m|
         const float dd = dot3(dir, ddir);
         dmu[0] += (ddir.x - dir.x * dd) * inv_len;
         dmu[1] += (ddir.y - dir.y * dd) * inv_len;
         dmu[2] += (ddir.z - dir.z * dd) * inv_len;
-    } else if (g.dshs) {
+    } else if (g.dshs && !a_sh) {
         for (int k = 0; k < nsh; ++k) g.dshs[(size_t)idx * nsh + k] = 0.f;
     }
 
@@ -290,7 +296,7 @@ __global__ void __launch_bounds__(256) texgs_preprocess_bwd(const RasterParams p
     float3 dnv = f3(acc[10], acc[11], acc[12]);
     if (p.mode == TEXGS_MODE_TEXTURE) {
         const float3 duv = f3(acc[13], acc[14], acc[15]);
-        if (g.duvs) { g.duvs[3 * idx] = duv.x; g.duvs[3 * idx + 1] = duv.y; g.duvs[3 * idx + 2] = duv.z; }
+        if (g.duvs) { put(g.duvs + 3 * idx, duv.x, a_uv); put(g.duvs + 3 * idx + 1, duv.y, a_uv); put(g.duvs + 3 * idx + 2, duv.z, a_uv); }
         const float S0 = acc[16], S1 = acc[17], S2 = acc[18], S3 = acc[19];
         // J'^T duv, J'[i][c] = sum_r J[i][r] V[r][c]
         const float* J = p.gradient_uvs + (size_t)9 * idx;
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(256) texgs_preprocess_bwd(const RasterParams p
 
     // ---- 2-D mean -> clip -> world -----------------------------------------------------------
     const float dndx = acc[0] * 0.5f * (float)p.W, dndy = acc[1] * 0.5f * (float)p.H;   // NDC units
-    if (g.dmeans2D) { g.dmeans2D[3 * idx] = dndx; g.dmeans2D[3 * idx + 1] = dndy; g.dmeans2D[3 * idx + 2] = 0.f; }
+    if (g.dmeans2D) { put(g.dmeans2D + 3 * idx, dndx, a_m2); put(g.dmeans2D + 3 * idx + 1, dndy, a_m2); if (!a_m2) g.dmeans2D[3 * idx + 2] = 0.f; }
     {
         const float dphx = dndx * o.pw, dphy = dndy * o.pw;
         const float dphw = -(dndx * o.ph.x + dndy * o.ph.y) * o.pw * o.pw;
@@ -386,12 +392,12 @@ __global__ void __launch_bounds__(256) texgs_preprocess_bwd(const RasterParams p
     }
 
     // ---- outputs -----------------------------------------------------------------------------
-    if (g.dmeans3D) { g.dmeans3D[3 * idx] = dmu[0]; g.dmeans3D[3 * idx + 1] = dmu[1]; g.dmeans3D[3 * idx + 2] = dmu[2]; }
-    if (g.dopacity) g.dopacity[idx] = acc[5];
+    if (g.dmeans3D) { put(g.dmeans3D + 3 * idx, dmu[0], a_m3); put(g.dmeans3D + 3 * idx + 1, dmu[1], a_m3); put(g.dmeans3D + 3 * idx + 2, dmu[2], a_m3); }
+    if (g.dopacity) put(g.dopacity + idx, acc[5], a_op);
     if (g.dscales) {
-        g.dscales[3 * idx] = ds[0] * p.scale_modifier;
-        g.dscales[3 * idx + 1] = ds[1] * p.scale_modifier;
-        g.dscales[3 * idx + 2] = ds[2] * p.scale_modifier;
+        put(g.dscales + 3 * idx, ds[0] * p.scale_modifier, a_sc);
+        put(g.dscales + 3 * idx + 1, ds[1] * p.scale_modifier, a_sc);
+        put(g.dscales + 3 * idx + 2, ds[2] * p.scale_modifier, a_sc);
     }
     if (g.drotations) {
         const float4 q = *reinterpret_cast<const float4*>(p.rotations + 4 * idx);
@@ -401,6 +407,8 @@ __global__ void __launch_bounds__(256) texgs_preprocess_bwd(const RasterParams p
         dq.y = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]);
         dq.z = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]);
         dq.w = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]);
-        *reinterpret_cast<float4*>(g.drotations + 4 * idx) = dq;
+        float4* dst = reinterpret_cast<float4*>(g.drotations + 4 * idx);
+        if (a_ro) { const float4 o4 = *dst; dq.x += o4.x; dq.y += o4.y; dq.z += o4.z; dq.w += o4.w; }
+        *dst = dq;
     }
 }

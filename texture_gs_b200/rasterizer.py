@@ -253,6 +253,20 @@ class _RasterizeGaussians(torch.autograd.Function):
             _last_stats.v = RasterStats(K, V, maxlen, blo | (bhi << 32), cap)
 
         ctx.st, ctx.mode, ctx.cap, ctx.prof, ctx.tex4 = st, mode, cap, prof, tex4
+        # fused gradient accumulation (texture_gs_b200.dist.GradBucket.fused): resolved now because
+        # backward runs on autograd's thread. Only inputs that ARE bucket leaves qualify.
+        ctx.fuse = None
+        if any(ctx.needs_input_grad):
+            from .dist import current_fused_bucket
+            bucket = current_fused_bucket()
+            if bucket is not None:
+                ctx.fuse = {}
+                for name, t in (("means3D", means3D), ("shs", shs), ("colors_precomp", colors_precomp), ("opacities", opacities),
+                                ("scales", scales), ("rotations", rotations), ("uvs", uvs), ("texture", texture)):
+                    if t is not None and t.is_leaf and t.requires_grad and t.is_contiguous() and t.dtype == torch.float32:
+                        tgt = bucket.storage_for(t)
+                        if tgt is not None and (name != "texture" or tgt[1] == (tex4 is not None)):
+                            ctx.fuse[name] = tgt[0]
         ctx.dev = dev
         ctx.has = (shs is not None, colors_precomp is not None, uvs is not None, texture is not None)
         ctx.save_for_backward(m3, sh, cp, op, sc, ro, uv, guv, tex, geom, binw, imgw)
@@ -282,16 +296,37 @@ class _RasterizeGaussians(torch.autograd.Function):
             def out(flag, *shape):
                 return torch.empty(*shape, device=dev, dtype=torch.float32) if flag else None
 
-            d_m3 = out(need[0], P, 3)
+            fuse = ctx.fuse or {}
+            accmask = 0
+
+            def out_or_fused(name, bit, flag, *shape):
+                # returns (tensor the kernel writes, gradient handed to autograd)
+                nonlocal accmask
+                if not flag:
+                    return None, None
+                if name in fuse:
+                    accmask |= bit
+                    return fuse[name], None
+                t = torch.empty(*shape, device=dev, dtype=torch.float32)
+                return t, t
+
+            k_m3, d_m3 = out_or_fused("means3D", L.ACC_MEANS3D, need[0], P, 3)
             d_m2 = out(need[1], P, 3)
-            d_sh = out(need[2] and sh is not None, *(sh.shape if sh is not None else (0,)))
-            d_cp = out(need[3] and cp is not None, P, 3)
-            d_op = out(need[4], P, 1)
-            d_sc = out(need[5], P, 3)
-            d_ro = out(need[6], P, 4)
-            d_uv = out(need[7] and uv is not None, P, 3)
+            k_sh, d_sh = out_or_fused("shs", L.ACC_SHS, need[2] and sh is not None, *(sh.shape if sh is not None else (0,)))
+            k_cp, d_cp = out_or_fused("colors_precomp", L.ACC_COLORS, need[3] and cp is not None, P, 3)
+            k_op, d_op = out_or_fused("opacities", L.ACC_OPACITY, need[4], P, 1)
+            k_sc, d_sc = out_or_fused("scales", L.ACC_SCALES, need[5], P, 3)
+            k_ro, d_ro = out_or_fused("rotations", L.ACC_ROTATIONS, need[6], P, 4)
+            k_uv, d_uv = out_or_fused("uvs", L.ACC_UVS, need[7] and uv is not None, P, 3)
             d_tex, d_tex4 = None, None
-            if need[9] and tex is not None:
+            zero_tex = 1
+            if need[9] and tex is not None and "texture" in fuse:
+                zero_tex = 0                       # accumulate into the bucket; autograd gets no texture grad
+                if ctx.tex4 is not None:
+                    d_tex4 = fuse["texture"]
+                else:
+                    b.dL_dtexture = _ptr(fuse["texture"])
+            elif need[9] and tex is not None:
                 if ctx.tex4 is not None:
                     # padded gradient: 128-bit vector atomics in the kernel; the (6,R,R,3) gradient
                     # autograd sees is a strided view of it (no unpack pass)
@@ -299,13 +334,16 @@ class _RasterizeGaussians(torch.autograd.Function):
                     d_tex = d_tex4[..., :3]
                 else:
                     d_tex = torch.empty(tex.shape, device=dev, dtype=torch.float32)
-            b.dL_dmeans3D, b.dL_dmeans2D, b.dL_dshs, b.dL_dcolors_precomp = _ptr(d_m3), _ptr(d_m2), _ptr(d_sh), _ptr(d_cp)
-            b.dL_dopacity, b.dL_dscales, b.dL_drotations, b.dL_duvs = _ptr(d_op), _ptr(d_sc), _ptr(d_ro), _ptr(d_uv)
+            b.dL_dmeans3D, b.dL_dmeans2D, b.dL_dshs, b.dL_dcolors_precomp = _ptr(k_m3), _ptr(d_m2), _ptr(k_sh), _ptr(k_cp)
+            b.dL_dopacity, b.dL_dscales, b.dL_drotations, b.dL_duvs = _ptr(k_op), _ptr(k_sc), _ptr(k_ro), _ptr(k_uv)
             if d_tex4 is not None:
                 b.dL_dtexture_rgba = _ptr(d_tex4)
-            else:
+            elif d_tex is not None:
                 b.dL_dtexture = _ptr(d_tex)
-            b.zero_texture_grad = 1
+            b.zero_texture_grad = zero_tex
+            b.accumulate_mask = accmask
+            if zero_tex == 0:
+                d_tex = None
             L.check(lib.texgs_backward(C.byref(b), C.c_void_p(stream)), "texgs_backward")
         return d_m3, d_m2, d_sh, d_cp, d_op, d_sc, d_ro, d_uv, None, d_tex, None, None
 
