@@ -119,37 +119,42 @@ __device__ __forceinline__ int argmin3(float a, float b, float c) {
 // ---------------------------------------------------------------------------------------------
 struct CubeCoord {
     int face;        // 0..5
-    int axis;        // major axis 0/1/2
+    bool isx, isy;   // major axis x / y (else z)
     float inv_m;     // 1/|u_major|
     float sx, sy;    // face coordinates in [-1,1]
-    // sx = sgx * u[ix] * inv_m ; sy = sgy * u[iy] * inv_m ; m = sgm * u[axis]
-    int ix, iy;
+    // sx = sgx * u[ix] * inv_m ; sy = sgy * u[iy] * inv_m ; |u_major| = sgm * u[axis]
+    //   axis x: (ix,iy) = (2,1)   axis y: (0,2)   axis z: (0,1)
     float sgx, sgy, sgm;
 };
 
+// Branch-free face selection. With m = |major|:
+//   x: sx = -z/x , sy = -y/m     y: sx = x/m , sy = z/y     z: sx = x/z , sy = -y/m
 __device__ __forceinline__ CubeCoord cube_coord(float ux, float uy, float uz) {
     CubeCoord c;
     const float ax = fabsf(ux), ay = fabsf(uy), az = fabsf(uz);
-    float m;
-    if (ax >= ay && ax >= az) {
-        c.axis = 0; m = ax;
-        if (ux < 0.f) { c.face = 1; c.ix = 2; c.sgx = 1.f;  c.iy = 1; c.sgy = -1.f; c.sgm = -1.f; }
-        else          { c.face = 0; c.ix = 2; c.sgx = -1.f; c.iy = 1; c.sgy = -1.f; c.sgm = 1.f; }
-    } else if (ay >= az) {
-        c.axis = 1; m = ay;
-        if (uy < 0.f) { c.face = 3; c.ix = 0; c.sgx = 1.f; c.iy = 2; c.sgy = -1.f; c.sgm = -1.f; }
-        else          { c.face = 2; c.ix = 0; c.sgx = 1.f; c.iy = 2; c.sgy = 1.f;  c.sgm = 1.f; }
-    } else {
-        c.axis = 2; m = az;
-        if (uz < 0.f) { c.face = 5; c.ix = 0; c.sgx = -1.f; c.iy = 1; c.sgy = -1.f; c.sgm = -1.f; }
-        else          { c.face = 4; c.ix = 0; c.sgx = 1.f;  c.iy = 1; c.sgy = -1.f; c.sgm = 1.f; }
-    }
-    c.inv_m = __fdividef(1.0f, fmaxf(m, 1e-20f));
-    const float vx = (c.ix == 0) ? ux : ((c.ix == 1) ? uy : uz);
-    const float vy = (c.iy == 0) ? ux : ((c.iy == 1) ? uy : uz);
-    c.sx = c.sgx * vx * c.inv_m;
-    c.sy = c.sgy * vy * c.inv_m;
+    c.isx = (ax >= ay) && (ax >= az);
+    c.isy = !c.isx && (ay >= az);
+    const float maj = c.isx ? ux : (c.isy ? uy : uz);
+    const bool neg = maj < 0.f;
+    c.sgm = neg ? -1.f : 1.f;
+    c.face = (c.isx ? 0 : (c.isy ? 2 : 4)) + (neg ? 1 : 0);
+    c.inv_m = __fdividef(1.0f, fmaxf(fabsf(maj), 1e-20f));
+    const float a = c.isx ? uz : ux;
+    const float b = c.isy ? uz : uy;
+    c.sgx = c.isx ? -c.sgm : (c.isy ? 1.f : c.sgm);
+    c.sgy = c.isy ? c.sgm : -1.f;
+    c.sx = c.sgx * a * c.inv_m;
+    c.sy = c.sgy * b * c.inv_m;
     return c;
+}
+
+// d(sx,sy)/du applied to (dsx, dsy) (both already multiplied by inv_m): gradient w.r.t. u
+__device__ __forceinline__ void cube_coord_bwd(const CubeCoord& c, float dsx, float dsy, float (&gu)[3]) {
+    const float gx = c.sgx * dsx, gy = c.sgy * dsy;
+    const float gm = -c.sgm * (c.sx * dsx + c.sy * dsy);
+    gu[0] = c.isx ? gm : gx;
+    gu[1] = c.isy ? gm : gy;
+    gu[2] = c.isx ? gx : (c.isy ? gy : gm);
 }
 
 struct Bilerp {
@@ -160,21 +165,22 @@ struct Bilerp {
 __device__ __forceinline__ Bilerp cube_bilerp(const CubeCoord& c, int R) {
     Bilerp b;
     const float halfR = 0.5f * (float)R;
-    const float fx = (c.sx + 1.0f) * halfR - 0.5f;
-    const float fy = (c.sy + 1.0f) * halfR - 0.5f;
+    // |minor|/|major| <= 1 up to rounding; the clamp also squashes inf/nan from degenerate inputs, so
+    // floor(f) is in [-1, R-1] and only one-sided index clamps remain
+    const float sx = fminf(fmaxf(c.sx, -1.0f), 1.0f), sy = fminf(fmaxf(c.sy, -1.0f), 1.0f);
+    const float fx = (sx + 1.0f) * halfR - 0.5f;
+    const float fy = (sy + 1.0f) * halfR - 0.5f;
     const float x0f = floorf(fx), y0f = floorf(fy);
     b.wx = fx - x0f;
     b.wy = fy - y0f;
-    // clamp in float first: u' may be garbage (inf/nan) for degenerate inputs
-    const int x0 = (int)fminf(fmaxf(x0f, -1.0f), (float)R);
-    const int y0 = (int)fminf(fmaxf(y0f, -1.0f), (float)R);
-    const int x0c = min(max(x0, 0), R - 1), x1c = min(max(x0 + 1, 0), R - 1);
-    const int y0c = min(max(y0, 0), R - 1), y1c = min(max(y0 + 1, 0), R - 1);
-    const int base = c.face * R;
-    b.i00 = (base + y0c) * R + x0c;
-    b.i01 = (base + y0c) * R + x1c;
-    b.i10 = (base + y1c) * R + x0c;
-    b.i11 = (base + y1c) * R + x1c;
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const int x0c = max(x0, 0), x1c = min(x0 + 1, R - 1);
+    const int y0c = max(y0, 0), y1c = min(y0 + 1, R - 1);
+    const int row0 = (c.face * R + y0c) * R, row1 = (c.face * R + y1c) * R;
+    b.i00 = row0 + x0c;
+    b.i01 = row0 + x1c;
+    b.i10 = row1 + x0c;
+    b.i11 = row1 + x1c;
     return b;
 }
 

@@ -60,7 +60,9 @@ __device__ __forceinline__ PixelGeom pixel_geom(const RasterParams& p) {
 // chunk c+1 are landing and the id / cull-sector loads of chunk c+2 are in flight. There is no
 // block-level barrier in the loop and every warp stops on its own.
 // ---------------------------------------------------------------------------------------------
-#define TEXGS_CHUNK 32
+#ifndef TEXGS_CHUNK
+#define TEXGS_CHUNK 32          // list entries per chunk (<= 32: one per lane) = records per stage
+#endif
 #define TEXGS_STAGES 2
 
 struct __align__(128) WarpSmem {
@@ -104,7 +106,7 @@ struct ChunkLoad {       // registers carried across one blend phase
 __device__ __forceinline__ unsigned stream_load_id(const RasterParams& p, unsigned start, unsigned limit, int chunk, int lane,
                                                    bool& valid) {
     const unsigned e = (unsigned)chunk * TEXGS_CHUNK + (unsigned)lane;
-    valid = (chunk >= 0) && (e < limit);
+    valid = (chunk >= 0) && (lane < TEXGS_CHUNK) && (e < limit);
     return valid ? __ldg(p.sorted_ids + start + e) : 0u;
 }
 
@@ -468,12 +470,8 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
                         red_add_v4(dtex + 4 * bl.i10, gt[0] * w10, gt[1] * w10, gt[2] * w10, 0.f);
                         red_add_v4(dtex + 4 * bl.i11, gt[0] * w11, gt[1] * w11, gt[2] * w11, 0.f);
                     }
-                    const float dsx = dwx * halfR * cc.inv_m, dsy = dwy * halfR * cc.inv_m;
-                    const float ax = cc.sgx * dsx, ay = cc.sgy * dsy;
-                    const float am = -cc.sgm * (cc.sx * dsx + cc.sy * dsy);
                     float gu[3];
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) gu[q] = (q == cc.ix ? ax : 0.f) + (q == cc.iy ? ay : 0.f) + (q == cc.axis ? am : 0.f);
+                    cube_coord_bwd(cc, dwx * halfR * cc.inv_m, dwy * halfR * cc.inv_m, gu);
                     v[13] = gu[0]; v[14] = gu[1]; v[15] = gu[2];
                     if (e.safe) {
                         // g_v = J'^T gu ; s = (g_v . v) / nd
