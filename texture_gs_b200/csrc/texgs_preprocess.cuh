@@ -115,7 +115,8 @@ __device__ __forceinline__ void project_gaussian(const RasterParams& p, int idx,
     if ((o.rx1 - o.rx0) * (o.ry1 - o.ry0) <= 0) return;
     // E8: facing disc normal
     o.kmin = argmin3(p.scales[3 * idx], p.scales[3 * idx + 1], p.scales[3 * idx + 2]);
-    const float3 nraw = f3(o.R[o.kmin], o.R[3 + o.kmin], o.R[6 + o.kmin]);
+    // column kmin of R, selected without dynamic indexing (keeps R in registers)
+    const float3 nraw = (o.kmin == 0) ? f3(o.R[0], o.R[3], o.R[6]) : ((o.kmin == 1) ? f3(o.R[1], o.R[4], o.R[7]) : f3(o.R[2], o.R[5], o.R[8]));
     o.m = f3(mu.x - p.campos[0], mu.y - p.campos[1], mu.z - p.campos[2]);
     o.nsign = (dot3(nraw, o.m) > 0.f) ? -1.f : 1.f;
     o.nv = rot_w2v(p.view, f3(o.nsign * nraw.x, o.nsign * nraw.y, o.nsign * nraw.z));
@@ -386,9 +387,13 @@ __global__ void __launch_bounds__(256) texgs_preprocess_bwd(const RasterParams p
         const float3 w = rot_v2w(p.view, dpv);
         dmu[0] += w.x; dmu[1] += w.y; dmu[2] += w.z;
         const float3 dn = rot_v2w(p.view, dnv);     // dL/d n (world, facing)
-        dR[0 + o.kmin] += o.nsign * dn.x;
-        dR[3 + o.kmin] += o.nsign * dn.y;
-        dR[6 + o.kmin] += o.nsign * dn.z;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float on = (o.kmin == k) ? o.nsign : 0.f;
+            dR[0 + k] += on * dn.x;
+            dR[3 + k] += on * dn.y;
+            dR[6 + k] += on * dn.z;
+        }
     }
 
     // ---- outputs -----------------------------------------------------------------------------

@@ -28,3 +28,20 @@ for r in rows[2:]:
             print(f"| {label} (`{k}`) | {d[k]} {units[hdr.index(k)]} |")
     dr, dw = d.get("dram__bytes_read.sum"), d.get("dram__bytes_write.sum")
     print()
+
+# optional: python tools/ncu_summary.py rep --traffic-json out.json  -> {"render_fwd": bytes, "render_bwd": bytes, ...}
+if "--traffic-json" in sys.argv:
+    import json, re
+    out = {}
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        name = re.sub(r"^void ", "", d["Kernel Name"]).split("<")[0].split("(")[0].replace("texgs_", "")
+        def tobytes(v, u):
+            v = float(v.replace(",", ""))
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+        rd = tobytes(d["dram__bytes_read.sum"], units[hdr.index("dram__bytes_read.sum")])
+        wr = tobytes(d["dram__bytes_write.sum"], units[hdr.index("dram__bytes_write.sum")])
+        out.setdefault(name, []).append(rd + wr)
+    out = {k: int(sum(v) / len(v)) for k, v in out.items()}
+    Path = __import__("pathlib").Path
+    Path(sys.argv[sys.argv.index("--traffic-json") + 1]).write_text(json.dumps(out, indent=1) + "\n")
