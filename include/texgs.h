@@ -73,6 +73,11 @@ typedef struct TexgsFwdArgs {
      * texgs_pack_texture; when given the render kernels fetch one 128-bit texel per tap instead
      * of three scalars. Must correspond to ``texture``. NULL = read ``texture`` directly. */
     const float* texture_rgba;
+    /* optional DUAL render (texture mode only): a second (3,H,W) image blended in the same pass from
+     * the colour the splats have with sh_degree = 0, max(0, C0*tex + 0.5) — what the reference obtains
+     * with a second full render (models/texture_gaussian3d.py:375-389, 505-511). NULL = off. In
+     * texgs_backward the forward args must carry the same pointer state (NULL / non-NULL). */
+    float* out_image_nosh;
     /* optional per-kernel timing: HOST array of TEXGS_EV_COUNT cudaEvent_t (as void*), recorded on
      * the stream at the stage boundaries below; NULL = off. Forward fills slots 0..5, backward
      * (through TexgsBwdArgs.fwd) slots 6..9. */
@@ -133,6 +138,7 @@ typedef struct TexgsBwdArgs {
     const float* dL_dnorm;       /* (3,H,W) */
     const float* dL_dalpha;      /* (1,H,W) */
     const float* dL_dextra;      /* (E,H,W) */
+    const float* dL_dimage_nosh; /* (3,H,W) cotangent of the dual image (or NULL)                */
     /* scratch (device): P*TEXGS_BWD_ACC_FLOATS floats, zeroed by the library */
     float* acc_ws;
     /* gradient outputs (device). Per-Gaussian ones are fully written by the library (no

@@ -289,13 +289,19 @@ def cube_sample(texture: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
 
 def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient_uvs, texture,
               settings: RasterSettings, sw: Switches = Switches(), colors_precomp=None,
-              extra_attrs=None, max_elems: int = 6_000_000, tile_subset=None, return_aux=False):
+              extra_attrs=None, max_elems: int = 6_000_000, tile_subset=None, return_aux=False,
+              dual_no_sh: bool = False):
     """Returns (image(3,H,W), depth(1,H,W), norm(3,H,W), alpha(1,H,W), radii(N,), extra|None)
     [+ aux dict]. ``texture=None`` selects the plain-3DGS colour path (``diff_gauss``): colour is
     ``colors_precomp`` (N,3) if given, else max(0, SH_full(shs)+0.5) with shs (N,(deg+1)^2,3).
 
     ``tile_subset``: optional iterable of tile indices to render (CPU-baseline sampling); pixels of
-    other tiles stay zero."""
+    other tiles stay zero.
+
+    ``dual_no_sh``: additionally blend the colour the SAME splats have with
+    ``sh_degree = 0`` — max(0, C0*tex + 0.5) — into a second image, returned as
+    ``aux["image_no_sh"]``; identical to a second call with ``sh_degree=0`` (what the reference does
+    at models/texture_gaussian3d.py:375-389,505-511)."""
     assert not sw.seamless_cube, "only clamp-to-edge is implemented"
     st = settings
     dt, dev = means3D.dtype, means3D.device
@@ -322,6 +328,7 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
 
     npix_pad = gx * gy * TILE * TILE
     acc_c = torch.zeros(npix_pad, 3, dtype=dt, device=dev)
+    acc_c0 = torch.zeros(npix_pad, 3, dtype=dt, device=dev) if (dual_no_sh and textured) else None
     acc_d = torch.zeros(npix_pad, dtype=dt, device=dev)
     acc_n = torch.zeros(npix_pad, 3, dtype=dt, device=dev)
     acc_a = torch.zeros(npix_pad, dtype=dt, device=dev)
@@ -437,6 +444,8 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
                 u = uvs[g] + (Jg @ delta[:, :, None]).squeeze(-1)            # E10
                 tex = cube_sample(texture, u)                                 # E11
                 col = torch.clamp_min(C0 * tex + pre["csh"][g] + 0.5, 0.0)   # E12
+                if acc_c0 is not None:
+                    acc_c0 = acc_c0.index_add(0, pix, w_s[:, None] * torch.clamp_min(C0 * tex + 0.5, 0.0))
                 if sw.depth_of_intersection:
                     zc = (delta + mvec + st.campos.to(dt)) @ V[:3, 2] + V[3, 2]
                 else:
@@ -463,8 +472,9 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
     alpha_img = unpad(acc_a.reshape(-1, 1), 1)
     extra = unpad(acc_e, E) if E else None
     out = (image, depth, norm, alpha_img, pre["radii"], extra)
+    image_no_sh = (unpad(acc_c0, 3) + Tf * bg[:, None, None]) if acc_c0 is not None else None
     if return_aux:
-        aux = dict(final_T=Tf[0].detach(), n_contrib=unpad(n_contrib.reshape(-1, 1), 1)[0],
+        aux = dict(image_no_sh=image_no_sh, final_T=Tf[0].detach(), n_contrib=unpad(n_contrib.reshape(-1, 1), 1)[0],
                    ambiguous=unpad(ambiguous.reshape(-1, 1), 1)[0] | unpad(grazing.reshape(-1, 1), 1)[0],
                    threshold_ambiguous=unpad(ambiguous.reshape(-1, 1), 1)[0],
                    grazing=unpad(grazing.reshape(-1, 1), 1)[0], num_pairs=int(tile_of.shape[0]),

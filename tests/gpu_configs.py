@@ -24,6 +24,11 @@ def run(name, iters=12, warm=3):
                     g.active_sh_degree = 3 if r == 0 else 0     # retexture.py renders with SH, then sh_degree=0
                     uv_tex_render(cams[i % 8], g, None, bg)
                 g.active_sh_degree = 3
+    if wl.renders_per_view == 2 and "dual" in sys.argv:
+        from texture_gs_b200 import uv_tex_render_dual
+        def one(i):                                     # both images in one pass
+            with torch.no_grad():
+                uv_tex_render_dual(cams[i % 8], g, None, bg)
     for i in range(warm): one(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -36,5 +41,5 @@ def run(name, iters=12, warm=3):
                       "mem_gb": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
     del g; torch.cuda.empty_cache()
 
-for n in (sys.argv[1:] or ["cfg0_10k_256", "cfg1_300k_800x600", "cfg4_1m_4k"]):
+for n in ([a for a in sys.argv[1:] if a != "dual"] or ["cfg0_10k_256", "cfg1_300k_800x600", "cfg4_1m_4k"]):
     run(n)

@@ -308,6 +308,52 @@ def test_fused_bucket_accumulation_equals_autograd_accumulation():
         assert rel_err(res[1][k], res[0][k]) < 1e-5, k
 
 
+def test_dual_render_equals_two_reference_style_renders():
+    """uv_tex_render_dual == (render with active SH degree, render with sh_degree=0),
+    forward and backward, against the oracle run twice (as the reference's compute_loss does,
+    models/texture_gaussian3d.py:375-389)."""
+    from oracle import raster_ref as RR
+    from util import oracle_settings
+    from texture_gs_b200 import uv_tex_render, uv_tex_render_dual
+    N, W, H, R = 3000, 144, 96, 64
+    g = sphere_shell_scene(N, R, sh_degree=3, seed=21, tex_seed=22)
+    cam = orbit_cameras(1, W, H, seed=23)[0]
+    bgc = (0.2, 0.1, 0.3)
+    _, aux0, _ = run_oracle(g, cam, bg=bgc)
+    keep = (~aux0["ambiguous"]).float()
+    gen = torch.Generator().manual_seed(5)
+    cot = [c * keep for c in output_cotangents(H, W, seed=24)]
+    cot2 = torch.randn(3, H, W, generator=gen) * keep
+    # oracle: one dual call (fp32) and, independently, two separate calls
+    t = g.to(dtype=torch.float32, requires_grad=True).tensors()
+    st = oracle_settings(cam, 3, bg=bgc)
+    o = RR.rasterize(t["xyz"], None, t["shs"], t["opacity"], t["scaling"], t["rotation"], t["uvs"], t["grad_uvs"], t["texture"], st,
+                     return_aux=True, dual_no_sh=True)
+    st0 = oracle_settings(cam, 0, bg=bgc)
+    o0 = RR.rasterize(t["xyz"], None, t["shs"], t["opacity"], t["scaling"], t["rotation"], t["uvs"], t["grad_uvs"], t["texture"], st0)
+    assert float((o[-1]["image_no_sh"] - o0[0]).abs().max()) < 1e-6          # oracle self-consistency
+    Lr = sum((a * b).sum() for a, b in zip(o[:4], cot)) + (o0[0] * cot2).sum()
+    Lr.backward()
+    # cuda: single dual pass
+    gc = g.to("cuda", requires_grad=True)
+    pkg = uv_tex_render_dual(cam.to("cuda"), gc, None, torch.tensor(bgc, device="cuda"))
+    Lc = sum((pkg[k] * c.cuda()).sum() for k, c in zip(("render", "depth", "norm", "alpha"), cot)) + (pkg["render_no_sh"] * cot2.cuda()).sum()
+    Lc.backward()
+    amb = aux0["ambiguous"]
+    d1 = (pkg["render"].detach().cpu() - o[0].detach()).abs().amax(0)
+    d2 = (pkg["render_no_sh"].detach().cpu() - o0[0].detach()).abs().amax(0)
+    assert float(d1[~amb].max()) <= ABS_TOL and float(d2[~amb].max()) <= ABS_TOL
+    for k, v in gc.tensors().items():
+        if v is not None and v.grad is not None:
+            e = rel_err(v.grad.cpu(), t[k].grad)
+            assert e <= GRAD_RTOL, (k, e)
+    # and the dual image equals what a second plain call with active_sh_degree = 0 returns
+    gc.active_sh_degree = 0
+    with torch.no_grad():
+        plain0 = uv_tex_render(cam.to("cuda"), gc, None, torch.tensor(bgc, device="cuda"))["render"]
+    assert float((plain0 - pkg["render_no_sh"].detach()).abs().max()) <= 1e-6
+
+
 def test_capacity_overflow_retry_is_transparent():
     from texture_gs_b200 import rasterizer as RZ
     g = sphere_shell_scene(3000, 16, sh_degree=0, seed=1)

@@ -205,3 +205,18 @@ def test_band_limited_texture_is_smooth_and_in_range():
     rgb = C0 * t + 0.5
     assert float(rgb.min()) >= -1e-6 and float(rgb.max()) <= 1 + 1e-6
     assert float((rgb[:, :, 1:] - rgb[:, :, :-1]).abs().max()) < 0.35
+
+
+def test_dual_no_sh_image_equals_a_second_render_with_degree_zero():
+    """aux["image_no_sh"] == the image of a second call with sh_degree = 0, which is
+    how the reference gets it (models/texture_gaussian3d.py:375-389)."""
+    g = sphere_shell_scene(200, 16, sh_degree=3, seed=31).to(dtype=torch.float64)
+    cam = orbit_cameras(1, 48, 32, seed=32)[0]
+    t = g.tensors()
+    st3 = oracle_settings(cam, 3, dtype=torch.float64, bg=(0.3, 0.2, 0.1))
+    st0 = oracle_settings(cam, 0, dtype=torch.float64, bg=(0.3, 0.2, 0.1))
+    a = RR.rasterize(t["xyz"], None, t["shs"], t["opacity"], t["scaling"], t["rotation"], t["uvs"], t["grad_uvs"], t["texture"], st3,
+                     return_aux=True, dual_no_sh=True)
+    b = RR.rasterize(t["xyz"], None, t["shs"], t["opacity"], t["scaling"], t["rotation"], t["uvs"], t["grad_uvs"], t["texture"], st0)
+    assert float((a[-1]["image_no_sh"] - b[0]).abs().max()) < 1e-12
+    assert float((a[0] - b[0]).abs().max()) > 1e-3        # the SH term does change the first image

@@ -5,7 +5,7 @@ Public surface (mirrors what reference render/uv_tex_render.py and render/render
 """
 from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, invalidate_packed_cache,  # noqa: F401
                          last_stats)
-from .render import render, uv_tex_render, type2render_func  # noqa: F401
+from .render import render, uv_tex_render, uv_tex_render_dual, type2render_func  # noqa: F401
 
-__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "uv_tex_render", "render", "type2render_func",
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "uv_tex_render", "uv_tex_render_dual", "render", "type2render_func",
            "last_stats"]

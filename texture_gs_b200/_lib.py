@@ -37,6 +37,7 @@ class TexgsFwdArgs(C.Structure):
         ("means3D", _fp), ("shs", _fp), ("colors_precomp", _fp), ("opacities", _fp), ("scales", _fp),
         ("rotations", _fp), ("uvs", _fp), ("gradient_uvs", _fp), ("texture", _fp), ("extra_attrs", _fp),
         ("texture_rgba", _fp),
+        ("out_image_nosh", _fp),
         ("profile_events", C.POINTER(C.c_void_p)),
     ]
 
@@ -51,7 +52,7 @@ class TexgsBwdArgs(C.Structure):
     _fields_ = [
         ("fwd", TexgsFwdArgs),
         ("geom_ws", _fp), ("bin_ws", _fp), ("img_ws", _fp), ("pair_capacity", C.c_uint64),
-        ("dL_dimage", _fp), ("dL_ddepth", _fp), ("dL_dnorm", _fp), ("dL_dalpha", _fp), ("dL_dextra", _fp),
+        ("dL_dimage", _fp), ("dL_ddepth", _fp), ("dL_dnorm", _fp), ("dL_dalpha", _fp), ("dL_dextra", _fp), ("dL_dimage_nosh", _fp),
         ("acc_ws", _fp),
         ("dL_dmeans3D", _fp), ("dL_dmeans2D", _fp), ("dL_dopacity", _fp), ("dL_dscales", _fp),
         ("dL_drotations", _fp), ("dL_dshs", _fp), ("dL_dcolors_precomp", _fp), ("dL_duvs", _fp),

@@ -132,6 +132,7 @@ int fill_params(const TexgsFwdArgs* a, void* geom, void* bin, uint64_t cap, void
     p.pairs = (uint2*)(b + L.l.bin_pairs);
     p.sorted_ids = (unsigned*)(b + L.l.bin_sorted_ids);
     p.pair_capacity = cap;
+    p.out_image_nosh = (a->mode == TEXGS_MODE_TEXTURE) ? a->out_image_nosh : nullptr;
     p.final_T = (float*)(im + L.l.img_final_T);
     p.n_contrib = (unsigned*)(im + L.l.img_n_contrib);
     return 0;
@@ -146,14 +147,20 @@ int ensure_render_smem() {
     if (done_for_device == dev) return 0;
     const int bytes = (int)TEXGS_RENDER_SMEM;
 #define TEXGS_SET_SMEM(k) TEXGS_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
-    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, true>));
-    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, false>));
-    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_SH, false>));
-    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, true>));
-    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, false>));
-    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, true>));
-    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, false>));
-    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_SH, false, false>));
+    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, true, false>));
+    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, false, false>));
+    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, true, true>));
+    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, false, true>));
+    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_SH, false, false>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, true, false>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, false, false>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, true, false>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, false, false>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, true, true>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, false, true>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, true, true>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, false, true>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_SH, false, false, false>));
 #undef TEXGS_SET_SMEM
     done_for_device = dev;
     return 0;
@@ -226,12 +233,16 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
     TEXGS_KERNEL_CHECK("texgs_sort_tiles", debug, stream);
     TEXGS_EV(a, TEXGS_EV_FWD_SORT, stream);
     if (int rc = ensure_render_smem()) return rc;
-    if (p.mode == TEXGS_MODE_TEXTURE && p.texture_rgba)
-        texgs_render_fwd<TEXGS_MODE_TEXTURE, true><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha);
-    else if (p.mode == TEXGS_MODE_TEXTURE)
-        texgs_render_fwd<TEXGS_MODE_TEXTURE, false><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha);
-    else
-        texgs_render_fwd<TEXGS_MODE_SH, false><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha);
+    {
+        const bool t4 = p.texture_rgba != nullptr, dual = p.out_image_nosh != nullptr;
+#define TEXGS_LAUNCH_FWD(M, T4, DU) texgs_render_fwd<M, T4, DU><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha)
+        if (p.mode != TEXGS_MODE_TEXTURE) TEXGS_LAUNCH_FWD(TEXGS_MODE_SH, false, false);
+        else if (t4 && dual)  TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, true, true);
+        else if (t4)          TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, true, false);
+        else if (dual)        TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, false, true);
+        else                  TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, false, false);
+#undef TEXGS_LAUNCH_FWD
+    }
     TEXGS_KERNEL_CHECK("texgs_render_fwd", debug, stream);
     TEXGS_EV(a, TEXGS_EV_FWD_RENDER, stream);
     if (counters_host && debug) {   // debug: counters include the blend count, copied after the render
@@ -263,18 +274,23 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
     if (b->dL_dtexture_rgba && b->zero_texture_grad && p.mode == TEXGS_MODE_TEXTURE)
         TEXGS_CUDA_TRY(cudaMemsetAsync(b->dL_dtexture_rgba, 0, (size_t)6 * p.R * p.R * 4 * sizeof(float), stream));
     TEXGS_EV(a, TEXGS_EV_BWD_CLEAR, stream);
-    BwdIn in{b->dL_dimage, b->dL_ddepth, b->dL_dnorm, b->dL_dalpha};
+    BwdIn in{b->dL_dimage, b->dL_ddepth, b->dL_dnorm, b->dL_dalpha, b->dL_dimage_nosh};
     if (int rc = ensure_render_smem()) return rc;
-    // the four variants: texel reads packed or not  x  texel-gradient writes packed or not
+    // variants: texel reads packed or not  x  texel-gradient writes packed or not  x  dual image
     if (p.mode == TEXGS_MODE_TEXTURE) {
-        const bool rd4 = p.texture_rgba != nullptr, wr4 = b->dL_dtexture_rgba != nullptr;
+        const bool rd4 = p.texture_rgba != nullptr, wr4 = b->dL_dtexture_rgba != nullptr, dual = p.out_image_nosh != nullptr;
         float* dt = wr4 ? b->dL_dtexture_rgba : b->dL_dtexture;
-        if (rd4 && wr4)       texgs_render_bwd<TEXGS_MODE_TEXTURE, true, true><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, dt);
-        else if (rd4)         texgs_render_bwd<TEXGS_MODE_TEXTURE, true, false><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, dt);
-        else if (wr4)         texgs_render_bwd<TEXGS_MODE_TEXTURE, false, true><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, dt);
-        else                  texgs_render_bwd<TEXGS_MODE_TEXTURE, false, false><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, dt);
+#define TEXGS_LAUNCH_BWD(R4, W4, DU) texgs_render_bwd<TEXGS_MODE_TEXTURE, R4, W4, DU><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, dt)
+        if (dual) {
+            if (rd4 && wr4) TEXGS_LAUNCH_BWD(true, true, true); else if (rd4) TEXGS_LAUNCH_BWD(true, false, true);
+            else if (wr4) TEXGS_LAUNCH_BWD(false, true, true); else TEXGS_LAUNCH_BWD(false, false, true);
+        } else {
+            if (rd4 && wr4) TEXGS_LAUNCH_BWD(true, true, false); else if (rd4) TEXGS_LAUNCH_BWD(true, false, false);
+            else if (wr4) TEXGS_LAUNCH_BWD(false, true, false); else TEXGS_LAUNCH_BWD(false, false, false);
+        }
+#undef TEXGS_LAUNCH_BWD
     } else {
-        texgs_render_bwd<TEXGS_MODE_SH, false, false><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, nullptr);
+        texgs_render_bwd<TEXGS_MODE_SH, false, false, false><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, nullptr);
     }
     TEXGS_KERNEL_CHECK("texgs_render_bwd", debug, stream);
     TEXGS_EV(a, TEXGS_EV_BWD_RENDER, stream);

@@ -64,6 +64,7 @@ struct RasterParams {
     unsigned long long pair_capacity;
     float* final_T;
     unsigned* n_contrib;
+    float* out_image_nosh;   // dual render: second image (sh_degree = 0 colour), or NULL
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -154,7 +154,7 @@ __device__ __forceinline__ UvEval eval_uv(const float4& g1, const float4& g2, co
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <int MODE, bool TEX4>
+template <int MODE, bool TEX4, bool DUAL>
 __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(const RasterParams p, float* __restrict__ out_image,
                                                       float* __restrict__ out_depth, float* __restrict__ out_norm,
                                                       float* __restrict__ out_alpha) {
@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
     const int nchunks = (int)((n + TEXGS_CHUNK - 1) / TEXGS_CHUNK);
 
     float T = 1.0f, Cr = 0.f, Cg = 0.f, Cb = 0.f, D = 0.f, Nx = 0.f, Ny = 0.f, Nz = 0.f, A = 0.f;
+    float Er = 0.f, Eg = 0.f, Eb = 0.f;     // dual render: colour without the SH term
     unsigned last = 0, nblend = 0;
     bool done = !g.inside;
     const float pxf = (float)g.px, pyf = (float)g.py;
@@ -247,6 +248,12 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
                         cr = fmaxf(0.f, SH_C0 * tx3[0] + cr);
                         cg = fmaxf(0.f, SH_C0 * tx3[1] + cg);
                         cb = fmaxf(0.f, SH_C0 * tx3[2] + cb);
+                        if (DUAL) {
+                            const float w0 = alpha * T;
+                            Er += w0 * fmaxf(0.f, SH_C0 * tx3[0] + 0.5f);
+                            Eg += w0 * fmaxf(0.f, SH_C0 * tx3[1] + 0.5f);
+                            Eb += w0 * fmaxf(0.f, SH_C0 * tx3[2] + 0.5f);
+                        }
                     }
                     const float w = alpha * T;
                     Cr += w * cr; Cg += w * cg; Cb += w * cb;
@@ -275,6 +282,11 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
         out_image[g.pix] = Cr + T * p.bg[0];
         out_image[HW + g.pix] = Cg + T * p.bg[1];
         out_image[2 * HW + g.pix] = Cb + T * p.bg[2];
+        if (DUAL) {
+            p.out_image_nosh[g.pix] = Er + T * p.bg[0];
+            p.out_image_nosh[HW + g.pix] = Eg + T * p.bg[1];
+            p.out_image_nosh[2 * HW + g.pix] = Eb + T * p.bg[2];
+        }
         out_depth[g.pix] = D;
         const float3 nw = rot_v2w(p.view, f3(Nx, Ny, Nz));
         out_norm[g.pix] = nw.x;
@@ -298,10 +310,10 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
 // backward
 // ---------------------------------------------------------------------------------------------
 struct BwdIn {
-    const float *dL_dimage, *dL_ddepth, *dL_dnorm, *dL_dalpha;
+    const float *dL_dimage, *dL_ddepth, *dL_dnorm, *dL_dalpha, *dL_dimage_nosh;
 };
 
-template <int MODE, bool TEX4, bool GRAD4>
+template <int MODE, bool TEX4, bool GRAD4, bool DUAL>
 __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(const RasterParams p, const BwdIn in, float* __restrict__ acc,
                                                       float* __restrict__ dtex) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -332,7 +344,11 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
         if (in.dL_dnorm) gnv = rot_w2v(p.view, f3(in.dL_dnorm[g.pix], in.dL_dnorm[HW + g.pix], in.dL_dnorm[2 * HW + g.pix]));
         T_final = p.final_T[g.pix];
     }
-    const float bgdot = gr * p.bg[0] + gg * p.bg[1] + gb * p.bg[2];
+    float hr = 0.f, hg = 0.f, hb = 0.f;       // dual render: cotangent of the no-SH image
+    if (DUAL && g.inside && in.dL_dimage_nosh) {
+        hr = in.dL_dimage_nosh[g.pix]; hg = in.dL_dimage_nosh[HW + g.pix]; hb = in.dL_dimage_nosh[2 * HW + g.pix];
+    }
+    const float bgdot = (gr + hr) * p.bg[0] + (gg + hg) * p.bg[1] + (gb + hb) * p.bg[2];
     const float pxf = (float)g.px, pyf = (float)g.py;
     const float* __restrict__ tex = p.texture;
     const int R = p.R;
@@ -403,6 +419,7 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
                 const float w = alpha * T;
                 float cr = g3.y, cg = g3.z, cb = g3.w;
                 float mr = 1.f, mg = 1.f, mb = 1.f;
+                float xdual = 0.f, kr = 0.f, kg = 0.f, kb = 0.f;
                 UvEval e;
                 CubeCoord cc;
                 Bilerp bl;
@@ -425,8 +442,13 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
                     if (cr < 0.f) { cr = 0.f; mr = 0.f; }
                     if (cg < 0.f) { cg = 0.f; mg = 0.f; }
                     if (cb < 0.f) { cb = 0.f; mb = 0.f; }
+                    if (DUAL) {   // colour of the no-SH image and its clamp mask, folded into X / the texel gradient
+                        const float er = SH_C0 * tx3[0] + 0.5f, eg = SH_C0 * tx3[1] + 0.5f, eb = SH_C0 * tx3[2] + 0.5f;
+                        xdual = hr * fmaxf(er, 0.f) + hg * fmaxf(eg, 0.f) + hb * fmaxf(eb, 0.f);
+                        kr = (er < 0.f) ? 0.f : hr; kg = (eg < 0.f) ? 0.f : hg; kb = (eb < 0.f) ? 0.f : hb;
+                    }
                 }
-                const float X = gr * cr + gg * cg + gb * cb + gd * g1.z + gnv.x * g2.x + gnv.y * g2.y + gnv.z * g2.z + ga;
+                const float X = gr * cr + gg * cg + gb * cb + gd * g1.z + gnv.x * g2.x + gnv.y * g2.y + gnv.z * g2.z + ga + xdual;
                 acc_rec = last_alpha * last_X + (1.0f - last_alpha) * acc_rec;
                 const float dL_dalpha = (X - acc_rec) * T - (T_final * inv_1ma) * bgdot;
                 last_alpha = alpha;
@@ -446,7 +468,7 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
                 v[9] = w * gd;
                 v[10] = w * gnv.x; v[11] = w * gnv.y; v[12] = w * gnv.z;
                 if (MODE == TEXGS_MODE_TEXTURE) {
-                    const float gt[3] = {SH_C0 * wr, SH_C0 * wg, SH_C0 * wb};
+                    const float gt[3] = {SH_C0 * (wr + w * kr), SH_C0 * (wg + w * kg), SH_C0 * (wb + w * kb)};
                     float dwx = 0.f, dwy = 0.f;
                     const float w00 = (1.f - bl.wx) * (1.f - bl.wy), w01 = bl.wx * (1.f - bl.wy);
                     const float w10 = (1.f - bl.wx) * bl.wy, w11 = bl.wx * bl.wy;

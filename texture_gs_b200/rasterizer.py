@@ -193,7 +193,7 @@ def _build_args(st: GaussianRasterizationSettings, mode: int, means3D, shs, colo
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, shs, colors_precomp, opacities, scales, rotations, uvs, gradient_uvs,
-                texture, st: GaussianRasterizationSettings, mode: int):
+                texture, st: GaussianRasterizationSettings, mode: int, dual: bool = False):
         lib = L.load()
         if not means3D.is_cuda:
             raise L.TexgsError("the rasterizer runs on CUDA tensors only (no CPU fallback); got " + str(means3D.device))
@@ -227,6 +227,10 @@ class _RasterizeGaussians(torch.autograd.Function):
             norm = torch.empty(3, H, W, device=dev, dtype=torch.float32)
             alpha = torch.empty(1, H, W, device=dev, dtype=torch.float32)
             radii = torch.empty(P, device=dev, dtype=torch.int32)
+            dual = bool(dual and mode == L.MODE_TEXTURE)
+            image_nosh = torch.empty(3, H, W, device=dev, dtype=torch.float32) if dual else image.new_empty(0)
+            if dual:
+                a.out_image_nosh = _ptr(image_nosh)
             key = (dev.index, P, H, W)
             cap = _capacity_hint.get(key, max(1 << 16, 8 * P))
             pinned, event = _pinned_counters(dev.index)
@@ -252,7 +256,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             _capacity_hint[key] = max(cap, _capacity_hint.get(key, 0)) if not overflow else cap
             _last_stats.v = RasterStats(K, V, maxlen, blo | (bhi << 32), cap)
 
-        ctx.st, ctx.mode, ctx.cap, ctx.prof, ctx.tex4 = st, mode, cap, prof, tex4
+        ctx.st, ctx.mode, ctx.cap, ctx.prof, ctx.tex4, ctx.dual = st, mode, cap, prof, tex4, dual
         # fused gradient accumulation (texture_gs_b200.dist.GradBucket.fused): resolved now because
         # backward runs on autograd's thread. Only inputs that ARE bucket leaves qualify.
         ctx.fuse = None
@@ -270,12 +274,15 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.dev = dev
         ctx.has = (shs is not None, colors_precomp is not None, uvs is not None, texture is not None)
         ctx.save_for_backward(m3, sh, cp, op, sc, ro, uv, guv, tex, geom, binw, imgw)
-        ctx.mark_non_differentiable(radii)
-        return image, depth, norm, alpha, radii
+        if dual:
+            ctx.mark_non_differentiable(radii)
+        else:
+            ctx.mark_non_differentiable(radii, image_nosh)
+        return image, depth, norm, alpha, radii, image_nosh
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, g_image, g_depth, g_norm, g_alpha, _g_radii):
+    def backward(ctx, g_image, g_depth, g_norm, g_alpha, _g_radii, g_image_nosh):
         lib = L.load()
         m3, sh, cp, op, sc, ro, uv, guv, tex, geom, binw, imgw = ctx.saved_tensors
         st, mode, dev = ctx.st, ctx.mode, ctx.dev
@@ -290,6 +297,11 @@ class _RasterizeGaussians(torch.autograd.Function):
             b.geom_ws, b.bin_ws, b.img_ws, b.pair_capacity = _ptr(geom), _ptr(binw), _ptr(imgw), ctx.cap
             keep = [_prep(g, dev) for g in (g_image, g_depth, g_norm, g_alpha)]
             b.dL_dimage, b.dL_ddepth, b.dL_dnorm, b.dL_dalpha = (_ptr(k) for k in keep)
+            if ctx.dual:
+                # the kernels only need the pointer STATE of the dual output to pick the variant
+                b.fwd.out_image_nosh = C.c_void_p(1 << 8)
+                keep.append(_prep(g_image_nosh, dev))
+                b.dL_dimage_nosh = _ptr(keep[-1])
             acc = torch.empty(max(P, 1) * L.BWD_ACC_FLOATS, device=dev, dtype=torch.float32)
             b.acc_ws = _ptr(acc)
 
@@ -345,7 +357,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             if zero_tex == 0:
                 d_tex = None
             L.check(lib.texgs_backward(C.byref(b), C.c_void_p(stream)), "texgs_backward")
-        return d_m3, d_m2, d_sh, d_cp, d_op, d_sc, d_ro, d_uv, None, d_tex, None, None
+        return d_m3, d_m2, d_sh, d_cp, d_op, d_sc, d_ro, d_uv, None, d_tex, None, None, None
 
 
 class GaussianRasterizer(nn.Module):
@@ -372,7 +384,9 @@ class GaussianRasterizer(nn.Module):
         return present.bool()
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3Ds_precomp=None, uvs=None, gradient_uvs=None, texture=None, extra_attrs=None):
+                cov3Ds_precomp=None, uvs=None, gradient_uvs=None, texture=None, extra_attrs=None, dual_no_sh=False):
+        """``dual_no_sh=True`` (textured mode) appends a 7th result: the image the same
+        splats give with ``sh_degree = 0``, blended in the same pass."""
         st = self.raster_settings
         if extra_attrs is not None:
             raise NotImplementedError("extra_attrs is always None in the reference tree (render/uv_tex_render.py:7); not built yet")
@@ -388,6 +402,11 @@ class GaussianRasterizer(nn.Module):
             if (shs is None) == (colors_precomp is None):
                 raise ValueError("Please provide exactly one of either SHs or precomputed colors!")
             mode = L.MODE_SH if shs is not None else L.MODE_PRECOMP
-        image, depth, norm, alpha, radii = _RasterizeGaussians.apply(
-            means3D, means2D, shs, colors_precomp, opacities, scales, rotations, uvs, gradient_uvs, texture, st, mode)
+        if dual_no_sh and mode != L.MODE_TEXTURE:
+            raise ValueError("dual_no_sh needs the textured mode")
+        image, depth, norm, alpha, radii, image_nosh = _RasterizeGaussians.apply(
+            means3D, means2D, shs, colors_precomp, opacities, scales, rotations, uvs, gradient_uvs, texture, st, mode,
+            bool(dual_no_sh))
+        if dual_no_sh:
+            return image, depth, norm, alpha, radii, None, image_nosh
         return image, depth, norm, alpha, radii, None

@@ -56,6 +56,24 @@ def uv_tex_render(viewpoint_camera, gaussians, cfg=None, bg_color=None, scaling_
             "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "extra": extra, "radii": radii}
 
 
+def uv_tex_render_dual(viewpoint_camera, gaussians, cfg=None, bg_color=None, scaling_modifier=1.0, extra_attrs=None,
+                       debug=False):
+    """One pass for the reference's two renders per view: the normal textured render
+    plus ``"render_no_sh"``, the image the reference obtains by setting ``active_sh_degree = 0`` and
+    rendering again (models/texture_gaussian3d.py:375-389 in training, :505-511 in visual_step).
+    Geometry, binning, sort, intersections and texel fetches are shared; depth / norm / alpha are the
+    same for both and returned once."""
+    screenspace_points = _screenspace_points(gaussians)
+    rasterizer = GaussianRasterizer(raster_settings=_settings(viewpoint_camera, gaussians, bg_color, scaling_modifier, debug))
+    image, depth, norm, alpha, radii, extra, image_no_sh = rasterizer(
+        means3D=gaussians.get_xyz, means2D=screenspace_points, shs=gaussians.get_shs,
+        opacities=gaussians.get_opacity, scales=gaussians.get_scaling, rotations=gaussians.get_rotation,
+        uvs=gaussians.get_uvs, gradient_uvs=gaussians.get_grad_uvs, texture=gaussians.get_texture,
+        extra_attrs=extra_attrs, dual_no_sh=True)
+    return {"render": image, "render_no_sh": image_no_sh, "depth": depth, "norm": norm, "alpha": alpha,
+            "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "extra": extra, "radii": radii}
+
+
 def render(viewpoint_camera, gaussians, cfg=None, bg_color=None, scaling_modifier=1.0, override_color=None,
            extra_attrs=None, debug=False):
     """Plain 3DGS render (reference render/render.py:8): colour from full SH (``get_features``) or
@@ -71,4 +89,4 @@ def render(viewpoint_camera, gaussians, cfg=None, bg_color=None, scaling_modifie
             "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "extra": extra, "radii": radii}
 
 
-type2render_func = dict(render=render, uv_tex_render=uv_tex_render)   # reference render/__init__.py:4-7
+type2render_func = dict(render=render, uv_tex_render=uv_tex_render, uv_tex_render_dual=uv_tex_render_dual)   # reference render/__init__.py:4-7
