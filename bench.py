@@ -216,7 +216,9 @@ def run_reference(args, wl):
             "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1000.0 * VIEWS_PER_STEP / value,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl.name, "gaussians": wl.n_gaussians, "width": wl.width, "height": wl.height,
-                       "tex_res": wl.tex_res, "views_per_step": VIEWS_PER_STEP, "sh_degree": 3},
+                       "tex_res": wl.tex_res, "views_per_step": VIEWS_PER_STEP, "sh_degree": 3,
+                       "parallelism": f"host CPU, {threads} torch threads (rank 0 only)",
+                       "l2_policy": "n/a (CPU arm)"},
             "cpu_baseline": {"value": value, "unit": "views/s", "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -397,7 +399,7 @@ def run_e2e(args, wl, g, cams, cot_dev, bg, bucket, views, dev, world, sync_all)
                 pkg = uv_tex_render(cam, g, None, bg)
                 outs = [pkg["render"], pkg["depth"], pkg["norm"], pkg["alpha"]]
                 with torch.no_grad():
-                    total += sum((o.detach() * c).sum() for o, c in zip(outs, bufs[slot]))
+                    total += sum(torch.dot(o.detach().reshape(-1), c.reshape(-1)) for o, c in zip(outs, bufs[slot]))
                 torch.autograd.backward(outs, list(bufs[slot]))
             free[slot].record(main)
         bucket.all_reduce()
