@@ -28,9 +28,9 @@ def _need_cuda():
     _lib.load()   # fail loudly if the extension is missing
 
 
-def _check_forward(g, cam, bg=(0.0, 0.0, 0.0), max_amb=0.15):
-    ref, aux, _ = run_oracle(g, cam, bg=bg)
-    got, stats, _ = run_cuda(g, cam, bg=bg)
+def _check_forward(g, cam, bg=(0.0, 0.0, 0.0), max_amb=0.15, scale_modifier=1.0):
+    ref, aux, _ = run_oracle(g, cam, bg=bg, scale_modifier=scale_modifier)
+    got, stats, _ = run_cuda(g, cam, bg=bg, scale_modifier=scale_modifier)
     rep = compare_images(got[:4], ref[:4], aux["ambiguous"])
     print(rep, stats)
     assert stats.num_pairs == aux["num_pairs"], (stats, aux["num_pairs"])
@@ -44,7 +44,7 @@ def _check_forward(g, cam, bg=(0.0, 0.0, 0.0), max_amb=0.15):
     return rep
 
 
-def _check_backward(g, cam, bg=(0.0, 0.0, 0.0), seed=3, uv_tol=GRAD_RTOL, max_flag=0.2):
+def _check_backward(g, cam, bg=(0.0, 0.0, 0.0), seed=3, uv_tol=GRAD_RTOL, max_flag=0.2, scale_modifier=1.0):
     """Gradients of L = sum(out * cot) with the cotangents zeroed on the pixels the oracle flags as
     ill-conditioned in fp32 (a blend decision within a few ulp of its threshold, or a ray grazing a
     disc: t = n.m/n.d with |cos| < GRAZING_COS — there the fp32 ORACLE differs from the fp64 oracle
@@ -54,13 +54,14 @@ def _check_backward(g, cam, bg=(0.0, 0.0, 0.0), seed=3, uv_tol=GRAD_RTOL, max_fl
         err(cuda, o64) <= max(1e-3, 3 * err(o32, o64))
     i.e. BASELINE's 1e-3 wherever fp32 arithmetic can deliver it, and otherwise no worse than 3x the
     error the reference fp32 arithmetic (the oracle run in fp32) itself shows."""
-    _, aux, _ = run_oracle(g, cam, bg=bg)
+    kw = dict(scale_modifier=scale_modifier)
+    _, aux, _ = run_oracle(g, cam, bg=bg, **kw)
     keep = (~aux["ambiguous"]).float()
     assert float(1 - keep.mean()) <= max_flag     # low-res scenes: big discs near the silhouette cover many pixels
     cot = [c * keep for c in output_cotangents(cam.image_height, cam.image_width, seed=seed)]
-    _, _, g64 = run_oracle(g, cam, bg=bg, cot=cot, dtype=torch.float64)
-    _, _, g32 = run_oracle(g, cam, bg=bg, cot=cot)
-    _, _, ggot = run_cuda(g, cam, bg=bg, cot=cot)
+    _, _, g64 = run_oracle(g, cam, bg=bg, cot=cot, dtype=torch.float64, **kw)
+    _, _, g32 = run_oracle(g, cam, bg=bg, cot=cot, **kw)
+    _, _, ggot = run_cuda(g, cam, bg=bg, cot=cot, **kw)
     errs = {}
     for k, r in g64.items():
         if r is None:
@@ -352,6 +353,52 @@ def test_dual_render_equals_two_reference_style_renders():
     with torch.no_grad():
         plain0 = uv_tex_render(cam.to("cuda"), gc, None, torch.tensor(bgc, device="cuda"))["render"]
     assert float((plain0 - pkg["render_no_sh"].detach()).abs().max()) <= 1e-6
+
+
+def _variant_scene(n, r, seed, opacity_lo=0.3, opacity_hi=0.99, quat_scale=1.0, coverage=4.0, deg=3, radius_jitter=0.02):
+    g = sphere_shell_scene(n, r, sh_degree=deg, seed=seed, tex_seed=seed + 1, coverage=coverage)
+    t = {k: (v.detach().clone() if v is not None else None) for k, v in g.tensors().items()}
+    gen = torch.Generator().manual_seed(seed + 100)
+    t["opacity"] = opacity_lo + (opacity_hi - opacity_lo) * torch.rand(n, 1, generator=gen)
+    t["rotation"] = t["rotation"] * quat_scale
+    return SyntheticGaussians(active_sh_degree=deg, **t)
+
+
+def test_clamp_paths_unnormalised_quaternions_and_scale_modifier():
+    """alpha clamp min(0.99, o*G) active (opacity up to 1), quaternions of norm 1.3 (used as given),
+    scale_modifier != 1, non-zero background, SH degree 1."""
+    g = _variant_scene(2500, 32, seed=41, opacity_lo=0.6, opacity_hi=1.0, quat_scale=1.3, deg=1)
+    cam = orbit_cameras(1, 150, 100, seed=42)[0]
+    _check_forward(g, cam, bg=(0.9, 0.1, 0.5), scale_modifier=0.7, max_amb=0.3)     # smaller splats: more grazing pixels
+    _check_backward(g, cam, bg=(0.9, 0.1, 0.5), scale_modifier=0.7, max_flag=0.3)
+
+
+def test_saturating_layers_exercise_early_termination():
+    """Dense opaque coverage: T drops below 1e-4, pixels stop early, n_contrib < list length, the
+    backward walks only the contributors."""
+    g = _variant_scene(6000, 32, seed=43, opacity_lo=0.9, opacity_hi=0.99, coverage=40.0, deg=0)
+    cam = orbit_cameras(1, 128, 96, seed=44)[0]
+    ref, aux, _ = run_oracle(g, cam)
+    assert float(aux["final_T"].min()) < 2e-4                      # the stop rule really fires
+    got, stats, _ = run_cuda(g, cam)
+    rep = compare_images(got[:4], ref[:4], aux["ambiguous"])
+    for n in ("image", "depth", "norm", "alpha"):
+        assert rep[n]["max_clear"] <= ABS_TOL * (3.0 if n == "depth" else 1.0), (n, rep[n])
+    _check_backward(g, cam, max_flag=0.5)
+
+
+def test_camera_inside_the_scene_culls_and_clamps():
+    """Camera close to the shell: splats behind the near plane (z <= 0.2) are culled, splats far
+    outside the frustum hit the 1.3*tanfov clamp of the EWA Jacobian, big screen-space radii."""
+    from texture_gs_b200.scene import SyntheticCamera, look_at_w2c
+    g = _variant_scene(3000, 32, seed=45, deg=2, coverage=6.0)
+    c = torch.tensor([0.0, 0.3, 0.55], dtype=torch.float64)
+    w2c = look_at_w2c(c, torch.tensor([0.2, 0.1, -1.0], dtype=torch.float64), torch.tensor([0.0, -1.0, 0.0], dtype=torch.float64))
+    cam = SyntheticCamera(120, 90, math.radians(60.0), w2c)
+    ref, aux, _ = run_oracle(g, cam)
+    assert int((ref[4] == 0).sum()) > 100 and int((ref[4] > 0).sum()) > 100      # both culled and visible splats
+    _check_forward(g, cam, bg=(0.1, 0.2, 0.3), max_amb=0.5)
+    _check_backward(g, cam, bg=(0.1, 0.2, 0.3), max_flag=0.6, uv_tol=5e-3)
 
 
 def test_capacity_overflow_retry_is_transparent():

@@ -23,12 +23,13 @@ def oracle_settings(cam, sh_degree, dtype=torch.float32, bg=(0.0, 0.0, 0.0), dev
         sh_degree=sh_degree, campos=cam.camera_center.to(device=device, dtype=dtype))
 
 
-def run_oracle(g: SyntheticGaussians, cam, bg=(0.0, 0.0, 0.0), cot=None, dtype=torch.float32, sw=None, **kw):
+def run_oracle(g: SyntheticGaussians, cam, bg=(0.0, 0.0, 0.0), cot=None, dtype=torch.float32, sw=None,
+               scale_modifier=1.0, **kw):
     """Forward (+ backward if ``cot`` given) of the oracle on CPU. Returns (outputs, aux, grads)."""
     from oracle.raster_ref import Switches
     gg = g.to(device="cpu", dtype=dtype, requires_grad=cot is not None)
     t = gg.tensors()
-    st = oracle_settings(cam, g.active_sh_degree, dtype=dtype, bg=bg)
+    st = oracle_settings(cam, g.active_sh_degree, dtype=dtype, bg=bg, scale_modifier=scale_modifier)
     m2 = torch.zeros_like(t["xyz"], requires_grad=cot is not None)
     out = oracle_rasterize(t["xyz"], m2, t["shs"], t["opacity"], t["scaling"], t["rotation"], t["uvs"],
                            t["grad_uvs"], t["texture"], st, sw or Switches(), return_aux=True, **kw)
@@ -43,13 +44,13 @@ def run_oracle(g: SyntheticGaussians, cam, bg=(0.0, 0.0, 0.0), cot=None, dtype=t
     return (image.detach(), depth.detach(), norm.detach(), alpha.detach(), radii), aux, grads
 
 
-def run_cuda(g: SyntheticGaussians, cam, bg=(0.0, 0.0, 0.0), cot=None, debug=False, device="cuda"):
+def run_cuda(g: SyntheticGaussians, cam, bg=(0.0, 0.0, 0.0), cot=None, debug=False, device="cuda", scale_modifier=1.0):
     """Forward (+ backward) through the product operator ``uv_tex_render`` (-> C-ABI)."""
     from texture_gs_b200 import uv_tex_render, last_stats
     gg = g.to(device=device, dtype=torch.float32, requires_grad=cot is not None)
     cam_d = cam.to(device)
     bg_t = torch.tensor(bg, dtype=torch.float32, device=device)
-    pkg = uv_tex_render(cam_d, gg, None, bg_t, debug=debug)
+    pkg = uv_tex_render(cam_d, gg, None, bg_t, scaling_modifier=scale_modifier, debug=debug)
     grads = None
     if cot is not None:
         c = [x.to(device) for x in cot]
