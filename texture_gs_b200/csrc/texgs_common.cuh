@@ -299,3 +299,45 @@ __device__ __forceinline__ void fetch_taps(const float* __restrict__ tex, const 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+
+// Half-warp flavour of the transposing reduction: lanes 0-15 and 16-31 reduce independently (xor
+// distances 8,4,2,1 never cross the halves). On return, inside each half,
+//   outA on lane l holds the half's total of value (l & 15)                       (values 0..15)
+//   outB on lane l holds the half's total of value 16 + ((l >> 2) & 3)            (values 16..19)
+__device__ __forceinline__ void halfwarp_reduce20(const float (&v)[20], int lane, float& outA, float& outB) {
+    const unsigned full = 0xffffffffu;
+    const bool h3 = (lane & 8) != 0, h2 = (lane & 4) != 0, h1 = (lane & 2) != 0, h0 = (lane & 1) != 0;
+    float a8[8], a4[4], a2[2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = h3 ? v[i] : v[i + 8], keep = h3 ? v[i + 8] : v[i];
+        a8[i] = keep + __shfl_xor_sync(full, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = h2 ? a8[i] : a8[i + 4], keep = h2 ? a8[i + 4] : a8[i];
+        a4[i] = keep + __shfl_xor_sync(full, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h1 ? a4[i] : a4[i + 2], keep = h1 ? a4[i + 2] : a4[i];
+        a2[i] = keep + __shfl_xor_sync(full, send, 2);
+    }
+    {
+        const float send = h0 ? a2[0] : a2[1], keep = h0 ? a2[1] : a2[0];
+        outA = keep + __shfl_xor_sync(full, send, 1);      // value index 8*h3 + 4*h2 + 2*h1 + h0 = lane & 15
+    }
+    float b2[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h3 ? v[16 + i] : v[18 + i], keep = h3 ? v[18 + i] : v[16 + i];
+        b2[i] = keep + __shfl_xor_sync(full, send, 8);
+    }
+    {
+        const float send = h2 ? b2[0] : b2[1], keep = h2 ? b2[1] : b2[0];
+        float b1 = keep + __shfl_xor_sync(full, send, 4);   // value index 16 + 2*h3 + h2
+        b1 += __shfl_xor_sync(full, b1, 2);
+        b1 += __shfl_xor_sync(full, b1, 1);
+        outB = b1;
+    }
+}

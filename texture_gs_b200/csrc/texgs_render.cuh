@@ -28,7 +28,7 @@ __device__ __forceinline__ float texgs_exp(float x) {
 
 struct PixelGeom {
     int tile, px, py, pix;
-    int bx, by;      // origin of this warp's 8x4 pixel block
+    int bx, by;      // origin of this warp's 8x4 pixel block (= two 4x4 half-warp blocks side by side)
     bool inside;
     float vx, vy;    // view ray (vx, vy, 1)
 };
@@ -40,8 +40,10 @@ __device__ __forceinline__ PixelGeom pixel_geom(const RasterParams& p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     g.bx = tx * TEXGS_TILE + (warp & 1) * 8;
     g.by = ty * TEXGS_TILE + (warp >> 1) * 4;
-    g.px = g.bx + (lane & 7);
-    g.py = g.by + (lane >> 3);
+    // half-warp h = lane >> 4 owns the 4x4 block at (bx + 4h, by): the two halves walk their own
+    // survivor lists, so one pass of the blend loop serves two splats
+    g.px = g.bx + 4 * (lane >> 4) + (lane & 3);
+    g.py = g.by + ((lane >> 2) & 3);
     g.inside = (g.px < p.W) && (g.py < p.H);
     g.pix = g.py * p.W + g.px;
     g.vx = ((2.0f * (float)g.px + 1.0f) / (float)p.W - 1.0f) * p.tanfovx;
@@ -68,8 +70,9 @@ __device__ __forceinline__ PixelGeom pixel_geom(const RasterParams& p) {
 struct __align__(128) WarpSmem {
     GaussRec rec[TEXGS_STAGES][TEXGS_CHUNK];
     uint64_t bar[TEXGS_STAGES];
-    unsigned mask[TEXGS_STAGES];
-    unsigned pad[26];
+    unsigned maskL[TEXGS_STAGES];   // entries of the chunk that can touch the left  4x4 block (lanes 0-15)
+    unsigned maskR[TEXGS_STAGES];   //                                   ... the right 4x4 block (lanes 16-31)
+    unsigned pad[24];
 };
 static_assert(sizeof(WarpSmem) % 128 == 0, "WarpSmem must keep the records 128-byte aligned");
 #define TEXGS_RENDER_SMEM (8 * sizeof(WarpSmem))
@@ -113,14 +116,17 @@ __device__ __forceinline__ unsigned stream_load_id(const RasterParams& p, unsign
 // ballot the cull test of one chunk and gather the survivors into stage ``s``
 __device__ __forceinline__ void stream_issue(const RasterParams& p, WarpSmem& ws, int s, int lane, unsigned id, bool valid,
                                              const float4& q0, const float4& q1, const PixelGeom& g) {
-    const bool pass = valid && splat_hits_block(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, (float)g.bx, (float)(g.bx + 7),
-                                                (float)g.by, (float)(g.by + 3));
-    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    const float y0 = (float)g.by, y1 = (float)(g.by + 3);
+    const bool passL = valid && splat_hits_block(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, (float)g.bx, (float)(g.bx + 3), y0, y1);
+    const bool passR = valid && splat_hits_block(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, (float)(g.bx + 4), (float)(g.bx + 7), y0, y1);
+    const unsigned mL = __ballot_sync(0xffffffffu, passL), mR = __ballot_sync(0xffffffffu, passR);
+    const unsigned m = mL | mR;
     if (lane == 0) {
-        ws.mask[s] = m;
+        ws.maskL[s] = mL;
+        ws.maskR[s] = mR;
         mbar_arrive_expect_tx(&ws.bar[s], (unsigned)__popc(m) * (unsigned)sizeof(GaussRec));
     }
-    if (pass) {
+    if (passL || passR) {
         const int slot = __popc(m & ((1u << lane) - 1u));
         bulk_g2s(&ws.rec[s][slot], p.recs + id, (unsigned)sizeof(GaussRec), &ws.bar[s]);
     }
@@ -214,18 +220,19 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
 
             mbar_wait(&ws.bar[s], (unsigned)(c >> 1) & 1u);
             __syncwarp();
-            unsigned m = ws.mask[s];
-            int slot = 0;
+            const unsigned mL = ws.maskL[s], mR = ws.maskR[s], mU = mL | mR;
+            unsigned my = (lane & 16) ? mR : mL;          // this half-warp's survivors, in list order
             bool warp_done = false;
-            while (m) {
-                const int l = __ffs(m) - 1;
-                m &= m - 1;
-                const GaussRec& rec = ws.rec[s][slot++];
+            while (__any_sync(0xffffffffu, my != 0u)) {
+                const bool has = my != 0u;
+                const int l = has ? (__ffs(my) - 1) : 0;
+                my &= my - 1u;
+                const GaussRec& rec = ws.rec[s][__popc(mU & ((1u << l) - 1u))];   // half-uniform address
                 const float4 g0 = rec.q[0], g1 = rec.q[1];
                 const float dx = g0.x - pxf, dy = g0.y - pyf;
                 const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
                 const float alpha = fminf(TEXGS_ALPHA_MAX, g1.y * texgs_exp(power));
-                bool cand = !done && (power <= 0.0f) && (alpha >= TEXGS_ALPHA_MIN);
+                bool cand = has && !done && (power <= 0.0f) && (alpha >= TEXGS_ALPHA_MIN);
                 if (!__any_sync(0xffffffffu, cand)) continue;
                 const float test_T = T * (1.0f - alpha);
                 if (cand && test_T < TEXGS_T_STOP) { done = true; cand = false; }
@@ -393,12 +400,13 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
 
         mbar_wait(&ws.bar[s], (unsigned)(k >> 1) & 1u);
         __syncwarp();
-        unsigned m = ws.mask[s];
-        int slot = __popc(m);
-        while (m) {
-            const int l = 31 - __clz(m);
-            m &= ~(1u << l);
-            const GaussRec& rec = ws.rec[s][--slot];
+        const unsigned mL = ws.maskL[s], mR = ws.maskR[s], mU = mL | mR;
+        unsigned my = (lane & 16) ? mR : mL;              // this half-warp's survivors, walked back to front
+        while (__any_sync(0xffffffffu, my != 0u)) {
+            const bool has = my != 0u;
+            const int l = has ? (31 - __clz(my)) : 0;
+            my &= ~(1u << l);
+            const GaussRec& rec = ws.rec[s][__popc(mU & ((1u << l) - 1u))];       // half-uniform address
             const unsigned gi = (unsigned)c * TEXGS_CHUNK + (unsigned)l;   // 0-based position in the list
             const float4 g0 = rec.q[0], g1 = rec.q[1];
             const float dx = g0.x - pxf, dy = g0.y - pyf;
@@ -406,7 +414,7 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
             const float G = texgs_exp(power);
             const float aG = g1.y * G;
             const float alpha = fminf(TEXGS_ALPHA_MAX, aG);
-            const bool contrib = (gi < last) && (power <= 0.0f) && (alpha >= TEXGS_ALPHA_MIN);
+            const bool contrib = has && (gi < last) && (power <= 0.0f) && (alpha >= TEXGS_ALPHA_MIN);
             if (!__any_sync(0xffffffffu, contrib)) continue;
 
             float v[20];
@@ -508,12 +516,14 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
                     }
                 }
             }
+            // each half-warp reduces ITS splat's 20 partials over its 16 lanes (both halves in the same
+            // 20 shuffles) and adds them to that Gaussian's accumulators
             float outA, outB;
-            warp_reduce20(v, lane, outA, outB);
-            {
+            halfwarp_reduce20(v, lane, outA, outB);
+            if (has) {
                 float* dst = acc + (size_t)(unsigned)__float_as_int(rec.q[7].x) * TEXGS_BWD_ACC_FLOATS;
-                if ((lane & 1) == 0 && outA != 0.f) atomicAdd(dst + (lane >> 1), outA);
-                if ((lane & 7) == 1 && outB != 0.f) atomicAdd(dst + 16 + (lane >> 3), outB);
+                if (outA != 0.f) atomicAdd(dst + (lane & 15), outA);
+                if ((lane & 3) == 0 && outB != 0.f) atomicAdd(dst + 16 + ((lane >> 2) & 3), outB);
             }
         }
         __syncwarp();
