@@ -35,7 +35,8 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 VIEWS_PER_STEP = 32
-KERNELS_PER_VIEW = 7   # (+1 texgs_pack_texture_kernel per step) preprocess_fwd, scan_tiles, scatter_pairs, sort_tiles, render_fwd, render_bwd, preprocess_bwd
+KERNELS_PER_VIEW = 8   # (+1 texgs_pack_texture_kernel per step) preprocess_fwd, scan_tiles, scatter_pairs, sort_tiles_small,
+                       # sort_tiles, render_fwd, render_bwd, preprocess_bwd
 
 
 def parse():

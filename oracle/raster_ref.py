@@ -338,6 +338,7 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
     ambiguous = torch.zeros(npix_pad, dtype=torch.bool, device=dev)
     grazing = torch.zeros(npix_pad, dtype=torch.bool, device=dev)
     n_blend = 0
+    pair_contributes = np.zeros(tile_of.shape[0], dtype=bool)   # some pixel of the tile blends this (tile,Gaussian) pair
 
     # tile segments
     if tile_of.shape[0] > 0:
@@ -413,6 +414,10 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
         n_contrib[pflat.reshape(-1)] = last.reshape(-1)
         ambiguous[pflat.reshape(-1)] = amb.reshape(-1)
 
+        with torch.no_grad():
+            hit = include.any(dim=1)                                            # (B,L)
+            hb, hl = torch.nonzero(hit, as_tuple=True)
+            pair_contributes[(stt[hb] + hl).cpu().numpy()] = True
         # sparse heavy part
         bi, pi, li = torch.nonzero(include, as_tuple=True)
         n_blend += int(bi.shape[0])
@@ -479,6 +484,6 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
                    threshold_ambiguous=unpad(ambiguous.reshape(-1, 1), 1)[0],
                    grazing=unpad(grazing.reshape(-1, 1), 1)[0], num_pairs=int(tile_of.shape[0]),
                    num_visible=int(pre["visible"].sum()), num_blend=n_blend, pre=pre,
-                   tile_of=tile_of, gid_of=gid_of)
+                   tile_of=tile_of, gid_of=gid_of, pair_contributes=pair_contributes)
         return out + (aux,)
     return out

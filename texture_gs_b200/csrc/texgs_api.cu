@@ -175,7 +175,7 @@ int texgs_abi_version(void) { return TEXGS_ABI_VERSION; }
 const char* texgs_last_error(void) { return g_last_error.c_str(); }
 
 const char* texgs_kernel_names(void) {
-    return "texgs_preprocess_fwd,texgs_scan_tiles,texgs_scatter_pairs,texgs_sort_tiles,texgs_render_fwd,"
+    return "texgs_preprocess_fwd,texgs_scan_tiles,texgs_scatter_pairs,texgs_sort_tiles_small,texgs_sort_tiles,texgs_render_fwd,"
            "texgs_render_bwd,texgs_preprocess_bwd,texgs_mark_visible_kernel,texgs_pack_texture_kernel";
 }
 
@@ -229,6 +229,8 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
         TEXGS_KERNEL_CHECK("texgs_scatter_pairs", debug, stream);
     }
     TEXGS_EV(a, TEXGS_EV_FWD_SCATTER, stream);
+    texgs_sort_tiles_small<<<p.num_tiles, TEXGS_SORT_SMALL_THREADS, 0, stream>>>(p);
+    TEXGS_KERNEL_CHECK("texgs_sort_tiles_small", debug, stream);
     texgs_sort_tiles<<<p.num_tiles, TEXGS_SORT_THREADS, 0, stream>>>(p);
     TEXGS_KERNEL_CHECK("texgs_sort_tiles", debug, stream);
     TEXGS_EV(a, TEXGS_EV_FWD_SORT, stream);

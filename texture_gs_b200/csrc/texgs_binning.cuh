@@ -76,9 +76,11 @@ __global__ void __launch_bounds__(256) texgs_scatter_pairs(const RasterParams p)
     const uint2 rc = p.rects[idx];
     const int x0 = rc.x & 0xffff, x1 = rc.x >> 16, y0 = rc.y & 0xffff, y1 = rc.y >> 16;
     if (x1 <= x0 || y1 <= y0) return;
-    const unsigned depth_bits = __float_as_uint(p.recs[idx].q[1].z);
+    const float4 r0 = p.recs[idx].q[0], r1 = p.recs[idx].q[1];
+    const unsigned depth_bits = __float_as_uint(r1.z);
     for (int ty = y0; ty < y1; ++ty)
         for (int tx = x0; tx < x1; ++tx) {
+            if (!splat_hits_tile(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx, ty)) continue;   // same test as the count
             const int t = ty * p.grid_x + tx;
             const unsigned slot = p.tile_offset[t] + atomicAdd(&p.tile_cursor[t], 1u);
             p.pairs[slot] = make_uint2((unsigned)idx, depth_bits);
@@ -93,13 +95,56 @@ __device__ __forceinline__ void cmpxchg(unsigned long long& a, unsigned long lon
     if (a > b) { const unsigned long long t = a; a = b; b = t; }
 }
 
+// Short lists (the common case: a few hundred entries) are sorted by 64-thread CTAs with 4 KB of
+// shared memory — many more of them are resident per SM and their barriers cost two warps, not eight.
+#define TEXGS_SORT_SMALL 512
+#define TEXGS_SORT_SMALL_THREADS 64
+
+__global__ void __launch_bounds__(TEXGS_SORT_SMALL_THREADS) texgs_sort_tiles_small(const RasterParams p) {
+    __shared__ unsigned long long keys[TEXGS_SORT_SMALL];
+    if (p.counters->overflow) return;
+    const int tile = blockIdx.x;
+    const unsigned start = p.tile_offset[tile];
+    const unsigned n = p.tile_offset[tile + 1] - start;
+    if (n == 0 || n > TEXGS_SORT_SMALL) return;             // long lists: texgs_sort_tiles
+    unsigned long long* seg = reinterpret_cast<unsigned long long*>(p.pairs + start);
+    const unsigned tid = threadIdx.x;
+    unsigned npad = 2;
+    while (npad < n) npad <<= 1;
+    for (unsigned i = tid; i < npad; i += TEXGS_SORT_SMALL_THREADS) keys[i] = (i < n) ? seg[i] : ~0ull;
+    __syncthreads();
+    // k, j are powers of two: index arithmetic by shifts / masks (lk = log2 k, lj = log2 j)
+    for (unsigned k = 2, lk = 1; k <= npad; k <<= 1, ++lk) {
+        for (unsigned i = tid; i < npad / 2; i += TEXGS_SORT_SMALL_THREADS) {
+            const unsigned blk = i >> (lk - 1), off = i & ((k >> 1) - 1);
+            const unsigned lo = (blk << lk) + off, hi = (blk << lk) + (k - 1 - off);
+            const unsigned long long a = keys[lo], b = keys[hi];
+            if (a > b) { keys[lo] = b; keys[hi] = a; }
+        }
+        __syncthreads();
+        for (unsigned j = k >> 2, lj = lk - 2; j > 0; j >>= 1, --lj) {
+            for (unsigned i = tid; i < npad / 2; i += TEXGS_SORT_SMALL_THREADS) {
+                const unsigned lo = ((i >> lj) << (lj + 1)) + (i & (j - 1)), hi = lo + j;
+                const unsigned long long a = keys[lo], b = keys[hi];
+                if (a > b) { keys[lo] = b; keys[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (unsigned i = tid; i < n; i += TEXGS_SORT_SMALL_THREADS) {
+        const unsigned long long kv = keys[i];
+        seg[i] = kv;
+        p.sorted_ids[start + i] = (unsigned)(kv & 0xffffffffull);
+    }
+}
+
 __global__ void __launch_bounds__(TEXGS_SORT_THREADS) texgs_sort_tiles(const RasterParams p) {
     __shared__ unsigned long long keys[TEXGS_SORT_SMEM_ELEMS];
     if (p.counters->overflow) return;
     const int tile = blockIdx.x;
     const unsigned start = p.tile_offset[tile];
     const unsigned n = p.tile_offset[tile + 1] - start;
-    if (n == 0) return;
+    if (n <= TEXGS_SORT_SMALL) return;                      // short lists: texgs_sort_tiles_small
     unsigned long long* seg = reinterpret_cast<unsigned long long*>(p.pairs + start);
     const int tid = threadIdx.x;
     if (n == 1) {

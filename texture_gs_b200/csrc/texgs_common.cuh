@@ -185,6 +185,37 @@ __device__ __forceinline__ Bilerp cube_bilerp(const CubeCoord& c, int R) {
     return b;
 }
 
+// Can  q(d) = a dx^2 + 2 b dx dy + c dy^2  (d = p - mu) drop to <= tau somewhere on the rectangle
+// [x0,x1] x [y0,y1]?  q is convex with its minimum at mu, so the constrained minimum is either mu
+// itself (inside) or lies on an edge that FACES mu; at most two 1-D clamped minimisations.
+__device__ __forceinline__ bool splat_hits_block(float mx, float my, float a, float b, float c, float opacity,
+                                                 float x0, float x1, float y0, float y1) {
+    const bool inx = (mx >= x0) && (mx <= x1), iny = (my >= y0) && (my <= y1);
+    if (inx && iny) return true;
+    float q = 3.0e38f;
+    if (!inx) {
+        const float dx = ((mx < x0) ? x0 : x1) - mx;
+        const float dy = fminf(fmaxf(__fdividef(-b * dx, c), y0 - my), y1 - my);
+        q = a * dx * dx + 2.f * b * dx * dy + c * dy * dy;
+    }
+    if (!iny) {
+        const float dy = ((my < y0) ? y0 : y1) - my;
+        const float dx = fminf(fmaxf(__fdividef(-b * dy, a), x0 - mx), x1 - mx);
+        q = fminf(q, a * dx * dx + 2.f * b * dx * dy + c * dy * dy);
+    }
+    // alpha >= 1/255  <=>  q <= 2 ln(255 o); keep a margin far above the rounding of __expf/__logf
+    const float tau = 2.0f * __logf(255.0f * opacity);
+    return q <= tau * 1.001f + 0.02f;
+}
+
+// (tile, Gaussian) pair test used identically by the count (preprocess) and the scatter kernels: can the
+// splat reach alpha >= 1/255 anywhere on tile (tx, ty)? Exact up to the margin above, so dropping
+// the pair never changes a pixel; it only shortens the lists (spec E3's tile rect stays the outer bound).
+__device__ __forceinline__ bool splat_hits_tile(float mx, float my, float a, float b, float c, float opacity, int tx, int ty) {
+    const float x0 = (float)(tx * TEXGS_TILE), y0 = (float)(ty * TEXGS_TILE);
+    return splat_hits_block(mx, my, a, b, c, opacity, x0, x0 + (float)(TEXGS_TILE - 1), y0, y0 + (float)(TEXGS_TILE - 1));
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier + bulk async copy (TMA 1-D) — sm_90+/sm_100a PTX
 // ---------------------------------------------------------------------------------------------

@@ -180,8 +180,12 @@ __global__ void __launch_bounds__(256) texgs_preprocess_fwd(const RasterParams p
     r->q[6] = make_float4(Jp[5], Jp[6], Jp[7], Jp[8]);
     r->q[7] = make_float4(__int_as_float(idx), 0.f, 0.f, 0.f);
 
-    for (int ty = o.ry0; ty < o.ry1; ++ty)
-        for (int tx = o.rx0; tx < o.rx1; ++tx) atomicAdd(&p.tile_count[ty * p.grid_x + tx], 1u);
+    {   // the SAME floats the scatter kernel will read back from the record
+        const float4 r0 = r->q[0], r1 = r->q[1];
+        for (int ty = o.ry0; ty < o.ry1; ++ty)
+            for (int tx = o.rx0; tx < o.rx1; ++tx)
+                if (splat_hits_tile(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx, ty)) atomicAdd(&p.tile_count[ty * p.grid_x + tx], 1u);
+    }
     atomicAdd(&p.counters->num_visible, 1u);
 }
 

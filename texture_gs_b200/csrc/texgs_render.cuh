@@ -77,29 +77,6 @@ struct __align__(128) WarpSmem {
 static_assert(sizeof(WarpSmem) % 128 == 0, "WarpSmem must keep the records 128-byte aligned");
 #define TEXGS_RENDER_SMEM (8 * sizeof(WarpSmem))
 
-// Can  q(d) = a dx^2 + 2 b dx dy + c dy^2  (d = p - mu) drop to <= tau somewhere on the rectangle
-// [x0,x1] x [y0,y1]?  q is convex with its minimum at mu, so the constrained minimum is either mu
-// itself (inside) or lies on an edge that FACES mu; at most two 1-D clamped minimisations.
-__device__ __forceinline__ bool splat_hits_block(float mx, float my, float a, float b, float c, float opacity,
-                                                 float x0, float x1, float y0, float y1) {
-    const bool inx = (mx >= x0) && (mx <= x1), iny = (my >= y0) && (my <= y1);
-    if (inx && iny) return true;
-    float q = 3.0e38f;
-    if (!inx) {
-        const float dx = ((mx < x0) ? x0 : x1) - mx;
-        const float dy = fminf(fmaxf(__fdividef(-b * dx, c), y0 - my), y1 - my);
-        q = a * dx * dx + 2.f * b * dx * dy + c * dy * dy;
-    }
-    if (!iny) {
-        const float dy = ((my < y0) ? y0 : y1) - my;
-        const float dx = fminf(fmaxf(__fdividef(-b * dy, a), x0 - mx), x1 - mx);
-        q = fminf(q, a * dx * dx + 2.f * b * dx * dy + c * dy * dy);
-    }
-    // alpha >= 1/255  <=>  q <= 2 ln(255 o); keep a margin far above the rounding of __expf/__logf
-    const float tau = 2.0f * __logf(255.0f * opacity);
-    return q <= tau * 1.001f + 0.02f;
-}
-
 struct ChunkLoad {       // registers carried across one blend phase
     unsigned id;         // Gaussian id of this lane's entry (chunk c+2)
     float4 q0, q1;       // cull sector of this lane's entry (chunk c+1 at issue time)
