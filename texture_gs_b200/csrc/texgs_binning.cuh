@@ -91,10 +91,6 @@ __global__ void __launch_bounds__(256) texgs_scatter_pairs(const RasterParams p)
 #define TEXGS_SORT_THREADS 256
 #define TEXGS_SORT_SMEM_ELEMS 4096   // 32 KB of u64
 
-__device__ __forceinline__ void cmpxchg(unsigned long long& a, unsigned long long& b) {
-    if (a > b) { const unsigned long long t = a; a = b; b = t; }
-}
-
 // Short lists (the common case: a few hundred entries) are sorted by 64-thread CTAs with 4 KB of
 // shared memory — many more of them are resident per SM and their barriers cost two warps, not eight.
 #define TEXGS_SORT_SMALL 512
@@ -147,10 +143,6 @@ __global__ void __launch_bounds__(TEXGS_SORT_THREADS) texgs_sort_tiles(const Ras
     if (n <= TEXGS_SORT_SMALL) return;                      // short lists: texgs_sort_tiles_small
     unsigned long long* seg = reinterpret_cast<unsigned long long*>(p.pairs + start);
     const int tid = threadIdx.x;
-    if (n == 1) {
-        if (tid == 0) p.sorted_ids[start] = (unsigned)(seg[0] & 0xffffffffull);
-        return;
-    }
     unsigned npad = 2;
     while (npad < n) npad <<= 1;
     if (npad <= TEXGS_SORT_SMEM_ELEMS) {
