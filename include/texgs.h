@@ -181,6 +181,19 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream);
 /* (6,R,R,3) -> (6,R,R,4) repack of the cube texture (see TexgsFwdArgs.texture_rgba). */
 int texgs_pack_texture(const float* texture, int32_t R, float* texture_rgba, void* stream);
 
+/* ---- fused photometric loss of the training step ---------------------------------
+ * loss = (1-lambda)*mean|image-gt| + lambda*(1 - SSIM(image, gt))   (models/texture_gaussian3d.py:333-340,
+ * losses/pixelwise_loss.py:3-4, losses/ssim_loss.py:6-54: 11x11 Gaussian window, sigma 1.5, zero padding).
+ * image, gt: (C,H,W) fp32 device. ``ws`` (texgs_photometric_workspace_size bytes, 16-byte aligned) carries
+ * three derivative maps from forward to backward. out3 (device) = {loss, Ll1, Lssim = 1 - SSIM}.
+ * Backward: dL_dimage = coef2[0]*d(Ll1)/d(image) + coef2[1]*d(Lssim)/d(image), coef2 = 2 device floats
+ * (for  d loss: {(1-lambda)*g, lambda*g}  with g the incoming scalar gradient). */
+int texgs_photometric_workspace_size(int32_t C, int32_t H, int32_t W, size_t* bytes);
+int texgs_photometric_forward(const float* image, const float* gt, int32_t C, int32_t H, int32_t W, float lambda_dssim,
+                              void* ws, float* out3, void* stream);
+int texgs_photometric_backward(const float* image, const float* gt, int32_t C, int32_t H, int32_t W, const void* ws,
+                               const float* coef2, float* dL_dimage, void* stream);
+
 /* Frustum test only (upstream ``GaussianRasterizer.markVisible`` [EXT]; unused in the reference
  * tree). present (P,) int32: 1 if the Gaussian passes the near-plane cull. */
 int texgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix16_host,

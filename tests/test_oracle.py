@@ -220,3 +220,19 @@ def test_dual_no_sh_image_equals_a_second_render_with_degree_zero():
     b = RR.rasterize(t["xyz"], None, t["shs"], t["opacity"], t["scaling"], t["rotation"], t["uvs"], t["grad_uvs"], t["texture"], st0)
     assert float((a[-1]["image_no_sh"] - b[0]).abs().max()) < 1e-12
     assert float((a[0] - b[0]).abs().max()) > 1e-3        # the SH term does change the first image
+
+
+def test_loss_oracle_matches_the_reference_code_golden_vectors():
+    """oracle/loss_ref.py vs vectors generated by the reference's own losses/*.py (PINNED oracle)."""
+    import numpy as np
+    from oracle import loss_ref as LR
+    z = np.load(Path(__file__).resolve().parent / "golden" / "photometric_loss.npz")
+    for tag in ("a", "b", "c"):
+        img = torch.from_numpy(z[f"{tag}_img"]).requires_grad_(True)
+        gt = torch.from_numpy(z[f"{tag}_gt"])
+        loss, l1, lssim = LR.photometric_loss(img, gt, float(z[f"{tag}_lambda"]))
+        loss.backward()
+        assert abs(float(l1) - float(z[f"{tag}_l1"])) < 1e-7
+        assert abs(float(1 - lssim) - float(z[f"{tag}_ssim"])) < 1e-6
+        assert abs(float(loss) - float(z[f"{tag}_loss"])) < 1e-6
+        assert float((img.grad - torch.from_numpy(z[f"{tag}_grad"])).abs().max()) < 1e-8

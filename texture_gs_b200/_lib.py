@@ -79,6 +79,9 @@ SYMBOLS = {
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "texgs_backward": (C.c_int, [C.POINTER(TexgsBwdArgs), C.c_void_p]),
     "texgs_pack_texture": (C.c_int, [_fp, C.c_int32, _fp, C.c_void_p]),
+    "texgs_photometric_workspace_size": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "texgs_photometric_forward": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_float, _fp, _fp, C.c_void_p]),
+    "texgs_photometric_backward": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp, _fp, _fp, C.c_void_p]),
     "texgs_mark_visible": (C.c_int, [C.c_int32, _fp, C.POINTER(C.c_float), C.POINTER(C.c_float), _fp, C.c_void_p]),
 }
 

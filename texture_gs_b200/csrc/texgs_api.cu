@@ -7,6 +7,7 @@
 
 #include "texgs_binning.cuh"
 #include "texgs_common.cuh"
+#include "texgs_loss.cuh"
 #include "texgs_preprocess.cuh"
 #include "texgs_render.cuh"
 
@@ -176,7 +177,8 @@ const char* texgs_last_error(void) { return g_last_error.c_str(); }
 
 const char* texgs_kernel_names(void) {
     return "texgs_preprocess_fwd,texgs_scan_tiles,texgs_scatter_pairs,texgs_sort_tiles_small,texgs_sort_tiles,texgs_render_fwd,"
-           "texgs_render_bwd,texgs_preprocess_bwd,texgs_mark_visible_kernel,texgs_pack_texture_kernel";
+           "texgs_render_bwd,texgs_preprocess_bwd,texgs_mark_visible_kernel,texgs_pack_texture_kernel,"
+           "texgs_photometric_fwd_kernel,texgs_photometric_finalize_kernel,texgs_photometric_bwd_kernel";
 }
 
 int texgs_workspace_sizes(const TexgsFwdArgs* a, uint64_t pair_capacity, size_t* geom_bytes, size_t* bin_bytes,
@@ -330,6 +332,42 @@ int texgs_pack_texture(const float* texture, int32_t R, float* texture_rgba, voi
     texgs_pack_texture_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
         texture, reinterpret_cast<float4*>(texture_rgba), ntexel);
     TEXGS_KERNEL_CHECK("texgs_pack_texture_kernel", false, (cudaStream_t)stream_);
+    return 0;
+}
+
+int texgs_photometric_workspace_size(int32_t C, int32_t H, int32_t W, size_t* bytes) {
+    if (C <= 0 || H <= 0 || W <= 0 || !bytes) return fail(TEXGS_E_INVALID, "bad arguments");
+    *bytes = 256 + (size_t)3 * C * H * W * sizeof(float);     // [LossSums | pad] + 3 derivative maps
+    return 0;
+}
+
+int texgs_photometric_forward(const float* image, const float* gt, int32_t C, int32_t H, int32_t W, float lambda_dssim,
+                              void* ws, float* out3, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!image || !gt || !ws || !out3 || C <= 0 || H <= 0 || W <= 0 || C > 65535) return fail(TEXGS_E_INVALID, "bad arguments");
+    if ((uintptr_t)ws & 15) return fail(TEXGS_E_WORKSPACE, "workspace must be 16-byte aligned");
+    const size_t n = (size_t)C * H * W;
+    LossSums* sums = (LossSums*)ws;
+    float* maps = (float*)((char*)ws + 256);
+    TEXGS_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(LossSums), stream));
+    const dim3 grid((W + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE, (H + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE, C);
+    texgs_photometric_fwd_kernel<<<grid, dim3(TEXGS_LOSS_TILE, TEXGS_LOSS_TILE), 0, stream>>>(image, gt, H, W, maps, maps + n, maps + 2 * n, sums);
+    TEXGS_KERNEL_CHECK("texgs_photometric_fwd_kernel", false, stream);
+    texgs_photometric_finalize_kernel<<<1, 1, 0, stream>>>(sums, 1.0 / (double)n, lambda_dssim, out3);
+    TEXGS_KERNEL_CHECK("texgs_photometric_finalize_kernel", false, stream);
+    return 0;
+}
+
+int texgs_photometric_backward(const float* image, const float* gt, int32_t C, int32_t H, int32_t W, const void* ws,
+                               const float* coef2, float* dL_dimage, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!image || !gt || !ws || !coef2 || !dL_dimage || C <= 0 || H <= 0 || W <= 0 || C > 65535) return fail(TEXGS_E_INVALID, "bad arguments");
+    const size_t n = (size_t)C * H * W;
+    const float* maps = (const float*)((const char*)ws + 256);
+    const dim3 grid((W + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE, (H + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE, C);
+    texgs_photometric_bwd_kernel<<<grid, dim3(TEXGS_LOSS_TILE, TEXGS_LOSS_TILE), 0, stream>>>(image, gt, H, W, maps, maps + n, maps + 2 * n, coef2,
+                                                                                             (float)(1.0 / (double)n), dL_dimage);
+    TEXGS_KERNEL_CHECK("texgs_photometric_bwd_kernel", false, stream);
     return 0;
 }
 
