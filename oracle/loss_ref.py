@@ -38,7 +38,7 @@ def ssim(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     the fp32 1-D window, zero padding)."""
     C = x.shape[-3]
     w1 = gaussian_window_1d(torch.float32)
-    w2 = (w1[:, None] @ w1[None, :]).to(x.dtype)
+    w2 = (w1[:, None] @ w1[None, :]).to(dtype=x.dtype, device=x.device)
     win = w2.expand(C, 1, WINDOW, WINDOW).contiguous()
     a, b = x[None], y[None]
     conv = lambda t: F.conv2d(t, win, padding=WINDOW // 2, groups=C)

@@ -335,9 +335,14 @@ int texgs_pack_texture(const float* texture, int32_t R, float* texture_rgba, voi
     return 0;
 }
 
+static size_t loss_parts_bytes(int C, int H, int W) {
+    const size_t nb = (size_t)((W + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE) * ((H + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE) * C;
+    return (nb * sizeof(LossSums) + 255) / 256 * 256;
+}
+
 int texgs_photometric_workspace_size(int32_t C, int32_t H, int32_t W, size_t* bytes) {
     if (C <= 0 || H <= 0 || W <= 0 || !bytes) return fail(TEXGS_E_INVALID, "bad arguments");
-    *bytes = 256 + (size_t)3 * C * H * W * sizeof(float);     // [LossSums | pad] + 3 derivative maps
+    *bytes = loss_parts_bytes(C, H, W) + (size_t)3 * C * H * W * sizeof(float);     // per-CTA partial sums + 3 derivative maps
     return 0;
 }
 
@@ -348,12 +353,11 @@ int texgs_photometric_forward(const float* image, const float* gt, int32_t C, in
     if ((uintptr_t)ws & 15) return fail(TEXGS_E_WORKSPACE, "workspace must be 16-byte aligned");
     const size_t n = (size_t)C * H * W;
     LossSums* sums = (LossSums*)ws;
-    float* maps = (float*)((char*)ws + 256);
-    TEXGS_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(LossSums), stream));
+    float* maps = (float*)((char*)ws + loss_parts_bytes(C, H, W));
     const dim3 grid((W + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE, (H + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE, C);
     texgs_photometric_fwd_kernel<<<grid, dim3(TEXGS_LOSS_TILE, TEXGS_LOSS_TILE), 0, stream>>>(image, gt, H, W, maps, maps + n, maps + 2 * n, sums);
     TEXGS_KERNEL_CHECK("texgs_photometric_fwd_kernel", false, stream);
-    texgs_photometric_finalize_kernel<<<1, 1, 0, stream>>>(sums, 1.0 / (double)n, lambda_dssim, out3);
+    texgs_photometric_finalize_kernel<<<1, 1024, 0, stream>>>(sums, (int)(grid.x * grid.y * grid.z), 1.0 / (double)n, lambda_dssim, out3);
     TEXGS_KERNEL_CHECK("texgs_photometric_finalize_kernel", false, stream);
     return 0;
 }
@@ -363,7 +367,7 @@ int texgs_photometric_backward(const float* image, const float* gt, int32_t C, i
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!image || !gt || !ws || !coef2 || !dL_dimage || C <= 0 || H <= 0 || W <= 0 || C > 65535) return fail(TEXGS_E_INVALID, "bad arguments");
     const size_t n = (size_t)C * H * W;
-    const float* maps = (const float*)((const char*)ws + 256);
+    const float* maps = (const float*)((const char*)ws + loss_parts_bytes(C, H, W));
     const dim3 grid((W + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE, (H + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE, C);
     texgs_photometric_bwd_kernel<<<grid, dim3(TEXGS_LOSS_TILE, TEXGS_LOSS_TILE), 0, stream>>>(image, gt, H, W, maps, maps + n, maps + 2 * n, coef2,
                                                                                              (float)(1.0 / (double)n), dL_dimage);

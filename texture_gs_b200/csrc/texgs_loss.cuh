@@ -82,20 +82,33 @@ __global__ void __launch_bounds__(256) texgs_photometric_fwd_kernel(const float*
     }
     if ((tid & 31) == 0) { red[0][tid >> 5] = my_ssim; red[1][tid >> 5] = my_l1; }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0) {   // one partial per CTA, summed in a fixed order by the finalize kernel (deterministic)
         double s = 0.0, l = 0.0;
         for (int w = 0; w < 8; ++w) { s += red[0][w]; l += red[1][w]; }
-        atomicAdd(&sums->ssim, s);
-        atomicAdd(&sums->l1, l);
+        const size_t bid = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        sums[bid].ssim = s;
+        sums[bid].l1 = l;
     }
 }
 
-__global__ void texgs_photometric_finalize_kernel(const LossSums* __restrict__ sums, double inv_n, float lambda, float* __restrict__ out3) {
-    const float l1 = (float)(sums->l1 * inv_n);
-    const float lssim = 1.0f - (float)(sums->ssim * inv_n);
-    out3[0] = (1.0f - lambda) * l1 + lambda * lssim;
-    out3[1] = l1;
-    out3[2] = lssim;
+__global__ void __launch_bounds__(1024) texgs_photometric_finalize_kernel(const LossSums* __restrict__ sums, int nparts, double inv_n,
+                                                                        float lambda, float* __restrict__ out3) {
+    __shared__ double red[2][32];
+    double s = 0.0, l = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) { s += sums[i].ssim; l += sums[i].l1; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); l += __shfl_xor_sync(0xffffffffu, l, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = l; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tl = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ts += red[0][w]; tl += red[1][w]; }
+        const float l1 = (float)(tl * inv_n);
+        const float lssim = 1.0f - (float)(ts * inv_n);
+        out3[0] = (1.0f - lambda) * l1 + lambda * lssim;
+        out3[1] = l1;
+        out3[2] = lssim;
+    }
 }
 
 // d image = coef[0] * d(L1 mean)/d image + coef[1] * d(1 - SSIM mean)/d image
