@@ -236,7 +236,10 @@ struct BwdOut {
     unsigned acc;   // TEXGS_ACC_* bits: add into the output instead of overwriting it
 };
 
-__global__ void __launch_bounds__(256) texgs_preprocess_bwd(const RasterParams p, const int* __restrict__ radii_unused,
+#ifndef TEXGS_PREBWD_MIN_CTAS
+#define TEXGS_PREBWD_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(256, TEXGS_PREBWD_MIN_CTAS) texgs_preprocess_bwd(const RasterParams p, const int* __restrict__ radii_unused,
                                                           const float* __restrict__ acc_all, const BwdOut g) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.P) return;
