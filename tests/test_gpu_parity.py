@@ -411,6 +411,24 @@ def test_camera_inside_the_scene_culls_and_clamps():
     _check_backward(g, cam, bg=(0.1, 0.2, 0.3), max_flag=0.6, uv_tol=5e-3)
 
 
+def test_heterogeneous_scales_with_very_large_splats():
+    """Scales log-uniform over two decades: some splats span hundreds of pixels (tile rects of
+    dozens of tiles, lists mixing tiny and huge splats), isotropic-ish and needle-like discs."""
+    n = 1500
+    g = sphere_shell_scene(n, 32, sh_degree=2, seed=51, coverage=2.0)
+    t = {k: (v.detach().clone() if v is not None else None) for k, v in g.tensors().items()}
+    gen = torch.Generator().manual_seed(52)
+    s = torch.exp(torch.rand(n, 2, generator=gen) * (math.log(0.4) - math.log(0.004)) + math.log(0.004))
+    t["scaling"] = torch.cat([s, torch.full((n, 1), math.exp(-20.0))], dim=1)
+    t["opacity"] = 0.05 + 0.6 * torch.rand(n, 1, generator=gen)
+    gg = SyntheticGaussians(active_sh_degree=2, **t)
+    cam = orbit_cameras(1, 160, 128, seed=53)[0]
+    ref, aux, _ = run_oracle(gg, cam)
+    assert int(ref[4].max()) > 100                                     # really large screen-space radii
+    _check_forward(gg, cam, bg=(0.2, 0.2, 0.2), max_amb=0.6)
+    _check_backward(gg, cam, bg=(0.2, 0.2, 0.2), max_flag=0.7, uv_tol=5e-3)
+
+
 def test_capacity_overflow_retry_is_transparent():
     from texture_gs_b200 import rasterizer as RZ
     g = sphere_shell_scene(3000, 16, sh_degree=0, seed=1)
