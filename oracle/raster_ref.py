@@ -54,6 +54,7 @@ ALPHA_MAX = 0.99
 T_STOP = 1e-4
 NEAR_CULL = 0.2
 ND_EPS = 1e-8
+FACE_TIE_REL = 1e-4   # test-side conditioning flag: |u'| major/second-major tie (cube face chosen by rounding)
 GRAZING_COS = 0.05    # test-side conditioning flag only (never changes the rendered values); calibrated so that
                       # the fp32 and fp64 oracles agree to 1e-3 on every gradient once flagged pixels carry no cotangent
 
@@ -447,6 +448,13 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
                     delta = delta.detach()
                 Jg = gradient_uvs[g].reshape(-1, 3, 3)
                 u = uvs[g] + (Jg @ delta[:, :, None]).squeeze(-1)            # E10
+                with torch.no_grad():
+                    # conditioning flag: clamp-to-edge cube sampling (E11) is discontinuous across face
+                    # edges; a contribution whose two largest |u'| components tie within 1e-4 (relative)
+                    # picks its face by rounding
+                    ua = u.detach().abs()
+                    top2 = torch.topk(ua, 2, dim=-1).values
+                    ambiguous[pix[(top2[:, 0] - top2[:, 1]) < FACE_TIE_REL * top2[:, 0]]] = True
                 tex = cube_sample(texture, u)                                 # E11
                 col = torch.clamp_min(C0 * tex + pre["csh"][g] + 0.5, 0.0)   # E12
                 if acc_c0 is not None:
