@@ -301,7 +301,7 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
     if (p.P > 0) {
         BwdOut g{b->dL_dmeans3D, b->dL_dmeans2D, b->dL_dopacity, b->dL_dscales, b->dL_drotations,
                  b->dL_dshs, b->dL_dcolors_precomp, b->dL_duvs, b->dL_dextra_attrs, b->accumulate_mask};
-        texgs_preprocess_bwd<<<(p.P + 255) / 256, 256, 0, stream>>>(p, nullptr, b->acc_ws, g);
+        texgs_preprocess_bwd<<<(p.P + 255) / 256, 256, 0, stream>>>(p, b->acc_ws, g);
         TEXGS_KERNEL_CHECK("texgs_preprocess_bwd", debug, stream);
     }
     TEXGS_EV(a, TEXGS_EV_BWD_PREPROCESS, stream);

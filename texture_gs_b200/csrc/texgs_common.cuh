@@ -10,7 +10,6 @@
 #include "../../include/texgs.h"
 
 #define TEXGS_TILE 16
-#define TEXGS_TILE_PIX 256
 #define TEXGS_ALPHA_MIN (1.0f / 255.0f)
 #define TEXGS_ALPHA_MAX 0.99f
 #define TEXGS_T_STOP 1e-4f
@@ -252,60 +251,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 16);
-    v += __shfl_xor_sync(0xffffffffu, v, 8);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    return v;
-}
 
-// Transposing warp reduction of 20 per-lane values: instead of 5 shuffles per value (100), every
-// step halves the number of values a lane still owns (16 -> 8 -> 4 -> 2 -> 1, then 4 -> 2 -> 1),
-// 22 shuffles in total. On return
-//   outA on lane l holds the warp total of value ((l >> 1) & 15)            (values 0..15)
-//   outB on lane l holds the warp total of value 16 + 2*bit4(l) + bit3(l)   (values 16..19)
-__device__ __forceinline__ void warp_reduce20(const float (&v)[20], int lane, float& outA, float& outB) {
-    const unsigned full = 0xffffffffu;
-    const bool h4 = (lane & 16) != 0, h3 = (lane & 8) != 0, h2 = (lane & 4) != 0, h1 = (lane & 2) != 0;
-    float a8[8], a4[4], a2[2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float send = h4 ? v[i] : v[i + 8], keep = h4 ? v[i + 8] : v[i];
-        a8[i] = keep + __shfl_xor_sync(full, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = h3 ? a8[i] : a8[i + 4], keep = h3 ? a8[i + 4] : a8[i];
-        a4[i] = keep + __shfl_xor_sync(full, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = h2 ? a4[i] : a4[i + 2], keep = h2 ? a4[i + 2] : a4[i];
-        a2[i] = keep + __shfl_xor_sync(full, send, 4);
-    }
-    {
-        const float send = h1 ? a2[0] : a2[1], keep = h1 ? a2[1] : a2[0];
-        float a1 = keep + __shfl_xor_sync(full, send, 2);
-        a1 += __shfl_xor_sync(full, a1, 1);
-        outA = a1;
-    }
-    float b2[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = h4 ? v[16 + i] : v[18 + i], keep = h4 ? v[18 + i] : v[16 + i];
-        b2[i] = keep + __shfl_xor_sync(full, send, 16);
-    }
-    {
-        const float send = h3 ? b2[0] : b2[1], keep = h3 ? b2[1] : b2[0];
-        float b1 = keep + __shfl_xor_sync(full, send, 8);
-        b1 += __shfl_xor_sync(full, b1, 4);
-        b1 += __shfl_xor_sync(full, b1, 2);
-        b1 += __shfl_xor_sync(full, b1, 1);
-        outB = b1;
-    }
-}
 
 // four bilinear taps as rgb triples, from the packed (float4) or the plain (3 floats) layout
 template <bool TEX4>
@@ -331,8 +277,10 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// Half-warp flavour of the transposing reduction: lanes 0-15 and 16-31 reduce independently (xor
-// distances 8,4,2,1 never cross the halves). On return, inside each half,
+// Transposing reduction of 20 per-lane values inside each half-warp: instead of 4 shuffles per value
+// (80), every step halves the number of values a lane still owns (16 -> 8 -> 4 -> 2 -> 1, then 4 -> 2 ->
+// 1): 20 shuffles, and lanes 0-15 / 16-31 reduce independently in the same instructions (xor distances
+// 8,4,2,1 never cross the halves). On return, inside each half,
 //   outA on lane l holds the half's total of value (l & 15)                       (values 0..15)
 //   outB on lane l holds the half's total of value 16 + ((l >> 2) & 3)            (values 16..19)
 __device__ __forceinline__ void halfwarp_reduce20(const float (&v)[20], int lane, float& outA, float& outB) {

@@ -239,7 +239,7 @@ struct BwdOut {
 #ifndef TEXGS_PREBWD_MIN_CTAS
 #define TEXGS_PREBWD_MIN_CTAS 3
 #endif
-__global__ void __launch_bounds__(256, TEXGS_PREBWD_MIN_CTAS) texgs_preprocess_bwd(const RasterParams p, const int* __restrict__ radii_unused,
+__global__ void __launch_bounds__(256, TEXGS_PREBWD_MIN_CTAS) texgs_preprocess_bwd(const RasterParams p,
                                                           const float* __restrict__ acc_all, const BwdOut g) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.P) return;

@@ -77,12 +77,6 @@ struct __align__(128) WarpSmem {
 static_assert(sizeof(WarpSmem) % 128 == 0, "WarpSmem must keep the records 128-byte aligned");
 #define TEXGS_RENDER_SMEM (8 * sizeof(WarpSmem))
 
-struct ChunkLoad {       // registers carried across one blend phase
-    unsigned id;         // Gaussian id of this lane's entry (chunk c+2)
-    float4 q0, q1;       // cull sector of this lane's entry (chunk c+1 at issue time)
-    bool valid;
-};
-
 __device__ __forceinline__ unsigned stream_load_id(const RasterParams& p, unsigned start, unsigned limit, int chunk, int lane,
                                                    bool& valid) {
     const unsigned e = (unsigned)chunk * TEXGS_CHUNK + (unsigned)lane;
