@@ -194,6 +194,22 @@ int texgs_photometric_forward(const float* image, const float* gt, int32_t C, in
 int texgs_photometric_backward(const float* image, const float* gt, int32_t C, int32_t H, int32_t W, const void* ws,
                                const float* coef2, float* dL_dimage, void* stream);
 
+/* ---- geometry losses of the same step (models/texture_gaussian3d.py:342-368) -------
+ *   Lalpha = mean|alpha - gt_alpha|                                         losses/pixelwise_loss.py:3-4
+ *   Lnorm  = sum((1 - <norm, gt_norm>) * gt_alpha) / (sum(gt_alpha) + 1e-6)   losses/norm_reg_loss.py:66-71
+ *   Lnsm   = smooth_loss(gt_image, norm, gt_alpha, gamma)                   losses/smooth_loss.py:4-27
+ * alpha (1,H,W), norm (3,H,W): rasterizer outputs. gt_alpha (1,H,W) may be NULL (= ones), gt_norm / gt_image
+ * (3,H,W) may be NULL (that loss is skipped and reads 0). out3 (device) = {Lalpha, Lnorm, Lnsm}.
+ * ``ws`` (texgs_geometry_loss_workspace_size bytes, 16-byte aligned) carries the normalisers to backward.
+ * Backward: dL_dalpha = coef3[0]*dLalpha/dalpha, dL_dnorm = coef3[1]*dLnorm/dnorm + coef3[2]*dLnsm/dnorm
+ * (coef3 = 3 device floats; either output pointer may be NULL). */
+int texgs_geometry_loss_workspace_size(int32_t H, int32_t W, size_t* bytes);
+int texgs_geometry_loss_forward(const float* alpha, const float* norm, const float* gt_alpha, const float* gt_norm,
+                                const float* gt_image, int32_t H, int32_t W, float gamma, void* ws, float* out3, void* stream);
+int texgs_geometry_loss_backward(const float* alpha, const float* norm, const float* gt_alpha, const float* gt_norm,
+                                 const float* gt_image, int32_t H, int32_t W, float gamma, const void* ws, const float* coef3,
+                                 float* dL_dalpha, float* dL_dnorm, void* stream);
+
 /* Frustum test only (upstream ``GaussianRasterizer.markVisible`` [EXT]; unused in the reference
  * tree). present (P,) int32: 1 if the Gaussian passes the near-plane cull. */
 int texgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix16_host,

@@ -10,6 +10,10 @@ generator tests/golden/make_loss_golden.py imports /root/reference/losses direct
                 ssim_map.mean()
   combination — reference models/texture_gaussian3d.py:333-340
                 loss = (1 - lambda_dssim) * L1 + lambda_dssim * (1 - SSIM)
+  norm_loss   — reference losses/norm_reg_loss.py:66-71    masked mean of 1 - <pred, gt>
+  smooth_loss — reference losses/smooth_loss.py:4-27       bilateral first-order smoothness, 4 directions
+  geometry_losses — the (Lalpha, Lnorm, Lnsm) triple of models/texture_gaussian3d.py:342-368
+                (golden vectors: tests/golden/geometry_loss.npz, generator make_geometry_loss_golden.py)
 """
 from __future__ import annotations
 
@@ -55,3 +59,37 @@ def photometric_loss(image: torch.Tensor, gt: torch.Tensor, lambda_dssim: float)
     ll1 = l1_loss(image, gt)
     lssim = 1.0 - ssim(image, gt)
     return (1.0 - lambda_dssim) * ll1 + lambda_dssim * lssim, ll1, lssim
+
+
+def norm_loss(pred: torch.Tensor, gt: torch.Tensor, mask: torch.Tensor = None) -> torch.Tensor:
+    """(3,H,W) normals; with a mask: sum((1 - <pred,gt>) * mask) / (sum(mask) + 1e-6)."""
+    cos = (pred * gt).sum(dim=0, keepdim=True)
+    if mask is None:
+        return (1.0 - cos).mean()
+    return ((1.0 - cos) * mask).sum() / (mask.sum() + 1e-6)
+
+
+def smooth_loss(rgb: torch.Tensor, value: torch.Tensor, mask: torch.Tensor = None, gamma: float = 0.1) -> torch.Tensor:
+    """Bilateral smoothness of ``value`` (C,H,W) guided by ``rgb`` (3,H,W): for the neighbour directions
+    right, down, down-right and up-right, weight = exp(-sum_c|rgb_a - rgb_b| / gamma) * mask_a * mask_b and
+    L_d = sum|w * (value_a - value_b)| / (sum(w) + 1e-6); returns the mean of the four."""
+    H, W = rgb.shape[-2:]
+    views = [  # (a, b) index pairs of each direction
+        ((slice(None), slice(0, W - 1)), (slice(None), slice(1, W))),
+        ((slice(0, H - 1), slice(None)), (slice(1, H), slice(None))),
+        ((slice(0, H - 1), slice(0, W - 1)), (slice(1, H), slice(1, W))),
+        ((slice(1, H), slice(0, W - 1)), (slice(0, H - 1), slice(1, W))),
+    ]
+    total = 0.0
+    for (ay, ax), (by, bx) in views:
+        w = torch.exp(-(rgb[:, ay, ax] - rgb[:, by, bx]).abs().sum(0, keepdim=True) / gamma)
+        if mask is not None:
+            m = mask.to(w.dtype)
+            w = w * (m[:, ay, ax] * m[:, by, bx])
+        total = total + (w * (value[:, ay, ax] - value[:, by, bx])).abs().sum() / (w.sum() + 1e-6)
+    return total / 4
+
+
+def geometry_losses(alpha, norm, gt_alpha, gt_norm, gt_image, gamma: float = 0.1):
+    """(Lalpha, Lnorm, Lnsm) as models/texture_gaussian3d.py:342-345, 354-358, 365-368 compute them."""
+    return l1_loss(alpha, gt_alpha), norm_loss(norm, gt_norm, gt_alpha), smooth_loss(gt_image, norm, gt_alpha, gamma)

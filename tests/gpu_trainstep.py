@@ -1,8 +1,9 @@
 """Reference-shaped training step on the headline config (stage 3 after iteration 10 000,
 models/texture_gaussian3d.py:315-410): two renders per view (with SH, and active_sh_degree = 0), photometric
-loss (1-l)*L1 + l*(1-SSIM) on both images, L1 on alpha, backward.
+loss (1-l)*L1 + l*(1-SSIM) on both images, L1 on alpha, masked normal loss, bilateral normal smoothness
+(the losses configs/texture_gaussian3d.yaml:77-88 enables), backward.
   A: as the reference does it — two rasterizer calls + the PyTorch loss formulation
-  B: this repo's next-row pieces — one dual render (N2) + fused photometric loss (N3)
+  B: this repo's next-row pieces — one dual render (N2) + fused photometric and geometry losses (N3)
 Prints one JSON line with ms per view for both."""
 import json, sys
 from pathlib import Path
@@ -10,7 +11,7 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from oracle import loss_ref as LR          # the reference's loss formulation (measurement harness only)
 from texture_gs_b200 import uv_tex_render, uv_tex_render_dual
-from texture_gs_b200.losses import photometric_loss
+from texture_gs_b200.losses import photometric_loss, geometry_losses
 from texture_gs_b200.scene import sphere_shell_scene, orbit_cameras
 
 N, W, H, R = 500000, 1920, 1080, 2048
@@ -19,13 +20,15 @@ cams = orbit_cameras(8, W, H, device="cuda")
 bg = torch.zeros(3, device="cuda")
 gen = torch.Generator().manual_seed(0)
 gt = torch.rand(3, H, W, generator=gen).cuda()
-gt_alpha = torch.ones(1, H, W, device="cuda")
-lam, lam_nosh = 0.2, 2.0
+gt_alpha = (torch.rand(1, H, W, generator=gen) > 0.2).float().cuda()
+gt_norm = torch.nn.functional.normalize(torch.randn(3, H, W, generator=gen), dim=0).cuda()
+lam, lam_nosh, lam_alpha, lam_norm, lam_nsm = 0.2, 2.0, 1.0, 0.1, 0.5
 
 
 def step_reference_style(i):
     pkg = uv_tex_render(cams[i % 8], g, None, bg)
-    loss = LR.photometric_loss(pkg["render"], gt, lam)[0] + (pkg["alpha"] - gt_alpha).abs().mean()
+    la, ln, ls = LR.geometry_losses(pkg["alpha"], pkg["norm"], gt_alpha, gt_norm, gt)
+    loss = LR.photometric_loss(pkg["render"], gt, lam)[0] + lam_alpha * la + lam_norm * ln + lam_nsm * ls
     deg = g.active_sh_degree
     g.active_sh_degree = 0
     img0 = uv_tex_render(cams[i % 8], g, None, bg)["render"]
@@ -37,7 +40,8 @@ def step_reference_style(i):
 
 def step_fused(i):
     pkg = uv_tex_render_dual(cams[i % 8], g, None, bg)
-    loss = photometric_loss(pkg["render"], gt, lam)[0] + (pkg["alpha"] - gt_alpha).abs().mean()
+    la, ln, ls = geometry_losses(pkg["alpha"], pkg["norm"], gt_alpha, gt_norm, gt)
+    loss = photometric_loss(pkg["render"], gt, lam)[0] + lam_alpha * la + lam_norm * ln + lam_nsm * ls
     loss = loss + lam_nosh * photometric_loss(pkg["render_no_sh"], gt, lam)[0]
     loss.backward()
     g.zero_grad()
@@ -54,5 +58,5 @@ def timeit(fn, n=12, warm=4):
 
 a = timeit(step_reference_style)
 b = timeit(step_fused)
-print(json.dumps({"config": "500k / 1080p / R2048, stage-3 step (2 images, L1+SSIM on both, alpha L1, backward)",
+print(json.dumps({"config": "500k / 1080p / R2048, stage-3 step (2 images, L1+SSIM on both, alpha L1, normal loss, normal smoothness, backward)",
                   "two_renders_torch_losses_ms": round(a, 3), "dual_render_fused_losses_ms": round(b, 3), "speedup": round(a / b, 2)}))

@@ -236,3 +236,21 @@ def test_loss_oracle_matches_the_reference_code_golden_vectors():
         assert abs(float(1 - lssim) - float(z[f"{tag}_ssim"])) < 1e-6
         assert abs(float(loss) - float(z[f"{tag}_loss"])) < 1e-6
         assert float((img.grad - torch.from_numpy(z[f"{tag}_grad"])).abs().max()) < 1e-8
+
+
+def test_geometry_loss_oracle_matches_the_reference_code_golden_vectors():
+    """oracle/loss_ref.geometry_losses vs vectors from the reference's own l1_loss / norm_loss / smooth_loss."""
+    import numpy as np
+    from oracle import loss_ref as LR
+    z = np.load(Path(__file__).resolve().parent / "golden" / "geometry_loss.npz")
+    for tag in ("a", "b", "c"):
+        alpha = torch.from_numpy(z[f"{tag}_alpha"]).requires_grad_(True)
+        norm = torch.from_numpy(z[f"{tag}_norm"]).requires_grad_(True)
+        gt = [torch.from_numpy(z[f"{tag}_{k}"]) for k in ("gt_alpha", "gt_norm", "gt_image")]
+        la, ln, ls = LR.geometry_losses(alpha, norm, *gt)
+        (1.0 * la + 0.1 * ln + 0.5 * ls).backward()
+        assert abs(float(la) - float(z[f"{tag}_Lalpha"])) < 1e-7
+        assert abs(float(ln) - float(z[f"{tag}_Lnorm"])) < 1e-6
+        assert abs(float(ls) - float(z[f"{tag}_Lnsm"])) < 1e-5
+        assert float((alpha.grad - torch.from_numpy(z[f"{tag}_galpha"])).abs().max()) < 1e-8
+        assert float((norm.grad - torch.from_numpy(z[f"{tag}_gnorm"])).abs().max()) < 1e-6

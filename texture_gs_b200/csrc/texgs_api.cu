@@ -178,7 +178,8 @@ const char* texgs_last_error(void) { return g_last_error.c_str(); }
 const char* texgs_kernel_names(void) {
     return "texgs_preprocess_fwd,texgs_scan_tiles,texgs_scatter_pairs,texgs_sort_tiles_small,texgs_sort_tiles,texgs_render_fwd,"
            "texgs_render_bwd,texgs_preprocess_bwd,texgs_mark_visible_kernel,texgs_pack_texture_kernel,"
-           "texgs_photometric_fwd_kernel,texgs_photometric_finalize_kernel,texgs_photometric_bwd_kernel";
+           "texgs_photometric_fwd_kernel,texgs_photometric_finalize_kernel,texgs_photometric_bwd_kernel,"
+           "texgs_geometry_loss_fwd_kernel,texgs_geometry_loss_finalize_kernel,texgs_geometry_loss_bwd_kernel";
 }
 
 int texgs_workspace_sizes(const TexgsFwdArgs* a, uint64_t pair_capacity, size_t* geom_bytes, size_t* bin_bytes,
@@ -372,6 +373,52 @@ int texgs_photometric_backward(const float* image, const float* gt, int32_t C, i
     texgs_photometric_bwd_kernel<<<grid, dim3(TEXGS_LOSS_TILE, TEXGS_LOSS_TILE), 0, stream>>>(image, gt, H, W, maps, maps + n, maps + 2 * n, coef2,
                                                                                              (float)(1.0 / (double)n), dL_dimage);
     TEXGS_KERNEL_CHECK("texgs_photometric_bwd_kernel", false, stream);
+    return 0;
+}
+
+static size_t geo_parts(int H, int W) {
+    return (size_t)((W + TEXGS_GEO_TX - 1) / TEXGS_GEO_TX) * ((H + TEXGS_GEO_TY - 1) / TEXGS_GEO_TY);
+}
+
+int texgs_geometry_loss_workspace_size(int32_t H, int32_t W, size_t* bytes) {
+    if (H <= 0 || W <= 0 || !bytes) return fail(TEXGS_E_INVALID, "bad arguments");
+    *bytes = 256 + geo_parts(H, W) * TEXGS_GEO_NSUM * sizeof(double);          // scales, then per-CTA partial sums
+    return 0;
+}
+
+static bool geo_args(GeoIn& g, const float* alpha, const float* norm, const float* gt_alpha, const float* gt_norm, const float* gt_image,
+                     int32_t H, int32_t W, float gamma) {
+    if (!alpha || !norm || H <= 0 || W <= 0 || !(gamma > 0.f)) return false;
+    g.alpha = alpha; g.norm = norm; g.gt_alpha = gt_alpha; g.gt_norm = gt_norm; g.gt_image = gt_image;
+    g.H = H; g.W = W; g.inv_gamma = 1.0f / gamma;
+    return true;
+}
+
+int texgs_geometry_loss_forward(const float* alpha, const float* norm, const float* gt_alpha, const float* gt_norm, const float* gt_image,
+                                int32_t H, int32_t W, float gamma, void* ws, float* out3, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GeoIn g;
+    if (!geo_args(g, alpha, norm, gt_alpha, gt_norm, gt_image, H, W, gamma) || !ws || !out3) return fail(TEXGS_E_INVALID, "bad arguments");
+    if ((uintptr_t)ws & 15) return fail(TEXGS_E_WORKSPACE, "workspace must be 16-byte aligned");
+    const dim3 grid((W + TEXGS_GEO_TX - 1) / TEXGS_GEO_TX, (H + TEXGS_GEO_TY - 1) / TEXGS_GEO_TY);
+    double* parts = (double*)((char*)ws + 256);
+    texgs_geometry_loss_fwd_kernel<<<grid, dim3(TEXGS_GEO_TX, TEXGS_GEO_TY), 0, stream>>>(g, parts);
+    TEXGS_KERNEL_CHECK("texgs_geometry_loss_fwd_kernel", false, stream);
+    texgs_geometry_loss_finalize_kernel<<<1, 1024, 0, stream>>>(parts, (int)geo_parts(H, W), 1.0 / ((double)H * W), (float*)ws, out3);
+    TEXGS_KERNEL_CHECK("texgs_geometry_loss_finalize_kernel", false, stream);
+    return 0;
+}
+
+int texgs_geometry_loss_backward(const float* alpha, const float* norm, const float* gt_alpha, const float* gt_norm, const float* gt_image,
+                                 int32_t H, int32_t W, float gamma, const void* ws, const float* coef3, float* dL_dalpha, float* dL_dnorm,
+                                 void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GeoIn g;
+    if (!geo_args(g, alpha, norm, gt_alpha, gt_norm, gt_image, H, W, gamma) || !ws || !coef3 || (!dL_dalpha && !dL_dnorm))
+        return fail(TEXGS_E_INVALID, "bad arguments");
+    const dim3 grid((W + TEXGS_GEO_TX - 1) / TEXGS_GEO_TX, (H + TEXGS_GEO_TY - 1) / TEXGS_GEO_TY);
+    texgs_geometry_loss_bwd_kernel<<<grid, dim3(TEXGS_GEO_TX, TEXGS_GEO_TY), 0, stream>>>(g, (const float*)ws, coef3, dL_dalpha, dL_dnorm);
+    TEXGS_KERNEL_CHECK("texgs_geometry_loss_bwd_kernel", false, stream);
     return 0;
 }
 

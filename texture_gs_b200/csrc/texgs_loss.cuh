@@ -159,3 +159,197 @@ __global__ void __launch_bounds__(256) texgs_photometric_bwd_kernel(const float*
         dimg[o] = inv_n * (coef[0] * sgn - coef[1] * dssim);
     }
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Geometry losses of the same training step (models/texture_gaussian3d.py:342-368), one kernel each way:
+//   Lalpha = l1_loss(alpha, gt_alpha)                      losses/pixelwise_loss.py:3-4
+//   Lnorm  = norm_loss(norm, gt_norm, gt_alpha)            losses/norm_reg_loss.py:66-71 (masked branch)
+//          = sum((1 - <norm, gt_norm>) * mask) / (sum(mask) + 1e-6)
+//   Lnsm   = smooth_loss(gt_image, norm, gt_alpha)         losses/smooth_loss.py:4-27
+//          = 1/4 * sum_d  sum|w_d * (v_a - v_b)| / (sum(w_d) + 1e-6),  four neighbour directions d
+//            (right, down, down-right, up-right), w_d = exp(-sum_c|rgb_a - rgb_b| / gamma) * mask_a * mask_b
+// The reference spends ~45 pointwise/reduction kernels forward on these and as many backward.
+// Pair (a, b) of direction d anchored at pixel (y, x):
+//   d=0: a=(y,x)   b=(y,x+1)      d=1: a=(y,x)   b=(y+1,x)
+//   d=2: a=(y,x)   b=(y+1,x+1)    d=3: a=(y+1,x) b=(y,x+1)
+#define TEXGS_GEO_TX 32
+#define TEXGS_GEO_TY 8
+#define TEXGS_GEO_NSUM 11      // alpha L1, norm num, mask sum, 4 x (w sum), 4 x (w |dv| sum)
+
+struct GeoIn {
+    const float* alpha;      // (1,H,W)
+    const float* norm;       // (3,H,W)
+    const float* gt_alpha;   // (1,H,W) or NULL (= ones, models/texture_gaussian3d.py:330)
+    const float* gt_norm;    // (3,H,W) or NULL (Lnorm skipped)
+    const float* gt_image;   // (3,H,W) or NULL (Lnsm skipped)
+    int H, W;
+    float inv_gamma;
+};
+
+// ws layout: [0..5] float scales {1/(HW), 1/(sum mask+eps), 1/(sum w_d + eps) x4}, then per-CTA partials
+struct GeoTile {
+    float rgb[3][TEXGS_GEO_TY + 2][TEXGS_GEO_TX + 2];
+    float nrm[3][TEXGS_GEO_TY + 2][TEXGS_GEO_TX + 2];
+    float msk[TEXGS_GEO_TY + 2][TEXGS_GEO_TX + 2];       // 0 outside the image
+};
+
+__device__ __forceinline__ void geo_load_tile(const GeoIn& g, GeoTile& t, int tid) {
+    const int x0 = blockIdx.x * TEXGS_GEO_TX - 1, y0 = blockIdx.y * TEXGS_GEO_TY - 1;
+    const size_t plane = (size_t)g.H * g.W;
+    for (int i = tid; i < (TEXGS_GEO_TY + 2) * (TEXGS_GEO_TX + 2); i += TEXGS_GEO_TX * TEXGS_GEO_TY) {
+        const int r = i / (TEXGS_GEO_TX + 2), c = i % (TEXGS_GEO_TX + 2);
+        const int gy = y0 + r, gx = x0 + c;
+        const bool in = gy >= 0 && gy < g.H && gx >= 0 && gx < g.W;
+        const size_t o = (size_t)(in ? gy : 0) * g.W + (in ? gx : 0);
+        t.msk[r][c] = in ? (g.gt_alpha ? g.gt_alpha[o] : 1.f) : 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            t.rgb[ch][r][c] = (in && g.gt_image) ? g.gt_image[ch * plane + o] : 0.f;
+            t.nrm[ch][r][c] = in ? g.norm[ch * plane + o] : 0.f;
+        }
+    }
+}
+
+// bilateral weight of the pair (ra,ca)-(rb,cb) in tile coordinates; `valid` = both pixels inside the image
+__device__ __forceinline__ float geo_weight(const GeoTile& t, int ra, int ca, int rb, int cb, bool valid, float inv_gamma) {
+    if (!valid) return 0.f;
+    const float d = fabsf(t.rgb[0][ra][ca] - t.rgb[0][rb][cb]) + fabsf(t.rgb[1][ra][ca] - t.rgb[1][rb][cb]) +
+                    fabsf(t.rgb[2][ra][ca] - t.rgb[2][rb][cb]);
+    return expf(-d * inv_gamma) * t.msk[ra][ca] * t.msk[rb][cb];
+}
+
+__global__ void __launch_bounds__(TEXGS_GEO_TX * TEXGS_GEO_TY) texgs_geometry_loss_fwd_kernel(const GeoIn g, double* __restrict__ parts) {
+    __shared__ GeoTile t;
+    __shared__ double red[TEXGS_GEO_NSUM][TEXGS_GEO_TX * TEXGS_GEO_TY / 32];
+    const int tid = threadIdx.y * TEXGS_GEO_TX + threadIdx.x;
+    geo_load_tile(g, t, tid);
+    __syncthreads();
+    const int px = blockIdx.x * TEXGS_GEO_TX + threadIdx.x, py = blockIdx.y * TEXGS_GEO_TY + threadIdx.y;
+    const int r = threadIdx.y + 1, c = threadIdx.x + 1;
+    double s[TEXGS_GEO_NSUM];
+#pragma unroll
+    for (int k = 0; k < TEXGS_GEO_NSUM; ++k) s[k] = 0.0;
+    if (px < g.W && py < g.H) {
+        const size_t o = (size_t)py * g.W + px, plane = (size_t)g.H * g.W;
+        const float m = t.msk[r][c];
+        s[0] = (double)fabsf(g.alpha[o] - m);
+        if (g.gt_norm) {
+            const float dot = t.nrm[0][r][c] * g.gt_norm[o] + t.nrm[1][r][c] * g.gt_norm[plane + o] + t.nrm[2][r][c] * g.gt_norm[2 * plane + o];
+            s[1] = (double)((1.0f - dot) * m);
+        }
+        s[2] = (double)m;
+        if (g.gt_image) {
+            const bool hr = px + 1 < g.W, hd = py + 1 < g.H;
+            const int ra[4] = {r, r, r, r + 1}, ca[4] = {c, c, c, c};
+            const int rb[4] = {r, r + 1, r + 1, r}, cb[4] = {c + 1, c, c + 1, c + 1};
+            const bool ok[4] = {hr, hd, hr && hd, hr && hd};
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const float w = geo_weight(t, ra[d], ca[d], rb[d], cb[d], ok[d], g.inv_gamma);
+                float a = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) a += fabsf(w * (t.nrm[ch][ra[d]][ca[d]] - t.nrm[ch][rb[d]][cb[d]]));
+                s[3 + d] = (double)w;
+                s[7 + d] = (double)a;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < TEXGS_GEO_NSUM; ++k) {
+        double v = s[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) red[k][tid >> 5] = v;
+    }
+    __syncthreads();
+    if (tid < TEXGS_GEO_NSUM) {
+        double v = 0.0;
+        for (int w = 0; w < TEXGS_GEO_TX * TEXGS_GEO_TY / 32; ++w) v += red[tid][w];
+        parts[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TEXGS_GEO_NSUM + tid] = v;
+    }
+}
+
+// out3 = {Lalpha, Lnorm, Lnsm}; scales[6] feed the backward kernel
+__global__ void __launch_bounds__(1024) texgs_geometry_loss_finalize_kernel(const double* __restrict__ parts, int nparts, double inv_hw,
+                                                                          float* __restrict__ scales, float* __restrict__ out3) {
+    __shared__ double red[TEXGS_GEO_NSUM][32];
+    __shared__ double tot[TEXGS_GEO_NSUM];
+    double s[TEXGS_GEO_NSUM];
+#pragma unroll
+    for (int k = 0; k < TEXGS_GEO_NSUM; ++k) s[k] = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x)
+#pragma unroll
+        for (int k = 0; k < TEXGS_GEO_NSUM; ++k) s[k] += parts[(size_t)i * TEXGS_GEO_NSUM + k];
+#pragma unroll
+    for (int k = 0; k < TEXGS_GEO_NSUM; ++k) {
+        double v = s[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < TEXGS_GEO_NSUM) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[threadIdx.x][w];
+        tot[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // fp32 arithmetic on the reduced sums, as the reference's torch.sum(...)/(torch.sum(...) + 1e-6)
+        const float inv_m = 1.0f / ((float)tot[2] + 1e-6f);
+        out3[0] = (float)(tot[0] * inv_hw);
+        out3[1] = (float)tot[1] * inv_m;
+        float nsm = 0.f;
+        scales[0] = (float)inv_hw;
+        scales[1] = inv_m;
+        for (int d = 0; d < 4; ++d) {
+            const float inv_w = 1.0f / ((float)tot[3 + d] + 1e-6f);
+            scales[2 + d] = inv_w;
+            nsm += (float)tot[7 + d] * inv_w;
+        }
+        out3[2] = nsm * 0.25f;
+    }
+}
+
+__device__ __forceinline__ float geo_sign(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
+
+// dL_dalpha = coef[0] * dLalpha/dalpha ;  dL_dnorm = coef[1] * dLnorm/dnorm + coef[2] * dLnsm/dnorm
+__global__ void __launch_bounds__(TEXGS_GEO_TX * TEXGS_GEO_TY) texgs_geometry_loss_bwd_kernel(const GeoIn g, const float* __restrict__ scales,
+                                                                                             const float* __restrict__ coef,
+                                                                                             float* __restrict__ dalpha, float* __restrict__ dnorm) {
+    __shared__ GeoTile t;
+    const int tid = threadIdx.y * TEXGS_GEO_TX + threadIdx.x;
+    geo_load_tile(g, t, tid);
+    __syncthreads();
+    const int px = blockIdx.x * TEXGS_GEO_TX + threadIdx.x, py = blockIdx.y * TEXGS_GEO_TY + threadIdx.y;
+    if (px >= g.W || py >= g.H) return;
+    const int r = threadIdx.y + 1, c = threadIdx.x + 1;
+    const size_t o = (size_t)py * g.W + px, plane = (size_t)g.H * g.W;
+    const float m = t.msk[r][c];
+    if (dalpha) dalpha[o] = coef[0] * scales[0] * geo_sign(g.alpha[o] - m);
+    if (!dnorm) return;
+    float gn[3] = {0.f, 0.f, 0.f};
+    if (g.gt_norm) {
+        const float k = -coef[1] * scales[1] * m;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) gn[ch] = k * g.gt_norm[ch * plane + o];
+    }
+    if (g.gt_image) {
+        const bool hl = px > 0, hr = px + 1 < g.W, hu = py > 0, hd = py + 1 < g.H;
+        // the 8 pairs this pixel belongs to: {other row, other col, direction, pair valid}; as `a` the
+        // term is +w*sign(v_p - v_q), as `b` it is -w*sign(v_q - v_p) — the same expression
+        const int qr[8] = {r, r + 1, r + 1, r - 1, r, r - 1, r - 1, r + 1};
+        const int qc[8] = {c + 1, c, c + 1, c + 1, c - 1, c, c - 1, c - 1};
+        const int dd[8] = {0, 1, 2, 3, 0, 1, 2, 3};
+        const bool ok[8] = {hr, hd, hr && hd, hu && hr, hl, hu, hu && hl, hd && hl};
+        const float k = 0.25f * coef[2];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float w = geo_weight(t, r, c, qr[e], qc[e], ok[e], g.inv_gamma) * scales[2 + dd[e]] * k;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) gn[ch] += w * geo_sign(t.nrm[ch][r][c] - t.nrm[ch][qr[e]][qc[e]]);
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) dnorm[ch * plane + o] = gn[ch];
+}

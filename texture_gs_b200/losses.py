@@ -8,6 +8,11 @@ and ``1 - losses.ssim_loss`` (``losses/ssim_loss.py:16-54``):
 
 in two CUDA kernels forward (+1 tiny finalize) and one backward, instead of the reference's five
 depthwise 11x11 convolutions, ~10 pointwise kernels and their autograd twins. No CPU fallback.
+
+``geometry_losses(alpha, norm, gt_alpha, gt_norm, gt_image, gamma)`` returns ``(Lalpha, Lnorm, Lnsm)`` of the
+same step (``models/texture_gaussian3d.py:342-345, 354-358, 365-368``: ``l1_loss``, ``norm_loss``
+``losses/norm_reg_loss.py:66-71``, ``smooth_loss`` ``losses/smooth_loss.py:4-27``) from one kernel forward
+(+ finalize) and one backward, differentiable w.r.t. the rasterizer outputs ``alpha`` and ``norm``.
 """
 from __future__ import annotations
 
@@ -67,3 +72,65 @@ class _PhotometricLoss(torch.autograd.Function):
 def photometric_loss(image: torch.Tensor, gt: torch.Tensor, lambda_dssim: float):
     """(loss, Ll1, Lssim) of ``models/texture_gaussian3d.py:333-340``; differentiable w.r.t. ``image``."""
     return _PhotometricLoss.apply(image, gt, float(lambda_dssim))
+
+
+def _opt(t, dev):
+    return None if t is None else t.detach().to(dev).float().contiguous()
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class _GeometryLosses(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alpha, norm, gt_alpha, gt_norm, gt_image, gamma: float):
+        lib = L.load()
+        if not alpha.is_cuda or not norm.is_cuda:
+            raise L.TexgsError("geometry_losses runs on CUDA tensors only (no CPU fallback)")
+        if alpha.dim() != 3 or alpha.shape[0] != 1 or norm.dim() != 3 or norm.shape[0] != 3 or alpha.shape[1:] != norm.shape[1:]:
+            raise L.TexgsError(f"alpha must be (1,H,W) and norm (3,H,W); got {tuple(alpha.shape)} and {tuple(norm.shape)}")
+        dev = alpha.device
+        H, W = alpha.shape[1:]
+        a, n = _opt(alpha, dev), _opt(norm, dev)
+        ga, gn, gi = _opt(gt_alpha, dev), _opt(gt_norm, dev), _opt(gt_image, dev)
+        for name, t, ch in (("gt_alpha", ga, 1), ("gt_norm", gn, 3), ("gt_image", gi, 3)):
+            if t is not None and tuple(t.shape) != (ch, H, W):
+                raise L.TexgsError(f"{name} must be ({ch},{H},{W}), got {tuple(t.shape)}")
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            nbytes = C.c_size_t()
+            L.check(lib.texgs_geometry_loss_workspace_size(H, W, C.byref(nbytes)), "texgs_geometry_loss_workspace_size")
+            ws = torch.empty(nbytes.value, device=dev, dtype=torch.uint8)
+            out3 = torch.empty(3, device=dev, dtype=torch.float32)
+            L.check(lib.texgs_geometry_loss_forward(_p(a), _p(n), _p(ga), _p(gn), _p(gi), H, W, float(gamma), _p(ws), _p(out3),
+                                                    C.c_void_p(stream)), "texgs_geometry_loss_forward")
+        ctx.tensors = (a, n, ga, gn, gi, ws)
+        ctx.gamma = float(gamma)
+        return out3[0], out3[1], out3[2]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_alpha, g_norm, g_nsm):
+        lib = L.load()
+        a, n, ga, gn, gi, ws = ctx.tensors
+        dev = a.device
+        H, W = a.shape[1:]
+        z = torch.zeros((), device=dev)
+        coef = torch.stack([z if g is None else g.float() for g in (g_alpha, g_norm, g_nsm)]).contiguous()
+        need_a, need_n = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        d_a = torch.empty_like(a) if need_a else None
+        d_n = torch.empty_like(n) if need_n else None
+        if need_a or need_n:
+            with torch.cuda.device(dev):
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                L.check(lib.texgs_geometry_loss_backward(_p(a), _p(n), _p(ga), _p(gn), _p(gi), H, W, ctx.gamma, _p(ws), _p(coef),
+                                                         _p(d_a), _p(d_n), C.c_void_p(stream)), "texgs_geometry_loss_backward")
+        return d_a, d_n, None, None, None, None
+
+
+def geometry_losses(alpha, norm, gt_alpha=None, gt_norm=None, gt_image=None, gamma: float = 0.1):
+    """(Lalpha, Lnorm, Lnsm) of ``models/texture_gaussian3d.py:342-368``; ``gt_alpha=None`` means ones
+    (``:330``), ``gt_norm`` / ``gt_image`` ``None`` skips that loss (it reads 0). Differentiable w.r.t. ``alpha``
+    and ``norm``."""
+    return _GeometryLosses.apply(alpha, norm, gt_alpha, gt_norm, gt_image, float(gamma))
