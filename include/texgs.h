@@ -210,6 +210,18 @@ int texgs_geometry_loss_backward(const float* alpha, const float* norm, const fl
                                  const float* gt_image, int32_t H, int32_t W, float gamma, const void* ws, const float* coef3,
                                  float* dL_dalpha, float* dL_dnorm, void* stream);
 
+/* ---- the texture's optimizer step -----------------------------------------------------
+ * Dense Adam with torch.optim.Adam's update (models/texture_gaussian3d.py:139-143 builds it with eps=1e-15,
+ * :439-440 steps it; no weight decay, no amsgrad), for a parameter of n_texels*3 floats:
+ *   m += (g-m)(1-b1);  v = v*b2 + (1-b2) g^2;  p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps)
+ * The gradient comes either as (n,3) ``grad3`` or as the padded (n,4) ``grad_rgba`` the rasterizer backward
+ * accumulates into (exactly one non-NULL); ``zero_grad`` != 0 clears it in the same pass. ``param_rgba``
+ * (optional) receives the packed (n,4) copy of the UPDATED parameter (= texgs_pack_texture of it).
+ * ``step`` is the 1-based step count. All buffers 16-byte aligned device memory. */
+int texgs_texture_adam_step(float* param, float* exp_avg, float* exp_avg_sq, const float* grad3, float* grad_rgba,
+                            float* param_rgba, uint64_t n_texels, float lr, float beta1, float beta2, float eps,
+                            int32_t step, int32_t zero_grad, void* stream);
+
 /* Frustum test only (upstream ``GaussianRasterizer.markVisible`` [EXT]; unused in the reference
  * tree). present (P,) int32: 1 if the Gaussian passes the near-plane cull. */
 int texgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix16_host,

@@ -58,5 +58,46 @@ def timeit(fn, n=12, warm=4):
 
 a = timeit(step_reference_style)
 b = timeit(step_fused)
+
+# the same two steps followed by the texture's optimizer step (models/texture_gaussian3d.py:439-444)
+from texture_gs_b200.dist import GradBucket
+from texture_gs_b200.optim import TextureAdam
+tex = g.get_texture
+opt_ref = torch.optim.Adam([{"params": [tex], "lr": 0.0025}], lr=0.0, eps=1e-15)
+
+
+def iter_reference_style(i):
+    pkg = uv_tex_render(cams[i % 8], g, None, bg)
+    la, ln, ls = LR.geometry_losses(pkg["alpha"], pkg["norm"], gt_alpha, gt_norm, gt)
+    loss = LR.photometric_loss(pkg["render"], gt, lam)[0] + lam_alpha * la + lam_norm * ln + lam_nsm * ls
+    deg = g.active_sh_degree
+    g.active_sh_degree = 0
+    img0 = uv_tex_render(cams[i % 8], g, None, bg)["render"]
+    g.active_sh_degree = deg
+    (loss + lam_nosh * LR.photometric_loss(img0, gt, lam)[0]).backward()
+    opt_ref.step()
+    g.zero_grad()                                  # zero_grad(set_to_none=True)
+
+
+c = timeit(iter_reference_style)
+g.zero_grad()
+bucket = GradBucket({"texture": tex})
+opt_new = TextureAdam([{"params": [tex], "lr": 0.0025}], lr=0.0, eps=1e-15, zero_grad_in_step=True)
+
+
+def iter_fused(i):
+    with bucket.fused():
+        pkg = uv_tex_render_dual(cams[i % 8], g, None, bg)
+        la, ln, ls = geometry_losses(pkg["alpha"], pkg["norm"], gt_alpha, gt_norm, gt)
+        loss = photometric_loss(pkg["render"], gt, lam)[0] + lam_alpha * la + lam_norm * ln + lam_nsm * ls
+        (loss + lam_nosh * photometric_loss(pkg["render_no_sh"], gt, lam)[0]).backward()
+    opt_new.step()
+    for k, v in g.tensors().items():
+        if v is not None and v is not tex:
+            v.grad = None
+
+
+d = timeit(iter_fused)
 print(json.dumps({"config": "500k / 1080p / R2048, stage-3 step (2 images, L1+SSIM on both, alpha L1, normal loss, normal smoothness, backward)",
-                  "two_renders_torch_losses_ms": round(a, 3), "dual_render_fused_losses_ms": round(b, 3), "speedup": round(a / b, 2)}))
+                  "two_renders_torch_losses_ms": round(a, 3), "dual_render_fused_losses_ms": round(b, 3), "speedup": round(a / b, 2),
+                  "with_texture_adam": {"torch_adam_ms": round(c, 3), "fused_bucket_texture_adam_ms": round(d, 3), "speedup": round(c / d, 2)}}))

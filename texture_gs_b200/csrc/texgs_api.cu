@@ -8,6 +8,7 @@
 #include "texgs_binning.cuh"
 #include "texgs_common.cuh"
 #include "texgs_loss.cuh"
+#include "texgs_optim.cuh"
 #include "texgs_preprocess.cuh"
 #include "texgs_render.cuh"
 
@@ -179,7 +180,7 @@ const char* texgs_kernel_names(void) {
     return "texgs_preprocess_fwd,texgs_scan_tiles,texgs_scatter_pairs,texgs_sort_tiles_small,texgs_sort_tiles,texgs_render_fwd,"
            "texgs_render_bwd,texgs_preprocess_bwd,texgs_mark_visible_kernel,texgs_pack_texture_kernel,"
            "texgs_photometric_fwd_kernel,texgs_photometric_finalize_kernel,texgs_photometric_bwd_kernel,"
-           "texgs_geometry_loss_fwd_kernel,texgs_geometry_loss_finalize_kernel,texgs_geometry_loss_bwd_kernel";
+           "texgs_geometry_loss_fwd_kernel,texgs_geometry_loss_finalize_kernel,texgs_geometry_loss_bwd_kernel,texgs_texture_adam_kernel";
 }
 
 int texgs_workspace_sizes(const TexgsFwdArgs* a, uint64_t pair_capacity, size_t* geom_bytes, size_t* bin_bytes,
@@ -419,6 +420,30 @@ int texgs_geometry_loss_backward(const float* alpha, const float* norm, const fl
     const dim3 grid((W + TEXGS_GEO_TX - 1) / TEXGS_GEO_TX, (H + TEXGS_GEO_TY - 1) / TEXGS_GEO_TY);
     texgs_geometry_loss_bwd_kernel<<<grid, dim3(TEXGS_GEO_TX, TEXGS_GEO_TY), 0, stream>>>(g, (const float*)ws, coef3, dL_dalpha, dL_dnorm);
     TEXGS_KERNEL_CHECK("texgs_geometry_loss_bwd_kernel", false, stream);
+    return 0;
+}
+
+int texgs_texture_adam_step(float* param, float* exp_avg, float* exp_avg_sq, const float* grad3, float* grad_rgba, float* param_rgba,
+                            uint64_t n_texels, float lr, float beta1, float beta2, float eps, int32_t step, int32_t zero_grad,
+                            void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!param || !exp_avg || !exp_avg_sq || (grad3 == nullptr) == (grad_rgba == nullptr) || step < 1 ||
+        !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f))
+        return fail(TEXGS_E_INVALID, "bad arguments (exactly one of grad3 / grad_rgba, step >= 1, betas in [0,1))");
+    if (n_texels == 0) return 0;
+    if (((uintptr_t)param | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq | (uintptr_t)grad3 | (uintptr_t)grad_rgba | (uintptr_t)param_rgba) & 15)
+        return fail(TEXGS_E_INVALID, "all buffers must be 16-byte aligned");
+    AdamArgs a;
+    a.p = param; a.m = exp_avg; a.v = exp_avg_sq; a.g3 = grad3; a.g4 = grad_rgba; a.rgba = param_rgba; a.n = n_texels;
+    // bias corrections in double on the host, as torch.optim.Adam's scalar path does
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    a.one_minus_b1 = 1.0f - beta1; a.b2 = beta2; a.one_minus_b2 = 1.0f - beta2;
+    a.step_size = (float)((double)lr / bc1); a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2)); a.eps = eps;
+    a.zero_grad = zero_grad;
+    const uint64_t ctas = (n_texels + TEXGS_ADAM_TEXELS - 1) / TEXGS_ADAM_TEXELS;
+    if (ctas > 0x7fffffffull) return fail(TEXGS_E_INVALID, "tensor too large");
+    texgs_texture_adam_kernel<<<(unsigned)ctas, TEXGS_ADAM_THREADS, 0, stream>>>(a);
+    TEXGS_KERNEL_CHECK("texgs_texture_adam_kernel", false, stream);
     return 0;
 }
 

@@ -1,0 +1,103 @@
+// texgs_optim.cuh — SURVEY §8f N4: the texture's optimizer step (reference models/texture_gaussian3d.py:139-143
+// builds torch.optim.Adam(lr=tex_lr, eps=1e-15) over the (6,R,R,3) texture, :439-440 steps it every iteration).
+// Dense Adam, same update as torch.optim.Adam (no weight decay, no amsgrad):
+//     m <- m + (g - m) * (1 - b1)          v <- v * b2 + (1 - b2) * g * g
+//     p <- p - (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// fused with what surrounds it on this path: the gradient is read straight from the padded (6,R,R,4) buffer the
+// rasterizer backward accumulates into (GradBucket), is zeroed for the next step in the same pass, and the packed
+// RGBA copy of the updated texture (TexgsFwdArgs.texture_rgba) is emitted too — instead of torch's ~8 foreach
+// passes + a fill + a repack. HBM-bound: 120 B per texel all options on (p, m, v read+write 72, g read 16 + zero 16,
+// rgba write 16), every global access a fully coalesced 16 B per thread (texel <-> flat re-indexing goes through
+// shared memory).
+#pragma once
+#include "texgs_common.cuh"
+
+#define TEXGS_ADAM_THREADS 256
+#define TEXGS_ADAM_TEXELS 1024                      // per CTA: 3072 parameter floats = 768 float4
+
+struct AdamArgs {
+    float* p; float* m; float* v;     // (n*3) floats each, 16-byte aligned
+    const float* g3;                  // (n,3) gradient or NULL
+    float* g4;                        // (n,4) padded gradient or NULL (exactly one of g3 / g4)
+    float* rgba;                      // (n,4) packed copy of the updated parameter, or NULL
+    unsigned long long n;             // texels (a flat tensor of k floats, k % 3 == 0, is n = k/3 "texels")
+    float one_minus_b1, b2, one_minus_b2, step_size, inv_sqrt_bc2, eps;
+    int zero_grad;
+};
+
+__device__ __forceinline__ void adam_elem(float& p, float& m, float& v, float g, const AdamArgs& a) {
+    m = m + (g - m) * a.one_minus_b1;
+    v = v * a.b2 + (a.one_minus_b2 * g) * g;
+    const float denom = sqrtf(v) * a.inv_sqrt_bc2 + a.eps;
+    p = p - a.step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(TEXGS_ADAM_THREADS) texgs_texture_adam_kernel(const AdamArgs a) {
+    __shared__ __align__(16) float sg[TEXGS_ADAM_TEXELS * 3];          // gradient, then the updated parameter
+    const unsigned long long t0 = (unsigned long long)blockIdx.x * TEXGS_ADAM_TEXELS;
+    const int tid = threadIdx.x;
+    const bool full = t0 + TEXGS_ADAM_TEXELS <= a.n;
+    if (full) {
+        // 1. gradient tile -> shared memory, flat (texel*3 + channel) order
+        if (a.g4) {
+            float4* g4 = reinterpret_cast<float4*>(a.g4) + t0;
+#pragma unroll
+            for (int k = 0; k < TEXGS_ADAM_TEXELS / TEXGS_ADAM_THREADS; ++k) {
+                const int t = tid + k * TEXGS_ADAM_THREADS;
+                const float4 g = g4[t];
+                sg[3 * t] = g.x; sg[3 * t + 1] = g.y; sg[3 * t + 2] = g.z;
+                if (a.zero_grad) g4[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            float4* g3 = reinterpret_cast<float4*>(const_cast<float*>(a.g3) + t0 * 3);
+#pragma unroll
+            for (int k = 0; k < 3 * TEXGS_ADAM_TEXELS / 4 / TEXGS_ADAM_THREADS; ++k) {
+                const int f = tid + k * TEXGS_ADAM_THREADS;
+                reinterpret_cast<float4*>(sg)[f] = g3[f];
+                if (a.zero_grad) g3[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncthreads();
+        // 2. elementwise update on flat float4s
+        float4* p4 = reinterpret_cast<float4*>(a.p + t0 * 3);
+        float4* m4 = reinterpret_cast<float4*>(a.m + t0 * 3);
+        float4* v4 = reinterpret_cast<float4*>(a.v + t0 * 3);
+#pragma unroll
+        for (int k = 0; k < 3 * TEXGS_ADAM_TEXELS / 4 / TEXGS_ADAM_THREADS; ++k) {
+            const int f = tid + k * TEXGS_ADAM_THREADS;
+            float4 p = p4[f], m = m4[f], v = v4[f];
+            const float4 g = reinterpret_cast<float4*>(sg)[f];
+            adam_elem(p.x, m.x, v.x, g.x, a); adam_elem(p.y, m.y, v.y, g.y, a);
+            adam_elem(p.z, m.z, v.z, g.z, a); adam_elem(p.w, m.w, v.w, g.w, a);
+            p4[f] = p; m4[f] = m; v4[f] = v;
+            reinterpret_cast<float4*>(sg)[f] = p;             // same thread, same slot: no hazard
+        }
+        // 3. packed copy of the updated texels
+        if (a.rgba) {
+            __syncthreads();
+            float4* o4 = reinterpret_cast<float4*>(a.rgba) + t0;
+#pragma unroll
+            for (int k = 0; k < TEXGS_ADAM_TEXELS / TEXGS_ADAM_THREADS; ++k) {
+                const int t = tid + k * TEXGS_ADAM_THREADS;
+                o4[t] = make_float4(sg[3 * t], sg[3 * t + 1], sg[3 * t + 2], 0.f);
+            }
+        }
+    } else {
+        // tail tile (n % 1024 texels): scalar, no alignment assumptions beyond 4 bytes
+        for (unsigned long long t = t0 + tid; t < a.n; t += TEXGS_ADAM_THREADS) {
+            float o[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const unsigned long long e = t * 3 + c;
+                const float g = a.g4 ? a.g4[t * 4 + c] : a.g3[e];
+                float p = a.p[e], m = a.m[e], v = a.v[e];
+                adam_elem(p, m, v, g, a);
+                a.p[e] = p; a.m[e] = m; a.v[e] = v;
+                o[c] = p;
+                if (a.zero_grad) { if (a.g4) a.g4[t * 4 + c] = 0.f; else const_cast<float*>(a.g3)[e] = 0.f; }
+            }
+            if (a.zero_grad && a.g4) a.g4[t * 4 + 3] = 0.f;
+            if (a.rgba) reinterpret_cast<float4*>(a.rgba)[t] = make_float4(o[0], o[1], o[2], 0.f);
+        }
+    }
+}

@@ -127,6 +127,28 @@ def _packed_texture(lib, texture_arg: torch.Tensor, tex: torch.Tensor, stream: i
     return tex4
 
 
+def packed_texture_buffer(texture: torch.Tensor) -> torch.Tensor:
+    """A (6,R,R,4) buffer for the packed copy of ``texture`` — the cached one if there is one (its content is about
+    to be replaced by the caller, see ``adopt_packed_texture``), else a new one."""
+    hit = _packed_cache.get(id(texture))
+    if hit is not None and hit[0]() is texture and hit[2] == texture.data_ptr() and hit[3].device == texture.device:
+        return hit[3]
+    return torch.empty(texture.shape[0], texture.shape[1], texture.shape[2], 4, device=texture.device, dtype=torch.float32)
+
+
+def adopt_packed_texture(texture: torch.Tensor, tex4: torch.Tensor) -> None:
+    """Register ``tex4`` as the packed copy of ``texture`` at its CURRENT version (texture_gs_b200.optim.TextureAdam
+    writes it in the same kernel as the parameter update, so the next forward skips the repack)."""
+    key = id(texture)
+    try:
+        ref = weakref.ref(texture, lambda _r, k=key: _packed_cache.pop(k, None))
+    except TypeError:
+        return
+    if len(_packed_cache) > 8 and key not in _packed_cache:
+        _packed_cache.clear()
+    _packed_cache[key] = (ref, texture._version, texture.data_ptr(), tex4)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
