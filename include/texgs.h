@@ -219,7 +219,7 @@ int texgs_geometry_loss_backward(const float* alpha, const float* norm, const fl
  * (optional) receives the packed (n,4) copy of the UPDATED parameter (= texgs_pack_texture of it).
  * ``step`` is the 1-based step count. All buffers 16-byte aligned device memory. */
 int texgs_texture_adam_step(float* param, float* exp_avg, float* exp_avg_sq, const float* grad3, float* grad_rgba,
-                            float* param_rgba, uint64_t n_texels, float lr, float beta1, float beta2, float eps,
+                            float* param_rgba, uint64_t n_texels, double lr, double beta1, double beta2, double eps,
                             int32_t step, int32_t zero_grad, void* stream);
 
 /* Frustum test only (upstream ``GaussianRasterizer.markVisible`` [EXT]; unused in the reference

@@ -40,8 +40,8 @@ def test_matches_torch_adam_over_several_steps(R):
         assert float((p_new - p_ref).abs().max()) <= 2e-6 * float(p_ref.abs().max()), i
     sr, sn = ref.state[p_ref], new.state[p_new]
     assert float(sn["step"]) == float(sr["step"]) == 6.0
-    assert float((sn["exp_avg"] - sr["exp_avg"]).abs().max()) <= 1e-6 * float(sr["exp_avg"].abs().max())
-    assert float((sn["exp_avg_sq"] - sr["exp_avg_sq"]).abs().max()) <= 1e-6 * float(sr["exp_avg_sq"].abs().max())
+    assert float((sn["exp_avg"] - sr["exp_avg"]).abs().max()) <= 2e-6 * float(sr["exp_avg"].abs().max())
+    assert float((sn["exp_avg_sq"] - sr["exp_avg_sq"]).abs().max()) <= 2e-6 * float(sr["exp_avg_sq"].abs().max())
 
 
 def test_state_dicts_interchange_with_torch_adam():

@@ -85,7 +85,7 @@ SYMBOLS = {
     "texgs_geometry_loss_workspace_size": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "texgs_geometry_loss_forward": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_float, _fp, _fp, C.c_void_p]),
     "texgs_geometry_loss_backward": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_float, _fp, _fp, _fp, _fp, C.c_void_p]),
-    "texgs_texture_adam_step": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_uint64, C.c_float, C.c_float, C.c_float, C.c_float,
+    "texgs_texture_adam_step": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double,
                                           C.c_int32, C.c_int32, C.c_void_p]),
     "texgs_mark_visible": (C.c_int, [C.c_int32, _fp, C.POINTER(C.c_float), C.POINTER(C.c_float), _fp, C.c_void_p]),
 }

@@ -424,21 +424,21 @@ int texgs_geometry_loss_backward(const float* alpha, const float* norm, const fl
 }
 
 int texgs_texture_adam_step(float* param, float* exp_avg, float* exp_avg_sq, const float* grad3, float* grad_rgba, float* param_rgba,
-                            uint64_t n_texels, float lr, float beta1, float beta2, float eps, int32_t step, int32_t zero_grad,
+                            uint64_t n_texels, double lr, double beta1, double beta2, double eps, int32_t step, int32_t zero_grad,
                             void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!param || !exp_avg || !exp_avg_sq || (grad3 == nullptr) == (grad_rgba == nullptr) || step < 1 ||
-        !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f))
+        !(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0))
         return fail(TEXGS_E_INVALID, "bad arguments (exactly one of grad3 / grad_rgba, step >= 1, betas in [0,1))");
     if (n_texels == 0) return 0;
     if (((uintptr_t)param | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq | (uintptr_t)grad3 | (uintptr_t)grad_rgba | (uintptr_t)param_rgba) & 15)
         return fail(TEXGS_E_INVALID, "all buffers must be 16-byte aligned");
     AdamArgs a;
     a.p = param; a.m = exp_avg; a.v = exp_avg_sq; a.g3 = grad3; a.g4 = grad_rgba; a.rgba = param_rgba; a.n = n_texels;
-    // bias corrections in double on the host, as torch.optim.Adam's scalar path does
-    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-    a.one_minus_b1 = 1.0f - beta1; a.b2 = beta2; a.one_minus_b2 = 1.0f - beta2;
-    a.step_size = (float)((double)lr / bc1); a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2)); a.eps = eps;
+    // scalars formed in double on the host and rounded once, as torch.optim.Adam's scalar path does
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    a.one_minus_b1 = (float)(1.0 - beta1); a.b2 = (float)beta2; a.one_minus_b2 = (float)(1.0 - beta2);
+    a.step_size = (float)(lr / bc1); a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2)); a.eps = (float)eps;
     a.zero_grad = zero_grad;
     const uint64_t ctas = (n_texels + TEXGS_ADAM_TEXELS - 1) / TEXGS_ADAM_TEXELS;
     if (ctas > 0x7fffffffull) return fail(TEXGS_E_INVALID, "tensor too large");
