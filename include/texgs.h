@@ -222,6 +222,34 @@ int texgs_texture_adam_step(float* param, float* exp_avg, float* exp_avg_sq, con
                             float* param_rgba, uint64_t n_texels, double lr, double beta1, double beta2, double eps,
                             int32_t step, int32_t zero_grad, void* stream);
 
+/* ---- UV + Jacobian producer --------------------------------------------------------------
+ * uv = normalize(mlp(relu(pre_mlp((xyz - offset) / scale) + emb)))   (models/modules/uv_net.py:19-36) and
+ * J[n, 3i+j] = d uv_i / d xyz_j  (TextureGaussian3D.get_grad_uvs, models/texture_gaussian3d.py:217-227) in ONE
+ * kernel: value + three forward-mode tangents per point are four rows of the same tcgen05 GEMMs.
+ * Network of configs/texture_gaussian3d.yaml:18-27: 3 -> 128 -ReLU-> 128 (+emb, ReLU) -> 128 -ReLU-> 128 -ReLU-> 3.
+ * Hidden weights W2..W4 (128,128) and W5 (3,128) are fp16 [out][in] row-major, W1 (128,3) fp32; biases fp32 or
+ * NULL (tiny-cuda-nn has none, the nn.Linear fallback models/modules/utils.py:44-55 has). Compute: fp16 operands,
+ * fp32 accumulation (the reference's tcnn path is fp16 too). ``stash[k]`` (optional, fp16 (N,128)) receives the
+ * post-activation inputs of layers 2..5 for a backward pass. All pointers device memory, 16-byte aligned. */
+typedef struct TexgsUvMlpArgs {
+    int32_t N;
+    const float* xyz;
+    float offset[3];
+    float inv_scale[3];
+    const float* W1;
+    const float* b1;
+    const void* W_hidden[3];      /* fp16 */
+    const float* b_hidden[3];
+    const float* emb;
+    const void* W5;               /* fp16 */
+    const float* b5;
+    float* uv;                    /* (N,3) */
+    float* jacobian;              /* (N,9) or NULL */
+    void* stash[4];               /* fp16 (N,128) each, or NULL */
+    float* debug_accumulators;    /* NULL, or [4*128*128 + 128*16] floats: raw accumulators of the first tile */
+} TexgsUvMlpArgs;
+int texgs_uvmlp_forward(const TexgsUvMlpArgs* a, void* stream);
+
 /* Frustum test only (upstream ``GaussianRasterizer.markVisible`` [EXT]; unused in the reference
  * tree). present (P,) int32: 1 if the Gaussian passes the near-plane cull. */
 int texgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix16_host,

@@ -9,6 +9,7 @@
 #include "texgs_common.cuh"
 #include "texgs_loss.cuh"
 #include "texgs_optim.cuh"
+#include "texgs_uvmlp.cuh"
 #include "texgs_preprocess.cuh"
 #include "texgs_render.cuh"
 
@@ -180,7 +181,7 @@ const char* texgs_kernel_names(void) {
     return "texgs_preprocess_fwd,texgs_scan_tiles,texgs_scatter_pairs,texgs_sort_tiles_small,texgs_sort_tiles,texgs_render_fwd,"
            "texgs_render_bwd,texgs_preprocess_bwd,texgs_mark_visible_kernel,texgs_pack_texture_kernel,"
            "texgs_photometric_fwd_kernel,texgs_photometric_finalize_kernel,texgs_photometric_bwd_kernel,"
-           "texgs_geometry_loss_fwd_kernel,texgs_geometry_loss_finalize_kernel,texgs_geometry_loss_bwd_kernel,texgs_texture_adam_kernel";
+           "texgs_geometry_loss_fwd_kernel,texgs_geometry_loss_finalize_kernel,texgs_geometry_loss_bwd_kernel,texgs_texture_adam_kernel,texgs_uvmlp_fwd_kernel";
 }
 
 int texgs_workspace_sizes(const TexgsFwdArgs* a, uint64_t pair_capacity, size_t* geom_bytes, size_t* bin_bytes,
@@ -444,6 +445,40 @@ int texgs_texture_adam_step(float* param, float* exp_avg, float* exp_avg_sq, con
     if (ctas > 0x7fffffffull) return fail(TEXGS_E_INVALID, "tensor too large");
     texgs_texture_adam_kernel<<<(unsigned)ctas, TEXGS_ADAM_THREADS, 0, stream>>>(a);
     TEXGS_KERNEL_CHECK("texgs_texture_adam_kernel", false, stream);
+    return 0;
+}
+
+int texgs_uvmlp_forward(const TexgsUvMlpArgs* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!a || a->N < 0) return fail(TEXGS_E_INVALID, "bad arguments");
+    if (a->N == 0) return 0;
+    if (!a->xyz || !a->W1 || !a->W_hidden[0] || !a->W_hidden[1] || !a->W_hidden[2] || !a->emb || !a->W5 || !a->uv)
+        return fail(TEXGS_E_INVALID, "xyz, W1, W_hidden[0..2], emb, W5 and uv are required");
+    uintptr_t al = (uintptr_t)a->W_hidden[0] | (uintptr_t)a->W_hidden[1] | (uintptr_t)a->W_hidden[2] | (uintptr_t)a->W5;
+    for (int i = 0; i < 4; ++i) al |= (uintptr_t)a->stash[i];
+    if (al & 15) return fail(TEXGS_E_INVALID, "fp16 weight / stash buffers must be 16-byte aligned");
+    UvMlpParams P;
+    P.N = a->N; P.xyz = a->xyz;
+    for (int i = 0; i < 3; ++i) {
+        P.off[i] = a->offset[i]; P.inv_scale[i] = a->inv_scale[i];
+        P.W[i] = (const __half*)a->W_hidden[i]; P.b[i] = a->b_hidden[i];
+    }
+    P.W1 = a->W1; P.b1 = a->b1; P.emb = a->emb; P.W5 = (const __half*)a->W5; P.b5 = a->b5;
+    P.uv = a->uv; P.J = a->jacobian;
+    for (int i = 0; i < 4; ++i) P.stash[i] = (__half*)a->stash[i];
+    P.dbg = a->debug_accumulators;
+    static thread_local int attr_set_for_device = -1;
+    int dev = 0, sms = 0;
+    TEXGS_CUDA_TRY(cudaGetDevice(&dev));
+    if (attr_set_for_device != dev) {
+        TEXGS_CUDA_TRY(cudaFuncSetAttribute(texgs_uvmlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UvMlpSmem::TOTAL));
+        attr_set_for_device = dev;
+    }
+    TEXGS_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int ntiles = (a->N + UVMLP_TILE - 1) / UVMLP_TILE;
+    const int ctas = std::max(1, std::min(sms, (ntiles + UVMLP_GROUPS - 1) / UVMLP_GROUPS));
+    texgs_uvmlp_fwd_kernel<<<ctas, UVMLP_THREADS, UvMlpSmem::TOTAL, stream>>>(P);
+    TEXGS_KERNEL_CHECK("texgs_uvmlp_fwd_kernel", false, stream);
     return 0;
 }
 

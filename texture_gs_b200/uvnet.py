@@ -1,0 +1,154 @@
+"""SURVEY §8f N1 — the UV + Jacobian producer of the training step, one kernel.
+
+The reference evaluates ``uv = uv_net(xyz, geo_emb)`` (``TextureGaussian3D.get_uvs``,
+``models/texture_gaussian3d.py:230-236``; network ``models/modules/uv_net.py:8-36``) and then
+``grad_uvs = jacobian(lambda x: uv_net(x, emb).sum(0), xyz)`` (``get_grad_uvs``, ``:217-227``): one forward and three
+backward passes through the MLP every iteration. ``FusedUVNet.uv_and_jacobian`` returns both from a single tcgen05
+kernel (value + three forward-mode tangents per point are four rows of the same GEMMs; fp16 operands, fp32
+accumulation — the reference's tiny-cuda-nn path computes in fp16 as well).
+
+``FusedUVNet`` keeps its parameters in the layout of the reference's ``nn.Linear`` networks
+(``models/modules/utils.py:44-55``; ``state_dict`` keys ``pre_mlp.{0,2}``, ``mlp.{0,2,4}``), with ``bias=False``
+for tiny-cuda-nn-style networks. ``uv`` is differentiable w.r.t. ``xyz``, ``emb`` and all parameters (backward =
+plain fp16 GEMMs on the activations the kernel stashed); ``grad_uvs`` carries no gradient, as in the reference
+(``:227``). No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import _lib as L
+
+HIDDEN = 128
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32(t, dev):
+    return None if t is None else t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+class _UvMlp(torch.autograd.Function):
+    """inputs: xyz, emb, W1, b1, W2, b2, W3, b3, W4, b4, W5, b5 (biases may be None), offset, inv_scale (3 floats each)."""
+
+    @staticmethod
+    def forward(ctx, xyz, emb, W1, b1, W2, b2, W3, b3, W4, b4, W5, b5, offset, inv_scale, debug):
+        lib = L.load()
+        if not xyz.is_cuda:
+            raise L.TexgsError("FusedUVNet runs on CUDA tensors only (no CPU fallback); got " + str(xyz.device))
+        if xyz.dim() != 2 or xyz.shape[1] != 3:
+            raise L.TexgsError(f"xyz must be (N,3), got {tuple(xyz.shape)}")
+        for name, w, shape in (("W1", W1, (HIDDEN, 3)), ("W2", W2, (HIDDEN, HIDDEN)), ("W3", W3, (HIDDEN, HIDDEN)),
+                               ("W4", W4, (HIDDEN, HIDDEN)), ("W5", W5, (3, HIDDEN)), ("emb", emb, (HIDDEN,))):
+            if tuple(w.shape) != shape:
+                raise L.TexgsError(f"{name} must be {shape}, got {tuple(w.shape)} (the kernel is built for the 128-wide network "
+                                   "of configs/texture_gaussian3d.yaml:18-27)")
+        dev = xyz.device
+        N = xyz.shape[0]
+        x = _f32(xyz, dev)
+        w1, e = _f32(W1, dev), _f32(emb, dev)
+        wh = [w.detach().to(device=dev, dtype=torch.float16).contiguous() for w in (W2, W3, W4, W5)]
+        bs = [_f32(b, dev) for b in (b1, b2, b3, b4, b5)]
+        need_grad = any(ctx.needs_input_grad[:12])
+        uv = torch.empty(N, 3, device=dev, dtype=torch.float32)
+        jac = torch.empty(N, 9, device=dev, dtype=torch.float32)
+        stash = [torch.empty(N, HIDDEN, device=dev, dtype=torch.float16) for _ in range(4)] if need_grad else [None] * 4
+        dbg = torch.zeros(4 * 128 * 128 + 128 * 16, device=dev, dtype=torch.float32) if debug else None
+        a = L.TexgsUvMlpArgs()
+        a.N = N
+        a.xyz = _p(x)
+        a.offset = (C.c_float * 3)(*[float(v) for v in offset])
+        a.inv_scale = (C.c_float * 3)(*[float(v) for v in inv_scale])
+        a.W1, a.b1 = _p(w1), _p(bs[0])
+        a.W_hidden = (C.c_void_p * 3)(*[w.data_ptr() for w in wh[:3]])
+        a.b_hidden = (C.c_void_p * 3)(*[(b.data_ptr() if b is not None else None) for b in bs[1:4]])
+        a.emb = _p(e)
+        a.W5, a.b5 = _p(wh[3]), _p(bs[4])
+        a.uv, a.jacobian = _p(uv), _p(jac)
+        a.stash = (C.c_void_p * 4)(*[(s.data_ptr() if s is not None else None) for s in stash])
+        a.debug_accumulators = _p(dbg)
+        if N > 0:
+            with torch.cuda.device(dev):
+                L.check(lib.texgs_uvmlp_forward(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "texgs_uvmlp_forward")
+        ctx.offset, ctx.inv_scale = [float(v) for v in offset], [float(v) for v in inv_scale]
+        ctx.has_bias = [b is not None for b in (b1, b2, b3, b4, b5)]
+        ctx.save_for_backward(x, w1, *wh, bs[4], uv, *[s for s in stash if s is not None])
+        ctx.mark_non_differentiable(jac)
+        if debug:
+            _UvMlp.last_debug = dbg
+        return uv, jac
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_uv, _g_jac):
+        """Plain GEMMs (cuBLAS through torch.mm) on the fp16 activations the forward kernel stashed: fp16 operands,
+        fp32 outputs for the weight gradients. The back-propagated signal is kept in fp16 under one power-of-two scale
+        chosen on the device from max|d loss/d out| (no host sync), as mixed-precision training does."""
+        saved = ctx.saved_tensors
+        x, w1, w2h, w3h, w4h, w5h, b5, uv = saved[:8]
+        a1, a2, a3, a4 = saved[8:12]
+        need = ctx.needs_input_grad
+        dev = x.device
+        f32, f16 = torch.float32, torch.float16
+        off = torch.tensor(ctx.offset, device=dev)
+        isc = torch.tensor(ctx.inv_scale, device=dev)
+        g_uv = g_uv.to(f32)
+        out = torch.mm(a4, w5h.T, out_dtype=f32)                               # recompute the pre-normalisation output
+        if b5 is not None:
+            out = out + b5
+        inv_len = 1.0 / out.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+        d = (g_uv - uv * (uv * g_uv).sum(-1, keepdim=True)) * inv_len           # d loss / d out  (N,3) fp32
+        scale = torch.exp2(torch.floor(torch.log2(256.0 / d.abs().max().clamp_min(1e-30))))
+        inv = 1.0 / scale
+        d16 = (d * scale).to(f16)
+        gW5, gb5 = torch.mm(d16.T, a4, out_dtype=f32) * inv, d.sum(0)
+        d16 = torch.mm(d16, w5h) * (a4 > 0)
+        gW4, gb4 = torch.mm(d16.T, a3, out_dtype=f32) * inv, d16.sum(0, dtype=f32) * inv
+        d16 = torch.mm(d16, w4h) * (a3 > 0)
+        gW3, gb3 = torch.mm(d16.T, a2, out_dtype=f32) * inv, d16.sum(0, dtype=f32) * inv
+        d16 = torch.mm(d16, w3h) * (a2 > 0)
+        gemb = d16.sum(0, dtype=f32) * inv
+        gW2 = torch.mm(d16.T, a1, out_dtype=f32) * inv
+        d16 = torch.mm(d16, w2h) * (a1 > 0)
+        xs16 = ((x - off) * isc).to(f16)
+        gW1, gb1 = torch.mm(d16.T, xs16, out_dtype=f32) * inv, d16.sum(0, dtype=f32) * inv
+        gx = torch.mm(d16, w1.to(f16), out_dtype=f32) * (isc * inv) if need[0] else None
+        hb = ctx.has_bias
+        return (gx, gemb, gW1, gb1 if hb[0] else None, gW2, gemb if hb[1] else None, gW3, gb3 if hb[2] else None,
+                gW4, gb4 if hb[3] else None, gW5, gb5 if hb[4] else None, None, None, None)
+
+
+class FusedUVNet(nn.Module):
+    """Drop-in for the reference's ``UVNet`` (``models/modules/uv_net.py:8-36``) with the 128-wide configuration of
+    ``configs/texture_gaussian3d.yaml:18-27``. ``forward(xyz, emb)`` returns uv like the reference;
+    ``uv_and_jacobian(xyz, emb)`` returns ``(uv, grad_uvs)`` — what ``get_uvs`` and ``get_grad_uvs`` return."""
+
+    def __init__(self, bias: bool = True, xyz_offset: Optional[Sequence[float]] = None, xyz_scale: Optional[Sequence[float]] = None):
+        super().__init__()
+        self.pre_mlp = nn.Sequential(nn.Linear(3, HIDDEN, bias=bias), nn.ReLU(), nn.Linear(HIDDEN, HIDDEN, bias=bias))
+        self.mlp = nn.Sequential(nn.Linear(HIDDEN, HIDDEN, bias=bias), nn.ReLU(), nn.Linear(HIDDEN, HIDDEN, bias=bias), nn.ReLU(),
+                                 nn.Linear(HIDDEN, 3, bias=bias))
+        if (xyz_offset is None) != (xyz_scale is None):
+            raise ValueError("xyz_offset and xyz_scale come together (models/modules/uv_net.py:22-25)")
+        self.xyz_offset = None if xyz_offset is None else [float(v) for v in xyz_offset]
+        self.xyz_scale = None if xyz_scale is None else [float(v) for v in xyz_scale]
+
+    def _call(self, xyz, emb, debug=None):
+        off = self.xyz_offset or [0.0, 0.0, 0.0]
+        isc = [1.0 / v for v in self.xyz_scale] if self.xyz_scale else [1.0, 1.0, 1.0]
+        l = (self.pre_mlp[0], self.pre_mlp[2], self.mlp[0], self.mlp[2], self.mlp[4])
+        return _UvMlp.apply(xyz, emb, l[0].weight, l[0].bias, l[1].weight, l[1].bias, l[2].weight, l[2].bias, l[3].weight, l[3].bias,
+                            l[4].weight, l[4].bias, off, isc, debug)
+
+    def forward(self, xyz: torch.Tensor, emb: torch.Tensor) -> torch.Tensor:
+        return self._call(xyz, emb)[0]
+
+    def uv_and_jacobian(self, xyz: torch.Tensor, emb: torch.Tensor):
+        """``(uv (N,3), grad_uvs (N,9))``; ``grad_uvs[n, 3i+j] = d uv_i / d xyz_j``, no gradient (reference ``:227``)."""
+        return self._call(xyz, emb)
