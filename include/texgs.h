@@ -246,9 +246,25 @@ typedef struct TexgsUvMlpArgs {
     float* uv;                    /* (N,3) */
     float* jacobian;              /* (N,9) or NULL */
     void* stash[4];               /* fp16 (N,128) each, or NULL */
+    float* stash_inv_len;         /* (N) 1/max(|mlp output|, 1e-12), or NULL */
     float* debug_accumulators;    /* NULL, or [4*128*128 + 128*16] floats: raw accumulators of the first tile */
 } TexgsUvMlpArgs;
 int texgs_uvmlp_forward(const TexgsUvMlpArgs* a, void* stream);
+
+/* Backward of uv w.r.t. xyz / emb / weights: the 128x128 products per hidden layer (delta @ W, delta^T @ a) are plain
+ * GEMMs the host issues through cuBLAS on the fp16 stash; these three streaming kernels are the glue around them.
+ * ``delta`` tensors are fp16 (N,128) under one power-of-two loss scale S chosen on the device from max|d loss/d out|.
+ *   head: from g_uv (N,3) and the stash (uv, inv_len, a4) and W5 (3,128 fp16): delta4 (out), scale (out, 1 float),
+ *         gW5 (3,128) += , gb5 (3) += (both UNscaled), colsum (128) += column sums of delta4 (scaled).
+ *         ``amax_scratch`` is 1 float of device scratch.
+ *   mask: delta <- delta * (a > 0) in place, colsum (128) += its column sums (scaled).
+ *   tail: gxyz (N,3) = delta1 @ W1 * inv_scale / S (may be NULL), gW1 (128,3) += delta1^T x' / S.
+ * Accumulated outputs must be zero-initialised by the caller. */
+int texgs_uvmlp_backward_head(int32_t N, const float* g_uv, const float* uv, const float* inv_len, const void* a4, const void* W5,
+                              float* amax_scratch, float* scale, void* delta4, float* gW5, float* gb5, float* colsum, void* stream);
+int texgs_uvmlp_backward_mask(int32_t N, void* delta, const void* a, float* colsum, void* stream);
+int texgs_uvmlp_backward_tail(int32_t N, const void* delta1, const float* xyz, const float* offset3_host, const float* inv_scale3_host,
+                              const float* W1, const float* scale, float* gxyz, float* gW1, void* stream);
 
 /* Frustum test only (upstream ``GaussianRasterizer.markVisible`` [EXT]; unused in the reference
  * tree). present (P,) int32: 1 if the Gaussian passes the near-plane cull. */

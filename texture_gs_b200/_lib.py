@@ -71,7 +71,7 @@ class TexgsUvMlpArgs(C.Structure):
     _fields_ = [("N", C.c_int32), ("xyz", C.c_void_p), ("offset", C.c_float * 3), ("inv_scale", C.c_float * 3),
                 ("W1", C.c_void_p), ("b1", C.c_void_p), ("W_hidden", C.c_void_p * 3), ("b_hidden", C.c_void_p * 3),
                 ("emb", C.c_void_p), ("W5", C.c_void_p), ("b5", C.c_void_p), ("uv", C.c_void_p), ("jacobian", C.c_void_p),
-                ("stash", C.c_void_p * 4), ("debug_accumulators", C.c_void_p)]
+                ("stash", C.c_void_p * 4), ("stash_inv_len", C.c_void_p), ("debug_accumulators", C.c_void_p)]
 
 
 # every symbol include/texgs.h declares: (name, restype, argtypes)
@@ -95,6 +95,9 @@ SYMBOLS = {
     "texgs_texture_adam_step": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double,
                                           C.c_int32, C.c_int32, C.c_void_p]),
     "texgs_uvmlp_forward": (C.c_int, [C.POINTER(TexgsUvMlpArgs), C.c_void_p]),
+    "texgs_uvmlp_backward_head": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "texgs_uvmlp_backward_mask": (C.c_int, [C.c_int32, _fp, _fp, _fp, C.c_void_p]),
+    "texgs_uvmlp_backward_tail": (C.c_int, [C.c_int32, _fp, _fp, C.POINTER(C.c_float), C.POINTER(C.c_float), _fp, _fp, _fp, _fp, C.c_void_p]),
     "texgs_mark_visible": (C.c_int, [C.c_int32, _fp, C.POINTER(C.c_float), C.POINTER(C.c_float), _fp, C.c_void_p]),
 }
 

@@ -181,7 +181,8 @@ const char* texgs_kernel_names(void) {
     return "texgs_preprocess_fwd,texgs_scan_tiles,texgs_scatter_pairs,texgs_sort_tiles_small,texgs_sort_tiles,texgs_render_fwd,"
            "texgs_render_bwd,texgs_preprocess_bwd,texgs_mark_visible_kernel,texgs_pack_texture_kernel,"
            "texgs_photometric_fwd_kernel,texgs_photometric_finalize_kernel,texgs_photometric_bwd_kernel,"
-           "texgs_geometry_loss_fwd_kernel,texgs_geometry_loss_finalize_kernel,texgs_geometry_loss_bwd_kernel,texgs_texture_adam_kernel,texgs_uvmlp_fwd_kernel";
+           "texgs_geometry_loss_fwd_kernel,texgs_geometry_loss_finalize_kernel,texgs_geometry_loss_bwd_kernel,texgs_texture_adam_kernel,texgs_uvmlp_fwd_kernel,"
+           "texgs_uvmlp_bwd_amax_kernel,texgs_uvmlp_bwd_head_kernel,texgs_uvmlp_bwd_mask_kernel,texgs_uvmlp_bwd_tail_kernel";
 }
 
 int texgs_workspace_sizes(const TexgsFwdArgs* a, uint64_t pair_capacity, size_t* geom_bytes, size_t* bin_bytes,
@@ -466,6 +467,7 @@ int texgs_uvmlp_forward(const TexgsUvMlpArgs* a, void* stream_) {
     P.W1 = a->W1; P.b1 = a->b1; P.emb = a->emb; P.W5 = (const __half*)a->W5; P.b5 = a->b5;
     P.uv = a->uv; P.J = a->jacobian;
     for (int i = 0; i < 4; ++i) P.stash[i] = (__half*)a->stash[i];
+    P.stash_inv_len = a->stash_inv_len;
     P.dbg = a->debug_accumulators;
     static thread_local int attr_set_for_device = -1;
     int dev = 0, sms = 0;
@@ -479,6 +481,44 @@ int texgs_uvmlp_forward(const TexgsUvMlpArgs* a, void* stream_) {
     const int ctas = std::max(1, std::min(sms, (ntiles + UVMLP_GROUPS - 1) / UVMLP_GROUPS));
     texgs_uvmlp_fwd_kernel<<<ctas, UVMLP_THREADS, UvMlpSmem::TOTAL, stream>>>(P);
     TEXGS_KERNEL_CHECK("texgs_uvmlp_fwd_kernel", false, stream);
+    return 0;
+}
+
+static inline unsigned uvbwd_ctas(int N) { return (unsigned)((N + UVBWD_ROWS_PER_CTA - 1) / UVBWD_ROWS_PER_CTA); }
+
+int texgs_uvmlp_backward_head(int32_t N, const float* g_uv, const float* uv, const float* inv_len, const void* a4, const void* W5,
+                              float* amax_scratch, float* scale, void* delta4, float* gW5, float* gb5, float* colsum, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (N <= 0 || !g_uv || !uv || !inv_len || !a4 || !W5 || !amax_scratch || !scale || !delta4 || !gW5 || !gb5 || !colsum)
+        return fail(TEXGS_E_INVALID, "bad arguments");
+    if (((uintptr_t)a4 | (uintptr_t)W5 | (uintptr_t)delta4) & 15) return fail(TEXGS_E_INVALID, "fp16 buffers must be 16-byte aligned");
+    TEXGS_CUDA_TRY(cudaMemsetAsync(amax_scratch, 0, sizeof(float), stream));
+    texgs_uvmlp_bwd_amax_kernel<<<std::min(1184, (N + 255) / 256), 256, 0, stream>>>(N, g_uv, uv, inv_len, amax_scratch);
+    TEXGS_KERNEL_CHECK("texgs_uvmlp_bwd_amax_kernel", false, stream);
+    texgs_uvmlp_bwd_head_kernel<<<uvbwd_ctas(N), UVBWD_THREADS, 0, stream>>>(N, g_uv, uv, inv_len, (const __half*)a4, (const __half*)W5, amax_scratch,
+                                                                             scale, (__half*)delta4, gW5, gb5, colsum);
+    TEXGS_KERNEL_CHECK("texgs_uvmlp_bwd_head_kernel", false, stream);
+    return 0;
+}
+
+int texgs_uvmlp_backward_mask(int32_t N, void* delta, const void* a, float* colsum, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (N <= 0 || !delta || !a || !colsum) return fail(TEXGS_E_INVALID, "bad arguments");
+    if (((uintptr_t)delta | (uintptr_t)a) & 15) return fail(TEXGS_E_INVALID, "fp16 buffers must be 16-byte aligned");
+    texgs_uvmlp_bwd_mask_kernel<<<uvbwd_ctas(N), UVBWD_THREADS, 0, stream>>>(N, (__half*)delta, (const __half*)a, colsum);
+    TEXGS_KERNEL_CHECK("texgs_uvmlp_bwd_mask_kernel", false, stream);
+    return 0;
+}
+
+int texgs_uvmlp_backward_tail(int32_t N, const void* delta1, const float* xyz, const float* offset3_host, const float* inv_scale3_host,
+                              const float* W1, const float* scale, float* gxyz, float* gW1, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (N <= 0 || !delta1 || !xyz || !offset3_host || !inv_scale3_host || !W1 || !scale || !gW1) return fail(TEXGS_E_INVALID, "bad arguments");
+    if ((uintptr_t)delta1 & 15) return fail(TEXGS_E_INVALID, "fp16 buffers must be 16-byte aligned");
+    texgs_uvmlp_bwd_tail_kernel<<<uvbwd_ctas(N), UVBWD_THREADS, 0, stream>>>(
+        N, (const __half*)delta1, xyz, make_float3(offset3_host[0], offset3_host[1], offset3_host[2]),
+        make_float3(inv_scale3_host[0], inv_scale3_host[1], inv_scale3_host[2]), W1, scale, gxyz, gW1);
+    TEXGS_KERNEL_CHECK("texgs_uvmlp_bwd_tail_kernel", false, stream);
     return 0;
 }
 

@@ -51,6 +51,7 @@ struct UvMlpParams {
     float* uv;                    // (N,3)
     float* J;                     // (N,9) row-major d uv_i / d x_j at 3 i + j, or NULL
     __half* stash[4];             // post-activation a1..a4 (N,128) for the backward pass, or NULL
+    float* stash_inv_len;         // (N) 1 / max(|mlp output|, eps) for the backward pass, or NULL
     float* dbg;                   // debug: raw accumulators of tile 0 — [4][128][128] then [128][16]
 };
 
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(UVMLP_THREADS, 1) texgs_uvmlp_fwd_kernel(const
             const float len = sqrtf(o0 * o0 + o1 * o1 + o2 * o2);
             const float inv = 1.0f / fmaxf(len, 1e-12f);                    // F.normalize(eps=1e-12)
             sUV[lane] = make_float4(o0 * inv, o1 * inv, o2 * inv, inv);
+            if (P.stash_inv_len && valid) P.stash_inv_len[pt] = inv;
         }
         uv_group_bar(g);
         if (s != 0) {
@@ -370,4 +372,197 @@ __global__ void __launch_bounds__(UVMLP_THREADS, 1) texgs_uvmlp_fwd_kernel(const
         uv_tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_cta), "r"((uint32_t)UVMLP_TMEM_COLS) : "memory");
     }
+}
+
+// =====================================================================================================
+// Backward of uv w.r.t. xyz / emb / weights. The two 128x128 products per hidden layer (delta @ W and
+// delta^T @ a) are plain GEMMs and go to cuBLAS (host side: torch.mm on the fp16 stash); what surrounds them is
+// memory-bound glue, fused here into three streaming kernels so that every (N,128) fp16 tensor is read and
+// written once per layer:
+//   head : normalize backward + output layer (K = 3): d = (g - u (u.g)) / |out|;  gW5 += d^T a4, gb5 += sum d,
+//          delta4 = S * (d W5) * (a4 > 0) in fp16, column sums of delta4
+//   mask : delta <- delta_pre * (a > 0) in place + column sums (bias / embedding gradients)
+//   tail : input layer (K = 3): gxyz = delta1 W1 * inv_scale / S,  gW1 += delta1^T x' / S
+// S is one power of two taken from max|d| on the device (mixed-precision loss scaling, no host sync).
+// Thread layout everywhere: 16 lanes x 8 columns cover a row (one uint4 each), 16 rows per 256-thread pass.
+// =====================================================================================================
+#define UVBWD_THREADS 256
+#define UVBWD_ROWS_PER_CTA 512
+
+__device__ __forceinline__ float uv_loss_scale(float amax) { return exp2f(floorf(log2f(256.0f / fmaxf(amax, 1e-30f)))); }
+
+__device__ __forceinline__ float3 uv_norm_bwd(const float* __restrict__ g_uv, const float* __restrict__ uv, const float* __restrict__ inv_len, int n) {
+    const float g0 = g_uv[3 * n], g1 = g_uv[3 * n + 1], g2 = g_uv[3 * n + 2];
+    const float u0 = uv[3 * n], u1 = uv[3 * n + 1], u2 = uv[3 * n + 2];
+    const float dt = g0 * u0 + g1 * u1 + g2 * u2, il = inv_len[n];
+    return make_float3((g0 - u0 * dt) * il, (g1 - u1 * dt) * il, (g2 - u2 * dt) * il);
+}
+
+__global__ void __launch_bounds__(256) texgs_uvmlp_bwd_amax_kernel(int N, const float* __restrict__ g_uv, const float* __restrict__ uv,
+                                                                  const float* __restrict__ inv_len, float* __restrict__ amax) {
+    float m = 0.f;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        const float3 d = uv_norm_bwd(g_uv, uv, inv_len, n);
+        m = fmaxf(m, fmaxf(fabsf(d.x), fmaxf(fabsf(d.y), fabsf(d.z))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f && isfinite(m)) atomicMax(reinterpret_cast<int*>(amax), __float_as_int(m));   // m >= 0: int order = float order
+}
+
+// reduces per-thread column accumulators acc[NV][8] (thread = row-lane tid/16, chunk tid%16) over the CTA and adds them
+// to global dst[v][128] (v < NV)
+template <int NV>
+__device__ __forceinline__ void uvbwd_flush(float (&acc)[NV][8], float* sred /* [NV*128] */, float* const (&dst)[NV], float mul) {
+    const int tid = threadIdx.x, chunk = tid & 15;
+    for (int i = tid; i < NV * 128; i += UVBWD_THREADS) sred[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float x = acc[v][c];
+            x += __shfl_xor_sync(0xffffffffu, x, 16);                     // the warp's two row-lanes of this chunk
+            if ((tid & 31) < 16) atomicAdd(&sred[v * 128 + chunk * 8 + c], x);
+        }
+    __syncthreads();
+    for (int i = tid; i < NV * 128; i += UVBWD_THREADS) atomicAdd(&dst[i >> 7][i & 127], sred[i] * mul);
+}
+
+__device__ __forceinline__ void uv_unpack8(const uint4& h, float (&f)[8]) {
+    const __half2* p = reinterpret_cast<const __half2*>(&h);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 t = __half22float2(p[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
+}
+
+__global__ void __launch_bounds__(UVBWD_THREADS) texgs_uvmlp_bwd_head_kernel(int N, const float* __restrict__ g_uv, const float* __restrict__ uv,
+                                                                           const float* __restrict__ inv_len, const __half* __restrict__ a4,
+                                                                           const __half* __restrict__ W5, const float* __restrict__ amax,
+                                                                           float* __restrict__ scale_out, __half* __restrict__ delta,
+                                                                           float* __restrict__ gW5, float* __restrict__ gb5, float* __restrict__ colsum) {
+    __shared__ float sred[4 * 128];
+    const int tid = threadIdx.x, chunk = tid & 15, rl = tid >> 4;
+    const float S = uv_loss_scale(*amax);
+    if (blockIdx.x == 0 && tid == 0) *scale_out = S;
+    float w[3][8];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) uv_unpack8(reinterpret_cast<const uint4*>(W5 + i * 128)[chunk], w[i]);
+    float acc[4][8];          // gW5 rows 0..2, column sums of delta4
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[v][c] = 0.f;
+    float gb[3] = {0.f, 0.f, 0.f};
+    const int r0 = blockIdx.x * UVBWD_ROWS_PER_CTA;
+    for (int r = r0 + rl; r < min(N, r0 + UVBWD_ROWS_PER_CTA); r += 16) {
+        const float3 d = uv_norm_bwd(g_uv, uv, inv_len, r);
+        float a[8];
+        uv_unpack8(reinterpret_cast<const uint4*>(a4 + (size_t)r * 128)[chunk], a);
+        float o[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            acc[0][c] += d.x * a[c]; acc[1][c] += d.y * a[c]; acc[2][c] += d.z * a[c];
+            const float pre = (d.x * w[0][c] + d.y * w[1][c] + d.z * w[2][c]) * S;
+            o[c] = (a[c] > 0.f) ? pre : 0.f;
+            acc[3][c] += o[c];
+        }
+        reinterpret_cast<uint4*>(delta + (size_t)r * 128)[chunk] =
+            make_uint4(uv_pack_half2(o[0], o[1]), uv_pack_half2(o[2], o[3]), uv_pack_half2(o[4], o[5]), uv_pack_half2(o[6], o[7]));
+        if (chunk == 0) { gb[0] += d.x; gb[1] += d.y; gb[2] += d.z; }
+    }
+    float* const dst[4] = {gW5, gW5 + 128, gW5 + 256, colsum};
+    uvbwd_flush<4>(acc, sred, dst, 1.0f);
+    if (chunk == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            float x = gb[i];
+            x += __shfl_xor_sync(0xffffffffu, x, 16);
+            if ((tid & 31) == 0) atomicAdd(&gb5[i], x);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(UVBWD_THREADS) texgs_uvmlp_bwd_mask_kernel(int N, __half* __restrict__ delta, const __half* __restrict__ a,
+                                                                           float* __restrict__ colsum) {
+    __shared__ float sred[128];
+    const int tid = threadIdx.x, chunk = tid & 15, rl = tid >> 4;
+    float acc[1][8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[0][c] = 0.f;
+    const int r0 = blockIdx.x * UVBWD_ROWS_PER_CTA;
+    for (int r = r0 + rl; r < min(N, r0 + UVBWD_ROWS_PER_CTA); r += 16) {
+        uint4* dp = reinterpret_cast<uint4*>(delta + (size_t)r * 128) + chunk;
+        uint4 dv = *dp;
+        const uint4 av = reinterpret_cast<const uint4*>(a + (size_t)r * 128)[chunk];
+        const __half2 zero2 = __float2half2_rn(0.f);
+        uint32_t* dw = reinterpret_cast<uint32_t*>(&dv);
+        const uint32_t* aw = reinterpret_cast<const uint32_t*>(&av);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            dw[k] &= __hgt2_mask(*reinterpret_cast<const __half2*>(&aw[k]), zero2);
+            const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&dw[k]));
+            acc[0][2 * k] += t.x; acc[0][2 * k + 1] += t.y;
+        }
+        *dp = dv;
+    }
+    float* const dst[1] = {colsum};
+    uvbwd_flush<1>(acc, sred, dst, 1.0f);
+}
+
+__global__ void __launch_bounds__(UVBWD_THREADS) texgs_uvmlp_bwd_tail_kernel(int N, const __half* __restrict__ delta, const float* __restrict__ xyz,
+                                                                           float3 off, float3 isc, const float* __restrict__ W1,
+                                                                           const float* __restrict__ scale, float* __restrict__ gxyz,
+                                                                           float* __restrict__ gW1 /* (128,3) */) {
+    __shared__ float sred[3 * 128];
+    const int tid = threadIdx.x, chunk = tid & 15, rl = tid >> 4;
+    const float invS = 1.0f / *scale;
+    float w[8][3];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) w[c][j] = W1[(chunk * 8 + c) * 3 + j];
+    float acc[3][8];
+#pragma unroll
+    for (int v = 0; v < 3; ++v)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[v][c] = 0.f;
+    const int r0 = blockIdx.x * UVBWD_ROWS_PER_CTA;
+    // every lane of a warp runs the same number of iterations (rows r and r + 1 share a warp): shuffles are safe
+    for (int rb = r0; rb < min(N, r0 + UVBWD_ROWS_PER_CTA); rb += 16) {
+        const int r = rb + rl;
+        const bool ok = r < N;
+        float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+        if (ok) {
+            uv_unpack8(reinterpret_cast<const uint4*>(delta + (size_t)r * 128)[chunk], d);
+            x0 = (xyz[3 * r] - off.x) * isc.x; x1 = (xyz[3 * r + 1] - off.y) * isc.y; x2 = (xyz[3 * r + 2] - off.z) * isc.z;
+        }
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            g0 += d[c] * w[c][0]; g1 += d[c] * w[c][1]; g2 += d[c] * w[c][2];
+            acc[0][c] += d[c] * x0; acc[1][c] += d[c] * x1; acc[2][c] += d[c] * x2;
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {                                  // the 16 lanes of a row
+            g0 += __shfl_xor_sync(0xffffffffu, g0, o); g1 += __shfl_xor_sync(0xffffffffu, g1, o); g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+        }
+        if (gxyz && ok && chunk == 0) {
+            gxyz[3 * r] = g0 * isc.x * invS; gxyz[3 * r + 1] = g1 * isc.y * invS; gxyz[3 * r + 2] = g2 * isc.z * invS;
+        }
+    }
+    // gW1 is (128,3): column c of accumulator j -> gW1[c*3 + j]; flush through a [3][128] staging then transpose on the add
+    const int t = threadIdx.x;
+    for (int i = t; i < 3 * 128; i += UVBWD_THREADS) sred[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < 3; ++v)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float x = acc[v][c];
+            x += __shfl_xor_sync(0xffffffffu, x, 16);
+            if ((t & 31) < 16) atomicAdd(&sred[v * 128 + chunk * 8 + c], x);
+        }
+    __syncthreads();
+    for (int i = t; i < 3 * 128; i += UVBWD_THREADS) atomicAdd(&gW1[(i & 127) * 3 + (i >> 7)], sred[i] * invS);
 }

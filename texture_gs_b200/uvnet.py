@@ -59,6 +59,7 @@ class _UvMlp(torch.autograd.Function):
         uv = torch.empty(N, 3, device=dev, dtype=torch.float32)
         jac = torch.empty(N, 9, device=dev, dtype=torch.float32)
         stash = [torch.empty(N, HIDDEN, device=dev, dtype=torch.float16) for _ in range(4)] if need_grad else [None] * 4
+        inv_len = torch.empty(N, device=dev, dtype=torch.float32) if need_grad else None
         dbg = torch.zeros(4 * 128 * 128 + 128 * 16, device=dev, dtype=torch.float32) if debug else None
         a = L.TexgsUvMlpArgs()
         a.N = N
@@ -72,13 +73,15 @@ class _UvMlp(torch.autograd.Function):
         a.W5, a.b5 = _p(wh[3]), _p(bs[4])
         a.uv, a.jacobian = _p(uv), _p(jac)
         a.stash = (C.c_void_p * 4)(*[(s.data_ptr() if s is not None else None) for s in stash])
+        a.stash_inv_len = _p(inv_len)
         a.debug_accumulators = _p(dbg)
         if N > 0:
             with torch.cuda.device(dev):
                 L.check(lib.texgs_uvmlp_forward(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "texgs_uvmlp_forward")
         ctx.offset, ctx.inv_scale = [float(v) for v in offset], [float(v) for v in inv_scale]
         ctx.has_bias = [b is not None for b in (b1, b2, b3, b4, b5)]
-        ctx.save_for_backward(x, w1, *wh, bs[4], uv, *[s for s in stash if s is not None])
+        if need_grad:
+            ctx.save_for_backward(x, w1, *wh, uv, inv_len, *stash)
         ctx.mark_non_differentiable(jac)
         if debug:
             _UvMlp.last_debug = dbg
@@ -87,38 +90,48 @@ class _UvMlp(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_uv, _g_jac):
-        """Plain GEMMs (cuBLAS through torch.mm) on the fp16 activations the forward kernel stashed: fp16 operands,
-        fp32 outputs for the weight gradients. The back-propagated signal is kept in fp16 under one power-of-two scale
-        chosen on the device from max|d loss/d out| (no host sync), as mixed-precision training does."""
+        """Per hidden layer two plain GEMMs (delta @ W and delta^T @ a: cuBLAS through torch.mm, fp16 operands on the
+        stash the forward kernel wrote, fp32 weight gradients) plus one streaming glue kernel of ours (ReLU mask + bias /
+        embedding column sums); the K = 3 input and output layers and the normalisation are handled entirely by the
+        ``head`` / ``tail`` kernels. The back-propagated signal stays in fp16 under one power-of-two scale chosen on
+        the device from max|d loss / d out| (no host sync), as mixed-precision training does."""
+        lib = L.load()
         saved = ctx.saved_tensors
-        x, w1, w2h, w3h, w4h, w5h, b5, uv = saved[:8]
-        a1, a2, a3, a4 = saved[8:12]
+        x, w1, w2h, w3h, w4h, w5h, uv, inv_len, a1, a2, a3, a4 = saved
         need = ctx.needs_input_grad
         dev = x.device
+        N = x.shape[0]
         f32, f16 = torch.float32, torch.float16
-        off = torch.tensor(ctx.offset, device=dev)
-        isc = torch.tensor(ctx.inv_scale, device=dev)
-        g_uv = g_uv.to(f32)
-        out = torch.mm(a4, w5h.T, out_dtype=f32)                               # recompute the pre-normalisation output
-        if b5 is not None:
-            out = out + b5
-        inv_len = 1.0 / out.norm(dim=-1, keepdim=True).clamp_min(1e-12)
-        d = (g_uv - uv * (uv * g_uv).sum(-1, keepdim=True)) * inv_len           # d loss / d out  (N,3) fp32
-        scale = torch.exp2(torch.floor(torch.log2(256.0 / d.abs().max().clamp_min(1e-30))))
-        inv = 1.0 / scale
-        d16 = (d * scale).to(f16)
-        gW5, gb5 = torch.mm(d16.T, a4, out_dtype=f32) * inv, d.sum(0)
-        d16 = torch.mm(d16, w5h) * (a4 > 0)
-        gW4, gb4 = torch.mm(d16.T, a3, out_dtype=f32) * inv, d16.sum(0, dtype=f32) * inv
-        d16 = torch.mm(d16, w4h) * (a3 > 0)
-        gW3, gb3 = torch.mm(d16.T, a2, out_dtype=f32) * inv, d16.sum(0, dtype=f32) * inv
-        d16 = torch.mm(d16, w3h) * (a2 > 0)
-        gemb = d16.sum(0, dtype=f32) * inv
-        gW2 = torch.mm(d16.T, a1, out_dtype=f32) * inv
-        d16 = torch.mm(d16, w2h) * (a1 > 0)
-        xs16 = ((x - off) * isc).to(f16)
-        gW1, gb1 = torch.mm(d16.T, xs16, out_dtype=f32) * inv, d16.sum(0, dtype=f32) * inv
-        gx = torch.mm(d16, w1.to(f16), out_dtype=f32) * (isc * inv) if need[0] else None
+        g = g_uv.to(f32).contiguous()
+        z = lambda *shape: torch.zeros(*shape, device=dev, dtype=f32)
+        gW5, gb5, gW1 = z(3, HIDDEN), z(3), z(HIDDEN, 3)
+        cs = z(4, HIDDEN)                       # column sums of delta4..delta1 (scaled): bias / embedding gradients
+        scratch, scale = z(1), z(1)
+        d = torch.empty(N, HIDDEN, device=dev, dtype=f16)
+        gx = torch.empty(N, 3, device=dev, dtype=f32) if need[0] else None
+        if N == 0:
+            zw = z(HIDDEN, HIDDEN)
+            hb = ctx.has_bias
+            return (gx, z(HIDDEN), gW1, z(HIDDEN) if hb[0] else None, zw, z(HIDDEN) if hb[1] else None, zw.clone(), z(HIDDEN) if hb[2] else None,
+                    zw.clone(), z(HIDDEN) if hb[3] else None, gW5, gb5 if hb[4] else None, None, None, None)
+        with torch.cuda.device(dev):
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            L.check(lib.texgs_uvmlp_backward_head(N, _p(g), _p(uv), _p(inv_len), _p(a4), _p(w5h), _p(scratch), _p(scale), _p(d), _p(gW5),
+                                                  _p(gb5), _p(cs[0]), st), "texgs_uvmlp_backward_head")
+            inv = 1.0 / scale
+            gW4 = torch.mm(d.T, a3, out_dtype=f32) * inv
+            d = torch.mm(d, w4h)
+            L.check(lib.texgs_uvmlp_backward_mask(N, _p(d), _p(a3), _p(cs[1]), st), "texgs_uvmlp_backward_mask")
+            gW3 = torch.mm(d.T, a2, out_dtype=f32) * inv
+            d = torch.mm(d, w3h)
+            L.check(lib.texgs_uvmlp_backward_mask(N, _p(d), _p(a2), _p(cs[2]), st), "texgs_uvmlp_backward_mask")
+            gW2 = torch.mm(d.T, a1, out_dtype=f32) * inv
+            d = torch.mm(d, w2h)
+            L.check(lib.texgs_uvmlp_backward_mask(N, _p(d), _p(a1), _p(cs[3]), st), "texgs_uvmlp_backward_mask")
+            off3, isc3 = (C.c_float * 3)(*ctx.offset), (C.c_float * 3)(*ctx.inv_scale)
+            L.check(lib.texgs_uvmlp_backward_tail(N, _p(d), _p(x), off3, isc3, _p(w1), _p(scale), _p(gx), _p(gW1), st), "texgs_uvmlp_backward_tail")
+            cs = cs * inv
+        gb4, gb3, gemb, gb1 = cs[0], cs[1], cs[2], cs[3]
         hb = ctx.has_bias
         return (gx, gemb, gW1, gb1 if hb[0] else None, gW2, gemb if hb[1] else None, gW3, gb3 if hb[2] else None,
                 gW4, gb4 if hb[3] else None, gW5, gb5 if hb[4] else None, None, None, None)
