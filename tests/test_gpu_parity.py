@@ -206,6 +206,84 @@ def test_plain_3dgs_modes_match_oracle():
             assert e <= GRAD_RTOL, (kind, name, e)
 
 
+@pytest.mark.parametrize("E,textured", [(11, True), (3, False)])
+def test_extra_attrs_forward_and_backward_match_oracle(E, textured):
+    """``extra_attrs`` (P,E) -> ``extra`` (E,H,W): blended with the weights of the main render, no background
+    (render/uv_tex_render.py:7,66; render/render.py:8,84). Gradients reach extra_attrs and, through the alpha chain,
+    opacity / 2-D mean / covariance — on top of those of the four standard outputs. E = 11 spans two channel groups
+    of the kernel with a ragged tail."""
+    from oracle import raster_ref as RR
+    from util import oracle_settings
+    from texture_gs_b200 import GaussianRasterizationSettings, GaussianRasterizer
+    N, W, H, R = 2500, 112, 80, 32
+    g = sphere_shell_scene(N, R, sh_degree=2, seed=51, tex_seed=52)
+    cam = orbit_cameras(1, W, H, seed=53)[0]
+    gen = torch.Generator().manual_seed(54)
+    ex0 = torch.randn(N, E, generator=gen)
+    cols = torch.rand(N, 3, generator=gen)
+    _, aux0, _ = run_oracle(g, cam)
+    keep = (~aux0["ambiguous"]).float()
+    cot = [c * keep for c in output_cotangents(H, W, seed=55)]
+    cot_e = torch.randn(E, H, W, generator=gen) * keep
+
+    def oracle(dtype):
+        t = g.to(dtype=dtype, requires_grad=True).tensors()
+        ex = ex0.detach().clone().to(dtype).requires_grad_(True)
+        st = oracle_settings(cam, 2, dtype=dtype, bg=(0.2, 0.1, 0.3))
+        m2 = torch.zeros_like(t["xyz"], requires_grad=True)
+        if textured:
+            o = RR.rasterize(t["xyz"], m2, t["shs"], t["opacity"], t["scaling"], t["rotation"], t["uvs"], t["grad_uvs"], t["texture"], st,
+                             extra_attrs=ex)
+        else:
+            o = RR.rasterize(t["xyz"], m2, None, t["opacity"], t["scaling"], t["rotation"], None, None, None, st,
+                             colors_precomp=cols.to(dtype), extra_attrs=ex)
+        L = sum((a * b.to(dtype)).sum() for a, b in zip(o[:4], cot)) + (o[5] * cot_e.to(dtype)).sum()
+        L.backward()
+        gr = {"extra_attrs": ex.grad, "opacity": t["opacity"].grad, "xyz": t["xyz"].grad, "scaling": t["scaling"].grad,
+              "rotation": t["rotation"].grad, "means2D": m2.grad[:, :2]}
+        return [x.detach() for x in o[:4]] + [o[5].detach()], gr
+
+    ref32, g32 = oracle(torch.float32)
+    _, g64 = oracle(torch.float64)
+
+    tc = g.to("cuda", requires_grad=True).tensors()
+    exc = ex0.detach().clone().cuda().requires_grad_(True)
+    camd = cam.to("cuda")
+    stc = GaussianRasterizationSettings(H, W, math.tan(camd.FoVx / 2), math.tan(camd.FoVy / 2), torch.tensor([0.2, 0.1, 0.3], device="cuda"),
+                                        1.0, camd.world_view_transform, camd.full_proj_transform, 2, camd.camera_center, False, False)
+    m2c = torch.zeros(N, 3, device="cuda", requires_grad=True)
+    if textured:
+        oc = GaussianRasterizer(stc)(means3D=tc["xyz"], means2D=m2c, opacities=tc["opacity"], shs=tc["shs"], scales=tc["scaling"],
+                                     rotations=tc["rotation"], uvs=tc["uvs"], gradient_uvs=tc["grad_uvs"], texture=tc["texture"],
+                                     extra_attrs=exc)
+    else:
+        oc = GaussianRasterizer(stc)(means3D=tc["xyz"], means2D=m2c, opacities=tc["opacity"], colors_precomp=cols.cuda(),
+                                     scales=tc["scaling"], rotations=tc["rotation"], extra_attrs=exc)
+    assert oc[5].shape == (E, H, W)
+    Lc = sum((a * b.cuda()).sum() for a, b in zip(oc[:4], cot)) + (oc[5] * cot_e.cuda()).sum()
+    Lc.backward()
+    got = [x.detach().cpu() for x in oc[:4]] + [oc[5].detach().cpu()]
+    rep = compare_images(got, ref32, aux0["ambiguous"], names=("image", "depth", "norm", "alpha", "extra"))
+    print(rep)
+    for n in ("image", "depth", "norm", "alpha", "extra"):
+        assert rep[n]["max_clear"] <= ABS_TOL * (3.0 if n in ("depth", "extra") else 1.0), (n, rep[n])   # extras are N(0,1)-scaled
+    gc = {"extra_attrs": exc.grad, "opacity": tc["opacity"].grad, "xyz": tc["xyz"].grad, "scaling": tc["scaling"].grad,
+          "rotation": tc["rotation"].grad, "means2D": m2c.grad[:, :2]}
+    for k, r in g64.items():
+        e_c, e_o = rel_err(gc[k].cpu().reshape(r.shape), r), rel_err(g32[k].reshape(r.shape), r)
+        print(k, "%.2e %.2e" % (e_c, e_o))
+        assert e_c <= max(GRAD_RTOL, 3.0 * e_o), (k, e_c, e_o)
+    # without a cotangent on ``extra`` the standard gradients are those of a call without extra_attrs
+    tc2 = g.to("cuda", requires_grad=True).tensors()
+    if textured:
+        o2 = GaussianRasterizer(stc)(means3D=tc2["xyz"], means2D=torch.zeros(N, 3, device="cuda", requires_grad=True), opacities=tc2["opacity"],
+                                     shs=tc2["shs"], scales=tc2["scaling"], rotations=tc2["rotation"], uvs=tc2["uvs"],
+                                     gradient_uvs=tc2["grad_uvs"], texture=tc2["texture"], extra_attrs=ex0.detach().clone().cuda().requires_grad_(True))
+        assert torch.equal(o2[0], oc[0].detach())
+        sum((a * b.cuda()).sum() for a, b in zip(o2[:4], cot)).backward()
+        assert tc2["opacity"].grad is not None and rel_err(tc2["uvs"].grad.cpu(), tc["uvs"].grad.cpu()) < 1e-5
+
+
 def test_edge_cases_empty_culled_single_and_ragged_sizes():
     from texture_gs_b200 import uv_tex_render
     bg = torch.tensor([0.3, 0.5, 0.7], device="cuda")

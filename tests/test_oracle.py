@@ -222,6 +222,28 @@ def test_dual_no_sh_image_equals_a_second_render_with_degree_zero():
     assert float((a[0] - b[0]).abs().max()) > 1e-3        # the SH term does change the first image
 
 
+def test_extra_attrs_blend_with_the_same_weights_as_depth_alpha_and_colour():
+    """``extra_attrs`` (render/uv_tex_render.py:7,66): channels blended with the weights of the main render and no
+    background — ones reproduce alpha, the view depth of the centres reproduces depth, the world normal the norm
+    output, and in the plain-3DGS mode precomputed colours reproduce the image rendered over a black background."""
+    g = sphere_shell_scene(250, 8, sh_degree=0, seed=41).to(dtype=torch.float64)
+    cam = orbit_cameras(1, 48, 40, seed=42)[0]
+    t = g.tensors()
+    st = oracle_settings(cam, 0, dtype=torch.float64, bg=(0.0, 0.0, 0.0))
+    pre = RR.preprocess(t["xyz"], None, t["scaling"], t["rotation"], t["opacity"], None, st)
+    cols = torch.rand(250, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(5))
+    ex = torch.cat([torch.ones(250, 1, dtype=torch.float64), pre["depth"][:, None], pre["normal"], cols], dim=1)
+    out = RR.rasterize(t["xyz"], None, None, t["opacity"], t["scaling"], t["rotation"], None, None, None, st,
+                       colors_precomp=cols, extra_attrs=ex)
+    image, depth, norm, alpha, _, extra = out
+    assert extra.shape == (8, 40, 48)
+    assert float((extra[0:1] - alpha).abs().max()) < 1e-12
+    assert float((extra[1:2] - depth).abs().max()) < 1e-12
+    assert float((extra[2:5] - norm).abs().max()) < 1e-12
+    assert float((extra[5:8] - image).abs().max()) < 1e-12
+    assert float(alpha.max()) > 0.5
+
+
 def test_loss_oracle_matches_the_reference_code_golden_vectors():
     """oracle/loss_ref.py vs vectors generated by the reference's own losses/*.py (PINNED oracle)."""
     import numpy as np

@@ -12,6 +12,7 @@
 #include "texgs_uvmlp.cuh"
 #include "texgs_preprocess.cuh"
 #include "texgs_render.cuh"
+#include "texgs_extra.cuh"
 
 namespace {
 
@@ -87,7 +88,7 @@ int max_degree_for(int M_rest) {
 int fill_params(const TexgsFwdArgs* a, void* geom, void* bin, uint64_t cap, void* img, const Layout& L, RasterParams& p) {
     if (a->mode != TEXGS_MODE_TEXTURE && a->mode != TEXGS_MODE_SH && a->mode != TEXGS_MODE_PRECOMP)
         return fail(TEXGS_E_INVALID, "unknown mode");
-    if (a->E != 0 || a->extra_attrs) return fail(TEXGS_E_INVALID, "extra_attrs is not supported yet (the reference never passes it)");
+    if (a->E < 0 || (a->E > 0 && a->P > 0 && !a->extra_attrs)) return fail(TEXGS_E_INVALID, "E > 0 needs extra_attrs (P,E)");
     if (a->P > 0 && (!a->means3D || !a->opacities || !a->scales || !a->rotations))
         return fail(TEXGS_E_INVALID, "means3D/opacities/scales/rotations must be given");
     if (((uintptr_t)a->rotations & 15) != 0) return fail(TEXGS_E_INVALID, "rotations must be 16-byte aligned");
@@ -104,7 +105,7 @@ int fill_params(const TexgsFwdArgs* a, void* geom, void* bin, uint64_t cap, void
     if (((uintptr_t)geom & 127) || ((uintptr_t)bin & 127) || ((uintptr_t)img & 127))
         return fail(TEXGS_E_WORKSPACE, "workspaces must be 128-byte aligned");
     memset(&p, 0, sizeof(p));
-    p.P = a->P; p.M = a->shs ? a->M : 0; p.E = 0; p.H = a->H; p.W = a->W; p.R = a->R; p.mode = a->mode;
+    p.P = a->P; p.M = a->shs ? a->M : 0; p.E = a->extra_attrs ? a->E : 0; p.H = a->H; p.W = a->W; p.R = a->R; p.mode = a->mode;
     const int m_rest = (a->mode == TEXGS_MODE_SH) ? p.M - 1 : p.M;
     int deg = a->sh_degree < 0 ? 0 : a->sh_degree;
     const int dmax = max_degree_for(m_rest);
@@ -122,7 +123,7 @@ int fill_params(const TexgsFwdArgs* a, void* geom, void* bin, uint64_t cap, void
     memcpy(p.bg, a->bg, sizeof(float) * 3);
     p.means3D = a->means3D; p.shs = a->shs; p.colors_precomp = a->colors_precomp; p.opacities = a->opacities;
     p.scales = a->scales; p.rotations = a->rotations; p.uvs = a->uvs; p.gradient_uvs = a->gradient_uvs;
-    p.texture = a->texture; p.extra_attrs = nullptr;
+    p.texture = a->texture; p.extra_attrs = a->extra_attrs;
     p.texture_rgba = (a->mode == TEXGS_MODE_TEXTURE) ? reinterpret_cast<const float4*>(a->texture_rgba) : nullptr;
     if (((uintptr_t)a->texture_rgba & 15) != 0) return fail(TEXGS_E_INVALID, "texture_rgba must be 16-byte aligned");
     char* g = (char*)geom; char* b = (char*)bin; char* im = (char*)img;
@@ -179,7 +180,7 @@ const char* texgs_last_error(void) { return g_last_error.c_str(); }
 
 const char* texgs_kernel_names(void) {
     return "texgs_preprocess_fwd,texgs_scan_tiles,texgs_scatter_pairs,texgs_sort_tiles_small,texgs_sort_tiles,texgs_render_fwd,"
-           "texgs_render_bwd,texgs_preprocess_bwd,texgs_mark_visible_kernel,texgs_pack_texture_kernel,"
+           "texgs_render_bwd,texgs_extra_fwd,texgs_extra_bwd,texgs_preprocess_bwd,texgs_mark_visible_kernel,texgs_pack_texture_kernel,"
            "texgs_photometric_fwd_kernel,texgs_photometric_finalize_kernel,texgs_photometric_bwd_kernel,"
            "texgs_geometry_loss_fwd_kernel,texgs_geometry_loss_finalize_kernel,texgs_geometry_loss_bwd_kernel,texgs_texture_adam_kernel,texgs_uvmlp_fwd_kernel,"
            "texgs_uvmlp_bwd_amax_kernel,texgs_uvmlp_bwd_head_kernel,texgs_uvmlp_bwd_mask_kernel,texgs_uvmlp_bwd_tail_kernel";
@@ -206,13 +207,13 @@ int texgs_workspace_layout(const TexgsFwdArgs* a, uint64_t pair_capacity, TexgsL
 int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t pair_capacity, void* img_ws,
                   float* out_image, float* out_depth, float* out_norm, float* out_alpha, int32_t* out_radii,
                   float* out_extra, TexgsCounters* counters_host, void* counters_ready_event, void* stream_) {
-    (void)out_extra;
     cudaStream_t stream = (cudaStream_t)stream_;
     Layout L;
     if (int rc = make_layout(a, pair_capacity, L)) return rc;
     RasterParams p;
     if (int rc = fill_params(a, geom_ws, bin_ws, pair_capacity, img_ws, L, p)) return rc;
     if (!out_image || !out_depth || !out_norm || !out_alpha || (!out_radii && a->P > 0)) return fail(TEXGS_E_INVALID, "output pointer is NULL");
+    if (a->E > 0 && !out_extra) return fail(TEXGS_E_INVALID, "E > 0 needs out_extra (E,H,W)");
     const bool debug = (a->flags & TEXGS_FLAG_DEBUG) != 0;
 
     TEXGS_EV(a, TEXGS_EV_FWD_START, stream);
@@ -252,6 +253,11 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
 #undef TEXGS_LAUNCH_FWD
     }
     TEXGS_KERNEL_CHECK("texgs_render_fwd", debug, stream);
+    if (a->E > 0) {   // cold path (the reference tree never passes extra_attrs): separate list walk, see texgs_extra.cuh
+        if (p.E > 0) texgs_extra_fwd<<<p.num_tiles, 256, 0, stream>>>(p, out_extra);
+        else TEXGS_CUDA_TRY(cudaMemsetAsync(out_extra, 0, (size_t)a->E * a->H * a->W * sizeof(float), stream));   // P == 0
+        TEXGS_KERNEL_CHECK("texgs_extra_fwd", debug, stream);
+    }
     TEXGS_EV(a, TEXGS_EV_FWD_RENDER, stream);
     if (counters_host && debug) {   // debug: counters include the blend count, copied after the render
         TEXGS_CUDA_TRY(cudaMemcpyAsync(counters_host, p.counters, sizeof(TexgsCounters), cudaMemcpyDeviceToHost, stream));
@@ -301,6 +307,13 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
         texgs_render_bwd<TEXGS_MODE_SH, false, false, false><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, nullptr);
     }
     TEXGS_KERNEL_CHECK("texgs_render_bwd", debug, stream);
+    if (p.E > 0 && p.P > 0) {
+        if (b->dL_dextra_attrs) TEXGS_CUDA_TRY(cudaMemsetAsync(b->dL_dextra_attrs, 0, (size_t)p.P * p.E * sizeof(float), stream));
+        if (b->dL_dextra) {
+            texgs_extra_bwd<<<p.num_tiles, 256, 0, stream>>>(p, b->dL_dextra, b->acc_ws, b->dL_dextra_attrs);
+            TEXGS_KERNEL_CHECK("texgs_extra_bwd", debug, stream);
+        }
+    }
     TEXGS_EV(a, TEXGS_EV_BWD_RENDER, stream);
     if (p.P > 0) {
         BwdOut g{b->dL_dmeans3D, b->dL_dmeans2D, b->dL_dopacity, b->dL_dscales, b->dL_drotations,

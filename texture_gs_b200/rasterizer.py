@@ -182,12 +182,12 @@ def last_stats() -> Optional[RasterStats]:
 
 
 def _build_args(st: GaussianRasterizationSettings, mode: int, means3D, shs, colors_precomp, opacities, scales,
-                rotations, uvs, gradient_uvs, texture, profile_arr=None) -> L.TexgsFwdArgs:
+                rotations, uvs, gradient_uvs, texture, profile_arr=None, extra_attrs=None) -> L.TexgsFwdArgs:
     a = L.TexgsFwdArgs()
     a.P = means3D.shape[0]
     a.M = 0 if shs is None else shs.shape[1]
     a.sh_degree = int(st.sh_degree)
-    a.E = 0
+    a.E = 0 if extra_attrs is None else extra_attrs.shape[1]
     a.H, a.W = int(st.image_height), int(st.image_width)
     a.R = 0 if texture is None else texture.shape[1]
     a.mode = mode
@@ -206,7 +206,7 @@ def _build_args(st: GaussianRasterizationSettings, mode: int, means3D, shs, colo
     a.uvs = _ptr(uvs)
     a.gradient_uvs = _ptr(gradient_uvs)
     a.texture = _ptr(texture)
-    a.extra_attrs = None
+    a.extra_attrs = _ptr(extra_attrs)
     if profile_arr is not None:
         a.profile_events = C.cast(profile_arr, C.POINTER(C.c_void_p))
     return a
@@ -215,7 +215,7 @@ def _build_args(st: GaussianRasterizationSettings, mode: int, means3D, shs, colo
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, shs, colors_precomp, opacities, scales, rotations, uvs, gradient_uvs,
-                texture, st: GaussianRasterizationSettings, mode: int, dual: bool = False):
+                texture, st: GaussianRasterizationSettings, mode: int, dual: bool = False, extra_attrs=None):
         lib = L.load()
         if not means3D.is_cuda:
             raise L.TexgsError("the rasterizer runs on CUDA tensors only (no CPU fallback); got " + str(means3D.device))
@@ -234,12 +234,15 @@ class _RasterizeGaussians(torch.autograd.Function):
             raise L.TexgsError(f"shs must be (P,M,3), got {tuple(sh.shape)}")
         if op.numel() != P or sc.shape != (P, 3) or ro.shape != (P, 4):
             raise L.TexgsError("opacities (P,1), scales (P,3), rotations (P,4) expected")
+        ex = _prep(extra_attrs, dev)
+        if ex is not None and (ex.dim() != 2 or ex.shape[0] != P or ex.shape[1] < 1):
+            raise L.TexgsError(f"extra_attrs must be (P,E) with E >= 1, got {tuple(ex.shape)}")
 
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             from .profiling import current_event_array
             prof = current_event_array()      # captured here: backward runs on autograd's thread
-            a = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex, prof)
+            a = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex, prof, ex)
             tex4 = None
             if mode == L.MODE_TEXTURE and USE_PACKED_TEXTURE:
                 tex4 = _packed_texture(lib, texture, tex, stream)
@@ -249,6 +252,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             norm = torch.empty(3, H, W, device=dev, dtype=torch.float32)
             alpha = torch.empty(1, H, W, device=dev, dtype=torch.float32)
             radii = torch.empty(P, device=dev, dtype=torch.int32)
+            extra = torch.empty(ex.shape[1], H, W, device=dev, dtype=torch.float32) if ex is not None else image.new_empty(0)
             dual = bool(dual and mode == L.MODE_TEXTURE)
             image_nosh = torch.empty(3, H, W, device=dev, dtype=torch.float32) if dual else image.new_empty(0)
             if dual:
@@ -264,7 +268,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 imgw = torch.empty(max(is_.value, 256), device=dev, dtype=torch.uint8)
                 with _pinned_lock:
                     L.check(lib.texgs_forward(C.byref(a), _ptr(geom), _ptr(binw), cap, _ptr(imgw), _ptr(image), _ptr(depth),
-                                              _ptr(norm), _ptr(alpha), _ptr(radii), None,
+                                              _ptr(norm), _ptr(alpha), _ptr(radii), _ptr(extra) if ex is not None else None,
                                               C.c_void_p(pinned.data_ptr()), C.c_void_p(event.cuda_event), C.c_void_p(stream)),
                             "texgs_forward")
                     # waits only until the tile scan is done (early in the stream), not for the render
@@ -295,25 +299,27 @@ class _RasterizeGaussians(torch.autograd.Function):
                             ctx.fuse[name] = tgt[0]
         ctx.dev = dev
         ctx.has = (shs is not None, colors_precomp is not None, uvs is not None, texture is not None)
-        ctx.save_for_backward(m3, sh, cp, op, sc, ro, uv, guv, tex, geom, binw, imgw)
-        if dual:
-            ctx.mark_non_differentiable(radii)
-        else:
-            ctx.mark_non_differentiable(radii, image_nosh)
-        return image, depth, norm, alpha, radii, image_nosh
+        ctx.save_for_backward(m3, sh, cp, op, sc, ro, uv, guv, tex, ex, geom, binw, imgw)
+        nondiff = [radii]
+        if not dual:
+            nondiff.append(image_nosh)
+        if ex is None:
+            nondiff.append(extra)
+        ctx.mark_non_differentiable(*nondiff)
+        return image, depth, norm, alpha, radii, image_nosh, extra
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, g_image, g_depth, g_norm, g_alpha, _g_radii, g_image_nosh):
+    def backward(ctx, g_image, g_depth, g_norm, g_alpha, _g_radii, g_image_nosh, g_extra):
         lib = L.load()
-        m3, sh, cp, op, sc, ro, uv, guv, tex, geom, binw, imgw = ctx.saved_tensors
+        m3, sh, cp, op, sc, ro, uv, guv, tex, ex, geom, binw, imgw = ctx.saved_tensors
         st, mode, dev = ctx.st, ctx.mode, ctx.dev
         P = m3.shape[0]
-        need = ctx.needs_input_grad   # means3D, means2D, shs, colors_precomp, opacities, scales, rotations, uvs, gradient_uvs, texture
+        need = ctx.needs_input_grad   # means3D, means2D, shs, colors_precomp, opacities, scales, rotations, uvs, gradient_uvs, texture, st, mode, dual, extra_attrs
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             b = L.TexgsBwdArgs()
-            b.fwd = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex, ctx.prof)
+            b.fwd = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex, ctx.prof, ex)
             if ctx.tex4 is not None:
                 b.fwd.texture_rgba = _ptr(ctx.tex4)
             b.geom_ws, b.bin_ws, b.img_ws, b.pair_capacity = _ptr(geom), _ptr(binw), _ptr(imgw), ctx.cap
@@ -324,6 +330,13 @@ class _RasterizeGaussians(torch.autograd.Function):
                 b.fwd.out_image_nosh = C.c_void_p(1 << 8)
                 keep.append(_prep(g_image_nosh, dev))
                 b.dL_dimage_nosh = _ptr(keep[-1])
+            d_ex = None
+            if ex is not None:
+                keep.append(_prep(g_extra, dev))
+                b.dL_dextra = _ptr(keep[-1])
+                if need[13]:
+                    d_ex = torch.empty_like(ex)       # cleared by the library
+                    b.dL_dextra_attrs = _ptr(d_ex)
             acc = torch.empty(max(P, 1) * L.BWD_ACC_FLOATS, device=dev, dtype=torch.float32)
             b.acc_ws = _ptr(acc)
 
@@ -379,7 +392,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             if zero_tex == 0:
                 d_tex = None
             L.check(lib.texgs_backward(C.byref(b), C.c_void_p(stream)), "texgs_backward")
-        return d_m3, d_m2, d_sh, d_cp, d_op, d_sc, d_ro, d_uv, None, d_tex, None, None, None
+        return d_m3, d_m2, d_sh, d_cp, d_op, d_sc, d_ro, d_uv, None, d_tex, None, None, None, d_ex
 
 
 class GaussianRasterizer(nn.Module):
@@ -410,8 +423,6 @@ class GaussianRasterizer(nn.Module):
         """``dual_no_sh=True`` (textured mode) appends a 7th result: the image the same
         splats give with ``sh_degree = 0``, blended in the same pass."""
         st = self.raster_settings
-        if extra_attrs is not None:
-            raise NotImplementedError("extra_attrs is always None in the reference tree (render/uv_tex_render.py:7); not built yet")
         if cov3Ds_precomp is not None:
             raise NotImplementedError("cov3Ds_precomp: the disc normal / intersection need scales + rotations")
         if scales is None or rotations is None:
@@ -426,9 +437,11 @@ class GaussianRasterizer(nn.Module):
             mode = L.MODE_SH if shs is not None else L.MODE_PRECOMP
         if dual_no_sh and mode != L.MODE_TEXTURE:
             raise ValueError("dual_no_sh needs the textured mode")
-        image, depth, norm, alpha, radii, image_nosh = _RasterizeGaussians.apply(
+        image, depth, norm, alpha, radii, image_nosh, extra = _RasterizeGaussians.apply(
             means3D, means2D, shs, colors_precomp, opacities, scales, rotations, uvs, gradient_uvs, texture, st, mode,
-            bool(dual_no_sh))
+            bool(dual_no_sh), extra_attrs)
+        if extra_attrs is None:
+            extra = None
         if dual_no_sh:
-            return image, depth, norm, alpha, radii, None, image_nosh
-        return image, depth, norm, alpha, radii, None
+            return image, depth, norm, alpha, radii, extra, image_nosh
+        return image, depth, norm, alpha, radii, extra
