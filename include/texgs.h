@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TEXGS_ABI_VERSION 1
+#define TEXGS_ABI_VERSION 2
 
 #define TEXGS_E_INVALID   1001   /* bad argument */
 #define TEXGS_E_WORKSPACE 1002   /* workspace too small */
@@ -68,7 +68,14 @@ typedef struct TexgsFwdArgs {
     const float* uvs;            /* (P,3)   or NULL                              */
     const float* gradient_uvs;   /* (P,9) row-major d uv_i / d x_j, or NULL      */
     const float* texture;        /* (6,R,R,3) or NULL                            */
-    const float* extra_attrs;    /* (P,E) or NULL                                */
+    const float* extra_attrs;    /* (P,E) or NULL: blended into out_extra (E,H,W) with the weights of the main
+                                    render, no background (render/uv_tex_render.py:66, render/render.py:84)    */
+    /* diff_gauss only (render/render.py:52-53,83): world-space covariances given instead of scales +
+     * rotations, 6 floats per Gaussian in the order xx,xy,xz,yy,yz,zz (utils/general.py:73-82), used as
+     * given (scale_modifier is NOT applied: the reference applies it in get_covariance). scales and
+     * rotations must then be NULL; the disc normal is the unit eigenvector of the smallest eigenvalue,
+     * facing the camera, and carries no gradient. Not available in TEXGS_MODE_TEXTURE. */
+    const float* cov3Ds_precomp; /* (P,6) or NULL                                */
     /* optional: the same texture repacked as (6,R,R,4) fp32 (rgb + one pad float) by
      * texgs_pack_texture; when given the render kernels fetch one 128-bit texel per tap instead
      * of three scalars. Must correspond to ``texture``. NULL = read ``texture`` directly. */
@@ -155,7 +162,8 @@ typedef struct TexgsBwdArgs {
     float* dL_dtexture;          /* (6,R,R,3) */
     float* dL_dtexture_rgba;     /* (6,R,R,4) alternative to dL_dtexture: accumulated with 128-bit vector
                                     atomics (red.global.add.v4.f32), 4th float stays 0; give exactly one */
-    float* dL_dextra_attrs;      /* (P,E)   */
+    float* dL_dextra_attrs;      /* (P,E)   cleared and written by the library                                  */
+    float* dL_dcov3Ds;           /* (P,6)   when fwd.cov3Ds_precomp is given (off-diagonal entries count both halves) */
     int32_t zero_texture_grad;
     /* TEXGS_ACC_* bits: the marked per-Gaussian outputs are ADDED to (``out += grad``, rows of culled
      * Gaussians untouched) instead of overwritten — lets the caller point them at a persistent

@@ -121,7 +121,7 @@ def sh_rest(deg: int, shs: Optional[torch.Tensor], dirs: torch.Tensor) -> torch.
 
 
 def preprocess(means3D, means2D, scales, rotations, opacities, shs, st: RasterSettings,
-               sw: Switches = Switches()):
+               sw: Switches = Switches(), cov3Ds_precomp=None):
     """Per-Gaussian projection. Returns a dict of per-Gaussian tensors (differentiable where it
     matters) plus integer radius / tile rect (E1-E3)."""
     dt, dev = means3D.dtype, means3D.device
@@ -138,12 +138,19 @@ def preprocess(means3D, means2D, scales, rotations, opacities, shs, st: RasterSe
     depth = p_view[:, 2]
     in_front = depth > NEAR_CULL                                  # E1
 
-    q = rotations
-    if sw.normalize_quat:
-        q = q / q.norm(dim=-1, keepdim=True)
-    R = quat_to_rot(q)
-    L = R * (scales * st.scale_modifier)[:, None, :]              # R @ diag(s*mod)
-    Sigma = L @ L.transpose(1, 2)
+    if cov3Ds_precomp is None:
+        q = rotations
+        if sw.normalize_quat:
+            q = q / q.norm(dim=-1, keepdim=True)
+        R = quat_to_rot(q)
+        L = R * (scales * st.scale_modifier)[:, None, :]              # R @ diag(s*mod)
+        Sigma = L @ L.transpose(1, 2)
+    else:
+        # render/render.py:52-53: gaussians.get_covariance(scaling_modifier) -> (N,6) in the order
+        # xx,xy,xz,yy,yz,zz (utils/general.py:73-82), used as given
+        c6 = cov3Ds_precomp
+        Sigma = torch.stack([c6[:, 0], c6[:, 1], c6[:, 2], c6[:, 1], c6[:, 3], c6[:, 4],
+                             c6[:, 2], c6[:, 4], c6[:, 5]], dim=-1).reshape(N, 3, 3)
 
     # E2: EWA projection
     limx, limy = 1.3 * st.tanfovx, 1.3 * st.tanfovy
@@ -193,9 +200,15 @@ def preprocess(means3D, means2D, scales, rotations, opacities, shs, st: RasterSe
         radii = torch.where(visible, radius, torch.zeros_like(radius)).to(torch.int32)
 
     # E8: disc normal = rotation column of the smallest scale, facing the camera
-    with torch.no_grad():
-        kmin = torch.argmin(scales, dim=1)
-    n_raw = torch.gather(R, 2, kmin[:, None, None].expand(N, 3, 1)).squeeze(-1)
+    if cov3Ds_precomp is None:
+        with torch.no_grad():
+            kmin = torch.argmin(scales, dim=1)
+        n_raw = torch.gather(R, 2, kmin[:, None, None].expand(N, 3, 1)).squeeze(-1)
+    else:
+        # E8 with a precomputed covariance [spec choice]: the same direction, obtained as the unit eigenvector of
+        # the smallest eigenvalue (R[:, argmin s] IS that eigenvector when Sigma = R S^2 R^T); no gradient
+        with torch.no_grad():
+            n_raw = torch.linalg.eigh(Sigma.double()).eigenvectors[:, :, 0].to(dt)
     m = means3D - campos
     with torch.no_grad():
         flip = (n_raw * m).sum(-1) > 0
@@ -291,7 +304,7 @@ def cube_sample(texture: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
 def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient_uvs, texture,
               settings: RasterSettings, sw: Switches = Switches(), colors_precomp=None,
               extra_attrs=None, max_elems: int = 6_000_000, tile_subset=None, return_aux=False,
-              dual_no_sh: bool = False):
+              dual_no_sh: bool = False, cov3Ds_precomp=None):
     """Returns (image(3,H,W), depth(1,H,W), norm(3,H,W), alpha(1,H,W), radii(N,), extra|None)
     [+ aux dict]. ``texture=None`` selects the plain-3DGS colour path (``diff_gauss``): colour is
     ``colors_precomp`` (N,3) if given, else max(0, SH_full(shs)+0.5) with shs (N,(deg+1)^2,3).
@@ -311,9 +324,10 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
     N = means3D.shape[0]
 
     if textured:
+        assert cov3Ds_precomp is None, "cov3Ds_precomp is a diff_gauss (untextured) argument"
         pre = preprocess(means3D, means2D, scales, rotations, opacities, shs, st, sw)
     else:
-        pre = preprocess(means3D, means2D, scales, rotations, opacities, None, st, sw)
+        pre = preprocess(means3D, means2D, scales, rotations, opacities, None, st, sw, cov3Ds_precomp=cov3Ds_precomp)
         if colors_precomp is not None:
             pre["csh"] = colors_precomp - 0.5
         else:

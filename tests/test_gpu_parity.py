@@ -284,6 +284,69 @@ def test_extra_attrs_forward_and_backward_match_oracle(E, textured):
         assert tc2["opacity"].grad is not None and rel_err(tc2["uvs"].grad.cpu(), tc["uvs"].grad.cpu()) < 1e-5
 
 
+def test_cov3Ds_precomp_matches_oracle_and_the_scale_rotation_path():
+    """``cov3Ds_precomp`` (render/render.py:52-53,83, cfg.compute_cov3D_python): (P,6) covariances instead of
+    scales + rotations in the diff_gauss modes. Forward equals the oracle and the CUDA render with scales + rotations;
+    the covariance gradient equals the oracle's."""
+    from oracle import raster_ref as RR
+    from util import oracle_settings
+    from texture_gs_b200 import GaussianRasterizationSettings, GaussianRasterizer
+    N, W, H = 2000, 112, 80
+    g = sphere_shell_scene(N, 4, sh_degree=0, seed=71)
+    cam = orbit_cameras(1, W, H, seed=72)[0]
+    gen = torch.Generator().manual_seed(73)
+    cols = torch.rand(N, 3, generator=gen)
+    t0 = g.tensors()
+    Lm = RR.quat_to_rot(t0["rotation"].detach().double()) * t0["scaling"].detach().double()[:, None, :]
+    S = Lm @ Lm.transpose(1, 2)
+    cov0 = torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], dim=-1)
+    with torch.no_grad():
+        aux0 = RR.rasterize(t0["xyz"], None, None, t0["opacity"], None, None, None, None, None, oracle_settings(cam, 0, bg=(0.2, 0.1, 0.3)),
+                            colors_precomp=cols, cov3Ds_precomp=cov0.float(), return_aux=True)[-1]
+    keep = (~aux0["ambiguous"]).float()
+    cot = [c * keep for c in output_cotangents(H, W, seed=74)]
+    cot[2] = torch.zeros_like(cot[2])        # the normal carries no gradient in this mode
+
+    def oracle(dtype):
+        t = g.to(dtype=dtype, requires_grad=True).tensors()
+        cov = cov0.to(dtype).clone().requires_grad_(True)
+        st = oracle_settings(cam, 0, dtype=dtype, bg=(0.2, 0.1, 0.3))
+        m2 = torch.zeros_like(t["xyz"], requires_grad=True)
+        o = RR.rasterize(t["xyz"], m2, None, t["opacity"], None, None, None, None, None, st, colors_precomp=cols.to(dtype),
+                         cov3Ds_precomp=cov, return_aux=True)
+        sum((a * b.to(dtype)).sum() for a, b in zip(o[:4], cot)).backward()
+        return [x.detach() for x in o[:4]], o[4], o[-1], {"cov": cov.grad, "xyz": t["xyz"].grad, "opacity": t["opacity"].grad, "means2D": m2.grad[:, :2]}
+
+    ref32, radii_ref, aux, g32 = oracle(torch.float32)
+    _, _, _, g64 = oracle(torch.float64)
+    tc = g.to("cuda", requires_grad=True).tensors()
+    covc = cov0.float().cuda().requires_grad_(True)
+    camd = cam.to("cuda")
+    stc = GaussianRasterizationSettings(H, W, math.tan(camd.FoVx / 2), math.tan(camd.FoVy / 2), torch.tensor([0.2, 0.1, 0.3], device="cuda"),
+                                        1.0, camd.world_view_transform, camd.full_proj_transform, 0, camd.camera_center, False, False)
+    m2c = torch.zeros(N, 3, device="cuda", requires_grad=True)
+    oc = GaussianRasterizer(stc)(means3D=tc["xyz"], means2D=m2c, opacities=tc["opacity"], colors_precomp=cols.cuda(), cov3Ds_precomp=covc)
+    sum((a * b.cuda()).sum() for a, b in zip(oc[:4], cot)).backward()
+    rep = compare_images([x.detach().cpu() for x in oc[:4]], ref32, aux["ambiguous"])
+    print(rep)
+    for n in ("image", "depth", "norm", "alpha"):
+        assert rep[n]["max_clear"] <= ABS_TOL * (3.0 if n == "depth" else 1.0), (n, rep[n])
+    assert int((oc[4].cpu() != radii_ref).sum()) == 0
+    gc = {"cov": covc.grad, "xyz": tc["xyz"].grad, "opacity": tc["opacity"].grad, "means2D": m2c.grad[:, :2]}
+    for k, r in g64.items():
+        e_c, e_o = rel_err(gc[k].cpu().reshape(r.shape), r), rel_err(g32[k].reshape(r.shape), r)
+        print(k, "%.2e %.2e" % (e_c, e_o))
+        assert e_c <= max(GRAD_RTOL, 3.0 * e_o), (k, e_c, e_o)
+    # same picture as with scales + rotations
+    o2 = GaussianRasterizer(stc)(means3D=tc["xyz"].detach(), means2D=torch.zeros(N, 3, device="cuda"), opacities=tc["opacity"].detach(),
+                                 colors_precomp=cols.cuda(), scales=tc["scaling"].detach(), rotations=tc["rotation"].detach())
+    for a, b in zip(oc[:4], o2[:4]):
+        assert float((a.detach() - b).abs().max()) <= ABS_TOL
+    with pytest.raises(ValueError):
+        GaussianRasterizer(stc)(means3D=tc["xyz"], means2D=m2c, opacities=tc["opacity"], colors_precomp=cols.cuda(),
+                                scales=tc["scaling"], rotations=tc["rotation"], cov3Ds_precomp=covc)
+
+
 def test_edge_cases_empty_culled_single_and_ragged_sizes():
     from texture_gs_b200 import uv_tex_render
     bg = torch.tensor([0.3, 0.5, 0.7], device="cuda")

@@ -244,6 +244,43 @@ def test_extra_attrs_blend_with_the_same_weights_as_depth_alpha_and_colour():
     assert float(alpha.max()) > 0.5
 
 
+def _cov6(scaling, rotation, mod=1.0):
+    """models/gaussian3d.py:17-21 + utils/general.py:73-82,110-119: Sigma = (R S)(R S)^T as xx,xy,xz,yy,yz,zz."""
+    L = RR.quat_to_rot(rotation) * (scaling * mod)[:, None, :]
+    S = L @ L.transpose(1, 2)
+    return torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], dim=-1)
+
+
+def test_cov3Ds_precomp_equals_scales_and_rotations():
+    """render/render.py:52-53,83: a covariance precomputed in Python gives the same render as scales + rotations
+    (including the disc normal: smallest-eigenvalue eigenvector == rotation column of the smallest scale), and the
+    gradient w.r.t. the covariance chains to the same scale / rotation gradients when the norm output carries no
+    cotangent (the normal is not differentiated through the eigen-decomposition)."""
+    g = sphere_shell_scene(200, 8, sh_degree=0, seed=61).to(dtype=torch.float64)
+    cam = orbit_cameras(1, 48, 40, seed=62)[0]
+    st = oracle_settings(cam, 0, dtype=torch.float64, bg=(0.1, 0.2, 0.3), scale_modifier=1.3)
+    cols = torch.rand(200, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(7))
+    cot = [torch.randn(c, 40, 48, dtype=torch.float64, generator=torch.Generator().manual_seed(8 + c)) for c in (3, 1, 3, 1)]
+    cot[2] = torch.zeros_like(cot[2])
+    res = []
+    for use_cov in (False, True):
+        t = g.to(dtype=torch.float64, requires_grad=True).tensors()
+        if use_cov:
+            cov = _cov6(t["scaling"], t["rotation"], 1.3)
+            o = RR.rasterize(t["xyz"], None, None, t["opacity"], None, None, None, None, None, st, colors_precomp=cols, cov3Ds_precomp=cov)
+        else:
+            o = RR.rasterize(t["xyz"], None, None, t["opacity"], t["scaling"], t["rotation"], None, None, None, st, colors_precomp=cols)
+        sum((a * b).sum() for a, b in zip(o[:4], cot)).backward()
+        res.append(([x.detach() for x in o[:4]], o[4], {k: t[k].grad for k in ("xyz", "opacity", "scaling", "rotation")}))
+    # the scene stores its quaternions in fp32: |q| = 1 +- 1e-7, so R (used as given) is orthogonal to 1e-7 only
+    for a, b in zip(res[0][0], res[1][0]):
+        assert float((a - b).abs().max()) < 1e-6
+    assert torch.equal(res[0][1], res[1][1])
+    for k in res[0][2]:
+        a, b = res[0][2][k], res[1][2][k]
+        assert float((a - b).abs().max()) <= 1e-5 * max(1.0, float(a.abs().max())), k
+
+
 def test_loss_oracle_matches_the_reference_code_golden_vectors():
     """oracle/loss_ref.py vs vectors generated by the reference's own losses/*.py (PINNED oracle)."""
     import numpy as np

@@ -13,7 +13,7 @@ _PKG = Path(__file__).resolve().parent
 # TEXGS_LIB selects an alternative build of the same ABI (kernel-tuning experiments, tools/build_variants.py)
 LIB_PATH = Path(os.environ["TEXGS_LIB"]).resolve() if os.environ.get("TEXGS_LIB") else _PKG / "libtexgs.so"
 
-TEXGS_ABI_VERSION = 1
+TEXGS_ABI_VERSION = 2
 FLAG_PREFILTERED = 1
 FLAG_DEBUG = 2
 MODE_TEXTURE, MODE_SH, MODE_PRECOMP = 0, 1, 2
@@ -36,6 +36,7 @@ class TexgsFwdArgs(C.Structure):
         ("campos", C.c_float * 3), ("bg", C.c_float * 3),
         ("means3D", _fp), ("shs", _fp), ("colors_precomp", _fp), ("opacities", _fp), ("scales", _fp),
         ("rotations", _fp), ("uvs", _fp), ("gradient_uvs", _fp), ("texture", _fp), ("extra_attrs", _fp),
+        ("cov3Ds_precomp", _fp),
         ("texture_rgba", _fp),
         ("out_image_nosh", _fp),
         ("profile_events", C.POINTER(C.c_void_p)),
@@ -56,7 +57,7 @@ class TexgsBwdArgs(C.Structure):
         ("acc_ws", _fp),
         ("dL_dmeans3D", _fp), ("dL_dmeans2D", _fp), ("dL_dopacity", _fp), ("dL_dscales", _fp),
         ("dL_drotations", _fp), ("dL_dshs", _fp), ("dL_dcolors_precomp", _fp), ("dL_duvs", _fp),
-        ("dL_dtexture", _fp), ("dL_dtexture_rgba", _fp), ("dL_dextra_attrs", _fp),
+        ("dL_dtexture", _fp), ("dL_dtexture_rgba", _fp), ("dL_dextra_attrs", _fp), ("dL_dcov3Ds", _fp),
         ("zero_texture_grad", C.c_int32), ("accumulate_mask", C.c_uint32),
     ]
 

@@ -89,8 +89,13 @@ int fill_params(const TexgsFwdArgs* a, void* geom, void* bin, uint64_t cap, void
     if (a->mode != TEXGS_MODE_TEXTURE && a->mode != TEXGS_MODE_SH && a->mode != TEXGS_MODE_PRECOMP)
         return fail(TEXGS_E_INVALID, "unknown mode");
     if (a->E < 0 || (a->E > 0 && a->P > 0 && !a->extra_attrs)) return fail(TEXGS_E_INVALID, "E > 0 needs extra_attrs (P,E)");
-    if (a->P > 0 && (!a->means3D || !a->opacities || !a->scales || !a->rotations))
-        return fail(TEXGS_E_INVALID, "means3D/opacities/scales/rotations must be given");
+    if (a->P > 0 && (!a->means3D || !a->opacities)) return fail(TEXGS_E_INVALID, "means3D and opacities must be given");
+    if (a->cov3Ds_precomp) {
+        if (a->scales || a->rotations) return fail(TEXGS_E_INVALID, "give scales + rotations or cov3Ds_precomp, not both");
+        if (a->mode == TEXGS_MODE_TEXTURE) return fail(TEXGS_E_INVALID, "cov3Ds_precomp is a diff_gauss argument (render/render.py:83); the textured mode needs scales + rotations");
+    } else if (a->P > 0 && (!a->scales || !a->rotations)) {
+        return fail(TEXGS_E_INVALID, "scales and rotations (or cov3Ds_precomp) must be given");
+    }
     if (((uintptr_t)a->rotations & 15) != 0) return fail(TEXGS_E_INVALID, "rotations must be 16-byte aligned");
     if (a->mode == TEXGS_MODE_TEXTURE) {
         if ((a->P > 0 && (!a->uvs || !a->gradient_uvs)) || !a->texture || a->R <= 0)
@@ -123,7 +128,7 @@ int fill_params(const TexgsFwdArgs* a, void* geom, void* bin, uint64_t cap, void
     memcpy(p.bg, a->bg, sizeof(float) * 3);
     p.means3D = a->means3D; p.shs = a->shs; p.colors_precomp = a->colors_precomp; p.opacities = a->opacities;
     p.scales = a->scales; p.rotations = a->rotations; p.uvs = a->uvs; p.gradient_uvs = a->gradient_uvs;
-    p.texture = a->texture; p.extra_attrs = a->extra_attrs;
+    p.texture = a->texture; p.extra_attrs = a->extra_attrs; p.cov3Ds_precomp = a->cov3Ds_precomp;
     p.texture_rgba = (a->mode == TEXGS_MODE_TEXTURE) ? reinterpret_cast<const float4*>(a->texture_rgba) : nullptr;
     if (((uintptr_t)a->texture_rgba & 15) != 0) return fail(TEXGS_E_INVALID, "texture_rgba must be 16-byte aligned");
     char* g = (char*)geom; char* b = (char*)bin; char* im = (char*)img;
@@ -317,7 +322,7 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
     TEXGS_EV(a, TEXGS_EV_BWD_RENDER, stream);
     if (p.P > 0) {
         BwdOut g{b->dL_dmeans3D, b->dL_dmeans2D, b->dL_dopacity, b->dL_dscales, b->dL_drotations,
-                 b->dL_dshs, b->dL_dcolors_precomp, b->dL_duvs, b->dL_dextra_attrs, b->accumulate_mask};
+                 b->dL_dshs, b->dL_dcolors_precomp, b->dL_duvs, a->cov3Ds_precomp ? b->dL_dcov3Ds : nullptr, b->accumulate_mask};
         texgs_preprocess_bwd<<<(p.P + 255) / 256, 256, 0, stream>>>(p, b->acc_ws, g);
         TEXGS_KERNEL_CHECK("texgs_preprocess_bwd", debug, stream);
     }

@@ -49,7 +49,7 @@ struct RasterParams {
     float campos[3];
     float bg[3];
     const float *means3D, *shs, *colors_precomp, *opacities, *scales, *rotations, *uvs,
-        *gradient_uvs, *texture, *extra_attrs;
+        *gradient_uvs, *texture, *extra_attrs, *cov3Ds_precomp;
     const float4* texture_rgba;   // optional (6,R,R,4) copy of the texture
     // workspaces
     GaussRec* recs;
@@ -112,6 +112,41 @@ __device__ __forceinline__ int argmin3(float a, float b, float c) {
     if (b < m) { m = b; k = 1; }
     if (c < m) { k = 2; }
     return k;
+}
+
+// Unit eigenvector of the smallest eigenvalue of the symmetric 3x3 matrix S = (xx,xy,xz,yy,yz,zz): cyclic
+// Jacobi rotations (high relative accuracy also for the flat discs of this path, whose smallest eigenvalue
+// is ~1e-13 of the others). Cold path (cov3Ds_precomp only), kept out of line.
+#define TEXGS_JACOBI_ROT(app, aqq, apq, akp, akq, v0p, v0q, v1p, v1q, v2p, v2q)                           \
+    if (apq != 0.f) {                                                                                    \
+        const float theta = 0.5f * (aqq - app) / apq;                                                    \
+        const float t = copysignf(1.f, theta) / (fabsf(theta) + sqrtf(theta * theta + 1.f));             \
+        const float c = rsqrtf(t * t + 1.f), s = t * c, tau = s / (1.f + c);                             \
+        const float h = t * apq;                                                                         \
+        app -= h; aqq += h; apq = 0.f;                                                                   \
+        float g_ = akp, h_ = akq; akp = g_ - s * (h_ + g_ * tau); akq = h_ + s * (g_ - h_ * tau);        \
+        g_ = v0p; h_ = v0q; v0p = g_ - s * (h_ + g_ * tau); v0q = h_ + s * (g_ - h_ * tau);              \
+        g_ = v1p; h_ = v1q; v1p = g_ - s * (h_ + g_ * tau); v1q = h_ + s * (g_ - h_ * tau);              \
+        g_ = v2p; h_ = v2q; v2p = g_ - s * (h_ + g_ * tau); v2q = h_ + s * (g_ - h_ * tau);              \
+    }
+__device__ __noinline__ float3 smallest_eigvec_sym3(float a00, float a01, float a02, float a11, float a12, float a22) {
+    // scale-invariant in exact arithmetic; normalise so squares of ~1e-9 entries do not underflow
+    const float sc = fmaxf(fmaxf(fabsf(a00), fabsf(a11)), fmaxf(fabsf(a22), 1e-37f));
+    const float is = 1.0f / sc;
+    a00 *= is; a01 *= is; a02 *= is; a11 *= is; a12 *= is; a22 *= is;
+    float v00 = 1.f, v01 = 0.f, v02 = 0.f, v10 = 0.f, v11 = 1.f, v12 = 0.f, v20 = 0.f, v21 = 0.f, v22 = 1.f;
+#pragma unroll 1
+    for (int sweep = 0; sweep < 8; ++sweep) {
+        TEXGS_JACOBI_ROT(a00, a11, a01, a02, a12, v00, v01, v10, v11, v20, v21)
+        TEXGS_JACOBI_ROT(a00, a22, a02, a01, a12, v00, v02, v10, v12, v20, v22)
+        TEXGS_JACOBI_ROT(a11, a22, a12, a01, a02, v01, v02, v11, v12, v21, v22)
+    }
+    float3 n = make_float3(v00, v10, v20);
+    float lam = a00;
+    if (a11 < lam) { lam = a11; n = make_float3(v01, v11, v21); }
+    if (a22 < lam) { n = make_float3(v02, v12, v22); }
+    const float inv = rsqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
+    return make_float3(n.x * inv, n.y * inv, n.z * inv);
 }
 
 // ---------------------------------------------------------------------------------------------

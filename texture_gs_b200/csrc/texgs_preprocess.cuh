@@ -57,20 +57,29 @@ __device__ __forceinline__ void project_gaussian(const RasterParams& p, int idx,
     if (!(o.pv.z > TEXGS_NEAR)) return;                                     // E1
     o.ph = xform44(p.proj, mu);
     o.pw = 1.0f / (o.ph.w + 1e-7f);
-    const float4 q = *reinterpret_cast<const float4*>(p.rotations + 4 * idx);
-    quat_to_rot(q, o.R);
-    o.s = f3(p.scales[3 * idx] * p.scale_modifier, p.scales[3 * idx + 1] * p.scale_modifier,
-             p.scales[3 * idx + 2] * p.scale_modifier);
-    // L = R diag(s);  Sigma = L L^T
-    float L[9];
+    const bool covgiven = p.cov3Ds_precomp != nullptr;
+    if (!covgiven) {
+        const float4 q = *reinterpret_cast<const float4*>(p.rotations + 4 * idx);
+        quat_to_rot(q, o.R);
+        o.s = f3(p.scales[3 * idx] * p.scale_modifier, p.scales[3 * idx + 1] * p.scale_modifier,
+                 p.scales[3 * idx + 2] * p.scale_modifier);
+        // L = R diag(s);  Sigma = L L^T
+        float L[9];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) { L[3 * r] = o.R[3 * r] * o.s.x; L[3 * r + 1] = o.R[3 * r + 1] * o.s.y; L[3 * r + 2] = o.R[3 * r + 2] * o.s.z; }
-    o.Sig[0] = L[0] * L[0] + L[1] * L[1] + L[2] * L[2];
-    o.Sig[1] = L[0] * L[3] + L[1] * L[4] + L[2] * L[5];
-    o.Sig[2] = L[0] * L[6] + L[1] * L[7] + L[2] * L[8];
-    o.Sig[3] = L[3] * L[3] + L[4] * L[4] + L[5] * L[5];
-    o.Sig[4] = L[3] * L[6] + L[4] * L[7] + L[5] * L[8];
-    o.Sig[5] = L[6] * L[6] + L[7] * L[7] + L[8] * L[8];
+        for (int r = 0; r < 3; ++r) { L[3 * r] = o.R[3 * r] * o.s.x; L[3 * r + 1] = o.R[3 * r + 1] * o.s.y; L[3 * r + 2] = o.R[3 * r + 2] * o.s.z; }
+        o.Sig[0] = L[0] * L[0] + L[1] * L[1] + L[2] * L[2];
+        o.Sig[1] = L[0] * L[3] + L[1] * L[4] + L[2] * L[5];
+        o.Sig[2] = L[0] * L[6] + L[1] * L[7] + L[2] * L[8];
+        o.Sig[3] = L[3] * L[3] + L[4] * L[4] + L[5] * L[5];
+        o.Sig[4] = L[3] * L[6] + L[4] * L[7] + L[5] * L[8];
+        o.Sig[5] = L[6] * L[6] + L[7] * L[7] + L[8] * L[8];
+    } else {   // cov3Ds_precomp (render/render.py:52-53): used as given
+#pragma unroll
+        for (int k = 0; k < 6; ++k) o.Sig[k] = p.cov3Ds_precomp[(size_t)6 * idx + k];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) o.R[k] = 0.f;
+        o.s = f3(0.f, 0.f, 0.f);
+    }
     // E2: EWA projection
     const float limx = 1.3f * p.tanfovx, limy = 1.3f * p.tanfovy;
     const float tz = o.pv.z;
@@ -114,9 +123,15 @@ __device__ __forceinline__ void project_gaussian(const RasterParams& p, int idx,
     o.ry1 = (int)fminf(gyf, fmaxf(0.f, floorf((o.y + o.radius + (TEXGS_TILE - 1)) * (1.0f / TEXGS_TILE))));
     if ((o.rx1 - o.rx0) * (o.ry1 - o.ry0) <= 0) return;
     // E8: facing disc normal
-    o.kmin = argmin3(p.scales[3 * idx], p.scales[3 * idx + 1], p.scales[3 * idx + 2]);
-    // column kmin of R, selected without dynamic indexing (keeps R in registers)
-    const float3 nraw = (o.kmin == 0) ? f3(o.R[0], o.R[3], o.R[6]) : ((o.kmin == 1) ? f3(o.R[1], o.R[4], o.R[7]) : f3(o.R[2], o.R[5], o.R[8]));
+    float3 nraw;
+    if (!covgiven) {
+        o.kmin = argmin3(p.scales[3 * idx], p.scales[3 * idx + 1], p.scales[3 * idx + 2]);
+        // column kmin of R, selected without dynamic indexing (keeps R in registers)
+        nraw = (o.kmin == 0) ? f3(o.R[0], o.R[3], o.R[6]) : ((o.kmin == 1) ? f3(o.R[1], o.R[4], o.R[7]) : f3(o.R[2], o.R[5], o.R[8]));
+    } else {   // the same direction when Sigma = R S^2 R^T: eigenvector of the smallest eigenvalue
+        o.kmin = -1;
+        nraw = smallest_eigvec_sym3(o.Sig[0], o.Sig[1], o.Sig[2], o.Sig[3], o.Sig[4], o.Sig[5]);
+    }
     o.m = f3(mu.x - p.campos[0], mu.y - p.campos[1], mu.z - p.campos[2]);
     o.nsign = (dot3(nraw, o.m) > 0.f) ? -1.f : 1.f;
     o.nv = rot_w2v(p.view, f3(o.nsign * nraw.x, o.nsign * nraw.y, o.nsign * nraw.z));
@@ -232,7 +247,7 @@ __device__ __forceinline__ void sh_rest_bwd(int deg, const float* __restrict__ s
 }
 
 struct BwdOut {
-    float *dmeans3D, *dmeans2D, *dopacity, *dscales, *drotations, *dshs, *dcolors_precomp, *duvs, *dextra_attrs;
+    float *dmeans3D, *dmeans2D, *dopacity, *dscales, *drotations, *dshs, *dcolors_precomp, *duvs, *dcov3Ds;
     unsigned acc;   // TEXGS_ACC_* bits: add into the output instead of overwriting it
 };
 
@@ -259,6 +274,7 @@ __global__ void __launch_bounds__(256, TEXGS_PREBWD_MIN_CTAS) texgs_preprocess_b
         if (g.dshs && !a_sh) for (int k = 0; k < nsh; ++k) g.dshs[(size_t)idx * nsh + k] = 0.f;
         if (g.dcolors_precomp && !a_cp) { g.dcolors_precomp[3 * idx] = 0.f; g.dcolors_precomp[3 * idx + 1] = 0.f; g.dcolors_precomp[3 * idx + 2] = 0.f; }
         if (g.duvs && !a_uv) { g.duvs[3 * idx] = 0.f; g.duvs[3 * idx + 1] = 0.f; g.duvs[3 * idx + 2] = 0.f; }
+        if (g.dcov3Ds) for (int k = 0; k < 6; ++k) g.dcov3Ds[(size_t)6 * idx + k] = 0.f;
         return;
     }
     const float* acc = acc_all + (size_t)idx * TEXGS_BWD_ACC_FLOATS;
@@ -345,6 +361,10 @@ __global__ void __launch_bounds__(256, TEXGS_PREBWD_MIN_CTAS) texgs_preprocess_b
 #pragma unroll
         for (int j = 0; j < 3; ++j)
             GM[3 * i + j] = T[i] * (g00 * T[j] + g01 * T[3 + j]) + T[3 + i] * (g01 * T[j] + g11 * T[3 + j]);
+    if (g.dcov3Ds) {   // cov3Ds_precomp: Sigma is the input; an off-diagonal entry of the 6-vector stands for both halves
+        float* d = g.dcov3Ds + (size_t)6 * idx;
+        d[0] = GM[0]; d[1] = GM[1] + GM[3]; d[2] = GM[2] + GM[6]; d[3] = GM[4]; d[4] = GM[5] + GM[7]; d[5] = GM[8];
+    }
     // dL/dL = 2 GM L,  L = R diag(s)
     float dR[9];
     float ds[3] = {0.f, 0.f, 0.f};
@@ -411,7 +431,7 @@ __global__ void __launch_bounds__(256, TEXGS_PREBWD_MIN_CTAS) texgs_preprocess_b
         put(g.dscales + 3 * idx + 1, ds[1] * p.scale_modifier, a_sc);
         put(g.dscales + 3 * idx + 2, ds[2] * p.scale_modifier, a_sc);
     }
-    if (g.drotations) {
+    if (g.drotations && p.rotations) {
         const float4 q = *reinterpret_cast<const float4*>(p.rotations + 4 * idx);
         const float r = q.x, x = q.y, y = q.z, z = q.w;
         float4 dq;

@@ -182,7 +182,7 @@ def last_stats() -> Optional[RasterStats]:
 
 
 def _build_args(st: GaussianRasterizationSettings, mode: int, means3D, shs, colors_precomp, opacities, scales,
-                rotations, uvs, gradient_uvs, texture, profile_arr=None, extra_attrs=None) -> L.TexgsFwdArgs:
+                rotations, uvs, gradient_uvs, texture, profile_arr=None, extra_attrs=None, cov3Ds_precomp=None) -> L.TexgsFwdArgs:
     a = L.TexgsFwdArgs()
     a.P = means3D.shape[0]
     a.M = 0 if shs is None else shs.shape[1]
@@ -207,6 +207,7 @@ def _build_args(st: GaussianRasterizationSettings, mode: int, means3D, shs, colo
     a.gradient_uvs = _ptr(gradient_uvs)
     a.texture = _ptr(texture)
     a.extra_attrs = _ptr(extra_attrs)
+    a.cov3Ds_precomp = _ptr(cov3Ds_precomp)
     if profile_arr is not None:
         a.profile_events = C.cast(profile_arr, C.POINTER(C.c_void_p))
     return a
@@ -215,7 +216,8 @@ def _build_args(st: GaussianRasterizationSettings, mode: int, means3D, shs, colo
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, shs, colors_precomp, opacities, scales, rotations, uvs, gradient_uvs,
-                texture, st: GaussianRasterizationSettings, mode: int, dual: bool = False, extra_attrs=None):
+                texture, st: GaussianRasterizationSettings, mode: int, dual: bool = False, extra_attrs=None,
+                cov3Ds_precomp=None):
         lib = L.load()
         if not means3D.is_cuda:
             raise L.TexgsError("the rasterizer runs on CUDA tensors only (no CPU fallback); got " + str(means3D.device))
@@ -232,8 +234,16 @@ class _RasterizeGaussians(torch.autograd.Function):
                 raise L.TexgsError("uvs must be (P,3) and gradient_uvs (P,9)")
         if sh is not None and (sh.dim() != 3 or sh.shape[0] != P or sh.shape[2] != 3):
             raise L.TexgsError(f"shs must be (P,M,3), got {tuple(sh.shape)}")
-        if op.numel() != P or sc.shape != (P, 3) or ro.shape != (P, 4):
-            raise L.TexgsError("opacities (P,1), scales (P,3), rotations (P,4) expected")
+        cov = _prep(cov3Ds_precomp, dev)
+        if cov is not None:
+            if sc is not None or ro is not None or mode == L.MODE_TEXTURE:
+                raise L.TexgsError("cov3Ds_precomp replaces scales + rotations and is a diff_gauss (untextured) argument")
+            if cov.shape != (P, 6):
+                raise L.TexgsError(f"cov3Ds_precomp must be (P,6) [xx,xy,xz,yy,yz,zz], got {tuple(cov.shape)}")
+        elif sc is None or ro is None or sc.shape != (P, 3) or ro.shape != (P, 4):
+            raise L.TexgsError("scales (P,3) and rotations (P,4) expected")
+        if op.numel() != P:
+            raise L.TexgsError("opacities (P,1) expected")
         ex = _prep(extra_attrs, dev)
         if ex is not None and (ex.dim() != 2 or ex.shape[0] != P or ex.shape[1] < 1):
             raise L.TexgsError(f"extra_attrs must be (P,E) with E >= 1, got {tuple(ex.shape)}")
@@ -242,7 +252,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             stream = torch.cuda.current_stream(dev).cuda_stream
             from .profiling import current_event_array
             prof = current_event_array()      # captured here: backward runs on autograd's thread
-            a = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex, prof, ex)
+            a = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex, prof, ex, cov)
             tex4 = None
             if mode == L.MODE_TEXTURE and USE_PACKED_TEXTURE:
                 tex4 = _packed_texture(lib, texture, tex, stream)
@@ -299,7 +309,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                             ctx.fuse[name] = tgt[0]
         ctx.dev = dev
         ctx.has = (shs is not None, colors_precomp is not None, uvs is not None, texture is not None)
-        ctx.save_for_backward(m3, sh, cp, op, sc, ro, uv, guv, tex, ex, geom, binw, imgw)
+        ctx.save_for_backward(m3, sh, cp, op, sc, ro, uv, guv, tex, ex, cov, geom, binw, imgw)
         nondiff = [radii]
         if not dual:
             nondiff.append(image_nosh)
@@ -312,14 +322,14 @@ class _RasterizeGaussians(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_image, g_depth, g_norm, g_alpha, _g_radii, g_image_nosh, g_extra):
         lib = L.load()
-        m3, sh, cp, op, sc, ro, uv, guv, tex, ex, geom, binw, imgw = ctx.saved_tensors
+        m3, sh, cp, op, sc, ro, uv, guv, tex, ex, cov, geom, binw, imgw = ctx.saved_tensors
         st, mode, dev = ctx.st, ctx.mode, ctx.dev
         P = m3.shape[0]
-        need = ctx.needs_input_grad   # means3D, means2D, shs, colors_precomp, opacities, scales, rotations, uvs, gradient_uvs, texture, st, mode, dual, extra_attrs
+        need = ctx.needs_input_grad   # means3D, means2D, shs, colors_precomp, opacities, scales, rotations, uvs, gradient_uvs, texture, st, mode, dual, extra_attrs, cov3Ds_precomp
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             b = L.TexgsBwdArgs()
-            b.fwd = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex, ctx.prof, ex)
+            b.fwd = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex, ctx.prof, ex, cov)
             if ctx.tex4 is not None:
                 b.fwd.texture_rgba = _ptr(ctx.tex4)
             b.geom_ws, b.bin_ws, b.img_ws, b.pair_capacity = _ptr(geom), _ptr(binw), _ptr(imgw), ctx.cap
@@ -362,8 +372,10 @@ class _RasterizeGaussians(torch.autograd.Function):
             k_sh, d_sh = out_or_fused("shs", L.ACC_SHS, need[2] and sh is not None, *(sh.shape if sh is not None else (0,)))
             k_cp, d_cp = out_or_fused("colors_precomp", L.ACC_COLORS, need[3] and cp is not None, P, 3)
             k_op, d_op = out_or_fused("opacities", L.ACC_OPACITY, need[4], P, 1)
-            k_sc, d_sc = out_or_fused("scales", L.ACC_SCALES, need[5], P, 3)
-            k_ro, d_ro = out_or_fused("rotations", L.ACC_ROTATIONS, need[6], P, 4)
+            k_sc, d_sc = out_or_fused("scales", L.ACC_SCALES, need[5] and sc is not None, P, 3)
+            k_ro, d_ro = out_or_fused("rotations", L.ACC_ROTATIONS, need[6] and ro is not None, P, 4)
+            d_cov = out(need[14] and cov is not None, P, 6)
+            b.dL_dcov3Ds = _ptr(d_cov)
             k_uv, d_uv = out_or_fused("uvs", L.ACC_UVS, need[7] and uv is not None, P, 3)
             d_tex, d_tex4 = None, None
             zero_tex = 1
@@ -392,7 +404,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             if zero_tex == 0:
                 d_tex = None
             L.check(lib.texgs_backward(C.byref(b), C.c_void_p(stream)), "texgs_backward")
-        return d_m3, d_m2, d_sh, d_cp, d_op, d_sc, d_ro, d_uv, None, d_tex, None, None, None, d_ex
+        return d_m3, d_m2, d_sh, d_cp, d_op, d_sc, d_ro, d_uv, None, d_tex, None, None, None, d_ex, d_cov
 
 
 class GaussianRasterizer(nn.Module):
@@ -423,10 +435,11 @@ class GaussianRasterizer(nn.Module):
         """``dual_no_sh=True`` (textured mode) appends a 7th result: the image the same
         splats give with ``sh_degree = 0``, blended in the same pass."""
         st = self.raster_settings
-        if cov3Ds_precomp is not None:
-            raise NotImplementedError("cov3Ds_precomp: the disc normal / intersection need scales + rotations")
-        if scales is None or rotations is None:
-            raise ValueError("Please provide scales and rotations")
+        if ((scales is None or rotations is None) and cov3Ds_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3Ds_precomp is not None):
+            raise ValueError("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        if cov3Ds_precomp is not None and texture is not None:
+            raise ValueError("cov3Ds_precomp is a diff_gauss argument (render/render.py:83); the textured rasterizer needs scales and rotations")
         if texture is not None:
             mode = L.MODE_TEXTURE
             if colors_precomp is not None:
@@ -439,7 +452,7 @@ class GaussianRasterizer(nn.Module):
             raise ValueError("dual_no_sh needs the textured mode")
         image, depth, norm, alpha, radii, image_nosh, extra = _RasterizeGaussians.apply(
             means3D, means2D, shs, colors_precomp, opacities, scales, rotations, uvs, gradient_uvs, texture, st, mode,
-            bool(dual_no_sh), extra_attrs)
+            bool(dual_no_sh), extra_attrs, cov3Ds_precomp)
         if extra_attrs is None:
             extra = None
         if dual_no_sh:
