@@ -381,19 +381,24 @@ def run_e2e(args, wl, g, cams, cot_dev, bg, bucket, views, dev, world, sync_all)
 
     from texture_gs_b200 import invalidate_packed_cache
 
+    primed = [False]      # view 0 of the NEXT step is uploaded while the last view of this step renders (loader prefetch)
+
     def step():
         invalidate_packed_cache()
         bucket.zero()
         total = torch.zeros((), device=dev)
         main = torch.cuda.current_stream(dev)
-        for s in range(2):
-            free[s].record(main)
-        if views:
+        if views and not primed[0]:
+            for s in range(2):
+                free[s].record(main)
             upload(0)
+        nv = len(views)
         for i, v in enumerate(views):
             slot = i & 1
-            if i + 1 < len(views):
+            if i + 1 < nv:
                 upload((i + 1) & 1)
+            elif nv % 2 == 0:
+                upload(0)                      # next step's first view (slot 0 was released after view nv-2)
             main.wait_event(ready[slot])
             cam = cams[v % len(cams)]
             with bucket.fused():
@@ -403,6 +408,7 @@ def run_e2e(args, wl, g, cams, cot_dev, bg, bucket, views, dev, world, sync_all)
                     total += sum(torch.dot(o.detach().reshape(-1), c.reshape(-1)) for o, c in zip(outs, bufs[slot]))
                 torch.autograd.backward(outs, list(bufs[slot]))
             free[slot].record(main)
+        primed[0] = nv > 0 and nv % 2 == 0
         bucket.all_reduce()
         result_host.copy_(total.reshape(1), non_blocking=True)
 

@@ -19,3 +19,27 @@ for fn in (uv_tex_render, uv_tex_render_dual):
     g.zero_grad()
 torch.cuda.synchronize()
 print("sanitize run ok")
+# cold paths: extra_attrs channels (two channel groups) and cov3Ds_precomp in the plain 3DGS mode
+import math
+from texture_gs_b200 import GaussianRasterizationSettings, GaussianRasterizer
+t = g.tensors()
+st = GaussianRasterizationSettings(120, 200, math.tan(cam.FoVx / 2), math.tan(cam.FoVy / 2), bg, 1.0, cam.world_view_transform,
+                                   cam.full_proj_transform, 3, cam.camera_center, False, False)
+ex = torch.randn(t["xyz"].shape[0], 11, device="cuda", requires_grad=True)
+out = GaussianRasterizer(st)(means3D=t["xyz"], means2D=torch.zeros_like(t["xyz"], requires_grad=True), opacities=t["opacity"], shs=t["shs"],
+                             scales=t["scaling"], rotations=t["rotation"], uvs=t["uvs"], gradient_uvs=t["grad_uvs"], texture=t["texture"],
+                             extra_attrs=ex)
+(out[0].sum() + out[5].sum()).backward()
+g.zero_grad()
+q = t["rotation"].detach()
+r, x, y, z = q.unbind(-1)
+R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y), 2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                 2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], dim=-1).reshape(-1, 3, 3)
+Lm = R * t["scaling"].detach()[:, None, :]
+S = Lm @ Lm.transpose(1, 2)
+cov = torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], dim=-1).contiguous().requires_grad_(True)
+out = GaussianRasterizer(st)(means3D=t["xyz"], means2D=torch.zeros_like(t["xyz"], requires_grad=True), opacities=t["opacity"],
+                             colors_precomp=torch.rand_like(t["xyz"]), cov3Ds_precomp=cov)
+(out[0].sum() + out[1].sum()).backward()
+torch.cuda.synchronize()
+print("sanitize cold paths ok", float(ex.grad.abs().sum()), float(cov.grad.abs().sum()))

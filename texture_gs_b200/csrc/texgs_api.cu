@@ -281,6 +281,7 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
     RasterParams p;
     if (int rc = fill_params(a, (void*)b->geom_ws, (void*)b->bin_ws, b->pair_capacity, (void*)b->img_ws, L, p)) return rc;
     if (!b->acc_ws) return fail(TEXGS_E_WORKSPACE, "acc_ws is NULL");
+    if ((uintptr_t)b->acc_ws & 15) return fail(TEXGS_E_WORKSPACE, "acc_ws must be 16-byte aligned");
     const bool debug = (a->flags & TEXGS_FLAG_DEBUG) != 0;
 
     TEXGS_EV(a, TEXGS_EV_BWD_START, stream);
@@ -323,7 +324,11 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
     if (p.P > 0) {
         BwdOut g{b->dL_dmeans3D, b->dL_dmeans2D, b->dL_dopacity, b->dL_dscales, b->dL_drotations,
                  b->dL_dshs, b->dL_dcolors_precomp, b->dL_duvs, a->cov3Ds_precomp ? b->dL_dcov3Ds : nullptr, b->accumulate_mask};
-        texgs_preprocess_bwd<<<(p.P + 255) / 256, 256, 0, stream>>>(p, b->acc_ws, g);
+        const size_t smem = prebwd_smem_bytes(p.M);
+        if (smem > 200 * 1024) return fail(TEXGS_E_INVALID, "too many SH coefficients per Gaussian for the staged backward");
+        if (smem > 48 * 1024)   // idempotent; only reached with more than 15 coefficients per Gaussian
+            TEXGS_CUDA_TRY(cudaFuncSetAttribute(texgs_preprocess_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        texgs_preprocess_bwd<<<(p.P + 255) / 256, 256, smem, stream>>>(p, b->acc_ws, g);
         TEXGS_KERNEL_CHECK("texgs_preprocess_bwd", debug, stream);
     }
     TEXGS_EV(a, TEXGS_EV_BWD_PREPROCESS, stream);

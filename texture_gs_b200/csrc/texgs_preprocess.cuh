@@ -214,8 +214,10 @@ __global__ void __launch_bounds__(256) texgs_preprocess_fwd(const RasterParams p
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void put(float* p, float v, bool acc) { if (acc) *p += v; else *p = v; }
 
-__device__ __forceinline__ void sh_rest_bwd(int deg, const float* __restrict__ sh, float3 d, float3 g,
-                                            float* __restrict__ dsh, float3& ddir, bool accum) {
+// ``sh`` and ``dsh`` may be the SAME row (staged path: the gradient replaces the coefficients in shared memory; each
+// coefficient is read before it is overwritten), hence no __restrict__.
+__device__ __forceinline__ void sh_rest_bwd(int deg, const float* sh, float3 d, float3 g,
+                                            float* dsh, float3& ddir, bool accum) {
     // dsh_k = basis_k * g ;  ddir = sum_k dbasis_k/dd * (sh_k . g)
     ddir = f3(0.f, 0.f, 0.f);
     if (deg <= 0) return;
@@ -254,29 +256,38 @@ struct BwdOut {
 #ifndef TEXGS_PREBWD_MIN_CTAS
 #define TEXGS_PREBWD_MIN_CTAS 3
 #endif
-__global__ void __launch_bounds__(256, TEXGS_PREBWD_MIN_CTAS) texgs_preprocess_bwd(const RasterParams p,
-                                                          const float* __restrict__ acc_all, const BwdOut g) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.P) return;
+// zero gradient rows of a culled Gaussian: written in overwrite mode, nothing to add in accumulate mode
+__device__ __forceinline__ void prebwd_write_zero(const RasterParams& p, const BwdOut& g, int idx, bool skip_shs) {
     const int nsh = p.M * 3;
-    Proj o;
-    project_gaussian(p, idx, o);
-    float dmu[3] = {0.f, 0.f, 0.f};
     const bool a_m3 = g.acc & TEXGS_ACC_MEANS3D, a_m2 = g.acc & TEXGS_ACC_MEANS2D, a_op = g.acc & TEXGS_ACC_OPACITY;
     const bool a_sc = g.acc & TEXGS_ACC_SCALES, a_ro = g.acc & TEXGS_ACC_ROTATIONS, a_sh = g.acc & TEXGS_ACC_SHS;
     const bool a_cp = g.acc & TEXGS_ACC_COLORS, a_uv = g.acc & TEXGS_ACC_UVS;
-    if (!o.visible) {   // zero gradient: written in overwrite mode, nothing to add in accumulate mode
-        if (g.dmeans3D && !a_m3) { g.dmeans3D[3 * idx] = 0.f; g.dmeans3D[3 * idx + 1] = 0.f; g.dmeans3D[3 * idx + 2] = 0.f; }
-        if (g.dmeans2D && !a_m2) { g.dmeans2D[3 * idx] = 0.f; g.dmeans2D[3 * idx + 1] = 0.f; g.dmeans2D[3 * idx + 2] = 0.f; }
-        if (g.dopacity && !a_op) g.dopacity[idx] = 0.f;
-        if (g.dscales && !a_sc) { g.dscales[3 * idx] = 0.f; g.dscales[3 * idx + 1] = 0.f; g.dscales[3 * idx + 2] = 0.f; }
-        if (g.drotations && !a_ro) *reinterpret_cast<float4*>(g.drotations + 4 * idx) = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g.dshs && !a_sh) for (int k = 0; k < nsh; ++k) g.dshs[(size_t)idx * nsh + k] = 0.f;
-        if (g.dcolors_precomp && !a_cp) { g.dcolors_precomp[3 * idx] = 0.f; g.dcolors_precomp[3 * idx + 1] = 0.f; g.dcolors_precomp[3 * idx + 2] = 0.f; }
-        if (g.duvs && !a_uv) { g.duvs[3 * idx] = 0.f; g.duvs[3 * idx + 1] = 0.f; g.duvs[3 * idx + 2] = 0.f; }
-        if (g.dcov3Ds) for (int k = 0; k < 6; ++k) g.dcov3Ds[(size_t)6 * idx + k] = 0.f;
-        return;
-    }
+    if (g.dmeans3D && !a_m3) { g.dmeans3D[3 * idx] = 0.f; g.dmeans3D[3 * idx + 1] = 0.f; g.dmeans3D[3 * idx + 2] = 0.f; }
+    if (g.dmeans2D && !a_m2) { g.dmeans2D[3 * idx] = 0.f; g.dmeans2D[3 * idx + 1] = 0.f; g.dmeans2D[3 * idx + 2] = 0.f; }
+    if (g.dopacity && !a_op) g.dopacity[idx] = 0.f;
+    if (g.dscales && !a_sc) { g.dscales[3 * idx] = 0.f; g.dscales[3 * idx + 1] = 0.f; g.dscales[3 * idx + 2] = 0.f; }
+    if (g.drotations && !a_ro) *reinterpret_cast<float4*>(g.drotations + 4 * idx) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.dshs && !a_sh && !skip_shs) for (int k = 0; k < nsh; ++k) g.dshs[(size_t)idx * nsh + k] = 0.f;
+    if (g.dcolors_precomp && !a_cp) { g.dcolors_precomp[3 * idx] = 0.f; g.dcolors_precomp[3 * idx + 1] = 0.f; g.dcolors_precomp[3 * idx + 2] = 0.f; }
+    if (g.duvs && !a_uv) { g.duvs[3 * idx] = 0.f; g.duvs[3 * idx + 1] = 0.f; g.duvs[3 * idx + 2] = 0.f; }
+    if (g.dcov3Ds) for (int k = 0; k < 6; ++k) g.dcov3Ds[(size_t)6 * idx + k] = 0.f;
+}
+
+// gradients of one visible Gaussian. ``sh_row`` / ``dsh_row``: its SH coefficients and where their gradient goes —
+// global rows (accumulate per TEXGS_ACC_SHS) or, staged, the same shared-memory row (always overwritten; the
+// accumulation happens in the warp's coalesced store).
+__device__ __forceinline__ void prebwd_one(const RasterParams& p, const float* __restrict__ acc_all, const BwdOut& g, int idx,
+                                           const Proj& o, const float* sh_row, float* dsh_row) {
+    const int nsh = p.M * 3;
+    float dmu[3] = {0.f, 0.f, 0.f};
+    const bool a_m3 = g.acc & TEXGS_ACC_MEANS3D, a_m2 = g.acc & TEXGS_ACC_MEANS2D, a_op = g.acc & TEXGS_ACC_OPACITY;
+    const bool a_sc = g.acc & TEXGS_ACC_SCALES, a_ro = g.acc & TEXGS_ACC_ROTATIONS;
+    const bool a_cp = g.acc & TEXGS_ACC_COLORS, a_uv = g.acc & TEXGS_ACC_UVS;
+#if TEXGS_PREBWD_STAGE_SH
+    const bool a_sh = false;
+#else
+    const bool a_sh = g.acc & TEXGS_ACC_SHS;
+#endif
     const float* acc = acc_all + (size_t)idx * TEXGS_BWD_ACC_FLOATS;
     const float* V = p.view.m;
 
@@ -288,8 +299,8 @@ __global__ void __launch_bounds__(256, TEXGS_PREBWD_MIN_CTAS) texgs_preprocess_b
         const float len2 = dot3(o.m, o.m);
         const float inv_len = rsqrtf(len2);
         const float3 dir = f3(o.m.x * inv_len, o.m.y * inv_len, o.m.z * inv_len);
-        const float* sh = p.shs + (size_t)idx * nsh;
-        float* dsh = g.dshs ? g.dshs + (size_t)idx * nsh : nullptr;
+        const float* sh = sh_row;
+        float* dsh = dsh_row;
         const int deg = min(p.sh_degree, 3);
         const int nrest_active = (deg + 1) * (deg + 1) - 1;
         int first_rest = 0;
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__(256, TEXGS_PREBWD_MIN_CTAS) texgs_preprocess_b
         dmu[0] += (ddir.x - dir.x * dd) * inv_len;
         dmu[1] += (ddir.y - dir.y * dd) * inv_len;
         dmu[2] += (ddir.z - dir.z * dd) * inv_len;
-    } else if (g.dshs && !a_sh) {
+    } else if (g.dshs && !(g.acc & TEXGS_ACC_SHS)) {
         for (int k = 0; k < nsh; ++k) g.dshs[(size_t)idx * nsh + k] = 0.f;
     }
 
@@ -443,4 +454,76 @@ __global__ void __launch_bounds__(256, TEXGS_PREBWD_MIN_CTAS) texgs_preprocess_b
         if (a_ro) { const float4 o4 = *dst; dq.x += o4.x; dq.y += o4.y; dq.z += o4.z; dq.w += o4.w; }
         *dst = dq;
     }
+}
+
+// TEXGS_PREBWD_STAGE_SH: the SH coefficients (and their gradient) of the 32 Gaussians of a warp are one contiguous
+// block of global memory, but a thread that owns one Gaussian walks it with a stride of 12 M bytes: every load /
+// store instruction touches 32 sectors. Staged: the warp copies its block into shared memory with coalesced
+// accesses, every lane works on its row there (row stride odd: conflict-free), the gradient replaces the
+// coefficients in place and leaves with coalesced stores (read-modify-write in accumulate mode).
+#ifndef TEXGS_PREBWD_STAGE_SH
+#define TEXGS_PREBWD_STAGE_SH 0
+#endif
+__host__ __device__ __forceinline__ int prebwd_row_stride(int nsh) { return nsh | 1; }
+__host__ __forceinline__ size_t prebwd_smem_bytes(int M) {
+#if TEXGS_PREBWD_STAGE_SH
+    return M > 0 ? (size_t)8 * 32 * prebwd_row_stride(3 * M) * sizeof(float) : 0;
+#else
+    (void)M;
+    return 0;
+#endif
+}
+
+__global__ void __launch_bounds__(256, TEXGS_PREBWD_MIN_CTAS) texgs_preprocess_bwd(const RasterParams p,
+                                                          const float* __restrict__ acc_all, const BwdOut g) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nsh = p.M * 3;
+    const bool a_sh = g.acc & TEXGS_ACC_SHS;
+#if TEXGS_PREBWD_STAGE_SH
+    extern __shared__ float prebwd_smem[];
+    const int lane = threadIdx.x & 31;
+    const int ld = prebwd_row_stride(nsh);
+    float* const wrows = prebwd_smem + (size_t)(threadIdx.x >> 5) * 32 * ld;      // this warp's 32 rows
+    float* const myrow = wrows + lane * ld;
+    const int g0 = idx - lane;                                                    // first Gaussian of the warp
+    const int wcnt = max(0, min(32, p.P - g0)) * nsh;                             // floats in the warp's block
+    const bool staged = (p.shs != nullptr) && nsh > 0 && p.mode != TEXGS_MODE_PRECOMP;
+    if (staged) {
+        const float* __restrict__ src = p.shs + (size_t)g0 * nsh;
+        int r = lane / nsh, k = lane - r * nsh;
+        for (int i = lane; i < wcnt; i += 32) {
+            wrows[r * ld + k] = __ldg(src + i);
+            k += 32;
+            while (k >= nsh) { k -= nsh; ++r; }
+        }
+        __syncwarp();
+    }
+    // every lane stays until the cooperative store at the end: ``live`` replaces the early returns
+    const bool live = idx < p.P;
+    bool visible = false;
+    Proj o;
+    if (live) { project_gaussian(p, idx, o); visible = o.visible; }
+    if (staged && !visible) {
+        for (int k = 0; k < nsh; ++k) myrow[k] = 0.f;        // zero gradient row (adds nothing in accumulate mode)
+    }
+    if (live && visible) prebwd_one(p, acc_all, g, idx, o, myrow, myrow);
+    else if (live) prebwd_write_zero(p, g, idx, /*skip_shs=*/staged);
+    if (staged && g.dshs) {
+        __syncwarp();
+        float* __restrict__ dst = g.dshs + (size_t)g0 * nsh;
+        int r = lane / nsh, k = lane - r * nsh;
+        for (int i = lane; i < wcnt; i += 32) {
+            const float v = wrows[r * ld + k];
+            dst[i] = a_sh ? dst[i] + v : v;
+            k += 32;
+            while (k >= nsh) { k -= nsh; ++r; }
+        }
+    }
+#else
+    if (idx >= p.P) return;
+    Proj o;
+    project_gaussian(p, idx, o);
+    if (!o.visible) { prebwd_write_zero(p, g, idx, false); return; }
+    prebwd_one(p, acc_all, g, idx, o, p.shs ? p.shs + (size_t)idx * nsh : nullptr, g.dshs ? g.dshs + (size_t)idx * nsh : nullptr);
+#endif
 }
