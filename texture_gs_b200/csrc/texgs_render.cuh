@@ -18,6 +18,14 @@
 #ifndef TEXGS_FAST_EXP
 #define TEXGS_FAST_EXP 1
 #endif
+// timing ablation only (tools/build_variants.py): 1 = skip the per-contribution texture work (intersection, UV step,
+// cube lookup, taps and, in the backward, their gradients) to measure what the rest of the loop costs. Wrong images.
+#ifndef TEXGS_ABLATE_HEAVY
+#define TEXGS_ABLATE_HEAVY 0
+#endif
+#ifndef TEXGS_ABLATE_REDUCE
+#define TEXGS_ABLATE_REDUCE 0      // timing ablation only: no per-Gaussian lane reduction in the backward (wrong gradients)
+#endif
 __device__ __forceinline__ float texgs_exp(float x) {
 #if TEXGS_FAST_EXP
     return __expf(x);
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
                 if (cand) {
                     const float4 g2 = rec.q[2], g3 = rec.q[3];
                     float cr = g3.y, cg = g3.z, cb = g3.w;
-                    if (MODE == TEXGS_MODE_TEXTURE) {
+                    if (MODE == TEXGS_MODE_TEXTURE && !TEXGS_ABLATE_HEAVY) {
                         const float4 g4 = rec.q[4], g5 = rec.q[5], g6 = rec.q[6];
                         const UvEval e = eval_uv(g1, g2, g3, g4, g5, g6, g.vx, g.vy);
                         const CubeCoord cc = cube_coord(e.ux, e.uy, e.uz);
@@ -404,7 +412,7 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
                 Bilerp bl;
                 float t00[3], t01[3], t10[3], t11[3];
                 float4 g4, g5, g6;
-                if (MODE == TEXGS_MODE_TEXTURE) {
+                if (MODE == TEXGS_MODE_TEXTURE && !TEXGS_ABLATE_HEAVY) {
                     g4 = rec.q[4]; g5 = rec.q[5]; g6 = rec.q[6];
                     e = eval_uv(g1, g2, g3, g4, g5, g6, g.vx, g.vy);
                     cc = cube_coord(e.ux, e.uy, e.uz);
@@ -446,7 +454,7 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
                 v[6] = wr; v[7] = wg; v[8] = wb;
                 v[9] = w * gd;
                 v[10] = w * gnv.x; v[11] = w * gnv.y; v[12] = w * gnv.z;
-                if (MODE == TEXGS_MODE_TEXTURE) {
+                if (MODE == TEXGS_MODE_TEXTURE && !TEXGS_ABLATE_HEAVY) {
                     const float gt[3] = {SH_C0 * (wr + w * kr), SH_C0 * (wg + w * kg), SH_C0 * (wb + w * kb)};
                     float dwx = 0.f, dwy = 0.f;
                     const float w00 = (1.f - bl.wx) * (1.f - bl.wy), w01 = bl.wx * (1.f - bl.wy);
@@ -490,7 +498,14 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
             // each half-warp reduces ITS splat's 20 partials over its 16 lanes (both halves in the same
             // 20 shuffles) and adds them to that Gaussian's accumulators
             float outA, outB;
+#if TEXGS_ABLATE_REDUCE
+            outA = 0.f;
+#pragma unroll
+            for (int q = 0; q < 20; ++q) outA += v[q];
+            outB = outA;
+#else
             halfwarp_reduce20(v, lane, outA, outB);
+#endif
             if (has) {
                 float* dst = acc + (size_t)(unsigned)__float_as_int(rec.q[7].x) * TEXGS_BWD_ACC_FLOATS;
                 if (outA != 0.f) atomicAdd(dst + (lane & 15), outA);
