@@ -289,9 +289,19 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 
 
 // four bilinear taps as rgb triples, from the packed (float4) or the plain (3 floats) layout
+// timing ablation only: 1 = all taps read texels 0..255 (always L1 hits) — same instructions, no gather traffic
+#ifndef TEXGS_ABLATE_TAP_LOCALITY
+#define TEXGS_ABLATE_TAP_LOCALITY 0
+#endif
 template <bool TEX4>
-__device__ __forceinline__ void fetch_taps(const float* __restrict__ tex, const float4* __restrict__ tex4, const Bilerp& bl,
+__device__ __forceinline__ void fetch_taps(const float* __restrict__ tex, const float4* __restrict__ tex4, const Bilerp& bl_,
                                            float (&t00)[3], float (&t01)[3], float (&t10)[3], float (&t11)[3]) {
+#if TEXGS_ABLATE_TAP_LOCALITY
+    Bilerp bl = bl_;
+    bl.i00 &= 255; bl.i01 &= 255; bl.i10 &= 255; bl.i11 &= 255;
+#else
+    const Bilerp& bl = bl_;
+#endif
     if (TEX4) {
         const float4 a = __ldg(tex4 + bl.i00), b = __ldg(tex4 + bl.i01), c = __ldg(tex4 + bl.i10), d = __ldg(tex4 + bl.i11);
         t00[0] = a.x; t00[1] = a.y; t00[2] = a.z;

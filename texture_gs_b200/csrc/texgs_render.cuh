@@ -23,6 +23,9 @@
 #ifndef TEXGS_ABLATE_HEAVY
 #define TEXGS_ABLATE_HEAVY 0
 #endif
+#ifndef TEXGS_ABLATE_RED
+#define TEXGS_ABLATE_RED 0         // timing ablation only: no texel-gradient atomics in the backward (wrong texture gradient)
+#endif
 #ifndef TEXGS_ABLATE_REDUCE
 #define TEXGS_ABLATE_REDUCE 0      // timing ablation only: no per-Gaussian lane reduction in the backward (wrong gradients)
 #endif
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
                             atomicAdd(dtex + 3 * bl.i11 + ch, gt[ch] * w11);
                         }
                     }
-                    if (GRAD4 && dtex && (gt[0] != 0.f || gt[1] != 0.f || gt[2] != 0.f)) {
+                    if (GRAD4 && dtex && !TEXGS_ABLATE_RED && (gt[0] != 0.f || gt[1] != 0.f || gt[2] != 0.f)) {
                         red_add_v4(dtex + 4 * bl.i00, gt[0] * w00, gt[1] * w00, gt[2] * w00, 0.f);
                         red_add_v4(dtex + 4 * bl.i01, gt[0] * w01, gt[1] * w01, gt[2] * w01, 0.f);
                         red_add_v4(dtex + 4 * bl.i10, gt[0] * w10, gt[1] * w10, gt[2] * w10, 0.f);
