@@ -114,7 +114,7 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def algorithmic_bytes(N, M, V, K, U, P, R):
+def algorithmic_bytes(N, M, V, K, U, P, R, views_per_step=VIEWS_PER_STEP):
     """SURVEY.md §8d / DESIGN.md §4: algorithmic HBM bytes per view, split per kernel.
     N Gaussians, M SH-rest coeffs, V visible, K (tile,Gaussian) pairs, U unique texels touched,
     P pixels, R face resolution. Records are 128 B, accumulators 20 floats."""
@@ -125,7 +125,9 @@ def algorithmic_bytes(N, M, V, K, U, P, R):
     b["sort_tiles"] = K * 8 + K * 12
     b["render_fwd"] = K * (4 + 128) + U * 12 + P * 40
     b["render_bwd"] = P * 40 + K * (4 + 128) + U * 12 + 2 * U * 12 + 2 * V * 80
-    b["bwd_clear"] = 6 * R * R * 12 + N * 96
+    # per view: the accumulator clear; the dense texture-gradient zero fill happens once per step (GradBucket.zero()),
+    # outside the per-view kernels, and is charged to the view at 1 / views_per_step
+    b["bwd_clear"] = N * 96 + 6 * R * R * 16 // max(1, views_per_step)
     b["preprocess_bwd"] = N * (92 + 12 * M) + V * 80 + N * (68 + 12 * M)
     return b
 
@@ -316,7 +318,7 @@ def main():
 
     hbm_peak, peak_src = measured_peaks()
     N, M = wl.n_gaussians, 15
-    ab = algorithmic_bytes(N, M, stats.num_visible, stats.num_pairs, U, wl.width * wl.height, wl.tex_res)
+    ab = algorithmic_bytes(N, M, stats.num_visible, stats.num_pairs, U, wl.width * wl.height, wl.tex_res, args.views)
     per_kernel = {}
     for k, b in ab.items():
         if k in stage_ms and stage_ms[k] > 0:
