@@ -131,3 +131,36 @@ def test_product_package_never_imports_the_oracle():
         assert "import oracle" not in txt and "from oracle" not in txt, f
     for f in (ROOT / "diff_gauss_uv_tex" / "__init__.py", ROOT / "diff_gauss" / "__init__.py"):
         assert "oracle" not in f.read_text()
+
+
+def test_cold_path_arguments_are_validated_without_a_gpu():
+    """extra_attrs / cov3Ds_precomp (render/render.py:75-84): argument rules are enforced before anything is launched."""
+    lib = L.load()
+    ks = lib.texgs_kernel_names().decode().split(",")
+    assert "texgs_extra_fwd" in ks and "texgs_extra_bwd" in ks
+    dummy = C.c_void_p(256)                               # never dereferenced: validation fails first
+    a = _args()
+    a.means3D = a.opacities = a.scales = a.rotations = a.uvs = a.gradient_uvs = a.texture = dummy
+    a.E = 4                                               # E > 0 without extra_attrs
+    rc = lib.texgs_forward(C.byref(a), dummy, dummy, 10, dummy, dummy, dummy, dummy, dummy, dummy, None, None, None, None)
+    assert rc == 1001 and b"extra_attrs" in lib.texgs_last_error()
+    a = _args(mode=L.MODE_PRECOMP)
+    a.means3D = a.opacities = a.colors_precomp = a.scales = a.rotations = a.cov3Ds_precomp = dummy
+    rc = lib.texgs_forward(C.byref(a), dummy, dummy, 10, dummy, dummy, dummy, dummy, dummy, dummy, None, None, None, None)
+    assert rc == 1001 and b"not both" in lib.texgs_last_error()
+    a = _args()                                           # textured mode does not take a precomputed covariance
+    a.means3D = a.opacities = a.uvs = a.gradient_uvs = a.texture = a.cov3Ds_precomp = dummy
+    rc = lib.texgs_forward(C.byref(a), dummy, dummy, 10, dummy, dummy, dummy, dummy, dummy, dummy, None, None, None, None)
+    assert rc == 1001 and b"cov3Ds_precomp" in lib.texgs_last_error()
+    # operator level: same messages the reference's wrapper gives for inconsistent geometry arguments
+    from texture_gs_b200 import GaussianRasterizationSettings, GaussianRasterizer
+    st = GaussianRasterizationSettings(16, 16, 0.5, 0.5, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 0, torch.zeros(3))
+    r = GaussianRasterizer(st)
+    x = torch.zeros(4, 3)
+    with pytest.raises(ValueError):
+        r(means3D=x, means2D=x, opacities=torch.ones(4, 1), colors_precomp=x, scales=x, rotations=torch.zeros(4, 4), cov3Ds_precomp=torch.zeros(4, 6))
+    with pytest.raises(ValueError):
+        r(means3D=x, means2D=x, opacities=torch.ones(4, 1), colors_precomp=x)
+    with pytest.raises(ValueError):
+        r(means3D=x, means2D=x, opacities=torch.ones(4, 1), uvs=x, gradient_uvs=torch.zeros(4, 9), texture=torch.zeros(6, 2, 2, 3),
+          cov3Ds_precomp=torch.zeros(4, 6))
