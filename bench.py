@@ -252,19 +252,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL announces its version on stdout while the communicator is created; stdout carries exactly ONE JSON
-        # line, so file descriptor 1 points at stderr until the first collective has run
-        sys.stdout.flush()
-        saved_fd = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            dist.barrier()
-            torch.cuda.synchronize(dev)
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_fd, 1)
-            os.close(saved_fd)
+        from texture_gs_b200.dist import init_process_group_quiet
+        init_process_group_quiet("nccl", dev)        # keeps NCCL's version banner off stdout (one JSON line only)
     _lib.load()
 
     g, cams, cot = make_scene(wl, dev)

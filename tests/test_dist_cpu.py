@@ -67,3 +67,38 @@ def test_two_rank_gloo_allreduce_matches_single_process_sum():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+_QUIET_CHILD = r"""
+import os, sys
+sys.path.insert(0, os.environ["REPO_ROOT"])
+import torch, torch.distributed as dist
+from texture_gs_b200.dist import init_process_group_quiet
+rank = int(os.environ["RANK"])
+print("before", flush=True)                                  # stdout, rank-tagged below
+init_process_group_quiet("gloo", torch.device("cpu"))
+os.write(1, b"")                                              # fd 1 is usable again
+t = torch.ones(1) * (rank + 1)
+dist.all_reduce(t)
+print('{"rank": %d, "sum": %d}' % (rank, int(t.item())), flush=True)
+dist.destroy_process_group()
+"""
+
+
+def test_quiet_init_restores_stdout_and_the_group_works(tmp_path):
+    """bench.py's N>1 path: init + barrier with fd 1 parked on stderr, then exactly the JSON line on stdout."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    port = _free_port()
+    script = tmp_path / "child.py"
+    script.write_text(_QUIET_CHILD)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(r), WORLD_SIZE="2",
+                   REPO_ROOT=str(Path(__file__).resolve().parent.parent))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=120) for p in procs]
+    for r, (p, (so, se)) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, se
+        assert so.splitlines() == ["before", '{"rank": %d, "sum": 3}' % r], (so, se)

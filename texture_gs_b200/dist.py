@@ -17,6 +17,32 @@ import torch
 import torch.distributed as dist
 
 
+def init_process_group_quiet(backend: str, device: Optional[torch.device] = None, **kw) -> None:
+    """``dist.init_process_group`` + one barrier with file descriptor 1 pointed at stderr meanwhile.
+
+    NCCL announces its version on stdout while the communicator is created (at init when ``device_id`` is given,
+    else at the first collective). A launcher whose stdout carries a machine-readable result — ``bench.py`` prints
+    exactly one JSON line — must not have that line in front of it. Everything printed after this call goes to the
+    real stdout again."""
+    import os
+    import sys
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if device is not None and device.type == "cuda":
+            dist.init_process_group(backend, device_id=device, **kw)
+        else:
+            dist.init_process_group(backend, **kw)
+        dist.barrier()
+        if device is not None and device.type == "cuda":
+            torch.cuda.synchronize(device)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
+
+
 def shard_views(num_views: int, world_size: int, rank: int) -> List[int]:
     """Indices of the views rank ``rank`` renders: contiguous blocks, sizes differ by at most one."""
     base, rem = divmod(num_views, world_size)
