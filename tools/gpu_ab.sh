@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B timing of build variants on the headline config: bash tools/gpu_ab.sh name1 name2 ...  (default build first)
+# A/B timing of build variants (tools/build_variants.py name:-DFLAG=1 ...) on the headline config: bash tools/gpu_ab.sh name1 name2 ...  (default build first)
 O=gpurun_out; mkdir -p $O
 timeout 200 python tests/gpu_variants.py fused > $O/ab_default.json 2> $O/ab_default.err
 for n in "$@"; do
