@@ -148,9 +148,9 @@ _cpu_cache = {}
 
 
 def cpu_oracle_views_per_s(wl, sample_tiles: int, backward: bool = True):
-    """Times oracle forward+backward of ONE view restricted to a seeded subset of tiles and
-    extrapolates the per-tile part by the (tile,Gaussian)-pair fraction; the forward per-Gaussian
-    stage (projection + binning of all N Gaussians) is timed separately and counted once.
+    """Times oracle forward+backward of ONE view restricted to a seeded subset of tiles and scales the per-tile
+    part by the (tile,Gaussian)-pair ratio; the per-Gaussian stages (projection + binning of all N Gaussians and
+    their backward) are timed by a call that renders no tile and counted once.
     Returns (views/s, description, threads, sample seconds)."""
     import numpy as np
     from oracle import raster_ref as RR
@@ -170,32 +170,35 @@ def cpu_oracle_views_per_s(wl, sample_tiles: int, backward: bool = True):
     gx, gy = (wl.width + 15) // 16, (wl.height + 15) // 16
     ntiles = gx * gy
     if sample_tiles <= 0:
-        sample_tiles = max(8, ntiles // 40)            # 2.5 % of the tiles
-    sample_tiles = min(sample_tiles, ntiles)
-    subset = np.random.RandomState(0).choice(ntiles, size=sample_tiles, replace=False)
-    # (1) per-Gaussian stage alone (forward): projection of all N + binning
-    with torch.no_grad():
+        sample_tiles = max(8, ntiles // 20)            # 5 % of the tiles
+    sample_tiles = max(2, min(sample_tiles, ntiles))
+    # fixed per-call cost (projection + binning of all N Gaussians, their backward, output allocation) is measured by a
+    # call that renders ONE tile and counted once; only the per-tile part of the sample is scaled up
+    perm = np.random.RandomState(0).permutation(ntiles)
+    subset = perm[:sample_tiles]
+
+    def one(subset):
+        g.zero_grad()
         t0 = time.perf_counter()
-        pre = RR.preprocess(t["xyz"], None, t["scaling"], t["rotation"], t["opacity"], t["shs"], st)
-        RR.build_tile_lists(pre)
-        t_pre = time.perf_counter() - t0
-    # (2) sample: full per-Gaussian stage + the subset of tiles, forward + backward
-    g.zero_grad()
-    t0 = time.perf_counter()
-    m2 = torch.zeros_like(t["xyz"], requires_grad=backward)
-    out = RR.rasterize(t["xyz"], m2, t["shs"], t["opacity"], t["scaling"], t["rotation"], t["uvs"], t["grad_uvs"],
-                       t["texture"], st, tile_subset=subset, return_aux=True)
-    if backward:
-        L = sum((a * b).sum() for a, b in zip(out[:4], cot))
-        L.backward()
-    dt = time.perf_counter() - t0
-    tile_of = out[-1]["tile_of"]
-    frac = int(np.isin(tile_of, subset).sum()) / max(1, tile_of.shape[0])
-    est_full = t_pre + max(dt - t_pre, 0.0) / max(frac, 1e-9)
-    desc = (f"oracle fwd{'+bwd' if backward else ''} of 1 view: all {wl.n_gaussians} Gaussians projected+binned ({t_pre:.2f} s, counted once) + "
-            f"{sample_tiles}/{ntiles} seeded tiles = {frac:.4f} of the (tile,Gaussian) pairs ({dt:.2f} s incl. projection), tile part "
-            f"extrapolated by pair fraction (x{1.0 / max(frac, 1e-9):.1f}) -> {est_full:.1f} s/view; torch {torch.__version__}, {threads} threads")
-    return 1.0 / est_full, desc, threads, dt
+        m2 = torch.zeros_like(t["xyz"], requires_grad=backward)
+        out = RR.rasterize(t["xyz"], m2, t["shs"], t["opacity"], t["scaling"], t["rotation"], t["uvs"], t["grad_uvs"],
+                           t["texture"], st, tile_subset=subset, return_aux=True)
+        if backward:
+            L = sum((a * b).sum() for a, b in zip(out[:4], cot))
+            L.backward()
+        dt = time.perf_counter() - t0
+        tile_of = out[-1]["tile_of"]
+        return dt, int(np.isin(tile_of, subset).sum()), int(tile_of.shape[0])
+
+    t_fixed, pairs0, K = one(perm[:1])
+    dt, pairs, _ = one(subset)
+    per_pair = max(dt - t_fixed, 0.0) / max(pairs - pairs0, 1)
+    est_full = t_fixed + per_pair * max(K - pairs0, 0)
+    desc = (f"oracle fwd{'+bwd' if backward else ''} of 1 view: all {wl.n_gaussians} Gaussians projected+binned with one tile rendered "
+            f"{t_fixed:.2f} s (counted once) + {sample_tiles}/{ntiles} seeded tiles = {pairs} of the view's {K} (tile,Gaussian) pairs in "
+            f"{max(dt - t_fixed, 0.0):.2f} s more, that part scaled by the pair ratio (x{max(K - pairs0, 0) / max(pairs - pairs0, 1):.1f}) "
+            f"-> {est_full:.1f} s/view; torch {torch.__version__}, {threads} threads")
+    return 1.0 / est_full, desc, threads, t_fixed + dt
 
 
 def run_reference(args, wl):
@@ -207,7 +210,7 @@ def run_reference(args, wl):
     threads = 1
     t_all = time.perf_counter()
     for i in range(args.warmup + args.steps):
-        v, desc, threads, dt = cpu_oracle_views_per_s(wl, args.cpu_sample_tiles or 102)
+        v, desc, threads, dt = cpu_oracle_views_per_s(wl, args.cpu_sample_tiles)
         if i >= args.warmup:
             vals.append(v)
         if time.perf_counter() - t_all > 240:
@@ -415,7 +418,7 @@ def run_e2e(args, wl, g, cams, cot_dev, bg, bucket, views, dev, world, sync_all)
         bucket.all_reduce()
         result_host.copy_(total.reshape(1), non_blocking=True)
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(max(3, args.warmup)):
         step()
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
