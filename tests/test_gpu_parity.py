@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import ABS_TOL, GRAD_RTOL, compare_images, rel_err, run_cuda, run_oracle
+from util import ABS_TOL, GRAD_RTOL, check_backward, check_forward, compare_images, rel_err, run_cuda, run_oracle
 from texture_gs_b200.scene import (C0, SyntheticGaussians, orbit_cameras, output_cotangents, sphere_shell_scene)
 
 pytestmark = pytest.mark.gpu
@@ -28,56 +28,7 @@ def _need_cuda():
     _lib.load()   # fail loudly if the extension is missing
 
 
-def _check_forward(g, cam, bg=(0.0, 0.0, 0.0), max_amb=0.15, scale_modifier=1.0):
-    ref, aux, _ = run_oracle(g, cam, bg=bg, scale_modifier=scale_modifier)
-    got, stats, _ = run_cuda(g, cam, bg=bg, scale_modifier=scale_modifier)
-    rep = compare_images(got[:4], ref[:4], aux["ambiguous"])
-    print(rep, stats)
-    # the binning drops (tile, Gaussian) pairs that provably cannot reach alpha >= 1/255 on the tile:
-    # never more pairs than the spec's tile rects, never fewer than the pairs that really blend
-    assert int(aux["pair_contributes"].sum()) <= stats.num_pairs <= aux["num_pairs"], (stats, aux["num_pairs"])
-    assert stats.num_visible == aux["num_visible"]
-    assert (got[4] != ref[4]).sum() == 0, "radii differ"
-    assert rep["ambiguous_frac"] <= max_amb
-    for n in ("image", "depth", "norm", "alpha"):
-        assert rep[n]["max_clear"] <= ABS_TOL * (3.0 if n == "depth" else 1.0), (n, rep[n])   # depth is O(2.5)-scaled
-        assert rep[n]["frac_over"] <= 2e-3, (n, rep[n])
-        assert rep[n]["max_all"] <= 0.1, (n, rep[n])      # flagged pixels may flip one contribution, not more
-    return rep
-
-
-def _check_backward(g, cam, bg=(0.0, 0.0, 0.0), seed=3, uv_tol=GRAD_RTOL, max_flag=0.2, scale_modifier=1.0, tol_over=None):
-    """Gradients of L = sum(out * cot) with the cotangents zeroed on the pixels the oracle flags as
-    ill-conditioned in fp32 (a blend decision within a few ulp of its threshold, or a ray grazing a
-    disc: t = n.m/n.d with |cos| < GRAZING_COS — there the fp32 ORACLE differs from the fp64 oracle
-    by more than the tolerance too, see tests/gpu_diag2.py).
-
-    Assertion per gradient tensor, max-norm relative error against the fp64 oracle:
-        err(cuda, o64) <= max(1e-3, 3 * err(o32, o64))
-    i.e. BASELINE's 1e-3 wherever fp32 arithmetic can deliver it, and otherwise no worse than 3x the
-    error the reference fp32 arithmetic (the oracle run in fp32) itself shows."""
-    kw = dict(scale_modifier=scale_modifier)
-    _, aux, _ = run_oracle(g, cam, bg=bg, **kw)
-    keep = (~aux["ambiguous"]).float()
-    assert float(1 - keep.mean()) <= max_flag     # low-res scenes: big discs near the silhouette cover many pixels
-    cot = [c * keep for c in output_cotangents(cam.image_height, cam.image_width, seed=seed)]
-    _, _, g64 = run_oracle(g, cam, bg=bg, cot=cot, dtype=torch.float64, **kw)
-    _, _, g32 = run_oracle(g, cam, bg=bg, cot=cot, **kw)
-    _, _, ggot = run_cuda(g, cam, bg=bg, cot=cot, **kw)
-    errs = {}
-    for k, r in g64.items():
-        if r is None:
-            continue
-        assert ggot[k] is not None, k
-        c, o = ggot[k], g32[k]
-        if k == "means2D":
-            c, r, o = c[:, :2], r[:, :2], o[:, :2]
-        errs[k] = (rel_err(c.reshape(r.shape), r), rel_err(o.reshape(r.shape), r))
-    print({k: ("%.2e" % a, "%.2e" % b) for k, (a, b) in errs.items()})
-    for k, (e_cuda, e_o32) in errs.items():
-        tol = uv_tol if k == "uvs" else (tol_over or {}).get(k, GRAD_RTOL)
-        assert e_cuda <= max(tol, 3.0 * e_o32), (k, e_cuda, e_o32)
-    return errs
+_check_forward, _check_backward = check_forward, check_backward      # shared with the emulated-kernel CPU suite (tests/util.py)
 
 
 def test_golden_tiny_scene():

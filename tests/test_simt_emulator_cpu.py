@@ -1,0 +1,142 @@
+"""The SIMT emulator itself (tests/simt/simt_emu.h) and the non-rasterizer kernels under it.
+
+1. ``selftest.cpp``: kernels with known answers, and kernels with known BUGS that the emulator must report (divergent
+   barrier, collective after a lane exited, shared memory read before the mbarrier wait, block exit with a bulk copy
+   in flight, wrong expect_tx byte count, stage overwritten while being read) — an emulator that ran everything
+   "successfully" would prove nothing about the kernels it is used on.
+2. The fused loss kernels against the oracle pinned by the reference's own ``losses/*.py``, and the
+   fused texture Adam kernel (N4) against ``torch.optim.Adam`` (the reference's optimizer), through the C-ABI of the
+   emulated library.
+"""
+import ctypes as C
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import loss_ref
+
+HERE = Path(__file__).resolve().parent
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="the SIMT emulator needs g++")
+
+
+def test_emulator_selftest_known_answers_and_known_bugs(tmp_path):
+    exe = tmp_path / "selftest"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fno-extern-tls-init", "-Wno-attributes", "-Wno-unknown-pragmas",
+                    "-I", str(HERE / "simt"), str(HERE / "simt" / "selftest.cpp"), "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    print(r.stdout)
+    assert r.returncode == 0 and "SELFTEST PASSED" in r.stdout and "FAIL" not in r.stdout
+    assert r.stdout.count("ok ") >= 11
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from simt import emu
+    return emu.build()
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _ws(nbytes):
+    from simt.emu import _aligned_empty
+    w = _aligned_empty(max(nbytes, 256))
+    w.fill_(0xA5)
+    return w
+
+
+@pytest.mark.parametrize("H,W", [(37, 53), (16, 16)])
+def test_emulated_photometric_loss_kernels_match_reference_pinned_oracle(lib, H, W):
+    """(1-l)*L1 + l*(1-SSIM) of models/texture_gaussian3d.py:333-340, forward values and dL/dimage."""
+    from simt.emu import check
+    gen = torch.Generator().manual_seed(H)
+    img = torch.rand(3, H, W, generator=gen).requires_grad_(True)
+    gt = (img.detach() + 0.2 * torch.randn(3, H, W, generator=gen)).clamp(0, 1)
+    lam = 0.2
+    loss, l1, lssim = loss_ref.photometric_loss(img.double(), gt.double(), lam)
+    coef = torch.tensor([0.7, -0.4, 1.3])            # cotangents of (loss, Ll1, Lssim)
+    (coef[0] * loss + coef[1] * l1 + coef[2] * lssim).backward()
+    n = C.c_size_t()
+    check(lib, lib.texgs_photometric_workspace_size(3, H, W, C.byref(n)), "ws")
+    ws, out3 = _ws(n.value), torch.empty(3)
+    x = img.detach().contiguous()
+    check(lib, lib.texgs_photometric_forward(_p(x), _p(gt), 3, H, W, lam, _p(ws), _p(out3), None), "photometric_forward")
+    for got, ref in zip(out3.tolist(), (loss.item(), l1.item(), lssim.item())):
+        assert abs(got - ref) <= 2e-6 + 1e-5 * abs(ref)
+    coef2 = torch.tensor([coef[0] * (1 - lam) + coef[1], coef[0] * lam + coef[2]])
+    dimg = torch.full_like(x, float("nan"))
+    check(lib, lib.texgs_photometric_backward(_p(x), _p(gt), 3, H, W, _p(ws), _p(coef2), _p(dimg), None), "photometric_backward")
+    ref = img.grad
+    assert float((dimg.double() - ref.double()).abs().max()) <= 1e-3 * float(ref.abs().max())
+
+
+def test_emulated_geometry_loss_kernels_match_reference_pinned_oracle(lib):
+    """Lalpha / Lnorm / Lnsm of models/texture_gaussian3d.py:342-368 (losses/norm_reg_loss.py:66-71, smooth_loss.py:4-27)."""
+    from simt.emu import check
+    H, W = 29, 70            # three 32x8 tiles wide with a ragged edge, four tiles high
+    gen = torch.Generator().manual_seed(3)
+    alpha = torch.rand(1, H, W, generator=gen).requires_grad_(True)
+    norm = torch.randn(3, H, W, generator=gen).requires_grad_(True)
+    gt_alpha = (torch.rand(1, H, W, generator=gen) > 0.3).float()
+    gt_norm = torch.nn.functional.normalize(torch.randn(3, H, W, generator=gen), dim=0)
+    gt_image = torch.rand(3, H, W, generator=gen)
+    la, ln, ls = loss_ref.geometry_losses(alpha.double(), norm.double(), gt_alpha.double(), gt_norm.double(), gt_image.double(), 0.1)
+    coef = torch.tensor([0.5, -1.5, 2.0])
+    (coef[0] * la + coef[1] * ln + coef[2] * ls).backward()
+    n = C.c_size_t()
+    check(lib, lib.texgs_geometry_loss_workspace_size(H, W, C.byref(n)), "ws")
+    ws, out3 = _ws(n.value), torch.empty(3)
+    a, nm = alpha.detach().contiguous(), norm.detach().contiguous()
+    check(lib, lib.texgs_geometry_loss_forward(_p(a), _p(nm), _p(gt_alpha), _p(gt_norm), _p(gt_image), H, W, 0.1, _p(ws), _p(out3), None), "geo_fwd")
+    for got, ref in zip(out3.tolist(), (la.item(), ln.item(), ls.item())):
+        assert abs(got - ref) <= 2e-6 + 1e-5 * abs(ref), (out3, la, ln, ls)
+    d_a, d_n = torch.full_like(a, float("nan")), torch.full_like(nm, float("nan"))
+    check(lib, lib.texgs_geometry_loss_backward(_p(a), _p(nm), _p(gt_alpha), _p(gt_norm), _p(gt_image), H, W, 0.1, _p(ws), _p(coef),
+                                                _p(d_a), _p(d_n), None), "geo_bwd")
+    assert float((d_a.double() - alpha.grad.double()).abs().max()) <= 1e-4 * float(alpha.grad.abs().max()) + 1e-9
+    assert float((d_n.double() - norm.grad.double()).abs().max()) <= 1e-3 * float(norm.grad.abs().max())
+
+
+@pytest.mark.parametrize("padded", [True, False])
+def test_emulated_texture_adam_kernel_matches_torch_adam(lib, padded):
+    """Three steps of the fused texture optimizer kernel == torch.optim.Adam(eps=1e-15) (models/texture_gaussian3d.py:139-143)
+    on a (6,R,R,3) texture whose texel count is not a multiple of the kernel's 1024-texel CTA tile; the padded
+    gradient is cleared in the same pass and the packed RGBA copy written."""
+    from simt.emu import _aligned_empty, check
+    R = 19
+    ntex = 6 * R * R
+    gen = torch.Generator().manual_seed(7)
+    p_ref = torch.randn(6, R, R, 3, generator=gen).requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=2.5e-3, betas=(0.9, 0.999), eps=1e-15)
+    p = _aligned_empty(ntex * 12).view(torch.float32).view(6, R, R, 3)
+    p.copy_(p_ref.detach())
+    m, v = _aligned_empty(ntex * 12).view(torch.float32), _aligned_empty(ntex * 12).view(torch.float32)
+    m.zero_(); v.zero_()
+    rgba = _aligned_empty(ntex * 16).view(torch.float32).view(6, R, R, 4)
+    rgba.fill_(float("nan"))
+    for step in range(1, 4):
+        g = torch.randn(6, R, R, 3, generator=gen) * (10.0 ** (step - 3))
+        g[0, :3] = 0.0                                        # untouched texels keep moving through their moments
+        p_ref.grad = g.clone()
+        opt.step()
+        if padded:
+            g4 = _aligned_empty(ntex * 16).view(torch.float32).view(6, R, R, 4)
+            g4[..., :3] = g
+            g4[..., 3] = 0.0
+            check(lib, lib.texgs_texture_adam_step(_p(p), _p(m), _p(v), None, _p(g4), _p(rgba), ntex, 2.5e-3, 0.9, 0.999, 1e-15, step, 1, None), "adam")
+            assert float(g4.abs().max()) == 0.0               # cleared for the next accumulation
+        else:
+            g3 = _aligned_empty(ntex * 12).view(torch.float32).view(6, R, R, 3)
+            g3.copy_(g)
+            check(lib, lib.texgs_texture_adam_step(_p(p), _p(m), _p(v), _p(g3), None, _p(rgba), ntex, 2.5e-3, 0.9, 0.999, 1e-15, step, 0, None), "adam")
+            assert torch.equal(g3, g)
+        assert float((p - p_ref.detach()).abs().max()) <= 2e-6, step
+        assert torch.equal(rgba[..., :3], p) and float(rgba[..., 3].abs().max()) == 0.0
+    st = opt.state[p_ref]
+    np.testing.assert_allclose(m.view(6, R, R, 3).numpy(), st["exp_avg"].numpy(), rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(v.view(6, R, R, 3).numpy(), st["exp_avg_sq"].numpy(), rtol=1e-5, atol=1e-12)

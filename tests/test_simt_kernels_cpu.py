@@ -1,0 +1,247 @@
+"""CPU-only parity of the REAL kernel source: the CUDA files of texture_gs_b200/csrc are compiled with g++ on top of
+the SIMT emulator in tests/simt (every CUDA thread a fiber; warp collectives, block barriers, mbarrier / bulk-copy
+pipelines and atomics emulated, see simt_emu.h) and driven through the same C-ABI call sequence as the product.
+
+These tests do not replace the ``-m gpu`` parity tests (the emulator says nothing about PTX semantics, memory ordering
+between real warps or performance); they check on a box without a GPU that the kernels' arithmetic, list handling and
+warp choreography reproduce the oracle — with the tolerances of the GPU suite (BASELINE.json: 1e-4 abs, 1e-3 rel).
+Sizes are small: the emulator runs about 1e5 warp collectives per second.
+"""
+import math
+import shutil
+
+import numpy as np
+import pytest
+import torch
+
+from util import ABS_TOL, GRAD_RTOL, check_backward, check_forward, compare_images, oracle_settings, rel_err, run_emu, run_oracle
+from texture_gs_b200.scene import SyntheticGaussians, orbit_cameras, output_cotangents, sphere_shell_scene
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="the SIMT emulator needs g++")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from simt import emu as E
+    E.build()
+    return E
+
+
+def _cam_kw(cam, bg, sh_degree):
+    return dict(H=cam.image_height, W=cam.image_width, tanfovx=math.tan(cam.FoVx / 2), tanfovy=math.tan(cam.FoVy / 2), bg=bg,
+                viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, campos=cam.camera_center, sh_degree=sh_degree)
+
+
+@pytest.mark.parametrize("n,w,h,r,deg,seed,eager", [(1500, 96, 64, 32, 3, 0, False), (1500, 96, 64, 32, 3, 0, True), (400, 70, 50, 16, 0, 4, False)])
+def test_emulated_kernels_match_oracle_forward_and_backward(emu, n, w, h, r, deg, seed, eager):
+    """The whole pipeline (preprocess, scan, scatter, per-tile sort, render forward / backward, preprocess backward)
+    against the oracle; the last case has an image size that is not a multiple of the tile and no SH. ``eager``: the
+    records' bulk copies land at issue instead of as late as legal — the two extreme timings of the 2-stage ring."""
+    g = sphere_shell_scene(n, r, sh_degree=deg, seed=seed, tex_seed=seed + 1)
+    cam = orbit_cameras(1, w, h, seed=seed + 2)[0]
+    emu.build().simt_set_eager_copies(1 if eager else 0)
+    try:
+        check_forward(g, cam, bg=(0.2, 0.4, 0.6), runner=run_emu, max_amb=0.3)
+        check_backward(g, cam, bg=(0.2, 0.4, 0.6), runner=run_emu, uv_tol=GRAD_RTOL if r > 16 else 5e-3, max_flag=0.3)
+    finally:
+        emu.build().simt_set_eager_copies(0)
+
+
+def test_emulated_binning_is_an_order_preserving_subsequence_of_the_oracle_lists(emu):
+    """Sorted per-tile lists == the oracle's (tile, depth, index) order (spec E4) minus pairs that cannot blend."""
+    g = sphere_shell_scene(1500, 16, sh_degree=0, seed=2)
+    cam = orbit_cameras(1, 96, 80, seed=5)[0]
+    _, stats, _ = run_emu(g, cam)
+    res = run_emu.last
+    _, aux, _ = run_oracle(g, cam)
+    offs = res.tile_offset.numpy().astype(np.int64)
+    ids = res.sorted_ids.numpy().astype(np.int64)
+    K = stats.num_pairs
+    assert offs[-1] == K and K <= aux["num_pairs"]
+    tile_of = np.repeat(np.arange(offs.shape[0] - 1), np.diff(offs))
+    ref_key = aux["tile_of"].astype(np.int64) * (1 << 32) + aux["gid_of"].astype(np.int64)
+    got_key = tile_of * (1 << 32) + ids
+    pos = {k: i for i, k in enumerate(ref_key.tolist())}
+    idx = np.array([pos[k] for k in got_key.tolist()])          # KeyError = a pair the spec does not have
+    assert (np.diff(idx) > 0).all()
+    kept = np.zeros(ref_key.shape[0], dtype=bool)
+    kept[idx] = True
+    assert kept[aux["pair_contributes"]].all()
+    assert K < aux["num_pairs"]
+
+
+def test_emulated_plain_texture_layout_dual_render_and_accumulation(emu):
+    """(a) the (6,R,R,3) kernels == the packed (6,R,R,4) kernels; (b) the dual render's second image and its cotangent
+    == the oracle's two renders; (c) accumulate_mask / zero_texture_grad = 0 add onto what the buffers
+    hold (the fused-bucket path of GradBucket) instead of overwriting."""
+    from oracle import raster_ref as RR
+    N, W, H, R = 1200, 80, 64, 32
+    g = sphere_shell_scene(N, R, sh_degree=3, seed=21, tex_seed=22)
+    cam = orbit_cameras(1, W, H, seed=23)[0]
+    bgc = (0.2, 0.1, 0.3)
+    _, aux0, _ = run_oracle(g, cam, bg=bgc)
+    keep = (~aux0["ambiguous"]).float()
+    cot = [c * keep for c in output_cotangents(H, W, seed=24)]
+    cot2 = torch.randn(3, H, W, generator=torch.Generator().manual_seed(5)) * keep
+    t = g.to(dtype=torch.float32, requires_grad=True).tensors()
+    kw = dict(means3D=t["xyz"], opacities=t["opacity"], scales=t["scaling"], rotations=t["rotation"], shs=t["shs"], uvs=t["uvs"],
+              gradient_uvs=t["grad_uvs"], texture=t["texture"], **_cam_kw(cam, bgc, 3))
+    a = emu.rasterize(cotangents=cot, **kw)
+    b = emu.rasterize(cotangents=cot, packed_texture=False, packed_texture_grad=False, **kw)
+    for x, y in zip((a.image, a.depth, a.norm, a.alpha), (b.image, b.depth, b.norm, b.alpha)):
+        assert torch.equal(x, y)
+    for k in a.grads:
+        assert rel_err(a.grads[k], b.grads[k]) < 1e-5, k
+    # (b) dual
+    st = oracle_settings(cam, 3, bg=bgc)
+    o = RR.rasterize(t["xyz"], None, t["shs"], t["opacity"], t["scaling"], t["rotation"], t["uvs"], t["grad_uvs"], t["texture"], st,
+                     return_aux=True, dual_no_sh=True)
+    (sum((x * y).sum() for x, y in zip(o[:4], cot)) + (o[-1]["image_no_sh"] * cot2).sum()).backward()
+    d = emu.rasterize(cotangents=cot, dual_no_sh=True, cot_nosh=cot2, **kw)
+    amb = aux0["ambiguous"]
+    assert float((d.image - o[0].detach()).abs().amax(0)[~amb].max()) <= ABS_TOL
+    assert float((d.image_nosh - o[-1]["image_no_sh"].detach()).abs().amax(0)[~amb].max()) <= ABS_TOL
+    names = {"means3D": "xyz", "opacities": "opacity", "scales": "scaling", "rotations": "rotation", "shs": "shs", "uvs": "uvs", "texture": "texture"}
+    for k, ok in names.items():
+        e = rel_err(d.grads[k].reshape(t[ok].grad.shape), t[ok].grad)
+        assert e <= GRAD_RTOL, (k, e)
+    # (c) accumulation on top of a constant
+    c = emu.rasterize(cotangents=cot, accumulate_onto=0.25, **kw)
+    for k in names:
+        assert rel_err(c.grads[k] - 0.25, a.grads[k]) < 1e-4, k
+    assert rel_err(c.grads["means2D"], a.grads["means2D"]) < 1e-6          # never accumulated: overwritten
+
+
+def test_emulated_plain_3dgs_modes_and_cov3d_match_oracle(emu):
+    """texture=None (the diff_gauss surface, render/render.py:75-84): colours from colors_precomp or full SH, and
+    ``cov3Ds_precomp`` in place of scales + rotations."""
+    from oracle import raster_ref as RR
+    N, W, H = 900, 80, 64
+    g = sphere_shell_scene(N, 4, sh_degree=3, seed=8)
+    cam = orbit_cameras(1, W, H, seed=9)[0]
+    gen = torch.Generator().manual_seed(1)
+    cols = torch.rand(N, 3, generator=gen)
+    shs_full = torch.cat([torch.randn(N, 1, 3, generator=gen), 0.1 * torch.randn(N, 15, 3, generator=gen)], dim=1)
+    bgc = (0.1, 0.1, 0.3)
+    st = oracle_settings(cam, 3, bg=bgc)
+    for kind in ("precomp", "sh", "cov"):
+        t = g.to(dtype=torch.float32, requires_grad=True).tensors()
+        c_ref = cols.clone().requires_grad_(True)
+        s_ref = shs_full.clone().requires_grad_(True)
+        cov = None
+        if kind == "cov":
+            Lm = RR.quat_to_rot(t["rotation"].detach().double()) * t["scaling"].detach().double()[:, None, :]
+            S = Lm @ Lm.transpose(1, 2)
+            cov = torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], dim=-1).float().requires_grad_(True)
+        with torch.no_grad():
+            aux0 = RR.rasterize(t["xyz"], None, s_ref if kind == "sh" else None, t["opacity"], None if cov is not None else t["scaling"],
+                                None if cov is not None else t["rotation"], None, None, None, st,
+                                colors_precomp=None if kind == "sh" else c_ref, cov3Ds_precomp=cov, return_aux=True)[-1]
+        keep = (~aux0["ambiguous"]).float()
+        cot = [c * keep for c in output_cotangents(H, W, seed=2)]
+        if kind == "cov":
+            cot[2] = torch.zeros_like(cot[2])        # the normal carries no gradient in this mode
+        o = RR.rasterize(t["xyz"], None, s_ref if kind == "sh" else None, t["opacity"], None if cov is not None else t["scaling"],
+                         None if cov is not None else t["rotation"], None, None, None, st,
+                         colors_precomp=None if kind == "sh" else c_ref, cov3Ds_precomp=cov, return_aux=True)
+        sum((x * y).sum() for x, y in zip(o[:4], cot)).backward()
+        r = emu.rasterize(means3D=t["xyz"], opacities=t["opacity"], scales=None if cov is not None else t["scaling"],
+                          rotations=None if cov is not None else t["rotation"], shs=s_ref if kind == "sh" else None,
+                          colors_precomp=None if kind == "sh" else c_ref, cov3Ds_precomp=cov, cotangents=cot, **_cam_kw(cam, bgc, 3))
+        rep = compare_images((r.image, r.depth, r.norm, r.alpha), [x.detach() for x in o[:4]], aux0["ambiguous"])
+        for nme in ("image", "depth", "norm", "alpha"):
+            assert rep[nme]["max_clear"] <= ABS_TOL * (3.0 if nme == "depth" else 1.0), (kind, nme, rep[nme])
+        assert int((r.radii != o[4]).sum()) == 0
+        pairs = [("means3D", t["xyz"].grad), ("opacities", t["opacity"].grad)]
+        pairs += [("cov3Ds_precomp", cov.grad)] if kind == "cov" else [("scales", t["scaling"].grad), ("rotations", t["rotation"].grad)]
+        pairs += [("shs", s_ref.grad)] if kind == "sh" else [("colors_precomp", c_ref.grad)]
+        for name, ref in pairs:
+            e = rel_err(r.grads[name].reshape(ref.shape), ref)
+            assert e <= (3e-3 if name == "cov3Ds_precomp" else GRAD_RTOL), (kind, name, e)
+
+
+def test_emulated_extra_attrs_match_oracle(emu):
+    """``extra_attrs`` (P,E) -> ``extra`` (E,H,W) with E = 11 (two channel groups of the kernel, ragged tail), forward
+    and backward including the alpha-chain share of the extra cotangent."""
+    from oracle import raster_ref as RR
+    N, W, H, R, E = 600, 48, 48, 16, 11
+    g = sphere_shell_scene(N, R, sh_degree=2, seed=51, tex_seed=52)
+    cam = orbit_cameras(1, W, H, seed=53)[0]
+    gen = torch.Generator().manual_seed(54)
+    ex0 = torch.randn(N, E, generator=gen)
+    bgc = (0.2, 0.1, 0.3)
+    _, aux0, _ = run_oracle(g, cam, bg=bgc)
+    keep = (~aux0["ambiguous"]).float()
+    cot = [c * keep for c in output_cotangents(H, W, seed=55)]
+    cot_e = torch.randn(E, H, W, generator=gen) * keep
+    t = g.to(dtype=torch.float32, requires_grad=True).tensors()
+    ex = ex0.clone().requires_grad_(True)
+    o = RR.rasterize(t["xyz"], None, t["shs"], t["opacity"], t["scaling"], t["rotation"], t["uvs"], t["grad_uvs"], t["texture"],
+                     oracle_settings(cam, 2, bg=bgc), extra_attrs=ex)
+    (sum((x * y).sum() for x, y in zip(o[:4], cot)) + (o[5] * cot_e).sum()).backward()
+    r = emu.rasterize(means3D=t["xyz"], opacities=t["opacity"], scales=t["scaling"], rotations=t["rotation"], shs=t["shs"], uvs=t["uvs"],
+                      gradient_uvs=t["grad_uvs"], texture=t["texture"], extra_attrs=ex, cotangents=cot, cot_extra=cot_e, **_cam_kw(cam, bgc, 2))
+    rep = compare_images((r.image, r.depth, r.norm, r.alpha, r.extra), [x.detach() for x in o[:4]] + [o[5].detach()], aux0["ambiguous"],
+                         names=("image", "depth", "norm", "alpha", "extra"))
+    for nme in ("image", "depth", "norm", "alpha", "extra"):
+        assert rep[nme]["max_clear"] <= ABS_TOL * (3.0 if nme in ("depth", "extra") else 1.0), (nme, rep[nme])
+    for name, ref in (("extra_attrs", ex.grad), ("opacities", t["opacity"].grad), ("means3D", t["xyz"].grad), ("scales", t["scaling"].grad),
+                      ("rotations", t["rotation"].grad), ("uvs", t["uvs"].grad), ("texture", t["texture"].grad)):
+        e = rel_err(r.grads[name].reshape(ref.shape), ref)
+        assert e <= (5e-3 if name == "uvs" else GRAD_RTOL), (name, e)
+
+
+def test_emulated_edge_cases_empty_culled_single_and_overflow_retry(emu):
+    bgc = (0.3, 0.5, 0.7)
+    cam = orbit_cameras(1, 33, 17, seed=3)[0]
+    # (a) zero Gaussians: background only, nothing launched per Gaussian
+    g0 = sphere_shell_scene(4, 4, sh_degree=0)
+    t = {k: (v[:0] if (v is not None and k != "texture") else v) for k, v in g0.tensors().items()}
+    ge = SyntheticGaussians(active_sh_degree=0, **{k: (v.detach() if v is not None else None) for k, v in t.items()})
+    out, stats, grads = run_emu(ge, cam, bg=bgc, cot=output_cotangents(17, 33, seed=1))
+    assert torch.allclose(out[0], torch.tensor(bgc)[:, None, None].expand(3, 17, 33))
+    assert float(out[3].abs().max()) == 0.0 and stats.num_pairs == 0 and float(grads["texture"].abs().max()) == 0.0
+    # (b) everything behind the camera: culled, radii == 0, zero gradients
+    gb = sphere_shell_scene(64, 4, sh_degree=0)
+    tb = gb.tensors()
+    far = SyntheticGaussians(active_sh_degree=0, **{**{k: (v.detach() if v is not None else None) for k, v in tb.items()},
+                                                      "xyz": tb["xyz"].detach() * 0 + cam.camera_center * 2.0})
+    out, stats, grads = run_emu(far, cam, bg=bgc, cot=output_cotangents(17, 33, seed=1))
+    assert int(out[4].max()) == 0 and float(out[3].abs().max()) == 0.0 and stats.num_visible == 0
+    assert float(grads["xyz"].abs().max()) == 0.0
+    # (c) a single Gaussian on a ragged image, against the oracle
+    g1 = sphere_shell_scene(1, 8, sh_degree=1, seed=1, coverage=8.0)
+    c1 = orbit_cameras(1, 17, 33, seed=1)[0]
+    check_forward(g1, c1, bg=bgc, max_amb=0.5, runner=run_emu)
+    # (d) pair capacity too small on the first attempt: the kernels self-disable, the retry is transparent
+    g = sphere_shell_scene(600, 16, sh_degree=0, seed=1)
+    cam2 = orbit_cameras(1, 64, 64, seed=2)[0]
+    o1, s1, _ = run_emu(g, cam2)
+    o2, s2, _ = run_emu(g, cam2, pair_capacity=64)
+    assert s2.num_pairs == s1.num_pairs and s2.pair_capacity >= s2.num_pairs > 64
+    for x, y in zip(o1, o2):
+        assert torch.equal(x, y)
+
+
+def test_emulated_long_lists_take_the_large_sort_kernel_and_early_termination(emu):
+    """One 16x16 tile that sees ~700 splats (> 512: the 256-thread sort kernel; 22 chunks through the 2-stage ring) with
+    opacities high enough that pixels stop early (n_contrib < list length: the backward starts mid-list)."""
+    n = 700
+    g = sphere_shell_scene(n, 8, sh_degree=0, seed=5, coverage=4.0)
+    t = g.tensors()
+    cam = orbit_cameras(1, 16, 16, seed=6)[0]
+    c = cam.camera_center / cam.camera_center.norm()
+    gen = torch.Generator().manual_seed(0)
+    xyz = c[None, :] * 1.0 + 0.02 * torch.randn(n, 3, generator=gen)
+    uv = xyz / xyz.norm(dim=1, keepdim=True)
+    gg = SyntheticGaussians(active_sh_degree=0, **{**{k: (v.detach() if v is not None else None) for k, v in t.items()},
+                                                    "xyz": xyz, "uvs": uv, "opacity": torch.full((n, 1), 0.5)})
+    ref, aux, _ = run_oracle(gg, cam)
+    got, stats, _ = run_emu(gg, cam)
+    assert stats.max_tile_len > 512
+    stopped = aux["final_T"] < 2e-4
+    assert bool(stopped.any()) and int(aux["n_contrib"][stopped].min()) < stats.max_tile_len     # the stop rule really fires
+    rep = compare_images(got[:4], ref[:4], aux["ambiguous"])
+    for nme in ("image", "alpha"):
+        assert rep[nme]["max_clear"] <= 2 * ABS_TOL, rep
+    check_backward(gg, cam, runner=run_emu, max_flag=0.9, uv_tol=5e-3)

@@ -5,7 +5,9 @@
 //     id, only written for visible Gaussians). One record = one L2 line = one cp.async.bulk.
 //   * pairs / sorted ids: per-tile contiguous segments (tile_offset[t] .. tile_offset[t+1]).
 #pragma once
+#ifndef TEXGS_HOST_EMU          // tests/simt/simt_emu.h (host-side SIMT emulation of these sources, tests only) stands in
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include "../../include/texgs.h"
 
@@ -253,6 +255,7 @@ __device__ __forceinline__ bool splat_hits_tile(float mx, float my, float a, flo
 // ---------------------------------------------------------------------------------------------
 // mbarrier + bulk async copy (TMA 1-D) — sm_90+/sm_100a PTX
 // ---------------------------------------------------------------------------------------------
+#ifndef TEXGS_HOST_EMU          // the emulator provides host versions of the PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -285,6 +288,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+#endif
 
 
 
@@ -318,9 +322,11 @@ __device__ __forceinline__ void fetch_taps(const float* __restrict__ tex, const 
 }
 
 // 128-bit vector reduction (sm_90+): one L2 atomic op for a whole padded texel
+#ifndef TEXGS_HOST_EMU
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+#endif
 
 // Transposing reduction of 20 per-lane values inside each half-warp: instead of 4 shuffles per value
 // (80), every step halves the number of values a lane still owns (16 -> 8 -> 4 -> 2 -> 1, then 4 -> 2 ->
