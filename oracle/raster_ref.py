@@ -55,6 +55,9 @@ T_STOP = 1e-4
 NEAR_CULL = 0.2
 ND_EPS = 1e-8
 FACE_TIE_REL = 1e-4   # test-side conditioning flag: |u'| major/second-major tie (cube face chosen by rounding)
+TEXEL_TIE = 2e-6      # test-side conditioning flag: a texel-space coordinate within TEXEL_TIE * R of an integer — the
+                      # bilinear VALUE is continuous there, its derivative w.r.t. u' is not (the cell is chosen by rounding;
+                      # fp32 resolves f = (s+1)R/2 - 1/2 to about 5e-7 * R)
 GRAZING_COS = 0.05    # test-side conditioning flag only (never changes the rendered values); calibrated so that
                       # the fp32 and fp64 oracles agree to 1e-3 on every gradient once flagged pixels carry no cotangent
 
@@ -352,6 +355,7 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
     n_contrib = torch.zeros(npix_pad, dtype=torch.int64, device=dev)
     ambiguous = torch.zeros(npix_pad, dtype=torch.bool, device=dev)
     grazing = torch.zeros(npix_pad, dtype=torch.bool, device=dev)
+    texel_edge = torch.zeros(npix_pad, dtype=torch.bool, device=dev)
     n_blend = 0
     pair_contributes = np.zeros(tile_of.shape[0], dtype=bool)   # some pixel of the tile blends this (tile,Gaussian) pair
 
@@ -469,6 +473,12 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
                     ua = u.detach().abs()
                     top2 = torch.topk(ua, 2, dim=-1).values
                     ambiguous[pix[(top2[:, 0] - top2[:, 1]) < FACE_TIE_REL * top2[:, 0]]] = True
+                    # conditioning flag: bilinear cell chosen by rounding (derivative jumps at texel boundaries)
+                    Rt = texture.shape[1]
+                    _, sxd, syd = cube_face_coords(u.detach())
+                    fxd, fyd = (sxd + 1.0) * (0.5 * Rt) - 0.5, (syd + 1.0) * (0.5 * Rt) - 0.5
+                    near = torch.minimum((fxd - fxd.round()).abs(), (fyd - fyd.round()).abs()) < TEXEL_TIE * Rt
+                    texel_edge[pix[near]] = True
                 tex = cube_sample(texture, u)                                 # E11
                 col = torch.clamp_min(C0 * tex + pre["csh"][g] + 0.5, 0.0)   # E12
                 if acc_c0 is not None:
@@ -503,8 +513,10 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
     if return_aux:
         aux = dict(image_no_sh=image_no_sh, final_T=Tf[0].detach(), n_contrib=unpad(n_contrib.reshape(-1, 1), 1)[0],
                    ambiguous=unpad(ambiguous.reshape(-1, 1), 1)[0] | unpad(grazing.reshape(-1, 1), 1)[0],
+                   # for GRADIENT comparisons only (values are continuous across texel boundaries)
+                   grad_ambiguous=unpad(ambiguous.reshape(-1, 1), 1)[0] | unpad(grazing.reshape(-1, 1), 1)[0] | unpad(texel_edge.reshape(-1, 1), 1)[0],
                    threshold_ambiguous=unpad(ambiguous.reshape(-1, 1), 1)[0],
-                   grazing=unpad(grazing.reshape(-1, 1), 1)[0], num_pairs=int(tile_of.shape[0]),
+                   grazing=unpad(grazing.reshape(-1, 1), 1)[0], texel_boundary=unpad(texel_edge.reshape(-1, 1), 1)[0], num_pairs=int(tile_of.shape[0]),
                    num_visible=int(pre["visible"].sum()), num_blend=n_blend, pre=pre,
                    tile_of=tile_of, gid_of=gid_of, pair_contributes=pair_contributes)
         return out + (aux,)
