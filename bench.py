@@ -92,9 +92,14 @@ class ClockSampler:
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                clk, clk_max = float(f[0]), float(f[1])
             except ValueError:
                 continue
+            sm.append(clk); mx.append(clk_max)
+            try:
+                pw.append(float(f[2]))
+            except ValueError:
+                pass                      # power.draw can read [N/A]; the clocks and the throttle reasons still count
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
@@ -336,9 +341,26 @@ def main():
             traffic = json.loads(tfile.read_text()).get(dom)
         except Exception:
             traffic = None
+    # second roof for the dominant kernel: instruction issue. Static warp-instruction count of the ncu capture of the same
+    # kernels and config (profiles/ncu_issue.json) over the duration measured live; peak = SMs x 4 schedulers x SM clock
+    issue = None
+    try:
+        ifile = ROOT / "profiles" / "ncu_issue.json"
+        if ifile.exists() and clock_rec and clock_rec.get("sm_mhz"):
+            rec = json.loads(ifile.read_text()).get(dom)
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            if rec:
+                rate = rec["warp_instructions"] / (per_kernel[dom]["ms"] * 1e-3) / 1e9
+                peak = sms * 4 * clock_rec["sm_mhz"] * 1e6 / 1e9
+                issue = {"warp_instructions_per_launch": rec["warp_instructions"], "achieved_ginst_s": round(rate, 1),
+                         "peak_ginst_s": round(peak, 1), "frac": round(rate / peak, 4),
+                         "active_threads_per_instruction": rec.get("active_threads_per_instruction"),
+                         "source": "instruction count from the ncu capture in profiles/ncu_issue.json, duration measured live"}
+    except Exception:
+        issue = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": per_kernel[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ab[dom], "per_kernel": per_kernel,
+                "algorithmic_bytes_per_launch": ab[dom], "issue": issue, "per_kernel": per_kernel,
                 "whole_path": {"alg_mb_per_view": round(sum(ab.values()) / 1e6, 1),
                                "gbs": round(sum(ab.values()) * value / 1e9 / max(world, 1), 1),
                                "frac": round(sum(ab.values()) * value / 1e9 / max(world, 1) / hbm_peak, 4)},
