@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_500k_1080p")
     ap.add_argument("--views", type=int, default=VIEWS_PER_STEP)
+    ap.add_argument("--streams", type=int, default=1,
+                    help="experimental: CUDA streams per rank that render alternate views concurrently (one gradient-bucket replica each)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-tiles", type=int, default=0, help="tiles in the CPU sample (0 = auto)")
@@ -267,7 +269,7 @@ def main():
     g, cams, cot = make_scene(wl, dev)
     bg = torch.zeros(3, device=dev)
     params = {k: v for k, v in g.tensors().items()}
-    bucket = GradBucket(params)
+    bucket = GradBucket(params, replicas=max(1, args.streams))
     views = shard_views(args.views, world, rank)
     timer = StageTimer(capacity=max(1, len(views)) * max(1, args.steps), device=dev)
 
@@ -282,7 +284,7 @@ def main():
         # one texture update per step: the packed (6,R,R,4) copy is rebuilt once per 32-view batch
         invalidate_packed_cache()
         bucket.zero()
-        render_views_accumulate(uv_tex_render, g, cams, cot, views, bg, timer=tm, bucket=bucket)
+        render_views_accumulate(uv_tex_render, g, cams, cot, views, bg, timer=tm, bucket=bucket, streams=args.streams)
         bucket.all_reduce()
 
     for _ in range(args.warmup):
@@ -375,7 +377,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl.name, "gaussians": wl.n_gaussians, "width": wl.width, "height": wl.height,
-                       "tex_res": wl.tex_res, "views_per_step": args.views, "sh_degree": 3,
+                       "tex_res": wl.tex_res, "views_per_step": args.views, "sh_degree": 3, "streams_per_rank": max(1, args.streams),
                        "parallelism": f"dp{world} (views sharded, 1 all-reduce of {bucket.nbytes / 1e6:.0f} MB/step)" if world > 1 else "single GPU",
                        "l2_policy": "inputs larger than L2 (texture 302 MB + records 64 MB, a different camera every view)"},
             "clocks": clock_rec, "e2e": e2e, "gpu_launches": (KERNELS_PER_VIEW * len(views) + 1) * args.steps,

@@ -127,6 +127,18 @@ def _packed_texture(lib, texture_arg: torch.Tensor, tex: torch.Tensor, stream: i
     return tex4
 
 
+def ensure_packed_texture(texture: torch.Tensor) -> Optional[torch.Tensor]:
+    """Build (or reuse) the packed copy of ``texture`` on the CURRENT stream. Callers that are about to render the same
+    texture from several CUDA streams do this before they fork, so that no stream reads a copy another one is still
+    writing (texture_gs_b200.dist.render_views_accumulate(..., streams=n))."""
+    if not USE_PACKED_TEXTURE or texture is None or not texture.is_cuda:
+        return None
+    lib = L.load()
+    tex = _prep(texture, texture.device)
+    with torch.cuda.device(texture.device):
+        return _packed_texture(lib, texture, tex, torch.cuda.current_stream(texture.device).cuda_stream)
+
+
 def packed_texture_buffer(texture: torch.Tensor) -> torch.Tensor:
     """A (6,R,R,4) buffer for the packed copy of ``texture`` — the cached one if there is one (its content is about
     to be replaced by the caller, see ``adopt_packed_texture``), else a new one."""
