@@ -58,6 +58,8 @@ FACE_TIE_REL = 1e-4   # test-side conditioning flag: |u'| major/second-major tie
 TEXEL_TIE = 2e-6      # test-side conditioning flag: a texel-space coordinate within TEXEL_TIE * R of an integer — the
                       # bilinear VALUE is continuous there, its derivative w.r.t. u' is not (the cell is chosen by rounding;
                       # fp32 resolves f = (s+1)R/2 - 1/2 to about 5e-7 * R)
+DEPTH_TIE_REL = 4e-7  # test-side conditioning flag: two splats that both blend into a pixel, adjacent in its list, with view-space
+                      # depths within ~3 ulp: their ORDER (spec E4) is decided by the rounding of z = p.V[:,2]
 GRAZING_COS = 0.05    # test-side conditioning flag only (never changes the rendered values); calibrated so that
                       # the fp32 and fp64 oracles agree to 1e-3 on every gradient once flagged pixels carry no cotangent
 
@@ -423,6 +425,10 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
                 ((alpha - ALPHA_MIN).abs() < rel * 64 * ALPHA_MIN)
             near_t = ok & ((T_test - T_STOP).abs() < rel * 64 * T_STOP)
             amb = (near_a | near_t).any(dim=2)
+            if Lmax > 1:
+                zl = pre["depth"][ids]                                           # (B,L), ascending inside a tile
+                tie = valid[:, 1:] & ((zl[:, 1:] - zl[:, :-1]).abs() <= DEPTH_TIE_REL * zl[:, 1:].abs())
+                amb = amb | (tie[:, None, :] & include[:, :, 1:] & include[:, :, :-1]).any(dim=2)
             last = torch.where(include, ar[None, None, :] + 1, torch.zeros_like(ar)[None, None, :]).amax(dim=2)
         a_inc = torch.where(include, alpha, torch.zeros_like(alpha))
         T_incl = torch.cumprod(1.0 - a_inc, dim=2)
