@@ -126,6 +126,10 @@ struct Global {
     // bulk copies: false = land as LATE as legal (exposes reads before the mbarrier wait), true = land at issue, i.e. as
     // EARLY as legal (exposes a stage overwritten while other lanes still read its previous content)
     bool eager_copies = false;
+    // fast-math intrinsics (__expf, __logf, __fdividef, rsqrtf): 0 = exact; n > 0 = results perturbed by a pseudo-random
+    // relative error of up to n * 2^-23 — the GPU's ex2.approx / rcp.approx / lg2.approx paths are not correctly rounded
+    unsigned fastmath_noise_ulps = 0;
+    uint32_t noise_state = 0x9e3779b9u;
 };
 inline Global& G() { static Global g; return g; }
 
@@ -282,11 +286,20 @@ inline void __threadfence_block() {}
 // scalar intrinsics
 // ---------------------------------------------------------------------------------------------
 template <class T> inline T __ldg(const T* p) { return *p; }
-inline float __expf(float x) { return expf(x); }
-inline float __logf(float x) { return logf(x); }
-inline float __fdividef(float a, float b) { return a / b; }
+namespace simt {
+inline float approx(float exact) {
+    Global& g = G();
+    if (g.fastmath_noise_ulps == 0 || !(exact == exact)) return exact;
+    g.noise_state = g.noise_state * 1664525u + 1013904223u;
+    const float r = (float)((int32_t)g.noise_state) * (1.0f / 2147483648.0f);          // [-1, 1)
+    return exact * (1.0f + r * (float)g.fastmath_noise_ulps * 1.1920929e-7f);
+}
+}  // namespace simt
+inline float __expf(float x) { return simt::approx(expf(x)); }
+inline float __logf(float x) { return simt::approx(logf(x)); }
+inline float __fdividef(float a, float b) { return simt::approx(a / b); }
 inline float __frcp_rn(float a) { return 1.0f / a; }
-inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+inline float rsqrtf(float x) { return simt::approx(1.0f / sqrtf(x)); }
 inline float __saturatef(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
 inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
