@@ -139,6 +139,55 @@ def algorithmic_bytes(N, M, V, K, U, P, R, views_per_step=VIEWS_PER_STEP):
     return b
 
 
+def roofline_report(wl, views_per_step, world, value, stage_ms, stats, U, clock_rec, sms):
+    """The ``roofline`` object of the JSON line (pure host arithmetic, unit-tested on CPU): per-kernel algorithmic bytes
+    over the CUDA-event durations measured in the timed region, the dominant kernel against the measured HBM peak, its
+    DRAM traffic and instruction count from the committed ncu captures."""
+    hbm_peak, peak_src = measured_peaks()
+    N, M = wl.n_gaussians, 15
+    ab = algorithmic_bytes(N, M, stats.num_visible, stats.num_pairs, U, wl.width * wl.height, wl.tex_res, views_per_step)
+    per_kernel = {}
+    for k, b in ab.items():
+        if k in stage_ms and stage_ms[k] > 0:
+            gbs = b / (stage_ms[k] * 1e-3) / 1e9
+            per_kernel[k] = {"ms": round(stage_ms[k], 4), "alg_mb": round(b / 1e6, 2), "gbs": round(gbs, 1), "frac": round(gbs / hbm_peak, 4)}
+    whole = {"alg_mb_per_view": round(sum(ab.values()) / 1e6, 1),
+             "gbs": round(sum(ab.values()) * value / 1e9 / max(world, 1), 1),
+             "frac": round(sum(ab.values()) * value / 1e9 / max(world, 1) / hbm_peak, 4)}
+    counts = {"V": stats.num_visible, "K": stats.num_pairs, "U": U, "max_tile_len": stats.max_tile_len}
+    if not per_kernel:          # no stage events recorded (profiling slots exhausted): report the whole path only
+        return {"bound": "hbm", "kernel": None, "achieved": whole["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": whole["frac"],
+                "traffic": None, "peak_source": peak_src, "per_kernel": {}, "whole_path": whole, "counts": counts}
+    dom = max((k for k in per_kernel), key=lambda k: per_kernel[k]["ms"])
+    traffic = None
+    tfile = ROOT / "profiles" / "ncu_traffic.json"
+    if tfile.exists():
+        try:
+            traffic = json.loads(tfile.read_text()).get(dom)
+        except Exception:
+            traffic = None
+    # second roof for the dominant kernel: instruction issue. Static warp-instruction count of the ncu capture of the same
+    # kernels and config (profiles/ncu_issue.json) over the duration measured live; peak = SMs x 4 schedulers x SM clock
+    issue = None
+    try:
+        ifile = ROOT / "profiles" / "ncu_issue.json"
+        if ifile.exists() and clock_rec and clock_rec.get("sm_mhz"):
+            rec = json.loads(ifile.read_text()).get(dom)
+            if rec:
+                rate = rec["warp_instructions"] / (per_kernel[dom]["ms"] * 1e-3) / 1e9
+                peak = sms * 4 * clock_rec["sm_mhz"] * 1e6 / 1e9
+                issue = {"warp_instructions_per_launch": rec["warp_instructions"], "achieved_ginst_s": round(rate, 1),
+                         "peak_ginst_s": round(peak, 1), "frac": round(rate / peak, 4),
+                         "active_threads_per_instruction": rec.get("active_threads_per_instruction"),
+                         "source": "instruction count from the ncu capture in profiles/ncu_issue.json, duration measured live"}
+    except Exception:
+        issue = None
+    return {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+            "frac": per_kernel[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": ab[dom], "issue": issue, "per_kernel": per_kernel,
+            "whole_path": whole, "counts": counts}
+
+
 def make_scene(wl, device, requires_grad=True):
     from texture_gs_b200.scene import orbit_cameras, output_cotangents, sphere_shell_scene
     g = sphere_shell_scene(wl.n_gaussians, wl.tex_res, sh_degree=3, seed=0, device=device, requires_grad=requires_grad)
@@ -327,46 +376,8 @@ def main():
             dist.destroy_process_group()
         return
 
-    hbm_peak, peak_src = measured_peaks()
-    N, M = wl.n_gaussians, 15
-    ab = algorithmic_bytes(N, M, stats.num_visible, stats.num_pairs, U, wl.width * wl.height, wl.tex_res, args.views)
-    per_kernel = {}
-    for k, b in ab.items():
-        if k in stage_ms and stage_ms[k] > 0:
-            gbs = b / (stage_ms[k] * 1e-3) / 1e9
-            per_kernel[k] = {"ms": round(stage_ms[k], 4), "alg_mb": round(b / 1e6, 2), "gbs": round(gbs, 1), "frac": round(gbs / hbm_peak, 4)}
-    dom = max((k for k in per_kernel), key=lambda k: per_kernel[k]["ms"])
-    traffic = None
-    tfile = ROOT / "profiles" / "ncu_traffic.json"
-    if tfile.exists():
-        try:
-            traffic = json.loads(tfile.read_text()).get(dom)
-        except Exception:
-            traffic = None
-    # second roof for the dominant kernel: instruction issue. Static warp-instruction count of the ncu capture of the same
-    # kernels and config (profiles/ncu_issue.json) over the duration measured live; peak = SMs x 4 schedulers x SM clock
-    issue = None
-    try:
-        ifile = ROOT / "profiles" / "ncu_issue.json"
-        if ifile.exists() and clock_rec and clock_rec.get("sm_mhz"):
-            rec = json.loads(ifile.read_text()).get(dom)
-            sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            if rec:
-                rate = rec["warp_instructions"] / (per_kernel[dom]["ms"] * 1e-3) / 1e9
-                peak = sms * 4 * clock_rec["sm_mhz"] * 1e6 / 1e9
-                issue = {"warp_instructions_per_launch": rec["warp_instructions"], "achieved_ginst_s": round(rate, 1),
-                         "peak_ginst_s": round(peak, 1), "frac": round(rate / peak, 4),
-                         "active_threads_per_instruction": rec.get("active_threads_per_instruction"),
-                         "source": "instruction count from the ncu capture in profiles/ncu_issue.json, duration measured live"}
-    except Exception:
-        issue = None
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": per_kernel[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": ab[dom], "issue": issue, "per_kernel": per_kernel,
-                "whole_path": {"alg_mb_per_view": round(sum(ab.values()) / 1e6, 1),
-                               "gbs": round(sum(ab.values()) * value / 1e9 / max(world, 1), 1),
-                               "frac": round(sum(ab.values()) * value / 1e9 / max(world, 1) / hbm_peak, 4)},
-                "counts": {"V": stats.num_visible, "K": stats.num_pairs, "U": U, "max_tile_len": stats.max_tile_len}}
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    roofline = roofline_report(wl, args.views, world, value, stage_ms, stats, U, clock_rec, sms)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:

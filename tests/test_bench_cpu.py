@@ -60,3 +60,33 @@ def test_product_arm_refuses_to_run_without_cuda():
         pytest.skip("CUDA present")
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_roofline_report_from_round1_measurements():
+    """The reporting arithmetic fed with the stage times and counters of the committed round-1 run reproduces the
+    per-kernel figures of profiles/r1_bench_1gpu.json; an empty stage table (no profiling slots) still yields a report."""
+    from collections import namedtuple
+    from texture_gs_b200.scene import WORKLOADS
+    ref = json.loads((ROOT / "profiles" / "r1_bench_1gpu.json").read_text())
+    rl = ref["roofline"]
+    Stats = namedtuple("Stats", "num_visible num_pairs max_tile_len")
+    stats = Stats(rl["counts"]["V"], rl["counts"]["K"], rl["counts"]["max_tile_len"])
+    stage_ms = {k: v["ms"] for k, v in rl["per_kernel"].items()}
+    stage_ms["forward_total"] = 1.0                      # keys without a byte formula are ignored
+    r = bench.roofline_report(WORKLOADS["cfg2_500k_1080p"], 32, 1, ref["value"], stage_ms, stats, rl["counts"]["U"], ref["clocks"], 148)
+    assert r["kernel"] == "render_bwd" and r["bound"] == "hbm" and r["unit"] == "GB/s"
+    peak, _ = bench.measured_peaks()
+    for k, v in rl["per_kernel"].items():
+        assert abs(r["per_kernel"][k]["alg_mb"] - v["alg_mb"]) < 0.02, k
+        assert abs(r["per_kernel"][k]["gbs"] - v["gbs"]) <= 0.002 * v["gbs"] + 0.2, k
+    assert abs(r["achieved"] - 755.0) < 1.0 and abs(r["frac"] - 755.0 / peak) < 1e-3
+    assert r["traffic"] == json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())["render_bwd"]
+    assert r["algorithmic_bytes_per_launch"] == 1121293796
+    assert abs(r["whole_path"]["alg_mb_per_view"] - 2215.5) < 0.1
+    iss = r["issue"]
+    assert iss["warp_instructions_per_launch"] == 989917246 and 0.5 < iss["frac"] < 0.65      # ncu measured 61 % issue-slot use
+    assert abs(iss["peak_ginst_s"] - 148 * 4 * 1.965) < 0.1
+    json.dumps(r)
+    r0 = bench.roofline_report(WORKLOADS["cfg2_500k_1080p"], 32, 1, ref["value"], {}, stats, rl["counts"]["U"], None, 148)
+    assert r0["kernel"] is None and r0["per_kernel"] == {} and r0["achieved"] > 0
+    json.dumps(r0)
