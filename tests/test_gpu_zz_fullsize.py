@@ -1,0 +1,22 @@
+"""BASELINE.json configs[2] at FULL size (500 k Gaussians, 1920x1080, 6x2048^2 texture), forward and backward, compared
+DIRECTLY with the oracle: the scalar C + OpenMP oracle (oracle/raster_c.c, equal to the torch oracle to 1e-15, see
+tests/test_oracle_c.py) renders a whole 1080p view in seconds on the box's host cores. The property-based full-size test
+(test_gpu_parity.py::test_full_size_properties) stays; this one is the bit the properties cannot see.
+The comparison logic itself is exercised on CPU with the emulated kernels (tests/test_simt_kernels_cpu.py). Runs last."""
+import pytest
+import torch
+
+from util import check_against_c_oracle
+from texture_gs_b200.scene import orbit_cameras, sphere_shell_scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,w,h,r,view", [(500_000, 1920, 1080, 2048, 5)])
+def test_full_size_forward_and_backward_against_the_c_oracle(n, w, h, r, view):
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests selected (-m gpu) but no CUDA device is visible")
+    g = sphere_shell_scene(n, r, sh_degree=3, seed=0)
+    cam = orbit_cameras(32, w, h, seed=1)[view]
+    # R = 2048: a tap lands within TEXEL_TIE * R = 4e-3 texels of a texel boundary in a good part of the pixels
+    check_against_c_oracle(g, cam, bg=(0.1, 0.2, 0.3), max_flag=0.6)

@@ -373,3 +373,12 @@ def test_emulated_list_longer_than_the_shared_memory_sort_takes_the_global_netwo
     rep = compare_images(got[:4], ref[:4], aux["ambiguous"])
     for nme in ("image", "alpha"):
         assert rep[nme]["max_clear"] <= 2 * ABS_TOL, rep
+
+
+def test_comparison_against_the_c_oracle_used_at_full_size_on_the_gpu(emu):
+    """tests/test_gpu_zz_fullsize.py compares the CUDA kernels with the C oracle at 500 k / 1080p; the same helper is run
+    here with the emulated kernels on a scaled-down copy of that scene (same generator, same splats per pixel)."""
+    from util import check_against_c_oracle
+    g = sphere_shell_scene(2500, 64, sh_degree=3, seed=0)
+    cam = orbit_cameras(32, 136, 76, seed=1)[5]
+    check_against_c_oracle(g, cam, bg=(0.1, 0.2, 0.3), runner=run_emu, max_flag=0.6)
