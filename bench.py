@@ -211,7 +211,11 @@ def cpu_oracle_views_per_s(wl, sample_tiles: int = 0, backward: bool = True):
     from oracle import raster_c
     from oracle.raster_ref import RasterSettings
     from texture_gs_b200.scene import orbit_cameras, output_cotangents, sphere_shell_scene
-    threads = int(os.environ.get("OMP_NUM_THREADS", 0)) or (os.cpu_count() or 1)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    threads = int(os.environ.get("OMP_NUM_THREADS", 0)) or avail
     key = (wl.name, backward)
     if key not in _cpu_cache:
         g = sphere_shell_scene(wl.n_gaussians, wl.tex_res, sh_degree=3, seed=0, device="cpu", requires_grad=False)
