@@ -20,3 +20,15 @@ def test_full_size_forward_and_backward_against_the_c_oracle(n, w, h, r, view):
     cam = orbit_cameras(32, w, h, seed=1)[view]
     # R = 2048: a tap lands within TEXEL_TIE * R = 4e-3 texels of a texel boundary in a good part of the pixels
     check_against_c_oracle(g, cam, bg=(0.1, 0.2, 0.3), max_flag=0.6)
+
+
+@pytest.mark.parametrize("name,n,w,h,r", [("configs[1] stand-in", 300_000, 800, 600, 1024), ("configs[4]", 1_000_000, 3840, 2160, 4096)])
+def test_forward_only_baseline_configs_against_the_c_oracle(name, n, w, h, r):
+    """BASELINE.json configs[1] (300 k Gaussians, 800x600, R = 1024: the retexture.py shape; synthetic stand-in for the
+    DTU checkpoint) and configs[4] (1 M Gaussians, 3840x2160, R = 4096, the bandwidth stress case), forward, every pixel
+    of the four outputs against the C oracle."""
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests selected (-m gpu) but no CUDA device is visible")
+    g = sphere_shell_scene(n, r, sh_degree=3, seed=0)
+    cam = orbit_cameras(32, w, h, seed=1)[3]
+    check_against_c_oracle(g, cam, bg=(0.0, 0.0, 0.0), max_flag=0.7, backward=False)

@@ -178,7 +178,8 @@ def run_c_oracle(g: SyntheticGaussians, cam, bg=(0.0, 0.0, 0.0), cot=None, dtype
     return (img, dep, nrm, alp, radii), aux, aux["grads"]
 
 
-def check_against_c_oracle(g, cam, bg=(0.0, 0.0, 0.0), runner=None, seed=3, max_flag=0.5, scale_modifier=1.0, uv_tol=GRAD_RTOL):
+def check_against_c_oracle(g, cam, bg=(0.0, 0.0, 0.0), runner=None, seed=3, max_flag=0.5, scale_modifier=1.0, uv_tol=GRAD_RTOL,
+                           backward=True):
     """Forward and backward of ``runner`` (run_cuda by default) against the C oracle — the direct comparison that the
     torch oracle is too slow for at full size. Truth = the float64 build; the float32 build measures what fp32
     arithmetic can deliver:  outputs 1e-4 abs on the pixels the oracle does not flag (3e-4 for the O(2.5) depth),
@@ -193,10 +194,11 @@ def check_against_c_oracle(g, cam, bg=(0.0, 0.0, 0.0), runner=None, seed=3, max_
     keep = (~aux["grad_ambiguous"]).double()
     flagged = float(1 - keep.mean())
     assert flagged <= max_flag, flagged
-    cot = [c.double() * keep for c in output_cotangents(H, W, seed=seed)]
-    _, _, g64 = run_c_oracle(g, cam, bg=bg, cot=cot, scale_modifier=scale_modifier)
-    _, _, g32 = run_c_oracle(g, cam, bg=bg, cot=[c.float() for c in cot], dtype=torch.float32, scale_modifier=scale_modifier)
-    got, stats, ggot = runner(g, cam, bg=bg, cot=[c.float() for c in cot], scale_modifier=scale_modifier)
+    cot = [c.double() * keep for c in output_cotangents(H, W, seed=seed)] if backward else None
+    if backward:
+        _, _, g64 = run_c_oracle(g, cam, bg=bg, cot=cot, scale_modifier=scale_modifier)
+        _, _, g32 = run_c_oracle(g, cam, bg=bg, cot=[c.float() for c in cot], dtype=torch.float32, scale_modifier=scale_modifier)
+    got, stats, ggot = runner(g, cam, bg=bg, cot=[c.float() for c in cot] if backward else None, scale_modifier=scale_modifier)
     rep = compare_images(got[:4], [x.float() for x in ref[:4]], aux["ambiguous"])
     print({k: (v if not isinstance(v, dict) else {a: "%.2e" % b for a, b in v.items()}) for k, v in rep.items()}, stats, "flagged %.3f" % flagged)
     assert int(aux["num_visible"]) == stats.num_visible and stats.num_pairs <= aux["num_pairs"]
@@ -205,6 +207,8 @@ def check_against_c_oracle(g, cam, bg=(0.0, 0.0, 0.0), runner=None, seed=3, max_
         assert rep[n]["max_clear"] <= ABS_TOL * (3.0 if n == "depth" else 1.0), (n, rep[n])
         assert rep[n]["frac_over"] <= 5e-3, (n, rep[n])
     errs = {}
+    if not backward:
+        return rep, errs
     for k, r in g64.items():
         if r is None:
             continue
