@@ -55,13 +55,19 @@ static const real SH_C3[7] = {(real)-0.5900435899266435, (real)2.890611442640554
 /* test-side conditioning flags (never change a rendered value), same constants as oracle/raster_ref.py */
 #define FACE_TIE_REL ((real)1e-4)
 #define TEXEL_TIE ((real)2e-6)
-#define DEPTH_TIE_REL ((real)4e-7)
+#define DEPTH_TIE_REL ((real)1e-6)
 #define GRAZING_COS ((real)0.05)
 #define FLAG_THRESHOLD 1
 #define FLAG_GRAZING 2
 #define FLAG_FACE_TIE 4
 #define FLAG_TEXEL_TIE 8
 #define FLAG_DEPTH_TIE 16
+#define FLAG_RECT 32          /* a splat whose integer radius / tile rect (E3) is decided by rounding reaches this pixel */
+#ifndef THRESH_ULPS
+#define THRESH_ULPS 256      /* alpha / T threshold proximity, in units of rel (4e-6 in float32): see DESIGN.md section 7 */
+#endif
+#define RADIUS_TIE_REL ((real)1e-5)
+#define RECT_TIE_PX ((real)1e-3)
 
 typedef struct {
     int32_t P, M, sh_degree, H, W, R;
@@ -85,6 +91,7 @@ typedef struct {
 typedef struct {
     int visible, radius, rx0, ry0, rx1, ry1, kmin;
     real xy[2], conic[3], opacity, depth, normal[3], m[3], csh[3], flip;
+    real r3;            /* 3 sqrt(lambda_max) before the ceil; 0 if the Gaussian was culled before E3 */
 } Proj;
 
 typedef struct { real depth; int32_t id; } Entry;
@@ -176,7 +183,8 @@ static void project(const OracleArgs* a, int i, Proj* o) {
     /* E3: radius and tile rect */
     const real mid = (real)0.5 * (ca + cc);
     real disc = mid * mid - det; if (disc < (real)0.1) disc = (real)0.1;
-    const real radius = ceil((real)3.0 * sqrt(mid + sqrt(disc)));
+    const real r3 = (real)3.0 * sqrt(mid + sqrt(disc));
+    const real radius = ceil(r3);
     o->xy[0] = ((ph[0] * pw + (real)1.0) * a->W - (real)1.0) * (real)0.5;
     o->xy[1] = ((ph[1] * pw + (real)1.0) * a->H - (real)1.0) * (real)0.5;
     const int gx = (a->W + TILE - 1) / TILE, gy = (a->H + TILE - 1) / TILE;
@@ -189,6 +197,7 @@ static void project(const OracleArgs* a, int i, Proj* o) {
         v = floor((o->xy[1] + radius + (TILE - 1)) / TILE); o->ry1 = (int)(v < 0 ? 0 : (v > gy ? gy : v));
     }
     o->visible = in_front && det_ok && fin && (o->rx1 - o->rx0) * (o->ry1 - o->ry0) > 0;
+    o->r3 = (in_front && det_ok && fin) ? r3 : 0;
     o->radius = o->visible ? (int)radius : 0;
     o->opacity = a->opacity[i];
     /* E8: disc normal = rotation column of the smallest scale (first index wins ties), facing the camera */
@@ -320,15 +329,16 @@ int texgs_oracle_run(const OracleArgs* a) {
                         const real G = exp(power);
                         const real oG = q->opacity * G;
                         const real alpha = oG > ALPHA_MAX ? ALPHA_MAX : oG;
-                        if (fabs(alpha - ALPHA_MIN) < rel * 64 * ALPHA_MIN) flag |= FLAG_THRESHOLD;
+                        if (fabs(alpha - ALPHA_MIN) < rel * THRESH_ULPS * ALPHA_MIN) flag |= FLAG_THRESHOLD;
                         if (!(power <= 0) || !(alpha >= ALPHA_MIN)) continue;
                         const real Tn = T * ((real)1.0 - alpha);
-                        if (fabs(Tn - T_STOP) < rel * 64 * T_STOP) flag |= FLAG_THRESHOLD;
+                        if (fabs(Tn - T_STOP) < rel * THRESH_ULPS * T_STOP) flag |= FLAG_THRESHOLD;
                         if (Tn < T_STOP) break;                   /* stop BEFORE adding */
                         Contrib* c = &cs[nc++];
                         c->g = g; c->pos = l; c->alpha = alpha; c->T = T; c->G = G; c->dx = dx; c->dy = dy;
                         c->live = oG <= ALPHA_MAX ? (real)1.0 : (real)0.0;
-                        if (prev_pos == l - 1 && fabs(L[l].depth - L[l - 1].depth) <= DEPTH_TIE_REL * fabs(L[l].depth)) flag |= FLAG_DEPTH_TIE;
+                        /* the previous CONTRIBUTION of this pixel (not necessarily the previous list entry) at the same depth */
+                        if (prev_pos >= 0 && fabs(L[l].depth - L[prev_pos].depth) <= DEPTH_TIE_REL * fabs(L[l].depth)) flag |= FLAG_DEPTH_TIE;
                         prev_pos = l;
                         /* E9: ray - disc plane intersection, E10: first-order UV step */
                         c->nd = q->normal[0] * dw[0] + q->normal[1] * dw[1] + q->normal[2] * dw[2];
@@ -470,6 +480,37 @@ int texgs_oracle_run(const OracleArgs* a) {
         free(tacc);
     }
     if (a->counters) { a->counters[0] = K; a->counters[1] = nvis; a->counters[2] = nblend; a->counters[3] = longest; }
+
+    /* conditioning flag for E3: radius = ceil(3 sqrt(lambda)) and the tile rect are INTEGER decisions; an implementation
+     * whose fp32 rounding lands on the other side lists the splat in one more / one fewer row or column of tiles. Every
+     * pixel of such a tile that the splat reaches with alpha >= 1/255 is flagged (a handful of splats per view). */
+    if (a->flags)
+        for (int i = 0; i < P; ++i) {
+            const Proj* o = &pr[i];
+            if (!(o->r3 > 0)) continue;
+            const real near_int = fabs(o->r3 - floor(o->r3 + (real)0.5)) < RADIUS_TIE_REL * (o->r3 > 1 ? o->r3 : 1);
+            const real rad = ceil(o->r3);
+            const real r_lo = (near_int ? rad - 1 : rad) - RECT_TIE_PX, r_hi = (near_int ? rad + 1 : rad) + RECT_TIE_PX;
+            int lo[4], hi[4];     /* x0 x1 y0 y1 of the smallest / largest rect within the ambiguity */
+            real v;
+#define CLAMPI(val, top) ((int)((val) < 0 ? 0 : ((val) > (top) ? (top) : (val))))
+            v = floor((o->xy[0] - r_lo) / TILE); lo[0] = CLAMPI(v, gx); v = floor((o->xy[0] + r_lo + (TILE - 1)) / TILE); lo[1] = CLAMPI(v, gx);
+            v = floor((o->xy[1] - r_lo) / TILE); lo[2] = CLAMPI(v, gy); v = floor((o->xy[1] + r_lo + (TILE - 1)) / TILE); lo[3] = CLAMPI(v, gy);
+            v = floor((o->xy[0] - r_hi) / TILE); hi[0] = CLAMPI(v, gx); v = floor((o->xy[0] + r_hi + (TILE - 1)) / TILE); hi[1] = CLAMPI(v, gx);
+            v = floor((o->xy[1] - r_hi) / TILE); hi[2] = CLAMPI(v, gy); v = floor((o->xy[1] + r_hi + (TILE - 1)) / TILE); hi[3] = CLAMPI(v, gy);
+#undef CLAMPI
+            if (lo[0] == hi[0] && lo[1] == hi[1] && lo[2] == hi[2] && lo[3] == hi[3]) continue;
+            for (int ty = hi[2]; ty < hi[3]; ++ty)
+                for (int tx = hi[0]; tx < hi[1]; ++tx) {
+                    if (tx >= lo[0] && tx < lo[1] && ty >= lo[2] && ty < lo[3]) continue;      /* listed under every rounding */
+                    for (int py = ty * TILE; py < ty * TILE + TILE && py < H; ++py)
+                        for (int px = tx * TILE; px < tx * TILE + TILE && px < W; ++px) {
+                            const real dx = o->xy[0] - (real)px, dy = o->xy[1] - (real)py;
+                            const real power = (real)-0.5 * (o->conic[0] * dx * dx + o->conic[2] * dy * dy) - o->conic[1] * dx * dy;
+                            if (power <= 0 && o->opacity * exp(power) >= (real)0.5 * ALPHA_MIN) a->flags[py * W + px] |= FLAG_RECT;
+                        }
+                }
+        }
 
     if (backward) {
 #pragma omp parallel for schedule(static)
