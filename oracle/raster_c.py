@@ -15,7 +15,6 @@ import subprocess
 from pathlib import Path
 from typing import Optional, Sequence
 
-import numpy as np
 import torch
 
 HERE = Path(__file__).resolve().parent

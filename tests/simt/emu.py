@@ -11,7 +11,6 @@ from __future__ import annotations
 
 import ctypes as C
 import hashlib
-import re
 import shutil
 import subprocess
 from pathlib import Path

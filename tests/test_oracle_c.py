@@ -3,7 +3,6 @@ oracle (oracle/raster_ref.py: vectorised, autograd) — two independent restatem
 rounding in float64, forward AND backward, including the per-pixel conditioning flags; the float32 build stays within
 the parity tolerances of the float64 one. The C oracle is what makes direct (not property-based) parity checks at
 BASELINE.json's full sizes affordable (tests/test_gpu_zz_fullsize.py) and is the CPU arm of bench.py."""
-import math
 import shutil
 
 import pytest
