@@ -173,7 +173,7 @@ def test_extra_attrs_forward_and_backward_match_oracle(E, textured):
     ex0 = torch.randn(N, E, generator=gen)
     cols = torch.rand(N, 3, generator=gen)
     _, aux0, _ = run_oracle(g, cam)
-    keep = (~aux0["ambiguous"]).float()
+    keep = (~aux0["grad_ambiguous"]).float()
     cot = [c * keep for c in output_cotangents(H, W, seed=55)]
     cot_e = torch.randn(E, H, W, generator=gen) * keep
 
@@ -254,7 +254,7 @@ def test_cov3Ds_precomp_matches_oracle_and_the_scale_rotation_path():
     with torch.no_grad():
         aux0 = RR.rasterize(t0["xyz"], None, None, t0["opacity"], None, None, None, None, None, oracle_settings(cam, 0, bg=(0.2, 0.1, 0.3)),
                             colors_precomp=cols, cov3Ds_precomp=cov0.float(), return_aux=True)[-1]
-    keep = (~aux0["ambiguous"]).float()
+    keep = (~aux0["grad_ambiguous"]).float()
     cot = [c * keep for c in output_cotangents(H, W, seed=74)]
     cot[2] = torch.zeros_like(cot[2])        # the normal carries no gradient in this mode
 
@@ -332,7 +332,7 @@ def test_edge_cases_empty_culled_single_and_ragged_sizes():
 def _check_backward_small(g, cam, bg):
     """Tiny scenes (a handful of Gaussians, R=8): same comparison, looser flagged-fraction / uv bounds."""
     _, aux, _ = run_oracle(g, cam, bg=bg)
-    keep = (~aux["ambiguous"]).float()
+    keep = (~aux["grad_ambiguous"]).float()
     cot = [c * keep for c in output_cotangents(cam.image_height, cam.image_width, seed=3)]
     _, _, gref = run_oracle(g, cam, bg=bg, cot=cot)
     _, _, ggot = run_cuda(g, cam, bg=bg, cot=cot)
@@ -423,7 +423,7 @@ def test_dual_render_equals_two_reference_style_renders():
     cam = orbit_cameras(1, W, H, seed=23)[0]
     bgc = (0.2, 0.1, 0.3)
     _, aux0, _ = run_oracle(g, cam, bg=bgc)
-    keep = (~aux0["ambiguous"]).float()
+    keep = (~aux0["grad_ambiguous"]).float()
     gen = torch.Generator().manual_seed(5)
     cot = [c * keep for c in output_cotangents(H, W, seed=24)]
     cot2 = torch.randn(3, H, W, generator=gen) * keep

@@ -86,7 +86,7 @@ def test_emulated_plain_texture_layout_dual_render_and_accumulation(emu):
     cam = orbit_cameras(1, W, H, seed=23)[0]
     bgc = (0.2, 0.1, 0.3)
     _, aux0, _ = run_oracle(g, cam, bg=bgc)
-    keep = (~aux0["ambiguous"]).float()
+    keep = (~aux0["grad_ambiguous"]).float()
     cot = [c * keep for c in output_cotangents(H, W, seed=24)]
     cot2 = torch.randn(3, H, W, generator=torch.Generator().manual_seed(5)) * keep
     t = g.to(dtype=torch.float32, requires_grad=True).tensors()
@@ -143,7 +143,7 @@ def test_emulated_plain_3dgs_modes_and_cov3d_match_oracle(emu):
             aux0 = RR.rasterize(t["xyz"], None, s_ref if kind == "sh" else None, t["opacity"], None if cov is not None else t["scaling"],
                                 None if cov is not None else t["rotation"], None, None, None, st,
                                 colors_precomp=None if kind == "sh" else c_ref, cov3Ds_precomp=cov, return_aux=True)[-1]
-        keep = (~aux0["ambiguous"]).float()
+        keep = (~aux0["grad_ambiguous"]).float()
         cot = [c * keep for c in output_cotangents(H, W, seed=2)]
         if kind == "cov":
             cot[2] = torch.zeros_like(cot[2])        # the normal carries no gradient in this mode
@@ -177,7 +177,7 @@ def test_emulated_extra_attrs_match_oracle(emu):
     ex0 = torch.randn(N, E, generator=gen)
     bgc = (0.2, 0.1, 0.3)
     _, aux0, _ = run_oracle(g, cam, bg=bgc)
-    keep = (~aux0["ambiguous"]).float()
+    keep = (~aux0["grad_ambiguous"]).float()
     cot = [c * keep for c in output_cotangents(H, W, seed=55)]
     cot_e = torch.randn(E, H, W, generator=gen) * keep
     t = g.to(dtype=torch.float32, requires_grad=True).tensors()
