@@ -345,7 +345,12 @@ def main():
     # ---- e2e: same step, driven from host buffers ---------------------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, wl, g, cams, cot, bg, bucket, views, dev, world, sync_all)
+        try:
+            e2e = run_e2e(args, wl, g, cams, cot, bg, bucket, views, dev, world, sync_all)
+        except Exception as e:              # keep the device-resident measurement; the line then says why e2e is missing
+            if world > 1:
+                raise                       # a rank that drops out of the collectives would hang the others
+            e2e = {"value": None, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(e)[:300]}
 
     # ---- unique texels touched by one view (for the algorithmic byte count) ---------------------
     bucket.zero()
