@@ -26,7 +26,9 @@ def test_full_size_forward_and_backward_against_the_c_oracle(n, w, h, r, view):
 def test_forward_only_baseline_configs_against_the_c_oracle(name, n, w, h, r):
     """BASELINE.json configs[1] (300 k Gaussians, 800x600, R = 1024: the retexture.py shape; synthetic stand-in for the
     DTU checkpoint) and configs[4] (1 M Gaussians, 3840x2160, R = 4096, the bandwidth stress case), forward, every pixel
-    of the four outputs against the C oracle."""
+    of the four outputs against the C oracle. At 3840 pixels across, fp32 pixel coordinates resolve 2.4e-4 px: the float32
+    build of the oracle itself is off by more than 1e-4 on ~0.1 % of the unflagged pixels there (none at 800x600), which is
+    what the "no worse than 5x the float32 oracle" clause of the helper is for."""
     if not torch.cuda.is_available():
         pytest.fail("GPU tests selected (-m gpu) but no CUDA device is visible")
     g = sphere_shell_scene(n, r, sh_degree=3, seed=0)
