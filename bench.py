@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--views", type=int, default=VIEWS_PER_STEP)
     ap.add_argument("--streams", type=int, default=1,
                     help="experimental: CUDA streams per rank that render alternate views concurrently (one gradient-bucket replica each)")
+    ap.add_argument("--fwd-ilp2", action="store_true", help="experimental: forward blend kernel with two splats per half-warp per iteration")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-tiles", type=int, default=0, help="ignored (kept for old command lines): the CPU arm renders whole views")
@@ -296,6 +297,9 @@ def main():
         from texture_gs_b200.dist import init_process_group_quiet
         init_process_group_quiet("nccl", dev)        # keeps NCCL's version banner off stdout (one JSON line only)
     _lib.load()
+    if args.fwd_ilp2:
+        from texture_gs_b200 import rasterizer as _rz
+        _rz.FWD_ILP2 = True
 
     g, cams, cot = make_scene(wl, dev)
     bg = torch.zeros(3, device=dev)
@@ -380,6 +384,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl.name, "gaussians": wl.n_gaussians, "width": wl.width, "height": wl.height,
                        "tex_res": wl.tex_res, "views_per_step": args.views, "sh_degree": 3, "streams_per_rank": max(1, args.streams),
+                       "forward_kernel": "ilp2 (experimental)" if args.fwd_ilp2 else "default",
                        "parallelism": f"dp{world} (views sharded, 1 all-reduce of {bucket.nbytes / 1e6:.0f} MB/step)" if world > 1 else "single GPU",
                        "l2_policy": "inputs larger than L2 (texture 302 MB + records 64 MB, a different camera every view)"},
             "clocks": clock_rec, "e2e": e2e, "gpu_launches": (KERNELS_PER_VIEW * len(views) + 1) * args.steps,

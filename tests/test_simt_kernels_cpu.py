@@ -382,3 +382,25 @@ def test_comparison_against_the_c_oracle_used_at_full_size_on_the_gpu(emu):
     g = sphere_shell_scene(2500, 64, sh_degree=3, seed=0)
     cam = orbit_cameras(32, 136, 76, seed=1)[5]
     check_against_c_oracle(g, cam, bg=(0.1, 0.2, 0.3), runner=run_emu, max_flag=0.6)
+
+
+def test_experimental_ilp2_forward_kernel_is_bit_identical(emu):
+    """TEXGS_FLAG_FWD_ILP2 (two splats per half-warp per iteration, texgs_render.cuh): every float operation happens in
+    the order of the default forward kernel, so outputs, the dual image, the debug blend count and — through final_T /
+    n_contrib — every gradient of the backward are identical bit for bit; packed and plain texel layouts."""
+    for (n, w, h, r, deg, cov) in [(1200, 96, 64, 32, 3, 4.0), (300, 70, 50, 16, 0, 40.0), (3, 17, 9, 4, 1, 8.0)]:
+        g = sphere_shell_scene(n, r, sh_degree=deg, seed=1, tex_seed=2, coverage=cov)
+        cam = orbit_cameras(1, w, h, seed=3)[0]
+        t = g.tensors()
+        cot = output_cotangents(h, w, seed=4)
+        kw = dict(means3D=t["xyz"], opacities=t["opacity"], scales=t["scaling"], rotations=t["rotation"], shs=t["shs"], uvs=t["uvs"],
+                  gradient_uvs=t["grad_uvs"], texture=t["texture"], cotangents=cot, debug=True, **_cam_kw(cam, (0.1, 0.2, 0.3), deg))
+        for dual, packed in ((False, True), (True, False)):
+            r0 = emu.rasterize(dual_no_sh=dual, packed_texture=packed, **kw)
+            r1 = emu.rasterize(dual_no_sh=dual, packed_texture=packed, fwd_ilp2=True, **kw)
+            for x, y in zip((r0.image, r0.depth, r0.norm, r0.alpha), (r1.image, r1.depth, r1.norm, r1.alpha)):
+                assert torch.equal(x, y)
+            assert (not dual) or torch.equal(r0.image_nosh, r1.image_nosh)
+            assert r0.num_blend == r1.num_blend > 0
+            for k in r0.grads:
+                assert torch.equal(r0.grads[k], r1.grads[k]), k

@@ -3,7 +3,8 @@
 # round-1 GPU budget was spent gets its first measurement. Outputs in gpurun_out/r2_*.
 #   1. GPU test-suite + smoke (the multi-stream test runs last)
 #   2. bench with the driver defaults (reference: 373 views/s in round 1)
-#   3. bench with 2 and 3 streams per rank (experimental view pipeline)
+#   3. bench with 2 and 3 streams per rank (experimental view pipeline), with the experimental
+#      two-splats-per-iteration forward kernel (--fwd-ilp2), and with both
 #   4. launch list of a 4-view step with 2 streams (do the small kernels really overlap the render kernels?)
 set -u
 O=gpurun_out; mkdir -p $O
@@ -13,10 +14,12 @@ timeout 600 python bench.py > $O/r2_bench.json 2> $O/r2_bench.err
 for s in 2 3; do
   timeout 400 python bench.py --streams $s --no-cpu-baseline > $O/r2_bench_streams$s.json 2> $O/r2_bench_streams$s.err
 done
+timeout 400 python bench.py --fwd-ilp2 --no-cpu-baseline > $O/r2_bench_ilp2.json 2> $O/r2_bench_ilp2.err
+timeout 400 python bench.py --fwd-ilp2 --streams 2 --no-cpu-baseline > $O/r2_bench_ilp2_streams2.json 2> $O/r2_bench_ilp2_streams2.err
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_launches_streams2.csv \
     python bench.py --streams 2 --views 4 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $O/r2_launches_streams2.log 2>&1
 tail -3 $O/r2_pytest_gpu.log; tail -1 $O/r2_smoke.log
-for f in $O/r2_bench.json $O/r2_bench_streams2.json $O/r2_bench_streams3.json; do
+for f in $O/r2_bench.json $O/r2_bench_streams2.json $O/r2_bench_streams3.json $O/r2_bench_ilp2.json $O/r2_bench_ilp2_streams2.json; do
   python - "$f" <<'PY'
 import json, sys
 try:
