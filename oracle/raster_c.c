@@ -66,6 +66,9 @@ static const real SH_C3[7] = {(real)-0.5900435899266435, (real)2.890611442640554
 #ifndef THRESH_ULPS
 #define THRESH_ULPS 256      /* alpha / T threshold proximity, in units of rel (4e-6 in float32): see DESIGN.md section 7 */
 #endif
+#define FLAG_CLAMP_TIE 64      /* gradient tests only: a colour channel within rounding of the clamp max(0, .) — the value is
+                                 continuous there, the clamp mask (and with it d/dSH, d/dtexture, d/duv) is not */
+#define CLAMP_TIE ((real)4e-6)
 #define RADIUS_TIE_REL ((real)1e-5)
 #define RECT_TIE_PX ((real)1e-3)
 
@@ -345,7 +348,8 @@ int texgs_oracle_run(const OracleArgs* a) {
                         c->nmv = q->normal[0] * q->m[0] + q->normal[1] * q->m[1] + q->normal[2] * q->m[2];
                         c->safe = fabs(c->nd) >= ND_EPS;
                         const real nlen = sqrt(q->normal[0] * q->normal[0] + q->normal[1] * q->normal[1] + q->normal[2] * q->normal[2]);
-                        if (fabs(c->nd) / (dwlen * (nlen > (real)1e-30 ? nlen : (real)1e-30)) < GRAZING_COS) flag |= FLAG_GRAZING;
+                        const real cosang = fabs(c->nd) / (dwlen * (nlen > (real)1e-30 ? nlen : (real)1e-30));
+                        if (cosang < GRAZING_COS) flag |= FLAG_GRAZING;
                         const real tp = c->safe ? c->nmv / c->nd : 0;
                         const real* Jg = a->grad_uvs + (size_t)9 * g;
                         for (int k = 0; k < 3; ++k) { c->dw[k] = dw[k]; c->delta[k] = c->safe ? tp * dw[k] - q->m[k] : 0; }
@@ -362,7 +366,8 @@ int texgs_oracle_run(const OracleArgs* a) {
                         const real fxx = (c->cube.sx + (real)1.0) * ((real)0.5 * Rr) - (real)0.5, fyy = (c->cube.sy + (real)1.0) * ((real)0.5 * Rr) - (real)0.5;
                         {
                             const real ddx = fabs(fxx - floor(fxx + (real)0.5)), ddy = fabs(fyy - floor(fyy + (real)0.5));
-                            if ((ddx < ddy ? ddx : ddy) < TEXEL_TIE * Rr) flag |= FLAG_TEXEL_TIE;
+                            /* the intersection amplifies rounding by 1 / cos(angle(n, d)): so does the margin */
+                            if ((ddx < ddy ? ddx : ddy) * (cosang > GRAZING_COS ? cosang : GRAZING_COS) < TEXEL_TIE * Rr) flag |= FLAG_TEXEL_TIE;
                         }
                         const real x0f = floor(fxx), y0f = floor(fyy);
                         c->wx = fxx - x0f; c->wy = fyy - y0f;
@@ -378,6 +383,7 @@ int texgs_oracle_run(const OracleArgs* a) {
                             const real top = c->taps[0][ch] + c->wx * (c->taps[1][ch] - c->taps[0][ch]);
                             const real bot = c->taps[2][ch] + c->wx * (c->taps[3][ch] - c->taps[2][ch]);
                             const real pre = SH_C0 * (top + c->wy * (bot - top)) + q->csh[ch] + (real)0.5;
+                            if (fabs(pre) < CLAMP_TIE) flag |= FLAG_CLAMP_TIE;
                             c->mask[ch] = pre >= 0 ? (real)1.0 : (real)0.0;
                             c->col[ch] = pre >= 0 ? pre : 0;
                             C[ch] += w * c->col[ch];

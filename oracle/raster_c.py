@@ -20,7 +20,7 @@ import torch
 HERE = Path(__file__).resolve().parent
 SRC = HERE / "raster_c.c"
 BUILD = HERE / "_build"
-FLAG_THRESHOLD, FLAG_GRAZING, FLAG_FACE_TIE, FLAG_TEXEL_TIE, FLAG_DEPTH_TIE, FLAG_RECT = 1, 2, 4, 8, 16, 32
+FLAG_THRESHOLD, FLAG_GRAZING, FLAG_FACE_TIE, FLAG_TEXEL_TIE, FLAG_DEPTH_TIE, FLAG_RECT, FLAG_CLAMP_TIE = 1, 2, 4, 8, 16, 32, 64
 _libs = {}
 
 
@@ -140,7 +140,7 @@ def rasterize(means3D, shs, opacities, scales, rotations, uvs, gradient_uvs, tex
     value_flags = FLAG_THRESHOLD | FLAG_GRAZING | FLAG_FACE_TIE | FLAG_DEPTH_TIE | FLAG_RECT
     aux = dict(final_T=out["final_T"], n_contrib=n_contrib, flags=flags,
                ambiguous=torch.from_numpy((fl & value_flags) != 0), grad_ambiguous=torch.from_numpy(fl != 0),
-               grazing=torch.from_numpy((fl & FLAG_GRAZING) != 0), texel_boundary=torch.from_numpy((fl & FLAG_TEXEL_TIE) != 0), rect_tie=torch.from_numpy((fl & FLAG_RECT) != 0),
+               grazing=torch.from_numpy((fl & FLAG_GRAZING) != 0), texel_boundary=torch.from_numpy((fl & FLAG_TEXEL_TIE) != 0), rect_tie=torch.from_numpy((fl & FLAG_RECT) != 0), clamp_tie=torch.from_numpy((fl & FLAG_CLAMP_TIE) != 0),
                num_pairs=int(counters[0]), num_visible=int(counters[1]), num_blend=int(counters[2]), max_tile_len=int(counters[3]),
                grads=grads)
     return out["image"], out["depth"], out["norm"], out["alpha"], radii[:P], aux

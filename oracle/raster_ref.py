@@ -60,6 +60,7 @@ TEXEL_TIE = 2e-6      # test-side conditioning flag: a texel-space coordinate wi
                       # fp32 resolves f = (s+1)R/2 - 1/2 to about 5e-7 * R)
 DEPTH_TIE_REL = 1e-6  # test-side conditioning flag: two splats that both blend into a pixel, adjacent in its list, with view-space
                       # depths within ~8 ulp: their ORDER (spec E4) is decided by the rounding of z = p.V[:,2]
+CLAMP_TIE = 4e-6      # test-side conditioning flag (gradients only): a colour channel within rounding of the clamp max(0, .)
 THRESH_ULPS = 256     # test-side conditioning flag: alpha within THRESH_ULPS * 4e-6 (relative, fp32) of 1/255, T of 1e-4. 64 was
                       # enough for the small test scenes; at 500 k splats the fp32 conic of thin splats (det = ac - b^2 cancels)
                       # moves alpha by up to ~1e-3 relative (measured: float32 vs float64 build of oracle/raster_c.c)
@@ -491,10 +492,14 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
                     Rt = texture.shape[1]
                     _, sxd, syd = cube_face_coords(u.detach())
                     fxd, fyd = (sxd + 1.0) * (0.5 * Rt) - 0.5, (syd + 1.0) * (0.5 * Rt) - 0.5
-                    near = torch.minimum((fxd - fxd.round()).abs(), (fyd - fyd.round()).abs()) < TEXEL_TIE * Rt
+                    # the intersection amplifies rounding by 1 / cos(angle(n, d)): so does the margin
+                    near = torch.minimum((fxd - fxd.round()).abs(), (fyd - fyd.round()).abs()) * cosang.clamp_min(GRAZING_COS) < TEXEL_TIE * Rt
                     texel_edge[pix[near]] = True
                 tex = cube_sample(texture, u)                                 # E11
-                col = torch.clamp_min(C0 * tex + pre["csh"][g] + 0.5, 0.0)   # E12
+                col_pre = C0 * tex + pre["csh"][g] + 0.5
+                with torch.no_grad():
+                    texel_edge[pix[(col_pre.abs() < CLAMP_TIE).any(dim=-1)]] = True   # clamp mask decided by rounding
+                col = torch.clamp_min(col_pre, 0.0)                          # E12
                 if acc_c0 is not None:
                     acc_c0 = acc_c0.index_add(0, pix, w_s[:, None] * torch.clamp_min(C0 * tex + 0.5, 0.0))
                 if sw.depth_of_intersection:

@@ -72,11 +72,51 @@ struct dim3 {
 // ---------------------------------------------------------------------------------------------
 namespace simt {
 
+// Context switch between fibers. glibc's swapcontext saves the signal mask with a system call on every switch; a
+// warp collective costs 64 switches, so on x86-64 a minimal switch (callee-saved registers + stack pointer; nobody in
+// the emulated code changes the floating-point control words) is used instead. SIMT_USE_UCONTEXT=1 forces ucontext.
+#if defined(__x86_64__) && !defined(SIMT_USE_UCONTEXT)
+#define SIMT_FAST_SWITCH 1
+struct Context { void* sp = nullptr; };
+extern "C" void simt_switch_asm(void** save_sp, void* load_sp);
+__asm__(
+    ".text\n"
+    ".globl simt_switch_asm\n"
+    ".type simt_switch_asm,@function\n"
+    "simt_switch_asm:\n"
+    "    pushq %rbp\n    pushq %rbx\n    pushq %r12\n    pushq %r13\n    pushq %r14\n    pushq %r15\n"
+    "    movq %rsp, (%rdi)\n"
+    "    movq %rsi, %rsp\n"
+    "    popq %r15\n    popq %r14\n    popq %r13\n    popq %r12\n    popq %rbx\n    popq %rbp\n"
+    "    ret\n"
+    ".size simt_switch_asm,.-simt_switch_asm\n");
+inline void switch_context(Context* from, Context* to) { simt_switch_asm(&from->sp, to->sp); }
+inline void make_context(Context* c, char* stack, size_t bytes, void (*entry)()) {
+    uintptr_t top = ((uintptr_t)stack + bytes) & ~(uintptr_t)15;
+    void** sp = (void**)top;
+    *--sp = nullptr;                 // return address of ``entry`` (it never returns)
+    *--sp = (void*)entry;            // popped by the ``ret`` of the first switch: rsp is then 8 mod 16, as after a call
+    for (int i = 0; i < 6; ++i) *--sp = nullptr;      // rbp rbx r12 r13 r14 r15
+    c->sp = (void*)sp;
+}
+#else
+#define SIMT_FAST_SWITCH 0
+struct Context { ucontext_t uc; };
+inline void switch_context(Context* from, Context* to) { swapcontext(&from->uc, &to->uc); }
+inline void make_context(Context* c, char* stack, size_t bytes, void (*entry)()) {
+    getcontext(&c->uc);
+    c->uc.uc_stack.ss_sp = stack;
+    c->uc.uc_stack.ss_size = bytes;
+    c->uc.uc_link = nullptr;
+    makecontext(&c->uc, entry, 0);
+}
+#endif
+
 constexpr size_t kStackBytes = 160 * 1024;
 constexpr size_t kDynSmemMax = 232448;      // 227 KB, the sm_100 opt-in maximum
 
 struct Fiber {
-    ucontext_t ctx;
+    Context ctx;
     uint3 tid;
     int lin = 0, lane = 0, warp = 0;
     bool done = false;
@@ -108,7 +148,7 @@ struct Global {
     std::vector<Fiber> fibers;
     std::vector<char*> stacks;
     std::vector<Warp> warps;
-    ucontext_t sched;
+    Context sched;
     Fiber* cur = nullptr;
     void (*entry)(void*) = nullptr;
     void* entry_arg = nullptr;
@@ -127,7 +167,8 @@ struct Global {
     // EARLY as legal (exposes a stage overwritten while other lanes still read its previous content)
     bool eager_copies = false;
     // fast-math intrinsics (__expf, __logf, __fdividef, rsqrtf): 0 = exact; n > 0 = results perturbed by a pseudo-random
-    // relative error of up to n * 2^-23 — the GPU's ex2.approx / rcp.approx / lg2.approx paths are not correctly rounded
+    // (but repeatable: a hash of the value) relative error of up to n * 2^-23 — the GPU's ex2.approx / rcp.approx /
+    // lg2.approx paths are not correctly rounded
     unsigned fastmath_noise_ulps = 0;
     uint32_t noise_state = 0x9e3779b9u;
 };
@@ -144,7 +185,7 @@ inline void fail(const std::string& msg) {
     g.abort_block = true;
 }
 
-inline void yield_to_scheduler() { Global& g = G(); swapcontext(&g.cur->ctx, &g.sched); }
+inline void yield_to_scheduler() { Global& g = G(); switch_context(&g.cur->ctx, &g.sched); }
 
 // block the running fiber while *addr == val
 inline void wait_while_equal(const volatile unsigned* addr, unsigned val, const char* what) {
@@ -160,8 +201,7 @@ inline void wait_while_equal(const volatile unsigned* addr, unsigned val, const 
     }
 }
 
-inline void fiber_main(unsigned lo, unsigned hi) {
-    (void)lo; (void)hi;
+inline void fiber_main() {
     Global& g = G();
     g.entry(g.entry_arg);
     Fiber* f = g.cur;
@@ -290,8 +330,12 @@ namespace simt {
 inline float approx(float exact) {
     Global& g = G();
     if (g.fastmath_noise_ulps == 0 || !(exact == exact)) return exact;
-    g.noise_state = g.noise_state * 1664525u + 1013904223u;
-    const float r = (float)((int32_t)g.noise_state) * (1.0f / 2147483648.0f);          // [-1, 1)
+    // a deterministic function of the value, like the hardware units: the same input gives the same output in every
+    // kernel (the count and the scatter kernel of the binning rely on that, as do forward and backward)
+    uint32_t h;
+    memcpy(&h, &exact, 4);
+    h = (h ^ g.noise_state) * 0x9E3779B1u; h ^= h >> 15; h *= 0x85EBCA77u; h ^= h >> 13;
+    const float r = (float)((int32_t)h) * (1.0f / 2147483648.0f);                      // [-1, 1)
     return exact * (1.0f + r * (float)g.fastmath_noise_ulps * 1.1920929e-7f);
 }
 }  // namespace simt
@@ -445,11 +489,7 @@ inline void run_block() {
         f.tid = uint3{t % g.bdim.x, (t / g.bdim.x) % g.bdim.y, t / (g.bdim.x * g.bdim.y)};
         f.done = false; f.wait_addr = nullptr;
         g.warps[f.warp].exist |= 1u << f.lane;
-        getcontext(&f.ctx);
-        f.ctx.uc_stack.ss_sp = g.stacks[t];
-        f.ctx.uc_stack.ss_size = kStackBytes;
-        f.ctx.uc_link = &g.sched;
-        makecontext(&f.ctx, (void (*)())fiber_main, 2, 0u, 0u);
+        make_context(&f.ctx, g.stacks[t], kStackBytes, &fiber_main);
     }
     unsigned remaining = nthreads;
     while (remaining > 0 && !g.abort_block) {
@@ -465,7 +505,7 @@ inline void run_block() {
                     if (f.done) continue;
                     if (f.wait_addr && *f.wait_addr == f.wait_val) continue;
                     g.cur = &f;
-                    swapcontext(&g.sched, &f.ctx);
+                    switch_context(&g.sched, &f.ctx);
                     warp_ran = ran_any = true;
                     if (f.done) --remaining;
                     if (g.abort_block) break;

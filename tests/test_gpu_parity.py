@@ -66,7 +66,7 @@ def test_config0_10k_256_forward_and_backward():
     g = sphere_shell_scene(10_000, 512, sh_degree=3, seed=0)
     cam = orbit_cameras(1, 256, 256, seed=1)[0]
     _check_forward(g, cam)
-    _check_backward(g, cam)
+    _check_backward(g, cam, max_flag=0.3)     # R = 512: the (ray-angle-scaled) texel-boundary margin flags ~12 % of the pixels
 
 
 def test_binning_order_matches_oracle():
