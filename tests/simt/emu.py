@@ -26,7 +26,8 @@ CSRC = ROOT / "texture_gs_b200" / "csrc"
 BUILD = HERE / "_build"
 DYN_SMEM = (("unsigned char", "smem_raw"), ("float", "prebwd_smem"))     # every `extern __shared__` array of the sources
 GXX_FLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes",
-             "-fno-extern-tls-init"]     # `extern __shared__` arrays are plain extern thread_local arrays: no init wrapper
+             "-fno-extern-tls-init",     # `extern __shared__` arrays are plain extern thread_local arrays: no init wrapper
+             "-fno-gnu-unique", "-Wl,-Bsymbolic"]   # two builds (different -D flags) loaded into one process keep their own state
 SKIPPED_SYMBOLS = ("texgs_uvmlp_forward", "texgs_uvmlp_backward_head", "texgs_uvmlp_backward_mask", "texgs_uvmlp_backward_tail")
 
 
@@ -131,11 +132,9 @@ def build(extra_flags=()):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + r.stderr[-6000:])
-        for old in BUILD.glob("libtexgs_emu_*.so"):
-            if old != so:
-                old.unlink()
-        for old in BUILD.glob("texgs_emu_*.cpp"):
-            if old != cpp:
+        keep = {so, cpp} | {BUILD / f"libtexgs_emu_{t}.so" for t in _loaded} | {BUILD / f"texgs_emu_{t}.cpp" for t in _loaded}
+        for old in list(BUILD.glob("libtexgs_emu_*.so")) + list(BUILD.glob("texgs_emu_*.cpp")):
+            if old not in keep:
                 old.unlink()
     lib = C.CDLL(str(so))
     for name, (res, args) in L.SYMBOLS.items():
