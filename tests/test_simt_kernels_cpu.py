@@ -410,3 +410,23 @@ def test_experimental_ilp2_forward_kernel_is_bit_identical(emu):
             assert r0.num_blend == r1.num_blend > 0
             for k in r0.grads:
                 assert torch.equal(r0.grads[k], r1.grads[k]), k
+
+
+def test_tuning_macro_variants_compute_the_same_thing(emu):
+    """The build-time tuning knobs used for A/B timing on the GPU (tools/build_variants.py) must not change results:
+    16-entry chunks (TEXGS_CHUNK), the unstaged SH path of preprocess_bwd (TEXGS_PREBWD_STAGE_SH=0) and libm exp instead
+    of the fast intrinsic (TEXGS_FAST_EXP=0), all in one alternative build that lives in the same process as the default
+    one. Forward bit-identical (the blend order does not depend on the chunking), gradients equal up to summation order."""
+    alt = emu.build(extra_flags=("-DTEXGS_CHUNK=16", "-DTEXGS_PREBWD_STAGE_SH=0", "-DTEXGS_FAST_EXP=0"))
+    g = sphere_shell_scene(1200, 32, sh_degree=3, seed=5, tex_seed=6)
+    cam = orbit_cameras(1, 96, 64, seed=7)[0]
+    t = g.tensors()
+    cot = output_cotangents(64, 96, seed=8)
+    kw = dict(means3D=t["xyz"], opacities=t["opacity"], scales=t["scaling"], rotations=t["rotation"], shs=t["shs"], uvs=t["uvs"],
+              gradient_uvs=t["grad_uvs"], texture=t["texture"], cotangents=cot, **_cam_kw(cam, (0.1, 0.2, 0.3), 3))
+    a = emu.rasterize(**kw)
+    b = emu.rasterize(lib=alt, **kw)
+    for x, y in zip((a.image, a.depth, a.norm, a.alpha, a.radii), (b.image, b.depth, b.norm, b.alpha, b.radii)):
+        assert torch.equal(x, y)
+    for k in a.grads:
+        assert rel_err(b.grads[k], a.grads[k]) < 1e-5, k
