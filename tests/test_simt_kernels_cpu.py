@@ -430,3 +430,33 @@ def test_tuning_macro_variants_compute_the_same_thing(emu):
         assert torch.equal(x, y)
     for k in a.grads:
         assert rel_err(b.grads[k], a.grads[k]) < 1e-5, k
+
+
+def test_full_size_criterion_is_not_vacuous(emu):
+    """Negative controls for tests/util.check_against_c_oracle (the comparison tests/test_gpu_zz_fullsize.py runs): a
+    renderer whose image is off by 3e-4 on 0.1 % of the pixels, one whose uv gradient is 1 % too large, and one that
+    drops a splat are all rejected; the unmodified emulated kernels pass."""
+    from util import check_against_c_oracle
+    g = sphere_shell_scene(3000, 64, sh_degree=3, seed=0)
+    cam = orbit_cameras(32, 160, 90, seed=1)[5]
+
+    def broken(kind):
+        def runner(gg, cc, bg=(0, 0, 0), cot=None, scale_modifier=1.0):
+            if kind == "drop":
+                t = {k: (v.detach().clone() if v is not None else None) for k, v in gg.tensors().items()}
+                t["opacity"][::50] = 0.0
+                gg = SyntheticGaussians(active_sh_degree=gg.active_sh_degree, **t)
+            outs, stats, grads = run_emu(gg, cc, bg=bg, cot=cot, scale_modifier=scale_modifier)
+            if kind == "image":
+                img = outs[0].clone()
+                img.view(3, -1)[:, ::1000] += 3e-4
+                outs = (img,) + tuple(outs[1:])
+            if kind == "uvs" and grads is not None:
+                grads = dict(grads, uvs=grads["uvs"] * 1.01)
+            return outs, stats, grads
+        return runner
+
+    check_against_c_oracle(g, cam, bg=(0.1, 0.2, 0.3), runner=run_emu, max_flag=0.6)
+    for kind in ("image", "uvs", "drop"):
+        with pytest.raises(AssertionError):
+            check_against_c_oracle(g, cam, bg=(0.1, 0.2, 0.3), runner=broken(kind), max_flag=0.6)
