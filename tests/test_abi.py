@@ -164,3 +164,30 @@ def test_cold_path_arguments_are_validated_without_a_gpu():
     with pytest.raises(ValueError):
         r(means3D=x, means2D=x, opacities=torch.ones(4, 1), uvs=x, gradient_uvs=torch.zeros(4, 9), texture=torch.zeros(6, 2, 2, 3),
           cov3Ds_precomp=torch.zeros(4, 6))
+
+
+def test_reference_call_sites_use_only_arguments_the_dropin_accepts():
+    """Static check against the reference's OWN source (skipped where /root/reference is absent): the keyword arguments
+    of ``GaussianRasterizationSettings(...)`` and of the ``rasterizer(...)`` call in render/uv_tex_render.py and
+    render/render.py are exactly / a subset of what the drop-in classes accept, and the call unpacks six results."""
+    import ast
+    import inspect
+    from texture_gs_b200 import GaussianRasterizationSettings, GaussianRasterizer
+    ref = Path("/root/reference/render")
+    if not ref.exists():
+        pytest.skip("reference tree not present")
+    accepted = set(inspect.signature(GaussianRasterizer.forward).parameters) - {"self"}
+    for fname in ("uv_tex_render.py", "render.py"):
+        tree = ast.parse((ref / fname).read_text())
+        settings_kw, call_kw, n_results = None, None, None
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id == "GaussianRasterizationSettings":
+                settings_kw = [k.arg for k in node.keywords]
+            if isinstance(node, ast.Assign) and isinstance(node.value, ast.Call) and isinstance(node.value.func, ast.Name) \
+                    and node.value.func.id == "rasterizer":
+                call_kw = [k.arg for k in node.value.keywords]
+                n_results = len(node.targets[0].elts)
+        assert settings_kw is not None and tuple(settings_kw) == GaussianRasterizationSettings._fields, (fname, settings_kw)
+        assert call_kw is not None and set(call_kw) <= accepted, (fname, set(call_kw) - accepted)
+        assert n_results == 6, fname
+        assert "dual_no_sh" not in call_kw          # our extension is opt-in, never required by the reference
