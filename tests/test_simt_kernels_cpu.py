@@ -460,3 +460,69 @@ def test_full_size_criterion_is_not_vacuous(emu):
     for kind in ("image", "uvs", "drop"):
         with pytest.raises(AssertionError):
             check_against_c_oracle(g, cam, bg=(0.1, 0.2, 0.3), runner=broken(kind), max_flag=0.6)
+
+
+def test_reference_plain_render_source_and_its_own_eval_sh_drive_the_emulated_kernels(emu, monkeypatch):
+    """The diff_gauss side of the boundary: the reference's OWN ``render/render.py`` (``device="cuda"`` re-targeted) with
+    its OWN ``utils/sh.py`` runs against the emulated kernels. ``cfg.convert_SHs_python = True`` makes the reference
+    evaluate the spherical harmonics itself (``eval_sh``) and hand over ``colors_precomp``; ``False`` hands the
+    coefficients to the rasterizer. Both must give the same picture — which pins the kernels' SH evaluation to the
+    reference's own code — and ``compute_cov3D_python`` (``cov3Ds_precomp``) must agree with scales + rotations."""
+    import sys
+    import types
+    from pathlib import Path
+    ref = Path("/root/reference")
+    if not (ref / "render" / "render.py").exists():
+        pytest.skip("reference tree not present")
+    from simt import emu_module
+    for name in ("diff_gauss",):
+        shim = types.ModuleType(name)
+        shim.GaussianRasterizationSettings = emu_module.GaussianRasterizationSettings
+        shim.GaussianRasterizer = emu_module.GaussianRasterizer
+        monkeypatch.setitem(sys.modules, name, shim)
+    sh_mod = types.ModuleType("utils.sh")
+    exec(compile((ref / "utils" / "sh.py").read_text(), str(ref / "utils" / "sh.py"), "exec"), sh_mod.__dict__)
+    pkg = types.ModuleType("utils")
+    pkg.sh = sh_mod
+    monkeypatch.setitem(sys.modules, "utils", pkg)
+    monkeypatch.setitem(sys.modules, "utils.sh", sh_mod)
+    src = (ref / "render" / "render.py").read_text()
+    assert src.count('device="cuda"') == 1
+    ns = {}
+    exec(compile(src.replace('device="cuda"', "device=gaussians.get_xyz.device"), str(ref / "render" / "render.py"), "exec"), ns)
+
+    N, W, H = 700, 64, 48
+    g0 = sphere_shell_scene(N, 4, sh_degree=3, seed=61)
+    t = g0.tensors()
+    gen = torch.Generator().manual_seed(62)
+    feats = torch.cat([torch.randn(N, 1, 3, generator=gen), 0.1 * torch.randn(N, 15, 3, generator=gen)], dim=1)
+
+    class G:      # the attributes render/render.py reads (models/gaussian3d.py)
+        get_xyz, get_opacity, get_scaling, get_rotation = t["xyz"].detach(), t["opacity"].detach(), t["scaling"].detach(), t["rotation"].detach()
+        get_features, max_sh_degree, active_sh_degree = feats, 3, 3
+
+        @staticmethod
+        def get_covariance(scaling_modifier=1.0):
+            from oracle.raster_ref import quat_to_rot
+            Lm = quat_to_rot(G.get_rotation.double()) * (G.get_scaling.double() * scaling_modifier)[:, None, :]
+            S = Lm @ Lm.transpose(1, 2)
+            return torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], dim=-1).float()
+
+    cam = orbit_cameras(1, W, H, seed=63)[0]
+    bg = torch.tensor([0.2, 0.1, 0.3])
+    Cfg = lambda sh_py, cov_py: types.SimpleNamespace(convert_SHs_python=sh_py, compute_cov3D_python=cov_py)
+    a = ns["render"](cam, G, Cfg(False, False), bg)          # SH evaluated by the kernels
+    b = ns["render"](cam, G, Cfg(True, False), bg)           # SH evaluated by the reference's eval_sh
+    c = ns["render"](cam, G, Cfg(False, True), bg)           # covariance computed "in Python"
+    assert set(a) == {"render", "depth", "norm", "alpha", "viewspace_points", "visibility_filter", "extra", "radii"}
+    assert float((a["render"] - b["render"]).detach().abs().max()) <= 2e-6, "kernel SH evaluation differs from the reference's eval_sh"
+    for k in ("depth", "alpha", "norm"):
+        assert torch.equal(a[k], b[k])
+    # covariance path: same picture on well-conditioned pixels (the two covariances differ by rounding)
+    from oracle import raster_ref as RR
+    st = oracle_settings(cam, 3, bg=(0.2, 0.1, 0.3))
+    o = RR.rasterize(G.get_xyz, None, feats, G.get_opacity, G.get_scaling, G.get_rotation, None, None, None, st, return_aux=True)
+    amb = o[-1]["ambiguous"]
+    assert float((a["render"] - o[0]).detach().abs().amax(0)[~amb].max()) <= ABS_TOL
+    assert float((c["render"] - a["render"]).detach().abs().amax(0)[~amb].max()) <= ABS_TOL
+    assert torch.equal(a["radii"], o[4].to(a["radii"].dtype))
