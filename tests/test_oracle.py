@@ -353,3 +353,50 @@ def test_depth_and_normal_outputs_mean_what_the_reference_consumers_assume():
     xyz = (torch.linalg.inv(cam.world_view_transform.t()) @ coord_c.reshape(4, -1)).reshape(4, H, W)[:3]
     r = xyz.norm(dim=0)[opaque]
     assert abs(float(r.mean()) - 1.0) < 0.01 and float(r.std()) < 0.01                     # on the unit sphere
+
+
+def test_camera_matrices_equal_the_reference_code():
+    """The synthetic cameras (texture_gs_b200/scene.py) against the reference's OWN ``utils/graphics.py`` executed where
+    it lies (skipped without /root/reference) and the recipe of ``utils/cameras.py:62-65``:
+    world_view_transform = getWorld2View2(R, T)^T, projection = getProjectionMatrix(0.01, 100, FoVx, FoVy)^T,
+    full_proj_transform = world_view_transform @ projection, camera_center = inverse(world_view_transform)[3, :3]."""
+    src = Path("/root/reference/utils/graphics.py")
+    if not src.exists():
+        pytest.skip("reference tree not present")
+    ns = {}
+    exec(compile(src.read_text(), str(src), "exec"), ns)
+    for cam in orbit_cameras(4, 80, 48, seed=9):
+        w2c = cam.world_view_transform.t().double().numpy()                 # our W2C; the reference stores R = W2C[:3,:3]^T
+        Rm, T = w2c[:3, :3].T, w2c[:3, 3]
+        wvt = torch.tensor(ns["getWorld2View2"](Rm, T)).transpose(0, 1)
+        proj = ns["getProjectionMatrix"](znear=0.01, zfar=100.0, fovX=cam.FoVx, fovY=cam.FoVy).transpose(0, 1)
+        full = (wvt.unsqueeze(0).bmm(proj.unsqueeze(0))).squeeze(0)
+        assert torch.allclose(wvt, cam.world_view_transform, atol=1e-6)
+        assert torch.allclose(proj, cam.projection_matrix, atol=1e-6)
+        assert torch.allclose(full, cam.full_proj_transform, atol=1e-5)
+        assert torch.allclose(wvt.inverse()[3, :3], cam.camera_center, atol=1e-5)
+
+
+def test_rotation_and_covariance_layout_equal_the_reference_code():
+    """``utils/general.py`` of the reference, executed where it lies with its hard-coded ``device="cuda"`` re-targeted
+    (skipped without /root/reference): ``build_rotation`` == the oracle's quaternion convention (r,x,y,z), the covariance
+    ``L L^T`` with ``L = build_scaling_rotation(s * modifier, q)`` stripped by ``strip_symmetric`` (what
+    ``gaussians.get_covariance`` hands to ``cov3Ds_precomp``, models/gaussian3d.py:17-21) == the oracle's Sigma in the
+    (xx,xy,xz,yy,yz,zz) order, and rendering with that covariance == rendering with scales + rotations."""
+    src = Path("/root/reference/utils/general.py")
+    if not src.exists():
+        pytest.skip("reference tree not present")
+    txt = src.read_text()
+    a, b = txt.index("def strip_lowerdiag"), txt.index("def safe_state")
+    ns = {"torch": torch}
+    exec(compile(txt[a:b].replace('device="cuda"', 'device="cpu"').replace("device='cuda'", "device='cpu'"), str(src), "exec"), ns)
+    gen = torch.Generator().manual_seed(3)
+    q = torch.nn.functional.normalize(torch.randn(50, 4, generator=gen), dim=1)
+    s = torch.exp(torch.randn(50, 3, generator=gen))
+    assert torch.allclose(ns["build_rotation"](q), RR.quat_to_rot(q), atol=1e-6)
+    L = ns["build_scaling_rotation"](0.8 * s, q)
+    cov6 = ns["strip_symmetric"](L @ L.transpose(1, 2))
+    Lo = RR.quat_to_rot(q.double()) * (0.8 * s.double())[:, None, :]
+    So = Lo @ Lo.transpose(1, 2)
+    ours = torch.stack([So[:, 0, 0], So[:, 0, 1], So[:, 0, 2], So[:, 1, 1], So[:, 1, 2], So[:, 2, 2]], dim=-1)
+    assert torch.allclose(cov6.double(), ours, rtol=1e-5, atol=1e-7)
