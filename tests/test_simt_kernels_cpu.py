@@ -526,3 +526,23 @@ def test_reference_plain_render_source_and_its_own_eval_sh_drive_the_emulated_ke
     assert float((a["render"] - o[0]).detach().abs().amax(0)[~amb].max()) <= ABS_TOL
     assert float((c["render"] - a["render"]).detach().abs().amax(0)[~amb].max()) <= ABS_TOL
     assert torch.equal(a["radii"], o[4].to(a["radii"].dtype))
+
+
+def test_textured_sh_rest_path_equals_the_full_sh_path_for_a_constant_texture(emu):
+    """The textured mode evaluates bands l >= 1 from ``shs`` (N,15,3) and takes the DC term from the texture
+    (models/texture_gaussian3d.py:97-98); the diff_gauss mode evaluates all 16 coefficients — the path pinned to the
+    reference's ``eval_sh`` above. With a constant texture t0 the two must give the same image when the full SH set is
+    [t0, rest]: the pin carries over to the SH-rest evaluation of the textured kernels."""
+    N, W, H = 900, 64, 48
+    g = sphere_shell_scene(N, 4, sh_degree=3, seed=71)
+    t = g.tensors()
+    cam = orbit_cameras(1, W, H, seed=72)[0]
+    t0 = torch.tensor([0.7, -0.4, 1.1])
+    tex = t0.expand(6, 4, 4, 3).contiguous()
+    common = dict(means3D=t["xyz"], opacities=t["opacity"], scales=t["scaling"], rotations=t["rotation"], **_cam_kw(cam, (0.1, 0.2, 0.3), 3))
+    a = emu.rasterize(shs=t["shs"], uvs=t["uvs"], gradient_uvs=t["grad_uvs"], texture=tex, **common)
+    full = torch.cat([t0.expand(N, 1, 3), t["shs"].detach()], dim=1).contiguous()
+    b = emu.rasterize(shs=full, **common)
+    assert float((a.image - b.image).abs().max()) <= 2e-6
+    for x, y in zip((a.depth, a.norm, a.alpha, a.radii), (b.depth, b.norm, b.alpha, b.radii)):
+        assert torch.equal(x, y)
