@@ -63,6 +63,17 @@ def test_cube_face_roundtrip_matches_reference_layout():
     def cube_to_dir(s, x, y):   # restated from the reference table
         one = torch.ones_like(x)
         return [torch.stack(v, -1) for v in ([one, -y, -x], [-one, -y, x], [x, one, y], [x, -one, -y], [x, -y, one], [-x, -y, -one])][s]
+    ref_src = Path("/root/reference/models/modules/NVDIFFREC/util.py")
+    if ref_src.exists():       # the reference's own function, cut out of its file (the module imports nvdiffrast) and executed
+        txt = ref_src.read_text()
+        a, b = txt.index("def cube_to_dir"), txt.index("def latlong_to_cubemap")
+        ns = {"torch": torch}
+        exec(compile(txt[a:b], str(ref_src), "exec"), ns)
+        restated = cube_to_dir
+        xs, ys = torch.linspace(-0.9, 0.9, 7, dtype=torch.float64), torch.linspace(-0.8, 0.7, 7, dtype=torch.float64)
+        for s in range(6):
+            assert torch.equal(ns["cube_to_dir"](s, xs, ys), restated(s, xs, ys))
+        cube_to_dir = ns["cube_to_dir"]
     gen = torch.Generator().manual_seed(0)
     x = torch.rand(1000, generator=gen, dtype=torch.float64) * 1.98 - 0.99
     y = torch.rand(1000, generator=gen, dtype=torch.float64) * 1.98 - 0.99
