@@ -364,6 +364,17 @@ def test_depth_and_normal_outputs_mean_what_the_reference_consumers_assume():
     xyz = (torch.linalg.inv(cam.world_view_transform.t()) @ coord_c.reshape(4, -1)).reshape(4, H, W)[:3]
     r = xyz.norm(dim=0)[opaque]
     assert abs(float(r.mean()) - 1.0) < 0.01 and float(r.std()) < 0.01                     # on the unit sphere
+    # the model's own consumer, TextureGaussian3D.depth2world (models/texture_gaussian3d.py:299-309): depth as clip w
+    msrc = Path("/root/reference/models/texture_gaussian3d.py").read_text()
+    a = msrc.index("    def depth2world(")
+    b = msrc.index("    def oneupSHdegree(")
+    import textwrap
+    ns2 = {"torch": torch}
+    exec(compile(textwrap.dedent(msrc[a:b]), "depth2world", "exec"), ns2)
+    xyz2 = ns2["depth2world"](None, depth[0], cam.full_proj_transform, 100.0, 0.01)         # (H, W, 3)
+    r2 = xyz2.norm(dim=-1)[opaque]
+    assert abs(float(r2.mean()) - 1.0) < 0.01 and float(r2.std()) < 0.01
+    assert float((xyz2.permute(2, 0, 1) - xyz)[:, opaque].abs().max()) < 1e-3               # both consumers agree
 
 
 def test_camera_matrices_equal_the_reference_code():
