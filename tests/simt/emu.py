@@ -101,6 +101,7 @@ def emulated_source() -> str:
     tail = ('\nextern "C" const char* simt_last_error(void) { return simt::G().err_msg.c_str(); }\n'
             'extern "C" unsigned long long simt_collectives(void) { return simt::G().collectives; }\n'
             'extern "C" void simt_set_eager_copies(int on) { simt::G().eager_copies = on != 0; }\n'
+            'extern "C" void simt_set_schedule_seed(unsigned seed) { simt::G().sched_seed = seed; simt::G().sched_state = seed * 2654435761u + 1u; }\n'
             'extern "C" void simt_set_fastmath_noise(unsigned ulps) { simt::G().fastmath_noise_ulps = ulps; simt::G().noise_state = 0x9e3779b9u; }\n')
     return head + api + tail
 
@@ -145,6 +146,7 @@ def build(extra_flags=()):
     lib.simt_last_error.restype = C.c_char_p
     lib.simt_collectives.restype = C.c_ulonglong
     lib.simt_set_eager_copies.argtypes = [C.c_int]
+    lib.simt_set_schedule_seed.argtypes = [C.c_uint]
     lib.simt_set_fastmath_noise.argtypes = [C.c_uint]
     _loaded[tag] = lib
     return lib

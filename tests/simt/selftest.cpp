@@ -138,6 +138,21 @@ __global__ void bug_overwrite_while_reading(const float4* src, float* out) {
     mbar_wait(bar, 1);
 }
 
+// inter-warp race: warp 1 reads what warp 0 writes without a block barrier in between
+__global__ void bug_missing_syncthreads(int* out) {
+    __shared__ int s[64];
+    const int tid = threadIdx.x;
+    s[tid] = 0;
+    __syncthreads();
+    for (int it = 0; it < 8; ++it) {
+        s[tid] = it + 1;
+        __syncwarp();                       // keeps every warp in step with itself, not with the other warp
+        // BUG: no __syncthreads() before reading the other warp's slot
+        if (s[tid ^ 32] != it + 1) atomicAdd(out, 1);
+        __syncthreads();
+    }
+}
+
 int main() {
     {
         int out[24] = {0};
@@ -200,6 +215,16 @@ int main() {
         if (!eager) EXPECT(simt::G().err == 0 && wrong == 0, "late-landing copies hide an overwrite-while-reading hazard ...");
         else EXPECT(simt::G().err == 0 && wrong > 0, "... early-landing copies (eager mode) expose it");
         simt::G().eager_copies = false;
+    }
+    {
+        int stale_det = 0, stale_rnd = 0;
+        SIMT_LAUNCH((bug_missing_syncthreads), 1, 64, 0, 0, &stale_det);
+        for (unsigned seed = 1; seed <= 8; ++seed) {
+            simt::G().sched_seed = seed; simt::G().sched_state = seed * 2654435761u + 1u;
+            SIMT_LAUNCH((bug_missing_syncthreads), 1, 64, 0, 0, &stale_rnd);
+        }
+        simt::G().sched_seed = 0;
+        EXPECT(simt::G().err == 0 && stale_det > 0 && stale_rnd > 0, "a missing __syncthreads between two warps is observed (fixed and random schedules)");
     }
     SIMT_LAUNCH((k_blockidx), 1, 2048, 0, 0, (unsigned*)nullptr);
     EXPECT(take_error("invalid configuration"), "more than 1024 threads per block is refused");

@@ -11,6 +11,8 @@
 //   * bulk copies (cp.async.bulk) are DEFERRED until no thread of the block can make progress without them, so shared
 //     memory read before the mbarrier wait holds stale data, and a block that ends with copies in flight is an error;
 //   * dynamic shared memory is filled with NaN patterns before every block;
+//   * the warps of a block can be interleaved at random (simt_set_schedule_seed) instead of running one after the other;
+//   * fast-math intrinsics can return results perturbed by a repeatable error of a few ulp (simt_set_fastmath_noise);
 //   * no runnable fiber while some are unfinished (divergent barrier, missing arrival) is reported as a deadlock.
 #pragma once
 #include <math.h>
@@ -169,6 +171,9 @@ struct Global {
     // fast-math intrinsics (__expf, __logf, __fdividef, rsqrtf): 0 = exact; n > 0 = results perturbed by a pseudo-random
     // (but repeatable: a hash of the value) relative error of up to n * 2^-23 — the GPU's ex2.approx / rcp.approx /
     // lg2.approx paths are not correctly rounded
+    // scheduling: 0 = warp after warp, each as far as it can go (deterministic); otherwise the seed of a random
+    // interleaving of the warps of a block (random order, random time slices, random first lane): intra-block races
+    unsigned sched_seed = 0, sched_state = 1;
     unsigned fastmath_noise_ulps = 0;
     uint32_t noise_state = 0x9e3779b9u;
 };
@@ -492,15 +497,24 @@ inline void run_block() {
         make_context(&f.ctx, g.stacks[t], kStackBytes, &fiber_main);
     }
     unsigned remaining = nthreads;
+    std::vector<unsigned> order(nwarps);
+    for (unsigned w = 0; w < nwarps; ++w) order[w] = w;
+    auto rnd = [&g]() { g.sched_state = g.sched_state * 1664525u + 1013904223u; return g.sched_state >> 8; };
     while (remaining > 0 && !g.abort_block) {
         bool ran_any = false;
-        for (unsigned w = 0; w < nwarps && !g.abort_block; ++w) {
+        if (g.sched_seed)                           // random warp order, random time slices, random first lane
+            for (unsigned i = nwarps; i > 1; --i) std::swap(order[i - 1], order[rnd() % i]);
+        for (unsigned wi = 0; wi < nwarps && !g.abort_block; ++wi) {
+            const unsigned w = order[wi];
             bool warp_ran = true;
-            while (warp_ran && !g.abort_block) {
+            unsigned budget = g.sched_seed ? 1 + rnd() % 6 : ~0u;
+            const unsigned l0 = g.sched_seed ? rnd() % 32 : 0;
+            while (warp_ran && budget-- > 0 && !g.abort_block) {
                 warp_ran = false;
-                for (unsigned l = 0; l < 32; ++l) {
+                for (unsigned li = 0; li < 32; ++li) {
+                    const unsigned l = (li + l0) & 31u;
                     const unsigned t = w * 32 + l;
-                    if (t >= nthreads) break;
+                    if (t >= nthreads) continue;
                     Fiber& f = g.fibers[t];
                     if (f.done) continue;
                     if (f.wait_addr && *f.wait_addr == f.wait_val) continue;

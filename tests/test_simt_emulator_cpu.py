@@ -33,10 +33,15 @@ def test_emulator_selftest_known_answers_and_known_bugs(tmp_path):
     assert r.stdout.count("ok ") >= 11
 
 
-@pytest.fixture(scope="module")
-def lib():
+@pytest.fixture(scope="module", params=[0, 5], ids=["warp-after-warp", "random-interleaving"])
+def lib(request):
+    """The emulated library, once with the deterministic schedule and once with the warps of every block interleaved at
+    random (block barriers and shared-memory staging of the loss / optimizer kernels must not depend on the order)."""
     from simt import emu
-    return emu.build()
+    lb = emu.build()
+    lb.simt_set_schedule_seed(request.param)
+    yield lb
+    lb.simt_set_schedule_seed(0)
 
 
 def _p(t):
