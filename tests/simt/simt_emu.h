@@ -11,7 +11,8 @@
 //   * bulk copies (cp.async.bulk) are DEFERRED until no thread of the block can make progress without them, so shared
 //     memory read before the mbarrier wait holds stale data, and a block that ends with copies in flight is an error;
 //   * dynamic shared memory is filled with NaN patterns before every block;
-//   * the warps of a block can be interleaved at random (simt_set_schedule_seed) instead of running one after the other;
+//   * the warps of a block can be interleaved at random, and the blocks of a launch run in random order
+//     (simt_set_schedule_seed), instead of block after block, warp after warp;
 //   * fast-math intrinsics can return results perturbed by a repeatable error of a few ulp (simt_set_fastmath_noise);
 //   * no runnable fiber while some are unfinished (divergent barrier, missing arrival) is reported as a deadlock.
 #pragma once
@@ -562,14 +563,23 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, F&& body) {
     g.launches++;
     static const bool trace = getenv("SIMT_TRACE") != nullptr;
     if (trace) fprintf(stderr, "simt launch #%llu grid (%u,%u,%u) block (%u,%u,%u) smem %zu\n", g.launches, grid.x, grid.y, grid.z, block.x, block.y, block.z, smem_bytes);
-    for (unsigned z = 0; z < grid.z; ++z)
-        for (unsigned y = 0; y < grid.y; ++y)
-            for (unsigned x = 0; x < grid.x; ++x) {
-                g.bid = dim3(x, y, z);
-                for (const DynSmem& d : dyn_smem_arrays()) memset(d.p, 0xff, std::min(d.bytes, smem_bytes));   // NaN pattern: shared memory starts undefined
-                run_block();
-                if (g.err) return;
-            }
+    const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
+    std::vector<unsigned> border;
+    if (g.sched_seed && nblocks <= (1u << 24)) {          // blocks in random order too: nothing may depend on block i running before block j
+        border.resize((size_t)nblocks);
+        for (unsigned i = 0; i < nblocks; ++i) border[i] = i;
+        for (unsigned i = (unsigned)nblocks; i > 1; --i) {
+            g.sched_state = g.sched_state * 1664525u + 1013904223u;
+            std::swap(border[i - 1], border[(g.sched_state >> 8) % i]);
+        }
+    }
+    for (unsigned long long b = 0; b < nblocks; ++b) {
+        const unsigned long long lin = border.empty() ? b : border[(size_t)b];
+        g.bid = dim3((unsigned)(lin % grid.x), (unsigned)((lin / grid.x) % grid.y), (unsigned)(lin / ((unsigned long long)grid.x * grid.y)));
+        for (const DynSmem& d : dyn_smem_arrays()) memset(d.p, 0xff, std::min(d.bytes, smem_bytes));   // NaN pattern: shared memory starts undefined
+        run_block();
+        if (g.err) return;
+    }
 }
 
 }  // namespace simt
