@@ -145,3 +145,18 @@ def test_emulated_texture_adam_kernel_matches_torch_adam(lib, padded):
     st = opt.state[p_ref]
     np.testing.assert_allclose(m.view(6, R, R, 3).numpy(), st["exp_avg"].numpy(), rtol=1e-5, atol=1e-9)
     np.testing.assert_allclose(v.view(6, R, R, 3).numpy(), st["exp_avg_sq"].numpy(), rtol=1e-5, atol=1e-12)
+
+
+def test_emulated_mark_visible_matches_the_near_plane_rule(lib):
+    """GaussianRasterizer.markVisible (upstream API, unused by the reference tree): z_view > 0.2 (spec E1)."""
+    from simt.emu import check
+    from texture_gs_b200.scene import orbit_cameras
+    cam = orbit_cameras(1, 64, 48, seed=3)[0]
+    pos = torch.randn(777, 3, generator=torch.Generator().manual_seed(1)) * 2.0
+    present = torch.full((777,), -1, dtype=torch.int32)
+    vm = (C.c_float * 16)(*cam.world_view_transform.reshape(-1).tolist())
+    pm = (C.c_float * 16)(*cam.full_proj_transform.reshape(-1).tolist())
+    check(lib, lib.texgs_mark_visible(777, _p(pos), vm, pm, _p(present), None), "texgs_mark_visible")
+    z = pos @ cam.world_view_transform[:3, 2] + cam.world_view_transform[3, 2]
+    clear = (z - 0.2).abs() > 1e-5
+    assert torch.equal(present.bool()[clear], (z > 0.2)[clear]) and int(present.min()) >= 0
