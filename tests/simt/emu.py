@@ -101,6 +101,12 @@ def emulated_source() -> str:
     tail = ('\nextern "C" const char* simt_last_error(void) { return simt::G().err_msg.c_str(); }\n'
             'extern "C" unsigned long long simt_collectives(void) { return simt::G().collectives; }\n'
             'extern "C" void simt_set_eager_copies(int on) { simt::G().eager_copies = on != 0; }\n'
+            'extern "C" void simt_profile_votes(int on) { simt::G().profile_votes = on != 0; if (on) simt::G().votes.clear(); }\n'
+            'extern "C" int simt_vote_sites(void) { return (int)simt::G().votes.size(); }\n'
+            'extern "C" void simt_vote_dump(unsigned long long* sites, unsigned long long* hist34) {\n'
+            '    size_t i = 0; for (auto& kv : simt::G().votes) { sites[i] = (unsigned long long)(uintptr_t)kv.first; hist34[34 * i] = kv.second.calls;\n'
+            '        for (int k = 0; k < 33; ++k) hist34[34 * i + 1 + k] = kv.second.hist[k]; ++i; } }\n'
+            'extern "C" const void* simt_anchor(void) { return (const void*)&simt_anchor; }\n'
             'extern "C" void simt_set_schedule_seed(unsigned seed) { simt::G().sched_seed = seed; simt::G().sched_state = seed * 2654435761u + 1u; }\n'
             'extern "C" void simt_set_fastmath_noise(unsigned ulps) { simt::G().fastmath_noise_ulps = ulps; simt::G().noise_state = 0x9e3779b9u; }\n')
     return head + api + tail
@@ -147,6 +153,11 @@ def build(extra_flags=()):
     lib.simt_collectives.restype = C.c_ulonglong
     lib.simt_set_eager_copies.argtypes = [C.c_int]
     lib.simt_set_schedule_seed.argtypes = [C.c_uint]
+    lib.simt_profile_votes.argtypes = [C.c_int]
+    lib.simt_vote_sites.restype = C.c_int
+    lib.simt_vote_dump.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    lib.simt_anchor.restype = C.c_void_p
+    lib._so_path = str(so)
     lib.simt_set_fastmath_noise.argtypes = [C.c_uint]
     _loaded[tag] = lib
     return lib
@@ -303,3 +314,30 @@ def rasterize(*, means3D, opacities, scales=None, rotations=None, shs=None, colo
         g["texture"] = g.pop("texture_rgba")[..., :3].contiguous()
     res.grads = g
     return res
+
+
+def vote_profile(lib):
+    """After ``lib.simt_profile_votes(1)`` and some launches: {source location of every __ballot/__any/__all_sync call site:
+    (calls, histogram[0..32] of the number of lanes that voted true)}. Locations come from addr2line on the emulated
+    library (built with -g), i.e. they name lines of the .cuh kernels."""
+    n = lib.simt_vote_sites()
+    sites = (C.c_ulonglong * max(n, 1))()
+    hist = (C.c_ulonglong * (34 * max(n, 1)))()
+    lib.simt_vote_dump(sites, hist)
+    # load base of the shared object: the anchor symbol's address minus its offset in the file
+    off = int(subprocess.run(["nm", "-D", "--defined-only", lib._so_path], capture_output=True, text=True).stdout.split(" T simt_anchor")[0].split()[-1], 16)
+    base = lib.simt_anchor() - off
+    out = {}
+    for i in range(n):
+        addr = sites[i] - base - 1
+        r = subprocess.run(["addr2line", "-e", lib._so_path, "-f", "-C", "-i", hex(addr)], capture_output=True, text=True).stdout.strip().splitlines()
+        loc = next((ln for ln in r if ".cuh:" in ln or ".cu:" in ln), r[-1] if r else "?")
+        fn = r[0] if r else "?"
+        key = f"{Path(loc.split(' ')[0]).name} [{fn.split('(')[0]}]"
+        calls = hist[34 * i]
+        h = [hist[34 * i + 1 + k] for k in range(33)]
+        if key in out:
+            calls += out[key][0]
+            h = [a + b for a, b in zip(h, out[key][1])]
+        out[key] = (calls, h)
+    return out

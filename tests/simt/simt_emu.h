@@ -175,6 +175,10 @@ struct Global {
     // scheduling: 0 = warp after warp, each as far as it can go (deterministic); otherwise the seed of a random
     // interleaving of the warps of a block (random order, random time slices, random first lane): intra-block races
     unsigned sched_seed = 0, sched_state = 1;
+    // vote profiler: per call site of __ballot/__any/__all_sync, how many lanes voted true (histogram 0..32)
+    bool profile_votes = false;
+    struct VoteStat { unsigned long long calls = 0, hist[33] = {0}; };
+    std::unordered_map<const void*, VoteStat> votes;
     unsigned fastmath_noise_ulps = 0;
     uint32_t noise_state = 0x9e3779b9u;
 };
@@ -309,19 +313,35 @@ template <class T> inline T __shfl_down_sync(unsigned mask, T v, unsigned delta,
     const int s = lane + (int)delta;
     return simt::from_bits<T>(out[(s <= (lane | (width - 1))) ? s : lane]);
 }
-inline unsigned __ballot_sync(unsigned mask, int pred) {
-    simt::Global& g = simt::G();
+namespace simt {
+// noipa + the empty asm: the compiler must not treat two calls as the same value and merge them
+__attribute__((noinline, noipa)) inline const void* call_site() {
+    const void* p = __builtin_return_address(0);
+    __asm__ volatile("" : "+r"(p));
+    return p;
+}
+inline unsigned ballot_at(const void* site, unsigned mask, int pred) {
+    Global& g = G();
     const unsigned eff = mask & g.warps[g.cur->warp].exist;
-    uint64_t* out = simt::warp_collective(mask, pred ? 1u : 0u);
+    const int lane = g.cur->lane;
+    uint64_t* out = warp_collective(mask, pred ? 1u : 0u);
     unsigned r = 0;
     for (int l = 0; l < 32; ++l) if ((eff >> l) & 1u) r |= (unsigned)(out[l] & 1u) << l;
+    if (g.profile_votes && lane == __builtin_ctz(eff)) {       // once per collective: the lowest participating lane records
+        Global::VoteStat& v = g.votes[site];
+        v.calls++;
+        v.hist[__builtin_popcount(r)]++;
+    }
     return r;
 }
-inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0u; }
-inline int __all_sync(unsigned mask, int pred) {
+}  // namespace simt
+// always inlined into the kernel, so that call_site() names the line of the kernel that votes
+__attribute__((always_inline)) inline unsigned __ballot_sync(unsigned mask, int pred) { return simt::ballot_at(simt::call_site(), mask, pred); }
+__attribute__((always_inline)) inline int __any_sync(unsigned mask, int pred) { return simt::ballot_at(simt::call_site(), mask, pred) != 0u; }
+__attribute__((always_inline)) inline int __all_sync(unsigned mask, int pred) {
     simt::Global& g = simt::G();
     const unsigned eff = mask & g.warps[g.cur->warp].exist;
-    return __ballot_sync(mask, pred) == eff;
+    return simt::ballot_at(simt::call_site(), mask, pred) == eff;
 }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { simt::warp_collective(mask, 0); }
 inline void __syncthreads() { simt::block_barrier(); }
