@@ -101,7 +101,9 @@ def emulated_source() -> str:
     tail = ('\nextern "C" const char* simt_last_error(void) { return simt::G().err_msg.c_str(); }\n'
             'extern "C" unsigned long long simt_collectives(void) { return simt::G().collectives; }\n'
             'extern "C" void simt_set_eager_copies(int on) { simt::G().eager_copies = on != 0; }\n'
-            'extern "C" void simt_profile_votes(int on) { simt::G().profile_votes = on != 0; if (on) simt::G().votes.clear(); }\n'
+            'extern "C" void simt_profile_votes(int on) { simt::G().profile_votes = on != 0; if (on) { simt::G().votes.clear(); simt::G().ballot_trace.clear(); } }\n'
+            'extern "C" unsigned long long simt_ballot_trace(unsigned* out, unsigned long long cap) { auto& t = simt::G().ballot_trace;\n'
+            '    if (out) for (size_t i = 0; i < t.size() && i < cap; ++i) out[i] = t[i]; return t.size(); }\n'
             'extern "C" int simt_vote_sites(void) { return (int)simt::G().votes.size(); }\n'
             'extern "C" void simt_vote_dump(unsigned long long* sites, unsigned long long* hist34) {\n'
             '    size_t i = 0; for (auto& kv : simt::G().votes) { sites[i] = (unsigned long long)(uintptr_t)kv.first; hist34[34 * i] = kv.second.calls;\n'
@@ -157,6 +159,8 @@ def build(extra_flags=()):
     lib.simt_vote_sites.restype = C.c_int
     lib.simt_vote_dump.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     lib.simt_anchor.restype = C.c_void_p
+    lib.simt_ballot_trace.argtypes = [C.POINTER(C.c_uint), C.c_ulonglong]
+    lib.simt_ballot_trace.restype = C.c_ulonglong
     lib._so_path = str(so)
     lib.simt_set_fastmath_noise.argtypes = [C.c_uint]
     _loaded[tag] = lib
@@ -341,3 +345,14 @@ def vote_profile(lib):
             h = [a + b for a, b in zip(h, out[key][1])]
         out[key] = (calls, h)
     return out
+
+
+def ballot_trace(lib):
+    """(n, 4) int64 array, columns (launch number, block, warp, lanes true), one row for every
+    __ballot_sync executed since ``simt_profile_votes(1)``, in execution order."""
+    import numpy as np
+    n = int(lib.simt_ballot_trace(None, 0))
+    buf = (C.c_uint * max(n, 1))()
+    lib.simt_ballot_trace(buf, n)
+    a = np.frombuffer(buf, dtype=np.uint32, count=n).reshape(-1, 3).astype(np.int64)
+    return np.stack([a[:, 0], a[:, 1] >> 8, a[:, 1] & 255, a[:, 2]], axis=1)

@@ -179,6 +179,9 @@ struct Global {
     bool profile_votes = false;
     struct VoteStat { unsigned long long calls = 0, hist[33] = {0}; };
     std::unordered_map<const void*, VoteStat> votes;
+    // with the profiler on, every __ballot_sync also leaves {launch number, block << 8 | warp, lanes true} here, in
+    // execution order: the per-warp sequence of survivor counts the list walk of the render kernels is made of
+    std::vector<uint32_t> ballot_trace;
     unsigned fastmath_noise_ulps = 0;
     uint32_t noise_state = 0x9e3779b9u;
 };
@@ -320,7 +323,7 @@ __attribute__((noinline, noipa)) inline const void* call_site() {
     __asm__ volatile("" : "+r"(p));
     return p;
 }
-inline unsigned ballot_at(const void* site, unsigned mask, int pred) {
+inline unsigned ballot_at(const void* site, unsigned mask, int pred, bool trace = false) {
     Global& g = G();
     const unsigned eff = mask & g.warps[g.cur->warp].exist;
     const int lane = g.cur->lane;
@@ -331,12 +334,17 @@ inline unsigned ballot_at(const void* site, unsigned mask, int pred) {
         Global::VoteStat& v = g.votes[site];
         v.calls++;
         v.hist[__builtin_popcount(r)]++;
+        if (trace) {
+            g.ballot_trace.push_back((uint32_t)g.launches);
+            g.ballot_trace.push_back((uint32_t)(g.bid.x << 8) | (uint32_t)g.cur->warp);
+            g.ballot_trace.push_back((uint32_t)__builtin_popcount(r));
+        }
     }
     return r;
 }
 }  // namespace simt
 // always inlined into the kernel, so that call_site() names the line of the kernel that votes
-__attribute__((always_inline)) inline unsigned __ballot_sync(unsigned mask, int pred) { return simt::ballot_at(simt::call_site(), mask, pred); }
+__attribute__((always_inline)) inline unsigned __ballot_sync(unsigned mask, int pred) { return simt::ballot_at(simt::call_site(), mask, pred, true); }
 __attribute__((always_inline)) inline int __any_sync(unsigned mask, int pred) { return simt::ballot_at(simt::call_site(), mask, pred) != 0u; }
 __attribute__((always_inline)) inline int __all_sync(unsigned mask, int pred) {
     simt::Global& g = simt::G();

@@ -77,6 +77,13 @@ __device__ __forceinline__ PixelGeom pixel_geom(const RasterParams& p) {
 #define TEXGS_CHUNK 32          // list entries per chunk (<= 32: one per lane) = records per stage
 #endif
 #define TEXGS_STAGES 2
+// experimental (tools/build_variants.py, default off): 1 = the two half-warps walk their survivor queues independently
+// inside the 2-stage ring — a half that has finished chunk c goes on with chunk c+1 while the other still works on c —
+// instead of meeting at every chunk boundary. Same float operations per pixel in the same order; 7.8 % fewer passes of the
+// blend loop at the headline size (tools/half_balance_sim.py, profiles/r1_vote_profile_emulated.md).
+#ifndef TEXGS_HALF_WINDOW
+#define TEXGS_HALF_WINDOW 0
+#endif
 
 struct __align__(128) WarpSmem {
     GaussRec rec[TEXGS_STAGES][TEXGS_CHUNK];
@@ -186,6 +193,10 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
                 stream_issue(p, ws, 1, lane, id1, v1, b0, b1, g);
             }
         }
+#if TEXGS_HALF_WINDOW
+        unsigned my = 0u;       // what is left of this half-warp's survivor queue in the chunk it works on
+        bool ahead = false;     // ... and whether that chunk is c + 1 (stage s ^ 1) instead of c
+#endif
         for (int c = 0; c < nchunks; ++c) {
             const int s = c & 1;
             // loads for the chunks ahead: cull sector of chunk c+2 (its id arrived during the last
@@ -202,14 +213,44 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
 
             mbar_wait(&ws.bar[s], (unsigned)(c >> 1) & 1u);
             __syncwarp();
+            bool warp_done = false;
+#if TEXGS_HALF_WINDOW
+            // a half that ran ahead into this chunk during the last visit keeps what is left of its queue
+            const unsigned mU = ws.maskL[s] | ws.maskR[s];
+            if (!ahead) my = (lane & 16) ? ws.maskR[s] : ws.maskL[s];
+            ahead = false;
+            unsigned mUn = 0u;
+            bool next_ready = false;
+            for (;;) {
+                const bool want = (my == 0u) && !ahead && (c + 1 < nchunks);
+                if (__any_sync(0xffffffffu, want)) {
+                    if (!next_ready) {
+                        mbar_wait(&ws.bar[s ^ 1], (unsigned)((c + 1) >> 1) & 1u);
+                        __syncwarp();
+                        next_ready = true;
+                        mUn = ws.maskL[s ^ 1] | ws.maskR[s ^ 1];
+                    }
+                    if (want) {
+                        my = (lane & 16) ? ws.maskR[s ^ 1] : ws.maskL[s ^ 1];
+                        ahead = true;
+                    }
+                }
+                if (!__any_sync(0xffffffffu, !ahead && my != 0u)) break;       // both halves have left chunk c
+                const bool has = my != 0u;
+                const int l = has ? (__ffs(my) - 1) : 0;
+                my &= my - 1u;
+                const GaussRec& rec = ws.rec[ahead ? (s ^ 1) : s][__popc((ahead ? mUn : mU) & ((1u << l) - 1u))];
+                const int c_of = c + (ahead ? 1 : 0);
+#else
             const unsigned mL = ws.maskL[s], mR = ws.maskR[s], mU = mL | mR;
             unsigned my = (lane & 16) ? mR : mL;          // this half-warp's survivors, in list order
-            bool warp_done = false;
             while (__any_sync(0xffffffffu, my != 0u)) {
                 const bool has = my != 0u;
                 const int l = has ? (__ffs(my) - 1) : 0;
                 my &= my - 1u;
                 const GaussRec& rec = ws.rec[s][__popc(mU & ((1u << l) - 1u))];   // half-uniform address
+                const int c_of = c;
+#endif
                 const float4 g0 = rec.q[0], g1 = rec.q[1];
                 const float dx = g0.x - pxf, dy = g0.y - pyf;
                 const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
@@ -250,7 +291,7 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
                     Nx += w * g2.x; Ny += w * g2.y; Nz += w * g2.z;
                     A += w;
                     T = test_T;
-                    last = (unsigned)c * TEXGS_CHUNK + (unsigned)l + 1u;
+                    last = (unsigned)c_of * TEXGS_CHUNK + (unsigned)l + 1u;
                     ++nblend;
                 }
                 if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
@@ -564,6 +605,10 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
             stream_issue(p, ws, 1, lane, id1, v1, b0, b1, g);
         }
     }
+#if TEXGS_HALF_WINDOW
+    unsigned my = 0u;           // what is left of this half-warp's survivor queue in the chunk it works on
+    bool ahead = false;         // ... and whether that chunk belongs to visit k + 1 (stage s ^ 1) instead of visit k
+#endif
     for (int k = 0; k <= c_top; ++k) {
         const int c = c_top - k;
         const int s = k & 1;
@@ -579,6 +624,34 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
 
         mbar_wait(&ws.bar[s], (unsigned)(k >> 1) & 1u);
         __syncwarp();
+#if TEXGS_HALF_WINDOW
+        // as in the forward: a half that has finished visit k goes on with visit k + 1 (chunk c - 1, stage s ^ 1)
+        const unsigned mU = ws.maskL[s] | ws.maskR[s];
+        if (!ahead) my = (lane & 16) ? ws.maskR[s] : ws.maskL[s];
+        ahead = false;
+        unsigned mUn = 0u;
+        bool next_ready = false;
+        for (;;) {
+            const bool want = (my == 0u) && !ahead && (k + 1 <= c_top);
+            if (__any_sync(0xffffffffu, want)) {
+                if (!next_ready) {
+                    mbar_wait(&ws.bar[s ^ 1], (unsigned)((k + 1) >> 1) & 1u);
+                    __syncwarp();
+                    next_ready = true;
+                    mUn = ws.maskL[s ^ 1] | ws.maskR[s ^ 1];
+                }
+                if (want) {
+                    my = (lane & 16) ? ws.maskR[s ^ 1] : ws.maskL[s ^ 1];
+                    ahead = true;
+                }
+            }
+            if (!__any_sync(0xffffffffu, !ahead && my != 0u)) break;           // both halves have left chunk c
+            const bool has = my != 0u;
+            const int l = has ? (31 - __clz(my)) : 0;
+            my &= ~(1u << l);
+            const GaussRec& rec = ws.rec[ahead ? (s ^ 1) : s][__popc((ahead ? mUn : mU) & ((1u << l) - 1u))];
+            const unsigned gi = (unsigned)(c - (ahead ? 1 : 0)) * TEXGS_CHUNK + (unsigned)l;   // 0-based position in the list
+#else
         const unsigned mL = ws.maskL[s], mR = ws.maskR[s], mU = mL | mR;
         unsigned my = (lane & 16) ? mR : mL;              // this half-warp's survivors, walked back to front
         while (__any_sync(0xffffffffu, my != 0u)) {
@@ -587,6 +660,7 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
             my &= ~(1u << l);
             const GaussRec& rec = ws.rec[s][__popc(mU & ((1u << l) - 1u))];       // half-uniform address
             const unsigned gi = (unsigned)c * TEXGS_CHUNK + (unsigned)l;   // 0-based position in the list
+#endif
             const float4 g0 = rec.q[0], g1 = rec.q[1];
             const float dx = g0.x - pxf, dy = g0.y - pyf;
             const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;

@@ -6,6 +6,8 @@
 #   3. bench with 2 and 3 streams per rank (experimental view pipeline), with the experimental
 #      two-splats-per-iteration forward kernel (--fwd-ilp2), and with both
 #   4. launch list of a 4-view step with 2 streams (do the small kernels really overlap the render kernels?)
+#   5. A/B of the half-window build (-DTEXGS_HALF_WINDOW=1: the half-warps walk their queues independently, 7.8 % fewer
+#      passes of the blend loop on the emulator): per-stage times of both builds, and the GPU parity tests on the variant
 set -u
 O=gpurun_out; mkdir -p $O
 ( time timeout 600 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider ) > $O/r2_pytest_gpu.log 2>&1
@@ -18,7 +20,12 @@ timeout 400 python bench.py --fwd-ilp2 --no-cpu-baseline > $O/r2_bench_ilp2.json
 timeout 400 python bench.py --fwd-ilp2 --streams 2 --no-cpu-baseline > $O/r2_bench_ilp2_streams2.json 2> $O/r2_bench_ilp2_streams2.err
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_launches_streams2.csv \
     python bench.py --streams 2 --views 4 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $O/r2_launches_streams2.log 2>&1
-tail -3 $O/r2_pytest_gpu.log; tail -1 $O/r2_smoke.log
+timeout 600 python tools/build_variants.py default: halfwin:-DTEXGS_HALF_WINDOW=1 > $O/r2_variants_build.log 2>&1
+for v in default halfwin; do
+  TEXGS_LIB=build/variants/libtexgs_$v.so timeout 300 python tests/gpu_variants.py fused > $O/r2_variant_$v.json 2> $O/r2_variant_$v.err
+done
+( TEXGS_LIB=build/variants/libtexgs_halfwin.so timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -p no:cacheprovider ) > $O/r2_pytest_halfwin.log 2>&1
+tail -3 $O/r2_pytest_gpu.log; tail -1 $O/r2_smoke.log; tail -2 $O/r2_pytest_halfwin.log; cat $O/r2_variant_default.json $O/r2_variant_halfwin.json
 for f in $O/r2_bench.json $O/r2_bench_streams2.json $O/r2_bench_streams3.json $O/r2_bench_ilp2.json $O/r2_bench_ilp2_streams2.json; do
   python - "$f" <<'PY'
 import json, sys
