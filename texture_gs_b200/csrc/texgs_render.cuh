@@ -196,6 +196,8 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
 #if TEXGS_HALF_WINDOW
         unsigned my = 0u;       // what is left of this half-warp's survivor queue in the chunk it works on
         bool ahead = false;     // ... and whether that chunk is c + 1 (stage s ^ 1) instead of c
+        const GaussRec* recp = ws.rec[0];      // ... the records of that chunk, the mask they were compacted with,
+        unsigned mUsel = 0u, bidx = 0u;        //     and the list position of its first entry
 #endif
         for (int c = 0; c < nchunks; ++c) {
             const int s = c & 1;
@@ -215,32 +217,48 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
             __syncwarp();
             bool warp_done = false;
 #if TEXGS_HALF_WINDOW
-            // a half that ran ahead into this chunk during the last visit keeps what is left of its queue
-            const unsigned mU = ws.maskL[s] | ws.maskR[s];
-            if (!ahead) my = (lane & 16) ? ws.maskR[s] : ws.maskL[s];
+            // a half that ran ahead into this chunk during the last visit keeps its queue and its view of the stage
+            if (!ahead) {
+                my = (lane & 16) ? ws.maskR[s] : ws.maskL[s];
+                recp = ws.rec[s];
+                mUsel = ws.maskL[s] | ws.maskR[s];
+                bidx = (unsigned)c * TEXGS_CHUNK;
+            }
             ahead = false;
-            unsigned mUn = 0u;
+            unsigned am = 0u;                  // warp-uniform: lanes of the halves that have moved on to chunk c + 1
             bool next_ready = false;
+            const bool has_next = c + 1 < nchunks;
             for (;;) {
-                const bool want = (my == 0u) && !ahead && (c + 1 < nchunks);
-                if (__any_sync(0xffffffffu, want)) {
-                    if (!next_ready) {
-                        mbar_wait(&ws.bar[s ^ 1], (unsigned)((c + 1) >> 1) & 1u);
-                        __syncwarp();
-                        next_ready = true;
-                        mUn = ws.maskL[s ^ 1] | ws.maskR[s ^ 1];
-                    }
-                    if (want) {
-                        my = (lane & 16) ? ws.maskR[s ^ 1] : ws.maskL[s ^ 1];
-                        ahead = true;
+                // ONE vote per pass, as in the lockstep loop; the common case costs two more integer instructions
+                const unsigned b = __ballot_sync(0xffffffffu, my != 0u);
+                const unsigned x = b | am;
+                if ((x & 0xffffu) == 0u || x < 0x10000u) {          // a half that is still in chunk c has run out
+                    if (!has_next) {
+                        if (b == 0u) break;
+                    } else {
+                        const bool eL = (x & 0xffffu) == 0u, eR = x < 0x10000u;
+                        if (!next_ready) {
+                            mbar_wait(&ws.bar[s ^ 1], (unsigned)((c + 1) >> 1) & 1u);
+                            __syncwarp();
+                            next_ready = true;
+                        }
+                        if ((lane & 16) ? eR : eL) {
+                            my = (lane & 16) ? ws.maskR[s ^ 1] : ws.maskL[s ^ 1];
+                            recp = ws.rec[s ^ 1];
+                            mUsel = ws.maskL[s ^ 1] | ws.maskR[s ^ 1];
+                            bidx = (unsigned)(c + 1) * TEXGS_CHUNK;
+                            ahead = true;
+                        }
+                        if (eL) am |= 0x0000ffffu;
+                        if (eR) am |= 0xffff0000u;
+                        if (am == 0xffffffffu) break;                 // both halves have left chunk c
                     }
                 }
-                if (!__any_sync(0xffffffffu, !ahead && my != 0u)) break;       // both halves have left chunk c
                 const bool has = my != 0u;
                 const int l = has ? (__ffs(my) - 1) : 0;
                 my &= my - 1u;
-                const GaussRec& rec = ws.rec[ahead ? (s ^ 1) : s][__popc((ahead ? mUn : mU) & ((1u << l) - 1u))];
-                const int c_of = c + (ahead ? 1 : 0);
+                const GaussRec& rec = recp[__popc(mUsel & ((1u << l) - 1u))];        // half-uniform address
+                const unsigned idx1 = bidx + (unsigned)l + 1u;
 #else
             const unsigned mL = ws.maskL[s], mR = ws.maskR[s], mU = mL | mR;
             unsigned my = (lane & 16) ? mR : mL;          // this half-warp's survivors, in list order
@@ -249,7 +267,7 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
                 const int l = has ? (__ffs(my) - 1) : 0;
                 my &= my - 1u;
                 const GaussRec& rec = ws.rec[s][__popc(mU & ((1u << l) - 1u))];   // half-uniform address
-                const int c_of = c;
+                const unsigned idx1 = (unsigned)c * TEXGS_CHUNK + (unsigned)l + 1u;
 #endif
                 const float4 g0 = rec.q[0], g1 = rec.q[1];
                 const float dx = g0.x - pxf, dy = g0.y - pyf;
@@ -291,7 +309,7 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
                     Nx += w * g2.x; Ny += w * g2.y; Nz += w * g2.z;
                     A += w;
                     T = test_T;
-                    last = (unsigned)c_of * TEXGS_CHUNK + (unsigned)l + 1u;
+                    last = idx1;
                     ++nblend;
                 }
                 if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
@@ -608,6 +626,8 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
 #if TEXGS_HALF_WINDOW
     unsigned my = 0u;           // what is left of this half-warp's survivor queue in the chunk it works on
     bool ahead = false;         // ... and whether that chunk belongs to visit k + 1 (stage s ^ 1) instead of visit k
+    const GaussRec* recp = ws.rec[0];          // ... the records of that chunk, the mask they were compacted with,
+    unsigned mUsel = 0u, bidx = 0u;            //     and the list position of its first entry
 #endif
     for (int k = 0; k <= c_top; ++k) {
         const int c = c_top - k;
@@ -626,31 +646,46 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
         __syncwarp();
 #if TEXGS_HALF_WINDOW
         // as in the forward: a half that has finished visit k goes on with visit k + 1 (chunk c - 1, stage s ^ 1)
-        const unsigned mU = ws.maskL[s] | ws.maskR[s];
-        if (!ahead) my = (lane & 16) ? ws.maskR[s] : ws.maskL[s];
+        if (!ahead) {
+            my = (lane & 16) ? ws.maskR[s] : ws.maskL[s];
+            recp = ws.rec[s];
+            mUsel = ws.maskL[s] | ws.maskR[s];
+            bidx = (unsigned)c * TEXGS_CHUNK;
+        }
         ahead = false;
-        unsigned mUn = 0u;
+        unsigned am = 0u;                      // warp-uniform: lanes of the halves that have moved on to visit k + 1
         bool next_ready = false;
+        const bool has_next = k + 1 <= c_top;
         for (;;) {
-            const bool want = (my == 0u) && !ahead && (k + 1 <= c_top);
-            if (__any_sync(0xffffffffu, want)) {
-                if (!next_ready) {
-                    mbar_wait(&ws.bar[s ^ 1], (unsigned)((k + 1) >> 1) & 1u);
-                    __syncwarp();
-                    next_ready = true;
-                    mUn = ws.maskL[s ^ 1] | ws.maskR[s ^ 1];
-                }
-                if (want) {
-                    my = (lane & 16) ? ws.maskR[s ^ 1] : ws.maskL[s ^ 1];
-                    ahead = true;
+            const unsigned b = __ballot_sync(0xffffffffu, my != 0u);           // the one vote per pass
+            const unsigned x = b | am;
+            if ((x & 0xffffu) == 0u || x < 0x10000u) {              // a half that is still in chunk c has run out
+                if (!has_next) {
+                    if (b == 0u) break;
+                } else {
+                    const bool eL = (x & 0xffffu) == 0u, eR = x < 0x10000u;
+                    if (!next_ready) {
+                        mbar_wait(&ws.bar[s ^ 1], (unsigned)((k + 1) >> 1) & 1u);
+                        __syncwarp();
+                        next_ready = true;
+                    }
+                    if ((lane & 16) ? eR : eL) {
+                        my = (lane & 16) ? ws.maskR[s ^ 1] : ws.maskL[s ^ 1];
+                        recp = ws.rec[s ^ 1];
+                        mUsel = ws.maskL[s ^ 1] | ws.maskR[s ^ 1];
+                        bidx = (unsigned)(c - 1) * TEXGS_CHUNK;
+                        ahead = true;
+                    }
+                    if (eL) am |= 0x0000ffffu;
+                    if (eR) am |= 0xffff0000u;
+                    if (am == 0xffffffffu) break;                     // both halves have left chunk c
                 }
             }
-            if (!__any_sync(0xffffffffu, !ahead && my != 0u)) break;           // both halves have left chunk c
             const bool has = my != 0u;
             const int l = has ? (31 - __clz(my)) : 0;
             my &= ~(1u << l);
-            const GaussRec& rec = ws.rec[ahead ? (s ^ 1) : s][__popc((ahead ? mUn : mU) & ((1u << l) - 1u))];
-            const unsigned gi = (unsigned)(c - (ahead ? 1 : 0)) * TEXGS_CHUNK + (unsigned)l;   // 0-based position in the list
+            const GaussRec& rec = recp[__popc(mUsel & ((1u << l) - 1u))];            // half-uniform address
+            const unsigned gi = bidx + (unsigned)l;                 // 0-based position in the list
 #else
         const unsigned mL = ws.maskL[s], mR = ws.maskR[s], mU = mL | mR;
         unsigned my = (lane & 16) ? mR : mL;              // this half-warp's survivors, walked back to front
