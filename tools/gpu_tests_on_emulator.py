@@ -3,6 +3,7 @@
 on a box without a GPU:
     python tools/gpu_tests_on_emulator.py            # ~3 min: 12 tests
     python tools/gpu_tests_on_emulator.py config0    # + BASELINE configs[0] forward/backward (several minutes)
+    python tools/gpu_tests_on_emulator.py -DTEXGS_HALF_WINDOW=1     # the same tests on a tuning-macro variant of the kernels
 Tests that build CUDA tensors themselves (operator-level tests, fused buckets, dual render, ...) cannot be redirected
 and are not selected. A pass here says nothing about PTX semantics or performance; it says the comparison code and the
 oracle's flags still accept kernels whose arithmetic is the shipped source."""
@@ -17,7 +18,16 @@ import pytest  # noqa: E402
 import torch  # noqa: E402
 import util  # noqa: E402
 
-util.run_cuda = util.run_emu
+FLAGS = tuple(a for a in sys.argv[1:] if a.startswith("-D"))
+if FLAGS:
+    from simt import emu  # noqa: E402
+    _variant = emu.build(extra_flags=FLAGS)
+
+    def _run_variant(*a, **kw):
+        return util.run_emu(*a, lib=_variant, **kw)
+    util.run_cuda = _run_variant
+else:
+    util.run_cuda = util.run_emu
 torch.cuda.is_available = lambda: True
 SEL = ("test_golden_tiny_scene or test_forward_parity_small or test_backward_parity_small or test_clamp_paths or test_saturating "
        "or test_camera_inside or test_heterogeneous or test_long_tile_lists or test_forward_is_deterministic")
