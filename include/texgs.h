@@ -36,8 +36,6 @@ extern "C" {
 
 #define TEXGS_FLAG_PREFILTERED 1u   /* GaussianRasterizationSettings.prefiltered (uv_tex_render.py:36) */
 #define TEXGS_FLAG_DEBUG       2u   /* GaussianRasterizationSettings.debug       (uv_tex_render.py:37) */
-#define TEXGS_FLAG_FWD_ILP2    4u   /* experimental: forward blend kernel that takes two splats per half-warp per iteration
-                                       (bit-identical results; texgs_render.cuh). Off unless the caller sets it.          */
 
 /* colour source of a splat */
 #define TEXGS_MODE_TEXTURE 0   /* diff_gauss_uv_tex: C0*cube(uv + J*delta) + SH_rest + 0.5, clamped at 0 */

@@ -203,7 +203,7 @@ def rasterize(*, means3D, opacities, scales=None, rotations=None, shs=None, colo
               texture=None, extra_attrs=None, cov3Ds_precomp=None, H, W, tanfovx, tanfovy, bg, scale_modifier=1.0,
               viewmatrix, projmatrix, campos, sh_degree, cotangents=None, dual_no_sh=False, packed_texture=True,
               packed_texture_grad=True, debug=False, cot_nosh=None, cot_extra=None, pair_capacity=None, lib=None,
-              accumulate_onto=None, fwd_ilp2=False):
+              accumulate_onto=None):
     """Forward (+ backward when ``cotangents`` = (dL/dimage, dL/ddepth, dL/dnorm, dL/dalpha) is given) of the emulated
     library on CPU tensors; the call sequence is the one of texture_gs_b200/rasterizer.py.
 
@@ -217,7 +217,7 @@ def rasterize(*, means3D, opacities, scales=None, rotations=None, shs=None, colo
     a = L.TexgsFwdArgs()
     a.P, a.M, a.sh_degree, a.E = P, (0 if sh is None else sh.shape[1]), int(sh_degree), (0 if ex is None else ex.shape[1])
     a.H, a.W, a.R, a.mode = int(H), int(W), (0 if tex is None else tex.shape[1]), mode
-    a.flags = (L.FLAG_DEBUG if debug else 0) | (L.FLAG_FWD_ILP2 if fwd_ilp2 else 0)
+    a.flags = (L.FLAG_DEBUG if debug else 0)
     a.tanfovx, a.tanfovy, a.scale_modifier = float(tanfovx), float(tanfovy), float(scale_modifier)
     a.viewmatrix = (C.c_float * 16)(*viewmatrix.reshape(-1).tolist())
     a.projmatrix = (C.c_float * 16)(*projmatrix.reshape(-1).tolist())

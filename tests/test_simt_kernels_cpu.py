@@ -390,28 +390,6 @@ def test_comparison_against_the_c_oracle_used_at_full_size_on_the_gpu(emu):
         emu.build().simt_set_fastmath_noise(0)
 
 
-def test_experimental_ilp2_forward_kernel_is_bit_identical(emu):
-    """TEXGS_FLAG_FWD_ILP2 (two splats per half-warp per iteration, texgs_render.cuh): every float operation happens in
-    the order of the default forward kernel, so outputs, the dual image, the debug blend count and — through final_T /
-    n_contrib — every gradient of the backward are identical bit for bit; packed and plain texel layouts."""
-    for (n, w, h, r, deg, cov) in [(1200, 96, 64, 32, 3, 4.0), (300, 70, 50, 16, 0, 40.0), (3, 17, 9, 4, 1, 8.0)]:
-        g = sphere_shell_scene(n, r, sh_degree=deg, seed=1, tex_seed=2, coverage=cov)
-        cam = orbit_cameras(1, w, h, seed=3)[0]
-        t = g.tensors()
-        cot = output_cotangents(h, w, seed=4)
-        kw = dict(means3D=t["xyz"], opacities=t["opacity"], scales=t["scaling"], rotations=t["rotation"], shs=t["shs"], uvs=t["uvs"],
-                  gradient_uvs=t["grad_uvs"], texture=t["texture"], cotangents=cot, debug=True, **_cam_kw(cam, (0.1, 0.2, 0.3), deg))
-        for dual, packed in ((False, True), (True, False)):
-            r0 = emu.rasterize(dual_no_sh=dual, packed_texture=packed, **kw)
-            r1 = emu.rasterize(dual_no_sh=dual, packed_texture=packed, fwd_ilp2=True, **kw)
-            for x, y in zip((r0.image, r0.depth, r0.norm, r0.alpha), (r1.image, r1.depth, r1.norm, r1.alpha)):
-                assert torch.equal(x, y)
-            assert (not dual) or torch.equal(r0.image_nosh, r1.image_nosh)
-            assert r0.num_blend == r1.num_blend > 0
-            for k in r0.grads:
-                assert torch.equal(r0.grads[k], r1.grads[k]), k
-
-
 def test_tuning_macro_variants_compute_the_same_thing(emu):
     """The build-time tuning knobs used for A/B timing on the GPU (tools/build_variants.py) must not change results:
     16-entry chunks (TEXGS_CHUNK), the unstaged SH path of preprocess_bwd (TEXGS_PREBWD_STAGE_SH=0) and libm exp instead
@@ -430,51 +408,6 @@ def test_tuning_macro_variants_compute_the_same_thing(emu):
         assert torch.equal(x, y)
     for k in a.grads:
         assert rel_err(b.grads[k], a.grads[k]) < 1e-5, k
-
-
-def test_half_window_variant_is_the_same_render_with_fewer_passes(emu):
-    """-DTEXGS_HALF_WINDOW=1 (experimental, tools/build_variants.py): the two half-warps of the render kernels walk their
-    survivor queues independently inside the 2-stage ring instead of meeting at every chunk boundary. Every pixel still
-    blends the same splats in the same order: outputs, final_T / n_contrib (through the gradients) and the blend count are
-    bit-identical, gradients equal up to the order of the atomics (1e-4: fp32 summation noise of the scale gradient). Checked with bulk copies landing as late AND as early
-    as legal (a stage re-filled while the half that ran ahead still reads it would show) and under a random warp
-    schedule; the pass count of the blend loop (the vote profiler's count of the `any(cand)` site) must go down."""
-    import shutil
-    have_binutils = bool(shutil.which("nm") and shutil.which("addr2line"))
-    alt = emu.build(extra_flags=("-DTEXGS_HALF_WINDOW=1",))
-    passes = {}
-    for (n, w, h, r, deg, cov) in [(4000, 96, 64, 32, 3, 12.0), (600, 70, 50, 16, 0, 40.0), (3, 17, 9, 4, 1, 8.0)]:
-        g = sphere_shell_scene(n, r, sh_degree=deg, seed=1, tex_seed=2, coverage=cov)
-        cam = orbit_cameras(1, w, h, seed=3)[0]
-        t = g.tensors()
-        cot = output_cotangents(h, w, seed=4)
-        kw = dict(means3D=t["xyz"], opacities=t["opacity"], scales=t["scaling"], rotations=t["rotation"], shs=t["shs"], uvs=t["uvs"],
-                  gradient_uvs=t["grad_uvs"], texture=t["texture"], cotangents=cot, debug=True, **_cam_kw(cam, (0.1, 0.2, 0.3), deg))
-        modes = ((False, True, 0, 0), (True, False, 1, 0), (False, True, 1, 7))
-        for dual, packed, eager, seed in (modes[:1] if n == 4000 else modes):
-            res = []
-            for lib in (emu.build(), alt):
-                lib.simt_set_eager_copies(eager)
-                lib.simt_set_schedule_seed(seed)
-                lib.simt_profile_votes(1)
-                try:
-                    res.append(emu.rasterize(lib=lib, dual_no_sh=dual, packed_texture=packed, **kw))
-                    prof = emu.vote_profile(lib) if have_binutils else {}
-                finally:
-                    lib.simt_profile_votes(0)
-                    lib.simt_set_eager_copies(0)
-                    lib.simt_set_schedule_seed(0)
-                # passes of a blend loop = calls of its any(cand) / any(contrib) vote, the least-called __any_sync site
-                passes[(n, dual, eager, seed, lib is alt)] = min((c for k, (c, _h) in prof.items() if "__any_sync" in k), default=0)
-            r0, r1 = res
-            for x, y in zip((r0.image, r0.depth, r0.norm, r0.alpha, r0.radii), (r1.image, r1.depth, r1.norm, r1.alpha, r1.radii)):
-                assert torch.equal(x, y)
-            assert (not dual) or torch.equal(r0.image_nosh, r1.image_nosh)
-            assert r0.num_blend == r1.num_blend > 0
-            for k in r0.grads:          # the default kernel against itself under another warp schedule differs by up to 2e-5
-                assert rel_err(r1.grads[k], r0.grads[k]) < 1e-4, k
-    if have_binutils:           # the profiler names its call sites with nm + addr2line
-        assert 0 < passes[(4000, False, 0, 0, True)] < 0.97 * passes[(4000, False, 0, 0, False)]
 
 
 def test_full_size_criterion_is_not_vacuous(emu):

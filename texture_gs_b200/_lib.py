@@ -16,7 +16,6 @@ LIB_PATH = Path(os.environ["TEXGS_LIB"]).resolve() if os.environ.get("TEXGS_LIB"
 TEXGS_ABI_VERSION = 2
 FLAG_PREFILTERED = 1
 FLAG_DEBUG = 2
-FLAG_FWD_ILP2 = 4          # experimental forward kernel (two splats per half-warp per iteration), same results
 MODE_TEXTURE, MODE_SH, MODE_PRECOMP = 0, 1, 2
 BWD_ACC_FLOATS = 24
 ACC_MEANS3D, ACC_MEANS2D, ACC_OPACITY, ACC_SCALES, ACC_ROTATIONS, ACC_SHS, ACC_COLORS, ACC_UVS = 1, 2, 4, 8, 16, 32, 64, 128

@@ -161,11 +161,6 @@ int ensure_render_smem() {
     TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, true, true>));
     TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, false, true>));
     TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_SH, false, false>));
-    TEXGS_SET_SMEM((texgs_render_fwd_ilp2<TEXGS_MODE_TEXTURE, true, false>));
-    TEXGS_SET_SMEM((texgs_render_fwd_ilp2<TEXGS_MODE_TEXTURE, false, false>));
-    TEXGS_SET_SMEM((texgs_render_fwd_ilp2<TEXGS_MODE_TEXTURE, true, true>));
-    TEXGS_SET_SMEM((texgs_render_fwd_ilp2<TEXGS_MODE_TEXTURE, false, true>));
-    TEXGS_SET_SMEM((texgs_render_fwd_ilp2<TEXGS_MODE_SH, false, false>));
     TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, true, false>));
     TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, false, false>));
     TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, true, false>));
@@ -189,7 +184,7 @@ int texgs_abi_version(void) { return TEXGS_ABI_VERSION; }
 const char* texgs_last_error(void) { return g_last_error.c_str(); }
 
 const char* texgs_kernel_names(void) {
-    return "texgs_preprocess_fwd,texgs_scan_tiles,texgs_scatter_pairs,texgs_sort_tiles_small,texgs_sort_tiles,texgs_render_fwd,texgs_render_fwd_ilp2,"
+    return "texgs_preprocess_fwd,texgs_scan_tiles,texgs_scatter_pairs,texgs_sort_tiles_small,texgs_sort_tiles,texgs_render_fwd,"
            "texgs_render_bwd,texgs_extra_fwd,texgs_extra_bwd,texgs_preprocess_bwd,texgs_mark_visible_kernel,texgs_pack_texture_kernel,"
            "texgs_photometric_fwd_kernel,texgs_photometric_finalize_kernel,texgs_photometric_bwd_kernel,"
            "texgs_geometry_loss_fwd_kernel,texgs_geometry_loss_finalize_kernel,texgs_geometry_loss_bwd_kernel,texgs_texture_adam_kernel,texgs_uvmlp_fwd_kernel,"
@@ -255,21 +250,12 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
     {
         const bool t4 = p.texture_rgba != nullptr, dual = p.out_image_nosh != nullptr;
 #define TEXGS_LAUNCH_FWD(M, T4, DU) texgs_render_fwd<M, T4, DU><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha)
-#define TEXGS_LAUNCH_FWD2(M, T4, DU) texgs_render_fwd_ilp2<M, T4, DU><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha)
-        if (a->flags & TEXGS_FLAG_FWD_ILP2) {      // experimental variant, same results (see texgs_render.cuh)
-            if (p.mode != TEXGS_MODE_TEXTURE) TEXGS_LAUNCH_FWD2(TEXGS_MODE_SH, false, false);
-            else if (t4 && dual)  TEXGS_LAUNCH_FWD2(TEXGS_MODE_TEXTURE, true, true);
-            else if (t4)          TEXGS_LAUNCH_FWD2(TEXGS_MODE_TEXTURE, true, false);
-            else if (dual)        TEXGS_LAUNCH_FWD2(TEXGS_MODE_TEXTURE, false, true);
-            else                  TEXGS_LAUNCH_FWD2(TEXGS_MODE_TEXTURE, false, false);
-        }
-        else if (p.mode != TEXGS_MODE_TEXTURE) TEXGS_LAUNCH_FWD(TEXGS_MODE_SH, false, false);
+        if (p.mode != TEXGS_MODE_TEXTURE) TEXGS_LAUNCH_FWD(TEXGS_MODE_SH, false, false);
         else if (t4 && dual)  TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, true, true);
         else if (t4)          TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, true, false);
         else if (dual)        TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, false, true);
         else                  TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, false, false);
 #undef TEXGS_LAUNCH_FWD
-#undef TEXGS_LAUNCH_FWD2
     }
     TEXGS_KERNEL_CHECK("texgs_render_fwd", debug, stream);
     if (a->E > 0) {   // cold path (the reference tree never passes extra_attrs): separate list walk, see texgs_extra.cuh

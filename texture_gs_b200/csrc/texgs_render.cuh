@@ -77,13 +77,6 @@ __device__ __forceinline__ PixelGeom pixel_geom(const RasterParams& p) {
 #define TEXGS_CHUNK 32          // list entries per chunk (<= 32: one per lane) = records per stage
 #endif
 #define TEXGS_STAGES 2
-// experimental (tools/build_variants.py, default off): 1 = the two half-warps walk their survivor queues independently
-// inside the 2-stage ring — a half that has finished chunk c goes on with chunk c+1 while the other still works on c —
-// instead of meeting at every chunk boundary. Same float operations per pixel in the same order; 7.8 % fewer passes of the
-// blend loop at the headline size (tools/half_balance_sim.py, profiles/r1_vote_profile_emulated.md).
-#ifndef TEXGS_HALF_WINDOW
-#define TEXGS_HALF_WINDOW 0
-#endif
 
 struct __align__(128) WarpSmem {
     GaussRec rec[TEXGS_STAGES][TEXGS_CHUNK];
@@ -193,12 +186,6 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
                 stream_issue(p, ws, 1, lane, id1, v1, b0, b1, g);
             }
         }
-#if TEXGS_HALF_WINDOW
-        unsigned my = 0u;       // what is left of this half-warp's survivor queue in the chunk it works on
-        bool ahead = false;     // ... and whether that chunk is c + 1 (stage s ^ 1) instead of c
-        const GaussRec* recp = ws.rec[0];      // ... the records of that chunk, the mask they were compacted with,
-        unsigned mUsel = 0u, bidx = 0u;        //     and the list position of its first entry
-#endif
         for (int c = 0; c < nchunks; ++c) {
             const int s = c & 1;
             // loads for the chunks ahead: cull sector of chunk c+2 (its id arrived during the last
@@ -216,50 +203,6 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
             mbar_wait(&ws.bar[s], (unsigned)(c >> 1) & 1u);
             __syncwarp();
             bool warp_done = false;
-#if TEXGS_HALF_WINDOW
-            // a half that ran ahead into this chunk during the last visit keeps its queue and its view of the stage
-            if (!ahead) {
-                my = (lane & 16) ? ws.maskR[s] : ws.maskL[s];
-                recp = ws.rec[s];
-                mUsel = ws.maskL[s] | ws.maskR[s];
-                bidx = (unsigned)c * TEXGS_CHUNK;
-            }
-            ahead = false;
-            unsigned am = 0u;                  // warp-uniform: lanes of the halves that have moved on to chunk c + 1
-            bool next_ready = false;
-            const bool has_next = c + 1 < nchunks;
-            for (;;) {
-                // ONE vote per pass, as in the lockstep loop; the common case costs two more integer instructions
-                const unsigned b = __ballot_sync(0xffffffffu, my != 0u);
-                const unsigned x = b | am;
-                if ((x & 0xffffu) == 0u || x < 0x10000u) {          // a half that is still in chunk c has run out
-                    if (!has_next) {
-                        if (b == 0u) break;
-                    } else {
-                        const bool eL = (x & 0xffffu) == 0u, eR = x < 0x10000u;
-                        if (!next_ready) {
-                            mbar_wait(&ws.bar[s ^ 1], (unsigned)((c + 1) >> 1) & 1u);
-                            __syncwarp();
-                            next_ready = true;
-                        }
-                        if ((lane & 16) ? eR : eL) {
-                            my = (lane & 16) ? ws.maskR[s ^ 1] : ws.maskL[s ^ 1];
-                            recp = ws.rec[s ^ 1];
-                            mUsel = ws.maskL[s ^ 1] | ws.maskR[s ^ 1];
-                            bidx = (unsigned)(c + 1) * TEXGS_CHUNK;
-                            ahead = true;
-                        }
-                        if (eL) am |= 0x0000ffffu;
-                        if (eR) am |= 0xffff0000u;
-                        if (am == 0xffffffffu) break;                 // both halves have left chunk c
-                    }
-                }
-                const bool has = my != 0u;
-                const int l = has ? (__ffs(my) - 1) : 0;
-                my &= my - 1u;
-                const GaussRec& rec = recp[__popc(mUsel & ((1u << l) - 1u))];        // half-uniform address
-                const unsigned idx1 = bidx + (unsigned)l + 1u;
-#else
             const unsigned mL = ws.maskL[s], mR = ws.maskR[s], mU = mL | mR;
             unsigned my = (lane & 16) ? mR : mL;          // this half-warp's survivors, in list order
             while (__any_sync(0xffffffffu, my != 0u)) {
@@ -268,7 +211,6 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
                 my &= my - 1u;
                 const GaussRec& rec = ws.rec[s][__popc(mU & ((1u << l) - 1u))];   // half-uniform address
                 const unsigned idx1 = (unsigned)c * TEXGS_CHUNK + (unsigned)l + 1u;
-#endif
                 const float4 g0 = rec.q[0], g1 = rec.q[1];
                 const float dx = g0.x - pxf, dy = g0.y - pyf;
                 const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
@@ -321,203 +263,6 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
                 break;
             }
             // stage s is free again: gather chunk c+2 into it
-            if (c + 2 < nchunks) stream_issue(p, ws, s, lane, idn, vn, q0n, q1n, g);
-        }
-    }
-
-    if (g.inside) {
-        const int HW = p.H * p.W;
-        out_image[g.pix] = Cr + T * p.bg[0];
-        out_image[HW + g.pix] = Cg + T * p.bg[1];
-        out_image[2 * HW + g.pix] = Cb + T * p.bg[2];
-        if (DUAL) {
-            p.out_image_nosh[g.pix] = Er + T * p.bg[0];
-            p.out_image_nosh[HW + g.pix] = Eg + T * p.bg[1];
-            p.out_image_nosh[2 * HW + g.pix] = Eb + T * p.bg[2];
-        }
-        out_depth[g.pix] = D;
-        const float3 nw = rot_v2w(p.view, f3(Nx, Ny, Nz));
-        out_norm[g.pix] = nw.x;
-        out_norm[HW + g.pix] = nw.y;
-        out_norm[2 * HW + g.pix] = nw.z;
-        out_alpha[g.pix] = A;
-        p.final_T[g.pix] = T;
-        p.n_contrib[g.pix] = last;
-    }
-    if (p.flags & TEXGS_FLAG_DEBUG) {
-        unsigned tot = nblend;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        if (lane == 0 && tot) {
-            atomicAdd(reinterpret_cast<unsigned long long*>(&p.counters->num_blend_lo), (unsigned long long)tot);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// forward, experimental variant (TEXGS_FLAG_FWD_ILP2): TWO survivors per half-warp per iteration.
-//
-// The blend loop above is one serial chain per pass (record -> exp -> vote -> division -> cube lookup -> 4 taps -> blend)
-// at 5-6 resident warps per scheduler: latency-bound (58 % of the issue slots). Here a pass takes
-// the next two survivors a, b of each half-warp: their alpha tests and the transmittance bookkeeping (cheap, and the only
-// part that is sequential: T after a decides about b) come first, then the texture work of a and b is evaluated by every
-// lane without a branch between the two — two independent chains the scheduler can interleave, eight texel loads in
-// flight per lane — and the contributions are added in list order (a, then b), so every float operation happens in the
-// same order as in texgs_render_fwd: the results are bit-identical (tests/test_simt_kernels_cpu.py checks that).
-// Addresses are clamped inside cube_bilerp, so lanes that do not contribute fetch valid texels they then ignore.
-// ---------------------------------------------------------------------------------------------
-template <bool TEX4>
-__device__ __forceinline__ void fwd_texture_colour(const GaussRec& rec, const float* __restrict__ tex, const float4* __restrict__ tex4,
-                                                   int R, float vx, float vy, float (&tx3)[3]) {
-    const float4 g1 = rec.q[1], g2 = rec.q[2], g3 = rec.q[3], g4 = rec.q[4], g5 = rec.q[5], g6 = rec.q[6];
-    const UvEval e = eval_uv(g1, g2, g3, g4, g5, g6, vx, vy);
-    const CubeCoord cc = cube_coord(e.ux, e.uy, e.uz);
-    const Bilerp bl = cube_bilerp(cc, R);
-    float t00[3], t01[3], t10[3], t11[3];
-    fetch_taps<TEX4>(tex, tex4, bl, t00, t01, t10, t11);
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        const float top = t00[ch] + bl.wx * (t01[ch] - t00[ch]);
-        const float bot = t10[ch] + bl.wx * (t11[ch] - t10[ch]);
-        tx3[ch] = top + bl.wy * (bot - top);
-    }
-}
-
-template <int MODE, bool TEX4, bool DUAL>
-__global__ void __launch_bounds__(256, 2) texgs_render_fwd_ilp2(const RasterParams p, float* __restrict__ out_image,
-                                                                float* __restrict__ out_depth, float* __restrict__ out_norm,
-                                                                float* __restrict__ out_alpha) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    if (p.counters->overflow) return;
-    const PixelGeom g = pixel_geom(p);
-    const int lane = threadIdx.x & 31;
-    WarpSmem& ws = reinterpret_cast<WarpSmem*>(smem_raw)[threadIdx.x >> 5];
-    const unsigned start = p.tile_offset[g.tile];
-    const unsigned n = p.tile_offset[g.tile + 1] - start;
-    const int nchunks = (int)((n + TEXGS_CHUNK - 1) / TEXGS_CHUNK);
-
-    float T = 1.0f, Cr = 0.f, Cg = 0.f, Cb = 0.f, D = 0.f, Nx = 0.f, Ny = 0.f, Nz = 0.f, A = 0.f;
-    float Er = 0.f, Eg = 0.f, Eb = 0.f;
-    unsigned last = 0, nblend = 0;
-    bool done = !g.inside;
-    const float pxf = (float)g.px, pyf = (float)g.py;
-    const float* __restrict__ tex = p.texture;
-    const int R = p.R;
-
-    if (nchunks > 0 && !__all_sync(0xffffffffu, done)) {
-        if (lane == 0) {
-            mbar_init(&ws.bar[0], 1);
-            mbar_init(&ws.bar[1], 1);
-            mbar_fence_init();
-        }
-        __syncwarp();
-        bool v0, v1, v2;
-        const unsigned id0 = stream_load_id(p, start, n, 0, lane, v0);
-        const unsigned id1 = stream_load_id(p, start, n, 1 < nchunks ? 1 : -1, lane, v1);
-        unsigned id2 = stream_load_id(p, start, n, 2 < nchunks ? 2 : -1, lane, v2);
-        {
-            const float4* r0 = reinterpret_cast<const float4*>(p.recs + id0);
-            const float4 a0 = v0 ? __ldg(r0) : make_float4(0.f, 0.f, 1.f, 0.f), a1 = v0 ? __ldg(r0 + 1) : make_float4(1.f, 0.f, 0.f, 0.f);
-            stream_issue(p, ws, 0, lane, id0, v0, a0, a1, g);
-            if (1 < nchunks) {
-                const float4* r1 = reinterpret_cast<const float4*>(p.recs + id1);
-                const float4 b0 = v1 ? __ldg(r1) : make_float4(0.f, 0.f, 1.f, 0.f), b1 = v1 ? __ldg(r1 + 1) : make_float4(1.f, 0.f, 0.f, 0.f);
-                stream_issue(p, ws, 1, lane, id1, v1, b0, b1, g);
-            }
-        }
-        for (int c = 0; c < nchunks; ++c) {
-            const int s = c & 1;
-            float4 q0n = make_float4(0.f, 0.f, 1.f, 0.f), q1n = make_float4(1.f, 0.f, 0.f, 0.f);
-            const unsigned idn = id2;
-            const bool vn = v2;
-            if (vn) {
-                const float4* rn = reinterpret_cast<const float4*>(p.recs + idn);
-                q0n = __ldg(rn);
-                q1n = __ldg(rn + 1);
-            }
-            id2 = stream_load_id(p, start, n, (c + 3 < nchunks) ? c + 3 : -1, lane, v2);
-
-            mbar_wait(&ws.bar[s], (unsigned)(c >> 1) & 1u);
-            __syncwarp();
-            const unsigned mL = ws.maskL[s], mR = ws.maskR[s], mU = mL | mR;
-            unsigned my = (lane & 16) ? mR : mL;
-            bool warp_done = false;
-            while (__any_sync(0xffffffffu, my != 0u)) {
-                // the next two survivors of this half, in list order
-                const bool has_a = my != 0u;
-                const int la = has_a ? (__ffs(my) - 1) : 0;
-                my &= my - 1u;
-                const bool has_b = my != 0u;
-                const int lb = has_b ? (__ffs(my) - 1) : 0;
-                my &= my - 1u;
-                const GaussRec& ra = ws.rec[s][__popc(mU & ((1u << la) - 1u))];
-                const GaussRec& rb = ws.rec[s][__popc(mU & ((1u << lb) - 1u))];
-                const float4 a0 = ra.q[0], a1 = ra.q[1], b0 = rb.q[0], b1 = rb.q[1];
-                const float dxa = a0.x - pxf, dya = a0.y - pyf, dxb = b0.x - pxf, dyb = b0.y - pyf;
-                const float pow_a = -0.5f * (a0.z * dxa * dxa + a1.x * dya * dya) - a0.w * dxa * dya;
-                const float pow_b = -0.5f * (b0.z * dxb * dxb + b1.x * dyb * dyb) - b0.w * dxb * dyb;
-                const float alpha_a = fminf(TEXGS_ALPHA_MAX, a1.y * texgs_exp(pow_a));
-                const float alpha_b = fminf(TEXGS_ALPHA_MAX, b1.y * texgs_exp(pow_b));
-                // transmittance bookkeeping: exactly the decisions of the one-at-a-time loop, a first
-                bool cand_a = has_a && !done && (pow_a <= 0.0f) && (alpha_a >= TEXGS_ALPHA_MIN);
-                const float T0 = T;
-                float test_T = T0 * (1.0f - alpha_a);
-                if (cand_a && test_T < TEXGS_T_STOP) { done = true; cand_a = false; }
-                const float T1 = cand_a ? test_T : T0;
-                bool cand_b = has_b && !done && (pow_b <= 0.0f) && (alpha_b >= TEXGS_ALPHA_MIN);
-                test_T = T1 * (1.0f - alpha_b);
-                if (cand_b && test_T < TEXGS_T_STOP) { done = true; cand_b = false; }
-                const float T2 = cand_b ? test_T : T1;
-                const bool any_a = __any_sync(0xffffffffu, cand_a), any_b = __any_sync(0xffffffffu, cand_b);
-                if (any_a || any_b) {
-                    const float4 a2 = ra.q[2], a3 = ra.q[3], b2 = rb.q[2], b3 = rb.q[3];
-                    float car = a3.y, cag = a3.z, cab = a3.w, cbr = b3.y, cbg = b3.z, cbb = b3.w;
-                    float ta3[3] = {0.f, 0.f, 0.f}, tb3[3] = {0.f, 0.f, 0.f};
-                    if (MODE == TEXGS_MODE_TEXTURE) {
-                        if (any_a && any_b) {          // the common case: both chains, no branch between them
-                            fwd_texture_colour<TEX4>(ra, tex, p.texture_rgba, R, g.vx, g.vy, ta3);
-                            fwd_texture_colour<TEX4>(rb, tex, p.texture_rgba, R, g.vx, g.vy, tb3);
-                        } else if (any_a) {
-                            fwd_texture_colour<TEX4>(ra, tex, p.texture_rgba, R, g.vx, g.vy, ta3);
-                        } else {
-                            fwd_texture_colour<TEX4>(rb, tex, p.texture_rgba, R, g.vx, g.vy, tb3);
-                        }
-                        car = fmaxf(0.f, SH_C0 * ta3[0] + car); cag = fmaxf(0.f, SH_C0 * ta3[1] + cag); cab = fmaxf(0.f, SH_C0 * ta3[2] + cab);
-                        cbr = fmaxf(0.f, SH_C0 * tb3[0] + cbr); cbg = fmaxf(0.f, SH_C0 * tb3[1] + cbg); cbb = fmaxf(0.f, SH_C0 * tb3[2] + cbb);
-                    }
-                    if (cand_a) {
-                        const float w = alpha_a * T0;
-                        if (DUAL && MODE == TEXGS_MODE_TEXTURE) {
-                            Er += w * fmaxf(0.f, SH_C0 * ta3[0] + 0.5f); Eg += w * fmaxf(0.f, SH_C0 * ta3[1] + 0.5f); Eb += w * fmaxf(0.f, SH_C0 * ta3[2] + 0.5f);
-                        }
-                        Cr += w * car; Cg += w * cag; Cb += w * cab;
-                        D += w * a1.z;
-                        Nx += w * a2.x; Ny += w * a2.y; Nz += w * a2.z;
-                        A += w;
-                        last = (unsigned)c * TEXGS_CHUNK + (unsigned)la + 1u;
-                        ++nblend;
-                    }
-                    if (cand_b) {
-                        const float w = alpha_b * T1;
-                        if (DUAL && MODE == TEXGS_MODE_TEXTURE) {
-                            Er += w * fmaxf(0.f, SH_C0 * tb3[0] + 0.5f); Eg += w * fmaxf(0.f, SH_C0 * tb3[1] + 0.5f); Eb += w * fmaxf(0.f, SH_C0 * tb3[2] + 0.5f);
-                        }
-                        Cr += w * cbr; Cg += w * cbg; Cb += w * cbb;
-                        D += w * b1.z;
-                        Nx += w * b2.x; Ny += w * b2.y; Nz += w * b2.z;
-                        A += w;
-                        last = (unsigned)c * TEXGS_CHUNK + (unsigned)lb + 1u;
-                        ++nblend;
-                    }
-                    T = T2;
-                }
-                if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
-            }
-            __syncwarp();
-            if (warp_done) {
-                if (c + 1 < nchunks) mbar_wait(&ws.bar[s ^ 1], (unsigned)((c + 1) >> 1) & 1u);
-                break;
-            }
             if (c + 2 < nchunks) stream_issue(p, ws, s, lane, idn, vn, q0n, q1n, g);
         }
     }
@@ -623,12 +368,6 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
             stream_issue(p, ws, 1, lane, id1, v1, b0, b1, g);
         }
     }
-#if TEXGS_HALF_WINDOW
-    unsigned my = 0u;           // what is left of this half-warp's survivor queue in the chunk it works on
-    bool ahead = false;         // ... and whether that chunk belongs to visit k + 1 (stage s ^ 1) instead of visit k
-    const GaussRec* recp = ws.rec[0];          // ... the records of that chunk, the mask they were compacted with,
-    unsigned mUsel = 0u, bidx = 0u;            //     and the list position of its first entry
-#endif
     for (int k = 0; k <= c_top; ++k) {
         const int c = c_top - k;
         const int s = k & 1;
@@ -644,49 +383,6 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
 
         mbar_wait(&ws.bar[s], (unsigned)(k >> 1) & 1u);
         __syncwarp();
-#if TEXGS_HALF_WINDOW
-        // as in the forward: a half that has finished visit k goes on with visit k + 1 (chunk c - 1, stage s ^ 1)
-        if (!ahead) {
-            my = (lane & 16) ? ws.maskR[s] : ws.maskL[s];
-            recp = ws.rec[s];
-            mUsel = ws.maskL[s] | ws.maskR[s];
-            bidx = (unsigned)c * TEXGS_CHUNK;
-        }
-        ahead = false;
-        unsigned am = 0u;                      // warp-uniform: lanes of the halves that have moved on to visit k + 1
-        bool next_ready = false;
-        const bool has_next = k + 1 <= c_top;
-        for (;;) {
-            const unsigned b = __ballot_sync(0xffffffffu, my != 0u);           // the one vote per pass
-            const unsigned x = b | am;
-            if ((x & 0xffffu) == 0u || x < 0x10000u) {              // a half that is still in chunk c has run out
-                if (!has_next) {
-                    if (b == 0u) break;
-                } else {
-                    const bool eL = (x & 0xffffu) == 0u, eR = x < 0x10000u;
-                    if (!next_ready) {
-                        mbar_wait(&ws.bar[s ^ 1], (unsigned)((k + 1) >> 1) & 1u);
-                        __syncwarp();
-                        next_ready = true;
-                    }
-                    if ((lane & 16) ? eR : eL) {
-                        my = (lane & 16) ? ws.maskR[s ^ 1] : ws.maskL[s ^ 1];
-                        recp = ws.rec[s ^ 1];
-                        mUsel = ws.maskL[s ^ 1] | ws.maskR[s ^ 1];
-                        bidx = (unsigned)(c - 1) * TEXGS_CHUNK;
-                        ahead = true;
-                    }
-                    if (eL) am |= 0x0000ffffu;
-                    if (eR) am |= 0xffff0000u;
-                    if (am == 0xffffffffu) break;                     // both halves have left chunk c
-                }
-            }
-            const bool has = my != 0u;
-            const int l = has ? (31 - __clz(my)) : 0;
-            my &= ~(1u << l);
-            const GaussRec& rec = recp[__popc(mUsel & ((1u << l) - 1u))];            // half-uniform address
-            const unsigned gi = bidx + (unsigned)l;                 // 0-based position in the list
-#else
         const unsigned mL = ws.maskL[s], mR = ws.maskR[s], mU = mL | mR;
         unsigned my = (lane & 16) ? mR : mL;              // this half-warp's survivors, walked back to front
         while (__any_sync(0xffffffffu, my != 0u)) {
@@ -695,7 +391,6 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
             my &= ~(1u << l);
             const GaussRec& rec = ws.rec[s][__popc(mU & ((1u << l) - 1u))];       // half-uniform address
             const unsigned gi = (unsigned)c * TEXGS_CHUNK + (unsigned)l;   // 0-based position in the list
-#endif
             const float4 g0 = rec.q[0], g1 = rec.q[1];
             const float dx = g0.x - pxf, dy = g0.y - pyf;
             const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;

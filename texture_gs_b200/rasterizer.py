@@ -104,9 +104,6 @@ def _pinned_counters(dev_index: int):
 # optimizer step bumps ``_version`` so the copy is rebuilt exactly once per texture update (the
 # reference renders 1-2 times per update, models/texture_gaussian3d.py:318,378; a view batch more).
 USE_PACKED_TEXTURE = True
-# experimental forward kernel variant (bit-identical results, texgs_render.cuh); TEXGS_FWD_ILP2=1 in the environment or
-# ``texture_gs_b200.rasterizer.FWD_ILP2 = True`` selects it for A/B timing
-FWD_ILP2 = os.environ.get("TEXGS_FWD_ILP2", "0") not in ("", "0")
 _packed_cache: dict = {}
 
 
@@ -207,7 +204,7 @@ def _build_args(st: GaussianRasterizationSettings, mode: int, means3D, shs, colo
     a.H, a.W = int(st.image_height), int(st.image_width)
     a.R = 0 if texture is None else texture.shape[1]
     a.mode = mode
-    a.flags = (L.FLAG_PREFILTERED if st.prefiltered else 0) | (L.FLAG_DEBUG if st.debug else 0) | (L.FLAG_FWD_ILP2 if FWD_ILP2 else 0)
+    a.flags = (L.FLAG_PREFILTERED if st.prefiltered else 0) | (L.FLAG_DEBUG if st.debug else 0)
     a.tanfovx, a.tanfovy, a.scale_modifier = float(st.tanfovx), float(st.tanfovy), float(st.scale_modifier)
     a.viewmatrix = (C.c_float * 16)(*_host_floats(st.viewmatrix, 16))
     a.projmatrix = (C.c_float * 16)(*_host_floats(st.projmatrix, 16))

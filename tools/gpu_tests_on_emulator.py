@@ -3,7 +3,7 @@
 on a box without a GPU:
     python tools/gpu_tests_on_emulator.py            # ~3 min: 12 tests
     python tools/gpu_tests_on_emulator.py config0    # + BASELINE configs[0] forward/backward (several minutes)
-    python tools/gpu_tests_on_emulator.py -DTEXGS_HALF_WINDOW=1     # the same tests on a tuning-macro variant of the kernels
+    python tools/gpu_tests_on_emulator.py -DTEXGS_CHUNK=16     # the same tests on a tuning-macro variant of the kernels
 Tests that build CUDA tensors themselves (operator-level tests, fused buckets, dual render, ...) cannot be redirected
 and are not selected. A pass here says nothing about PTX semantics or performance; it says the comparison code and the
 oracle's flags still accept kernels whose arithmetic is the shipped source."""
