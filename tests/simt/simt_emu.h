@@ -118,6 +118,8 @@ inline void make_context(Context* c, char* stack, size_t bytes, void (*entry)())
 constexpr size_t kStackBytes = 160 * 1024;
 constexpr size_t kDynSmemMax = 232448;      // 227 KB, the sm_100 opt-in maximum
 
+struct PendingCopy { void* dst; const void* src; unsigned bytes; };
+
 struct Fiber {
     Context ctx;
     uint3 tid;
@@ -127,6 +129,9 @@ struct Fiber {
     const volatile unsigned* wait_addr = nullptr;
     unsigned wait_val = 0;
     const char* wait_what = "";
+    // cp.async (LDGSTS): copies of the group being built and the committed groups still in flight, oldest first
+    std::vector<PendingCopy> cp_open;
+    std::deque<std::vector<PendingCopy>> cp_groups;
 };
 
 struct Warp {
@@ -143,8 +148,6 @@ struct MBar {
     int count = 0, pending = 0;
     long long tx = 0;
 };
-
-struct PendingCopy { void* dst; const void* src; unsigned bytes; };
 
 struct Global {
     dim3 bid, bdim, gdim;
@@ -219,6 +222,7 @@ inline void fiber_main() {
     g.entry(g.entry_arg);
     Fiber* f = g.cur;
     f->done = true;
+    if (!f->cp_open.empty() || !f->cp_groups.empty()) fail("a thread exited with cp.async copies in flight (no cp.async.wait_group covered them)");
     Warp& w = g.warps[f->warp];
     w.exited |= 1u << f->lane;
     if (w.arrived && (w.mask_in & (1u << f->lane))) fail("a lane exited while its warp waits for it in a *_sync collective");
@@ -476,6 +480,32 @@ inline void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint6
     simt::G().copies[bar].push_back(simt::PendingCopy{smem_dst, gmem_src, bytes});
     if (simt::G().eager_copies) simt::mbar_flush(bar);
 }
+// cp.async (per-thread asynchronous copy, LDGSTS): lands as LATE as legal — at the cp.async.wait_group that covers its
+// group — or, with eager copies, at issue (as EARLY as legal: a slot still being read is overwritten)
+inline void cp_async_n(void* smem_dst, const void* gmem_src, unsigned bytes) {
+    if (((uintptr_t)smem_dst & (bytes - 1)) || ((uintptr_t)gmem_src & (bytes - 1))) simt::fail("cp.async: addresses must be aligned to the copy size");
+    simt::Global& g = simt::G();
+    if (g.eager_copies) memcpy(smem_dst, gmem_src, bytes);
+    else g.cur->cp_open.push_back(simt::PendingCopy{smem_dst, gmem_src, bytes});
+}
+inline void cp_async16(void* smem_dst, const void* gmem_src) { cp_async_n(smem_dst, gmem_src, 16); }
+inline void cp_async4(void* smem_dst, const void* gmem_src) { cp_async_n(smem_dst, gmem_src, 4); }
+inline void cp_async_commit() {
+    simt::Fiber* f = simt::G().cur;
+    f->cp_groups.push_back(std::move(f->cp_open));
+    f->cp_open.clear();
+}
+template <int N> inline void cp_async_wait() {
+    simt::Fiber* f = simt::G().cur;
+    while ((int)f->cp_groups.size() > N) {
+        for (const simt::PendingCopy& c : f->cp_groups.front()) memcpy(c.dst, c.src, c.bytes);
+        f->cp_groups.pop_front();
+    }
+}
+template <class T> inline void ldg256(const T* p, float (&o)[8]) {
+    if ((uintptr_t)p & 31u) simt::fail("256-bit load: address must be 32-byte aligned");
+    memcpy(o, p, 32);
+}
 inline void red_add_v4(float* addr, float a, float b, float c, float d) {
     if ((uintptr_t)addr & 15u) simt::fail("red.global.add.v4.f32: address must be 16-byte aligned");
     addr[0] += a; addr[1] += b; addr[2] += c; addr[3] += d;
@@ -521,7 +551,7 @@ inline void run_block() {
         Fiber& f = g.fibers[t];
         f.lin = (int)t; f.lane = (int)(t & 31); f.warp = (int)(t >> 5);
         f.tid = uint3{t % g.bdim.x, (t / g.bdim.x) % g.bdim.y, t / (g.bdim.x * g.bdim.y)};
-        f.done = false; f.wait_addr = nullptr;
+        f.done = false; f.wait_addr = nullptr; f.cp_open.clear(); f.cp_groups.clear();
         g.warps[f.warp].exist |= 1u << f.lane;
         make_context(&f.ctx, g.stacks[t], kStackBytes, &fiber_main);
     }

@@ -10,7 +10,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 SRC = PKG / "csrc" / "texgs_api.cu"
 OUT = PKG / "libtexgs.so"
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--shared",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-ftz=true", "-lineinfo", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
 
 
