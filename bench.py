@@ -1,21 +1,23 @@
 #!/usr/bin/env python
-"""bench.py — views/s forward+backward of the Texture-GS rasterizer hot path (BASELINE.json metric).
+"""bench.py — views/s of the Texture-GS rasterizer hot path (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, sm_100a)
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the C + OpenMP oracle (port of the
                                                              # reference algorithm) on all host cores, whole views
+    python bench.py --workload cfg1_300k_800x600             # forward-only lines (BASELINE configs[1], [4])
 
-Workload (N=1 and N>1 alike): BASELINE.json configs[2]/[3] — 500k synthetic Gaussians ("sphere-shell",
-seed 0), 1920x1080, cube texture 6x2048^2x3, sh_degree 3; a *step* is one batch of 32 views
-(forward + backward with dense cotangents on all four outputs, gradients accumulated into one flat
-bucket). With N GPUs the 32 views are sharded over the ranks and the bucket is summed with one NCCL
-all-reduce per step (strong scaling: total work fixed). value = 32*K / time, time = max over ranks
-of CUDA-event time around the K steps bracketed by barrier + synchronize.
+Default workload (N=1 and N>1 alike): BASELINE.json configs[2]/[3] — 500k synthetic Gaussians ("sphere-shell",
+seed 0), 1920x1080, cube texture 6x2048^2x3, sh_degree 3; a *step* is one batch of 32 views (forward + backward with
+dense cotangents on all four outputs, gradients accumulated into one flat bucket), rendered on ``--streams`` CUDA
+streams per rank. With N GPUs the 32 views are sharded over the ranks and the bucket is summed with one NCCL
+all-reduce per step (strong scaling: total work fixed). value = 32*K / time, time = max over ranks of CUDA-event time
+around the K steps bracketed by barrier + synchronize.
 
-The JSON line also carries: e2e (same step driven from HOST buffers: per-view cotangent images are
-copied from pinned host memory, the per-step loss is read back), roofline (dominant kernel,
-algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json), cpu_baseline (the oracle timed on
-a bounded sample), clocks (nvidia-smi sampled during the timed region), gpu_launches.
+The JSON line also carries: e2e (the training-shaped step driven from HOST buffers: per view the uint8 ground-truth
+image, uint8 alpha mask and int8 normal map are copied from pinned host memory, the losses of the reference's
+compute_loss are evaluated by the fused loss kernels, the per-step loss is read back), roofline (dominant kernel,
+algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json), cpu_baseline (the oracle timed on a bounded
+sample), clocks (nvidia-smi sampled during the timed region), gpu_launches, grad_checksum.
 """
 from __future__ import annotations
 
@@ -39,6 +41,9 @@ KERNELS_PER_VIEW = 8   # (+1 texgs_pack_texture_kernel per step) preprocess_fwd,
                        # sort_tiles, render_fwd, render_bwd, preprocess_bwd
 
 
+DEFAULT_STREAMS = 3    # views in flight per rank (profiles/r2_variants.md: 1 -> 371, 2 -> 396, 3 -> 405 views/s)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -47,13 +52,24 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_500k_1080p")
     ap.add_argument("--views", type=int, default=VIEWS_PER_STEP)
-    ap.add_argument("--streams", type=int, default=1,
-                    help="experimental: CUDA streams per rank that render alternate views concurrently (one gradient-bucket replica each)")
-    ap.add_argument("--fwd-ilp2", action="store_true", help="experimental: forward blend kernel with two splats per half-warp per iteration")
+    ap.add_argument("--streams", type=int, default=DEFAULT_STREAMS,
+                    help="CUDA streams per rank that render alternate views concurrently (one gradient-bucket replica each)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-tiles", type=int, default=0, help="ignored (kept for old command lines): the CPU arm renders whole views")
+    ap.add_argument("--no-stage-pass", action="store_true", help="skip the single-stream per-kernel timing pass (roofline.per_kernel)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (default: every CPU in the affinity mask)")
     return ap.parse_args()
+
+
+def workload_config(wl, views):
+    """The ``config`` object — the SAME keys and values in both arms (what is being measured, nothing about how)."""
+    return {"workload": wl.name, "gaussians": wl.n_gaussians, "width": wl.width, "height": wl.height, "tex_res": wl.tex_res,
+            "views_per_step": views, "sh_degree": 3, "pass": "fwd+bwd" if wl.backward else "fwd",
+            "renders_per_view": wl.renders_per_view}
+
+
+def metric_name(wl):
+    return "views/s fwd+bwd" if wl.backward else "views/s fwd"
 
 
 # ---------------------------------------------------------------------------------------------
@@ -122,31 +138,33 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def algorithmic_bytes(N, M, V, K, U, P, R, views_per_step=VIEWS_PER_STEP):
-    """SURVEY.md §8d / DESIGN.md §4: algorithmic HBM bytes per view, split per kernel.
-    N Gaussians, M SH-rest coeffs, V visible, K (tile,Gaussian) pairs, U unique texels touched,
-    P pixels, R face resolution. Records are 128 B, accumulators 20 floats."""
+def algorithmic_bytes(N, M, V, K, U, P, R, views_per_step=VIEWS_PER_STEP, backward=True):
+    """algorithmic HBM bytes per view, split per kernel, with the survey's per-unit sizes (NOT the
+    sizes of this implementation's buffers: the 128-byte record, the 16-byte texel and the 24-float accumulator row
+    move more than this; that excess shows up as ``traffic`` > algorithmic).
+    N Gaussians, M SH-rest coeffs, V visible, K (tile,Gaussian) pairs, U unique texels touched, P pixels, R face res.
+      forward  = N(92+12M) + 64V + 24K + 116K + 12U + 40P
+      backward = 40P + 116K + 12U + 72R^2 [zero fill, once per STEP] + 24U + 136V + N(92+12M) + N(68+12M)"""
     b = {}
-    b["preprocess_fwd"] = N * (92 + 12 * M) + V * (128 + 8 + 4) + K * 4
+    b["preprocess_fwd"] = N * (92 + 12 * M) + V * 64
     b["scan_tiles"] = 0
-    b["scatter_pairs"] = V * 12 + K * 8
-    b["sort_tiles"] = K * 8 + K * 12
-    b["render_fwd"] = K * (4 + 128) + U * 12 + P * 40
-    b["render_bwd"] = P * 40 + K * (4 + 128) + U * 12 + 2 * U * 12 + 2 * V * 80
-    # per view: the accumulator clear; the dense texture-gradient zero fill happens once per step (GradBucket.zero()),
-    # outside the per-view kernels, and is charged to the view at 1 / views_per_step
-    b["bwd_clear"] = N * 96 + 6 * R * R * 16 // max(1, views_per_step)
-    b["preprocess_bwd"] = N * (92 + 12 * M) + V * 80 + N * (68 + 12 * M)
+    b["scatter_pairs"] = K * 12                      # key + value written once ...
+    b["sort_tiles"] = K * 12                         # ... and read once
+    b["render_fwd"] = K * 116 + U * 12 + P * 40
+    if backward:
+        b["render_bwd"] = P * 40 + K * 116 + U * 12 + 2 * U * 12 + 2 * V * 68
+        b["bwd_clear"] = 6 * R * R * 12 // max(1, views_per_step)
+        b["preprocess_bwd"] = N * (92 + 12 * M) + N * (68 + 12 * M)
     return b
 
 
-def roofline_report(wl, views_per_step, world, value, stage_ms, stats, U, clock_rec, sms):
+def roofline_report(wl, views_per_step, world, value, stage_ms, stats, U, clock_rec, sms, timing_note=None):
     """The ``roofline`` object of the JSON line (pure host arithmetic, unit-tested on CPU): per-kernel algorithmic bytes
     over the CUDA-event durations measured in the timed region, the dominant kernel against the measured HBM peak, its
     DRAM traffic and instruction count from the committed ncu captures."""
     hbm_peak, peak_src = measured_peaks()
     N, M = wl.n_gaussians, 15
-    ab = algorithmic_bytes(N, M, stats.num_visible, stats.num_pairs, U, wl.width * wl.height, wl.tex_res, views_per_step)
+    ab = algorithmic_bytes(N, M, stats.num_visible, stats.num_pairs, U, wl.width * wl.height, wl.tex_res, views_per_step, wl.backward)
     per_kernel = {}
     for k, b in ab.items():
         if k in stage_ms and stage_ms[k] > 0:
@@ -186,7 +204,7 @@ def roofline_report(wl, views_per_step, world, value, stage_ms, stats, U, clock_
     return {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
             "frac": per_kernel[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": ab[dom], "issue": issue, "per_kernel": per_kernel,
-            "whole_path": whole, "counts": counts}
+            "whole_path": whole, "counts": counts, "timing": timing_note}
 
 
 def make_scene(wl, device, requires_grad=True):
@@ -204,19 +222,30 @@ def make_scene(wl, device, requires_grad=True):
 _cpu_cache = {}
 
 
-def cpu_oracle_views_per_s(wl, sample_tiles: int = 0, backward: bool = True):
+def cpu_threads(requested: int = 0) -> int:
+    """Threads of the CPU arm: every CPU of the affinity mask. ``OMP_NUM_THREADS`` is deliberately NOT consulted —
+    torch.distributed.run injects OMP_NUM_THREADS=1 into every rank, which made the round-1 CPU arm single-threaded
+    under torchrun; ``--cpu-threads`` / TEXGS_CPU_THREADS override."""
+    if requested > 0:
+        return requested
+    env = int(os.environ.get("TEXGS_CPU_THREADS", "0") or 0)
+    if env > 0:
+        return env
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_oracle_views_per_s(wl, threads: int = 0):
     """CPU arm: the C + OpenMP oracle (oracle/raster_c.c, float32 build) renders ONE WHOLE view of the workload —
-    all Gaussians, all tiles, forward + backward — on all host threads OpenMP gives it. No sampling, no extrapolation
-    (the torch oracle needed both; at 40-170 s per view it could only be timed on 5 % of the tiles).
-    Returns (views/s, description, threads, seconds)."""
+    all Gaussians, all tiles, forward (+ backward where the workload has one) — on ``threads`` host threads.
+    No tile sampling, no extrapolation. Returns (views/s, description, threads, seconds)."""
     from oracle import raster_c
     from oracle.raster_ref import RasterSettings
     from texture_gs_b200.scene import orbit_cameras, output_cotangents, sphere_shell_scene
-    try:
-        avail = len(os.sched_getaffinity(0))
-    except AttributeError:
-        avail = os.cpu_count() or 1
-    threads = int(os.environ.get("OMP_NUM_THREADS", 0)) or avail
+    threads = cpu_threads(threads)
+    backward = wl.backward
     key = (wl.name, backward)
     if key not in _cpu_cache:
         g = sphere_shell_scene(wl.n_gaussians, wl.tex_res, sh_degree=3, seed=0, device="cpu", requires_grad=False)
@@ -230,40 +259,41 @@ def cpu_oracle_views_per_s(wl, sample_tiles: int = 0, backward: bool = True):
     st = RasterSettings(wl.height, wl.width, math.tan(cam.FoVx / 2), math.tan(cam.FoVy / 2), torch.zeros(3), 1.0,
                         cam.world_view_transform, cam.full_proj_transform, 3, cam.camera_center)
     t0 = time.perf_counter()
-    out = raster_c.rasterize(t["xyz"], t["shs"], t["opacity"], t["scaling"], t["rotation"], t["uvs"], t["grad_uvs"], t["texture"], st,
-                             cotangents=cot if backward else None, dtype=torch.float32, threads=threads)
+    reps = wl.renders_per_view if not backward else 1          # retexture.py renders every view twice (with SH, degree 0)
+    for _ in range(reps):
+        out = raster_c.rasterize(t["xyz"], t["shs"], t["opacity"], t["scaling"], t["rotation"], t["uvs"], t["grad_uvs"], t["texture"], st,
+                                 cotangents=cot if backward else None, dtype=torch.float32, threads=threads)
     dt = time.perf_counter() - t0
     aux = out[-1]
-    desc = (f"C + OpenMP oracle (oracle/raster_c.c, float32) fwd{'+bwd' if backward else ''} of 1 whole view: {wl.n_gaussians} Gaussians, "
+    desc = (f"C + OpenMP oracle (oracle/raster_c.c, float32) fwd{'+bwd' if backward else ''} of 1 whole view"
+            f"{' (x%d renders)' % reps if reps > 1 else ''}: {wl.n_gaussians} Gaussians, "
             f"{wl.width}x{wl.height}, {aux['num_pairs']} (tile,Gaussian) pairs, {aux['num_blend']} blended contributions in {dt:.2f} s "
-            f"on {threads} threads (no sampling, no extrapolation)")
+            f"on {threads} threads (no tile sampling, no extrapolation)")
     return 1.0 / dt, desc, threads, dt
 
 
 def run_reference(args, wl):
+    """``--impl reference``: rank 0 only. A timed *step* of this arm is a bounded sample of the workload's 32-view step:
+    ONE whole view (a different camera every step), so that K steps + W warm-ups end within minutes on host cores;
+    ``ms_per_step`` is the measured mean of those K sampled steps (not derived), every requested step is run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    desc = ""
-    threads = 1
-    t_all = time.perf_counter()
+    threads = cpu_threads(args.cpu_threads)
+    secs, desc = [], ""
     for i in range(args.warmup + args.steps):
-        v, desc, threads, dt = cpu_oracle_views_per_s(wl)
+        _v, desc, threads, dt = cpu_oracle_views_per_s(wl, threads)
         if i >= args.warmup:
-            vals.append(v)
-        if time.perf_counter() - t_all > 240:
-            break
-    if not vals:
-        vals = [v]
-    value = sum(vals) / len(vals)
-    line = {"impl": "reference", "metric": "views/s fwd+bwd", "value": value, "unit": "views/s", "n_gpus": args.gpus,
-            "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1000.0 * VIEWS_PER_STEP / value,
+            secs.append(dt)
+    mean_s = sum(secs) / max(1, len(secs))
+    value = 1.0 / mean_s if secs else 0.0
+    line = {"impl": "reference", "metric": metric_name(wl), "value": value, "unit": "views/s", "n_gpus": args.gpus,
+            "steps": len(secs), "warmup": args.warmup, "ms_per_step": 1000.0 * mean_s,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl.name, "gaussians": wl.n_gaussians, "width": wl.width, "height": wl.height,
-                       "tex_res": wl.tex_res, "views_per_step": VIEWS_PER_STEP, "sh_degree": 3,
-                       "parallelism": f"host CPU, {threads} OpenMP threads (rank 0 only)",
-                       "l2_policy": "n/a (CPU arm)"},
+            "config": workload_config(wl, args.views),
+            "impl_notes": {"parallelism": f"host CPU, {threads} OpenMP threads (rank 0 only; OMP_NUM_THREADS ignored, see cpu_threads())",
+                           "step_sample": "each timed step = 1 whole view of the 32-view step (bounded sample); ms_per_step is per sampled step",
+                           "l2_policy": "n/a (CPU arm)"},
             "cpu_baseline": {"value": value, "unit": "views/s", "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -282,8 +312,8 @@ def main():
         return run_reference(args, wl)
 
     import torch.distributed as dist
-    from texture_gs_b200 import _lib, last_stats, uv_tex_render
-    from texture_gs_b200.dist import GradBucket, render_views_accumulate, shard_views
+    from texture_gs_b200 import _lib, last_stats, uv_tex_render, uv_tex_render_dual
+    from texture_gs_b200.dist import GradBucket, bind_to_gpu_numa_node, render_views_accumulate, shard_views
     from texture_gs_b200.profiling import StageTimer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -293,20 +323,20 @@ def main():
         raise SystemExit("bench.py (impl=ours) needs a CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = bind_to_gpu_numa_node(dev)          # before any pinned allocation: host buffers land next to the GPU
     if world > 1:
         from texture_gs_b200.dist import init_process_group_quiet
         init_process_group_quiet("nccl", dev)        # keeps NCCL's version banner off stdout (one JSON line only)
     _lib.load()
-    if args.fwd_ilp2:
-        from texture_gs_b200 import rasterizer as _rz
-        _rz.FWD_ILP2 = True
 
-    g, cams, cot = make_scene(wl, dev)
+    bwd = wl.backward
+    streams = max(1, args.streams)
+    g, cams, cot = make_scene(wl, dev, requires_grad=bwd)
     bg = torch.zeros(3, device=dev)
-    params = {k: v for k, v in g.tensors().items()}
-    bucket = GradBucket(params, replicas=max(1, args.streams))
+    # retexture.py renders every view twice (with SH, then active_sh_degree = 0): one dual render here
+    render_fn = uv_tex_render_dual if (not bwd and wl.renders_per_view == 2) else uv_tex_render
+    bucket = GradBucket({k: v for k, v in g.tensors().items()}, replicas=streams) if bwd else None
     views = shard_views(args.views, world, rank)
-    timer = StageTimer(capacity=max(1, len(views)) * max(1, args.steps), device=dev)
 
     def sync_all():
         if world > 1:
@@ -315,12 +345,14 @@ def main():
 
     from texture_gs_b200 import invalidate_packed_cache
 
-    def step(tm=None):
+    def step(tm=None, nstreams=streams):
         # one texture update per step: the packed (6,R,R,4) copy is rebuilt once per 32-view batch
         invalidate_packed_cache()
-        bucket.zero()
-        render_views_accumulate(uv_tex_render, g, cams, cot, views, bg, timer=tm, bucket=bucket, streams=args.streams)
-        bucket.all_reduce()
+        if bwd:
+            bucket.zero()
+        render_views_accumulate(render_fn, g, cams, cot, views, bg, timer=tm, bucket=bucket, streams=nstreams, backward=bwd)
+        if bwd:
+            bucket.all_reduce()
 
     for _ in range(args.warmup):
         step()
@@ -332,35 +364,62 @@ def main():
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        step(timer)
+        step()
     e1.record()
     sync_all()
+    wall_ms = (time.perf_counter() - t0) * 1e3
     ms = e0.elapsed_time(e1)
     if world > 1:
-        tms = torch.tensor([ms], device=dev)
+        tms = torch.tensor([ms, wall_ms], device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+        ms, wall_ms = float(tms[0].item()), float(tms[1].item())
     clock_rec = clocks.stop() if rank == 0 else None
-    stage_ms = timer.summary()
     value = args.views * args.steps / (ms / 1e3)
 
-    # ---- e2e: same step, driven from host buffers ---------------------------------------------
+    # ---- checksum of the all-reduced gradient bucket: the same number at every N (up to the order of the atomics) ----
+    checksum = None
+    if bwd:
+        fl = bucket.flat.double()
+        checksum = {"l1": float(fl.abs().sum().item()), "sum": float(fl.sum().item()), "numel": bucket.flat.numel(),
+                    "what": f"all-reduced gradient bucket after the last timed step ({args.views} views)"}
+
+    # ---- per-kernel durations: ONE stream, so that no other view's kernels share the SMs with the kernel being timed ----
+    stage_ms, timing_note = {}, None
+    if not args.no_stage_pass:
+        nsteps = max(1, min(args.steps, 4))
+        timer = StageTimer(capacity=max(1, len(views)) * nsteps, device=dev)
+        for _ in range(nsteps):
+            step(timer, 1)
+        sync_all()
+        stage_ms = timer.summary()
+        timing_note = (f"CUDA events recorded by the library around every kernel, mean over {nsteps} single-stream steps run right after the "
+                       f"timed region ({streams} streams there: concurrent views would share the SMs with the kernel being timed)")
+
+    # ---- e2e: the training-shaped step, driven from host buffers -------------------------------
     e2e = None
     if not args.no_e2e:
         try:
-            e2e = run_e2e(args, wl, g, cams, cot, bg, bucket, views, dev, world, sync_all)
+            e2e = run_e2e(args, wl, g, cams, bg, bucket, views, dev, world, sync_all, render_fn, streams)
         except Exception as e:              # keep the device-resident measurement; the line then says why e2e is missing
             if world > 1:
                 raise                       # a rank that drops out of the collectives would hang the others
             e2e = {"value": None, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(e)[:300]}
 
     # ---- unique texels touched by one view (for the algorithmic byte count) ---------------------
-    bucket.zero()
-    render_views_accumulate(uv_tex_render, g, cams, [torch.ones_like(c) for c in cot], views[:1] or [0], bg, bucket=bucket)
-    U = int((bucket.grads()["texture"].abs().sum(dim=-1) > 0).sum().item())
-    bucket.zero()
+    if bwd:
+        bucket.zero()
+        render_views_accumulate(uv_tex_render, g, cams, [torch.ones_like(c) for c in cot], views[:1] or [0], bg, bucket=bucket)
+        U = int((bucket.grads()["texture"].abs().sum(dim=-1) > 0).sum().item())
+        bucket.zero()
+    else:
+        g2 = g.to(requires_grad=True)
+        pkg = uv_tex_render(cams[(views[:1] or [0])[0] % len(cams)], g2, None, bg)
+        torch.autograd.backward([pkg["render"], pkg["depth"], pkg["norm"], pkg["alpha"]], [torch.ones_like(c) for c in cot])
+        U = int((g2.get_texture.grad.abs().sum(dim=-1) > 0).sum().item())
+        del g2, pkg
 
     if rank != 0:
         if world > 1:
@@ -368,86 +427,143 @@ def main():
         return
 
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    roofline = roofline_report(wl, args.views, world, value, stage_ms, stats, U, clock_rec, sms)
+    roofline = roofline_report(wl, args.views, world, value, stage_ms, stats, U, clock_rec, sms, timing_note)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:
-            vs = [cpu_oracle_views_per_s(wl) for _ in range(3)]       # a few seconds each; first call builds the scene
+            vs = [cpu_oracle_views_per_s(wl, args.cpu_threads) for _ in range(3)]       # a few seconds each; first call builds the scene
             v, desc, threads, _ = max(vs, key=lambda r: r[0])
             cpu = {"value": v, "unit": "views/s", "cores": threads, "kind": "port", "sample": desc + "; best of 3 views"}
         except Exception as e:                                        # never lose the GPU measurement to the CPU leg
             cpu = {"value": None, "unit": "views/s", "cores": 0, "kind": "port", "sample": ("unavailable: " + repr(e))[:300]}
 
-    line = {"metric": "views/s fwd+bwd", "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,
+    kernels_per_view = (KERNELS_PER_VIEW if bwd else 6)
+    line = {"metric": metric_name(wl), "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl.name, "gaussians": wl.n_gaussians, "width": wl.width, "height": wl.height,
-                       "tex_res": wl.tex_res, "views_per_step": args.views, "sh_degree": 3, "streams_per_rank": max(1, args.streams),
-                       "forward_kernel": "ilp2 (experimental)" if args.fwd_ilp2 else "default",
-                       "parallelism": f"dp{world} (views sharded, 1 all-reduce of {bucket.nbytes / 1e6:.0f} MB/step)" if world > 1 else "single GPU",
-                       "l2_policy": "inputs larger than L2 (texture 302 MB + records 64 MB, a different camera every view)"},
-            "clocks": clock_rec, "e2e": e2e, "gpu_launches": (KERNELS_PER_VIEW * len(views) + 1) * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu}
+            "config": workload_config(wl, args.views),
+            "impl_notes": {"streams_per_rank": streams,
+                           "parallelism": (f"dp{world} (views sharded, 1 all-reduce of {bucket.nbytes / 1e6:.0f} MB/step)" if (world > 1 and bwd)
+                                           else (f"dp{world} (views sharded)" if world > 1 else "single GPU")),
+                           "l2_policy": "inputs larger than L2 (texture %d MB + records %d MB, a different camera every view)"
+                                        % (6 * wl.tex_res ** 2 * 12 // 1000000, wl.n_gaussians * 128 // 1000000),
+                           "render_fn": render_fn.__name__, "host_wall_ms_per_step": wall_ms / args.steps, "numa_node": numa_node},
+            "clocks": clock_rec, "e2e": e2e, "gpu_launches": (kernels_per_view * len(views) + 1) * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "grad_checksum": checksum}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_e2e(args, wl, g, cams, cot_dev, bg, bucket, views, dev, world, sync_all):
-    """The same step through the public operator with HOST inputs: for every view the four dense
-    cotangent images (the stand-in for the per-view supervision images of the reference's training
-    loop, train.py:147-149) are copied from pinned host memory on a side stream (double buffered),
-    the per-step scalar result is read back to the host. All copies are inside the timed region."""
+def make_supervision(wl, n_views: int, seed: int = 5):
+    """Per-view supervision of the training-shaped step in the formats a loader would hand over: uint8 RGB image,
+    uint8 alpha mask, int8 normal map (x127) — 7 bytes per pixel and view, pinned. Synthetic (band-limited noise)."""
+    gen = torch.Generator().manual_seed(seed)
+    H, W = wl.height, wl.width
+    out = []
+    for _ in range(n_views):
+        img = (torch.rand(3, H // 8 + 1, W // 8 + 1, generator=gen)[None])
+        img = torch.nn.functional.interpolate(img, size=(H, W), mode="bilinear", align_corners=False)[0]
+        nrm = torch.nn.functional.normalize(torch.randn(3, H // 8 + 1, W // 8 + 1, generator=gen), dim=0)[None]
+        nrm = torch.nn.functional.normalize(torch.nn.functional.interpolate(nrm, size=(H, W), mode="bilinear", align_corners=False)[0], dim=0)
+        yy, xx = torch.meshgrid(torch.linspace(-1, 1, H), torch.linspace(-1, 1, W), indexing="ij")
+        mask = ((xx * W / H) ** 2 + yy ** 2 < 0.95)[None]
+        out.append(((img * 255).round().to(torch.uint8).contiguous().pin_memory(),
+                    (mask.to(torch.uint8) * 255).contiguous().pin_memory(),
+                    (nrm * 127).round().to(torch.int8).contiguous().pin_memory()))
+    return out
+
+
+def run_e2e(args, wl, g, cams, bg, bucket, views, dev, world, sync_all, render_fn, streams):
+    """The step a user of the reference runs, through the public operators, with HOST inputs (train.py:147-149,
+    models/texture_gaussian3d.py:315-368 with the losses configs/texture_gaussian3d.yaml:77-88 enables): per view the
+    ground-truth image (uint8), the alpha mask (uint8) and the normal prior (int8) are copied from pinned host memory on
+    a copy stream (one slot per render stream + 1, so the copy of view i+1 runs under the render of view i), decoded on
+    the device, the render's losses (1-l)*L1 + l*(1-SSIM), L1(alpha), masked normal loss and bilateral normal smoothness
+    come from the fused loss kernels (texture_gs_b200.losses), backward, gradients into the bucket, all-reduce, and
+    the per-step loss is read back to the host. Forward-only workloads (retexture.py) read the rendered image back
+    instead. All copies are inside the timed region; the time is max(CUDA events, host wall clock)."""
     import torch.distributed as dist
-    from texture_gs_b200 import uv_tex_render
-    host = [c.cpu().pin_memory() for c in cot_dev]
-    bytes_view = sum(h.numel() * 4 for h in host) + (16 + 16 + 3) * 4
+    from texture_gs_b200 import invalidate_packed_cache
+    from texture_gs_b200.dist import render_views_accumulate
+    from texture_gs_b200.losses import geometry_losses, photometric_loss
+    bwd = wl.backward
+    H, W = wl.height, wl.width
+    lam, lam_alpha, lam_norm, lam_nsm = 0.2, 1.0, 0.1, 0.5          # configs/texture_gaussian3d.yaml:77-88
+    main = torch.cuda.current_stream(dev)
     copy_stream = torch.cuda.Stream(dev)
-    bufs = [[torch.empty_like(c) for c in cot_dev] for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    free = [torch.cuda.Event() for _ in range(2)]
+    nv = len(views)
     result_host = torch.zeros(1).pin_memory()
 
-    def upload(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(free[slot])
-            for d, h in zip(bufs[slot], host):
-                d.copy_(h, non_blocking=True)
-            ready[slot].record(copy_stream)
+    if not bwd:
+        # retexture.py-shaped: render, hand the 8-bit frame(s) to the host (it writes PNGs / feeds the viewer)
+        n_img = wl.renders_per_view
+        frames = [torch.empty(n_img, 3, H, W, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        h2d, d2h = (16 + 16 + 3) * 4 * nv, n_img * 3 * H * W * nv
 
-    from texture_gs_b200 import invalidate_packed_cache
+        def step():
+            invalidate_packed_cache()
+            for i, v in enumerate(views):
+                with torch.no_grad():
+                    pkg = render_fn(cams[v % len(cams)], g, None, bg)
+                    imgs = [pkg["render"]] + ([pkg["render_no_sh"]] if n_img == 2 else [])
+                    q = torch.stack([(im.clamp(0, 1) * 255).to(torch.uint8) for im in imgs])
+                done[i & 1].synchronize()                      # the pinned frame of two views ago has left the device
+                frames[i & 1].copy_(q, non_blocking=True)
+                done[i & 1].record(main)
+    else:
+        sup = make_supervision(wl, min(nv, 4) or 1)
+        nslots = streams + 1
+        slots = [[torch.empty_like(t, device=dev) for t in sup[0]] for _ in range(nslots)]
+        ready = [torch.cuda.Event() for _ in range(nslots)]
+        free = [torch.cuda.Event() for _ in range(nslots)]
+        h2d, d2h = (sum(t.numel() * t.element_size() for t in sup[0]) + (16 + 16 + 3) * 4) * nv, 4
+        total = torch.zeros(streams, device=dev)                       # one partial loss per render stream
 
-    primed = [False]      # view 0 of the NEXT step is uploaded while the last view of this step renders (loader prefetch)
+        def upload(i):
+            s = i % nslots
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[s])
+                for d, h in zip(slots[s], sup[i % len(sup)]):
+                    d.copy_(h, non_blocking=True)
+                ready[s].record(copy_stream)
 
-    def step():
-        invalidate_packed_cache()
-        bucket.zero()
-        total = torch.zeros((), device=dev)
-        main = torch.cuda.current_stream(dev)
-        if views and not primed[0]:
-            for s in range(2):
+        cur = [0]                                                      # slot of the view being rendered (host order)
+
+        def before_view(v, i):
+            cur[0] = i
+            if i + 1 < nv:
+                upload(i + 1)                                          # next view's supervision under this view's render
+            torch.cuda.current_stream(dev).wait_event(ready[i % nslots])
+
+        def loss_fn(pkg, v):
+            k = cur[0]
+            u8, m8, n8 = slots[k % nslots]
+            gt = u8.float().mul_(1.0 / 255.0)
+            gt_alpha = m8.float().mul_(1.0 / 255.0)
+            gt_norm = n8.float().mul_(1.0 / 127.0)
+            loss, _l1, _ls = photometric_loss(pkg["render"], gt, lam)
+            la, ln, lsm = geometry_losses(pkg["alpha"], pkg["norm"], gt_alpha, gt_norm, gt)
+            loss = loss + lam_alpha * la + lam_norm * ln + lam_nsm * lsm
+            total[k % streams] += loss.detach()
+            return loss
+
+        def after_view(v, i):
+            free[i % nslots].record(torch.cuda.current_stream(dev))
+
+        def step():
+            invalidate_packed_cache()
+            bucket.zero()
+            total.zero_()
+            for s in range(nslots):
                 free[s].record(main)
             upload(0)
-        nv = len(views)
-        for i, v in enumerate(views):
-            slot = i & 1
-            if i + 1 < nv:
-                upload((i + 1) & 1)
-            elif nv % 2 == 0:
-                upload(0)                      # next step's first view (slot 0 was released after view nv-2)
-            main.wait_event(ready[slot])
-            cam = cams[v % len(cams)]
-            with bucket.fused():
-                pkg = uv_tex_render(cam, g, None, bg)
-                outs = [pkg["render"], pkg["depth"], pkg["norm"], pkg["alpha"]]
-                with torch.no_grad():
-                    total += sum(torch.dot(o.detach().reshape(-1), c.reshape(-1)) for o, c in zip(outs, bufs[slot]))
-                torch.autograd.backward(outs, list(bufs[slot]))
-            free[slot].record(main)
-        primed[0] = nv > 0 and nv % 2 == 0
-        bucket.all_reduce()
-        result_host.copy_(total.reshape(1), non_blocking=True)
+            render_views_accumulate(render_fn, g, cams, None, views, bg, bucket=bucket, streams=streams, loss_fn=loss_fn,
+                                    before_view=before_view, after_view=after_view)
+            bucket.all_reduce()
+            result_host.copy_(total.sum().reshape(1), non_blocking=True)
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -459,14 +575,19 @@ def run_e2e(args, wl, g, cams, cot_dev, bg, bucket, views, dev, world, sync_all)
         step()
     e1.record()
     sync_all()
-    wall = time.perf_counter() - t0
-    ms = max(e0.elapsed_time(e1), wall * 1e3 * 0.0)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ev_ms = e0.elapsed_time(e1)
     if world > 1:
-        tms = torch.tensor([ms], device=dev)
+        tms = torch.tensor([ev_ms, wall_ms], device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
-    return {"value": args.views * args.steps / (ms / 1e3), "unit": "views/s", "h2d_bytes_per_step": bytes_view * len(views),
-            "d2h_bytes_per_step": 4, "ms_per_step": ms / args.steps, "result": float(result_host.item())}
+        ev_ms, wall_ms = float(tms[0].item()), float(tms[1].item())
+    ms = max(ev_ms, wall_ms)
+    return {"value": args.views * args.steps / (ms / 1e3), "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": ms / args.steps, "event_ms_per_step": ev_ms / args.steps, "host_wall_ms_per_step": wall_ms / args.steps,
+            "result": float(result_host.item()),
+            "what": ("render + uint8 frame(s) read back per view (retexture.py)" if not bwd else
+                     "uint8 image + uint8 mask + int8 normals H2D per view -> render -> fused losses (photometric, alpha, normal, "
+                     "normal smoothness) -> backward -> bucket all-reduce -> loss D2H per step")}
 
 
 if __name__ == "__main__":

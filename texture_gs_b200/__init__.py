@@ -3,7 +3,7 @@
 Public surface (mirrors what reference render/uv_tex_render.py and render/render.py use):
     GaussianRasterizationSettings, GaussianRasterizer, uv_tex_render, render
 """
-from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, invalidate_packed_cache,  # noqa: F401
+from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, invalidate_packed_cache, invalidate_settings_cache,  # noqa: F401
                          last_stats)
 from .render import render, uv_tex_render, uv_tex_render_dual, type2render_func  # noqa: F401
 

@@ -169,29 +169,58 @@ def _stream_pool(device: torch.device, n: int):
 
 
 def render_views_accumulate(render_fn, gaussians, cameras: Sequence, cotangents, view_ids: Iterable[int], bg,
-                            timer=None, bucket: Optional["GradBucket"] = None, streams: int = 1):
-    """Forward + backward of ``render_fn`` (``uv_tex_render``) for the given views with fixed dense
-    output cotangents; gradients accumulate into the leaves' ``.grad`` (i.e. the bucket) — from inside
-    the backward kernels when ``bucket`` is given (``bucket.fused()``), through autograd otherwise.
+                            timer=None, bucket: Optional["GradBucket"] = None, streams: int = 1, backward: bool = True,
+                            loss_fn=None, before_view=None, after_view=None):
+    """Forward (+ backward) of ``render_fn`` (``uv_tex_render``) for the given views; gradients accumulate into the
+    leaves' ``.grad`` (i.e. the bucket) — from inside the backward kernels when ``bucket`` is given
+    (``bucket.fused()``), through autograd otherwise.
 
-    ``streams`` > 1 (experimental; needs a bucket with as many replicas whose leaves are ALL the differentiable
-    inputs): view i runs on CUDA stream i mod ``streams`` and accumulates into that stream's replica, so the
-    latency-bound small kernels of one view (tile scan, scatter, sort) and the tails of its render kernels overlap
-    the render kernels of the next one. The packed texel copy is built once before the fork; the calling stream
-    joins all streams before returning, the replicas are folded by ``bucket.all_reduce()`` / ``reduce_replicas()``."""
+    What drives the backward: fixed dense output cotangents (``cotangents``: a 4-tuple for render / depth / norm /
+    alpha, or a callable view -> 4-tuple), or ``loss_fn(pkg, view) -> scalar`` (the training-shaped step: losses on
+    the rasterizer outputs, ``models/texture_gaussian3d.py:333-368``). ``backward=False`` renders only
+    (``retexture.py:18-37``). ``before_view(view, slot)`` / ``after_view(view, slot)`` run on the stream that renders
+    the view (stream waits / event records of a host-fed input pipeline); ``slot`` counts the views of this call.
+
+    ``streams`` > 1 (needs a bucket with as many replicas whose leaves are ALL the differentiable inputs when
+    ``backward``): view i runs on CUDA stream i mod ``streams`` and accumulates into that stream's replica, so the
+    latency-bound small kernels of one view (tile scan, scatter, sort) and the tails of its render kernels overlap the
+    render kernels of the next one (+9 % views/s at the headline size, profiles/r2_variants.md). The packed texel copy is
+    built once before the fork; the calling stream joins all streams before returning, the replicas are folded by
+    ``bucket.all_reduce()`` / ``reduce_replicas()``."""
     view_ids = list(view_ids)
-    if streams <= 1 or len(view_ids) <= 1:
-        for v in view_ids:
-            cam = cameras[v % len(cameras)]
-            cot = cotangents(v) if callable(cotangents) else cotangents
-            ctx = timer.view() if timer is not None else _null()
-            with ctx, (bucket.fused() if bucket is not None else _null()):
+
+    def one_view(slot, v, fused_ctx):
+        cam = cameras[v % len(cameras)]
+        ctx = timer.view(backward=backward) if timer is not None else _null()
+        with ctx, fused_ctx:
+            if before_view is not None:
+                before_view(v, slot)
+            if not backward:
+                with torch.no_grad():
+                    render_fn(cam, gaussians, None, bg)
+            else:
                 pkg = render_fn(cam, gaussians, None, bg)
-                torch.autograd.backward([pkg["render"], pkg["depth"], pkg["norm"], pkg["alpha"]], list(cot))
+                if loss_fn is not None:
+                    loss_fn(pkg, v).backward()
+                else:
+                    cot = cotangents(v) if callable(cotangents) else cotangents
+                    torch.autograd.backward([pkg["render"], pkg["depth"], pkg["norm"], pkg["alpha"]], list(cot))
+            if after_view is not None:
+                after_view(v, slot)
+
+    if streams <= 1 or len(view_ids) <= 1:
+        for i, v in enumerate(view_ids):
+            one_view(i, v, bucket.fused() if (bucket is not None and backward) else _null())
         return len(view_ids)
-    if bucket is None or len(bucket.flats) < streams:
-        raise ValueError("streams > 1 needs a GradBucket(..., replicas=streams): concurrent views must not share gradient buffers")
-    dev = bucket.flat.device
+    if backward:
+        if bucket is None or len(bucket.flats) < streams:
+            raise ValueError("streams > 1 needs a GradBucket(..., replicas=streams): concurrent views must not share gradient buffers")
+        # autograd would add the gradients of non-bucket leaves into ONE .grad tensor from several streams at once
+        for t in _differentiable_inputs(gaussians):
+            if t.requires_grad and (not t.is_leaf or bucket.storage_for(t) is None):
+                raise ValueError("streams > 1: every differentiable input of the render must be a leaf of the bucket "
+                                 "(activations computed outside it would be accumulated by autograd from several streams at once)")
+    dev = bucket.flat.device if bucket is not None else torch.device("cuda", torch.cuda.current_device())
     from .rasterizer import ensure_packed_texture
     tex = getattr(gaussians, "get_texture", None)
     if tex is not None:
@@ -202,15 +231,45 @@ def render_views_accumulate(render_fn, gaussians, cameras: Sequence, cotangents,
         s.wait_stream(main)
     for i, v in enumerate(view_ids):
         r = i % streams
-        cam = cameras[v % len(cameras)]
-        cot = cotangents(v) if callable(cotangents) else cotangents
-        ctx = timer.view() if timer is not None else _null()
-        with torch.cuda.stream(pool[r]), ctx, bucket.fused(replica=r):
-            pkg = render_fn(cam, gaussians, None, bg)
-            torch.autograd.backward([pkg["render"], pkg["depth"], pkg["norm"], pkg["alpha"]], list(cot))
+        with torch.cuda.stream(pool[r]):
+            one_view(i, v, bucket.fused(replica=r) if (bucket is not None and backward) else _null())
     for s in pool:
         main.wait_stream(s)
     return len(view_ids)
+
+
+def _differentiable_inputs(gaussians):
+    out = []
+    for name in ("get_xyz", "get_opacity", "get_scaling", "get_rotation", "get_shs", "get_texture", "get_uvs"):
+        t = getattr(gaussians, name, None)
+        if isinstance(t, torch.Tensor):
+            out.append(t)
+    return out
+
+
+def bind_to_gpu_numa_node(device: torch.device) -> Optional[int]:
+    """Restrict the calling process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that pinned host buffers
+    allocated afterwards are first-touched on that node and the host-to-device copies of a rank do not cross the
+    socket interconnect (round 1: eight ranks feeding from node 0 was what bent the end-to-end scaling curve).
+    Returns the node, or None when the topology cannot be read (nothing is changed then)."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
 
 
 class _null:

@@ -54,7 +54,9 @@ def _host_floats(t: torch.Tensor, n: int):
 
     The reference keeps these on the GPU (``utils/cameras.py:62-65``); reading them costs one
     device->host sync the first time a given tensor object is seen, afterwards the copy is served
-    from a cache keyed on object identity + in-place version counter."""
+    from a cache keyed on object identity + storage address + in-place version counter. Writes that bypass the
+    version counter (``t.data.copy_(...)``, raw-pointer updates from another library) are NOT seen: call
+    ``invalidate_settings_cache()`` after such a write (cameras are immutable in the reference, ``utils/cameras.py``)."""
     if not isinstance(t, torch.Tensor):
         vals = [float(v) for v in t]
         assert len(vals) == n
@@ -66,7 +68,7 @@ def _host_floats(t: torch.Tensor, n: int):
     key = id(t)
     with _host_cache_lock:
         hit = _host_cache.get(key)
-        if hit is not None and hit[0]() is t and hit[1] == t._version:
+        if hit is not None and hit[0]() is t and hit[1] == (t._version, t.data_ptr()):
             return hit[2]
     vals = t.detach().reshape(-1).to(torch.float32).cpu().tolist()
     assert len(vals) == n, f"expected {n} values, got {len(vals)}"
@@ -77,27 +79,33 @@ def _host_floats(t: torch.Tensor, n: int):
             ref = weakref.ref(t, lambda _r, k=key: _host_cache.pop(k, None))
         except TypeError:
             return vals
-        _host_cache[key] = (ref, t._version, vals)
+        _host_cache[key] = (ref, (t._version, t.data_ptr()), vals)
     return vals
 
 
 _capacity_hint: dict = {}          # (device index, P, H, W) -> pair capacity that last sufficed
-_pinned: dict = {}                 # device index -> (pinned int32[8], cuda event)
+_pinned: dict = {}                 # device index -> free list of (pinned int32[8], cuda event)
 _pinned_lock = threading.Lock()
 
 
-def _pinned_counters(dev_index: int):
+def _acquire_counters(dev_index: int):
+    """A private (pinned counter buffer, event) pair for ONE forward call: the lock only guards the free list, never a
+    wait, so forwards on different threads / streams of a device do not serialise on each other."""
     with _pinned_lock:
-        ent = _pinned.get(dev_index)
-        if ent is None:
-            buf = torch.zeros(8, dtype=torch.int32).pin_memory()
-            ev = torch.cuda.Event(enable_timing=False, blocking=False)
-            with torch.cuda.device(dev_index):
-                ev.record()          # torch creates the cudaEvent_t lazily; force it so .cuda_event is valid
-                ev.synchronize()
-            ent = (buf, ev)
-            _pinned[dev_index] = ent
-        return ent
+        free = _pinned.setdefault(dev_index, [])
+        if free:
+            return free.pop()
+    buf = torch.zeros(8, dtype=torch.int32).pin_memory()
+    ev = torch.cuda.Event(enable_timing=False, blocking=False)
+    with torch.cuda.device(dev_index):
+        ev.record()          # torch creates the cudaEvent_t lazily; force it so .cuda_event is valid
+        ev.synchronize()
+    return buf, ev
+
+
+def _release_counters(dev_index: int, ent) -> None:
+    with _pinned_lock:
+        _pinned.setdefault(dev_index, []).append(ent)
 
 
 # Packed (6,R,R,4) copy of a texture, cached per texture tensor object + in-place version: the
@@ -108,7 +116,15 @@ _packed_cache: dict = {}
 
 
 def invalidate_packed_cache():
+    """Forget every packed texel copy. Needed after a write to a texture that does not bump its version counter
+    (``texture.data.clamp_()``, a raw-pointer update); in-place ops and optimizer steps are seen without it."""
     _packed_cache.clear()
+
+
+def invalidate_settings_cache():
+    """Forget the host copies of camera matrices / campos / bg (see ``_host_floats``)."""
+    with _host_cache_lock:
+        _host_cache.clear()
 
 
 def _packed_texture(lib, texture_arg: torch.Tensor, tex: torch.Tensor, stream: int) -> torch.Tensor:
@@ -282,14 +298,14 @@ class _RasterizeGaussians(torch.autograd.Function):
                 a.out_image_nosh = _ptr(image_nosh)
             key = (dev.index, P, H, W)
             cap = _capacity_hint.get(key, max(1 << 16, 8 * P))
-            pinned, event = _pinned_counters(dev.index)
+            pinned, event = ent = _acquire_counters(dev.index)
             gs, bs, is_ = C.c_size_t(), C.c_size_t(), C.c_size_t()
             for _attempt in range(8):
                 L.check(lib.texgs_workspace_sizes(C.byref(a), cap, C.byref(gs), C.byref(bs), C.byref(is_)), "texgs_workspace_sizes")
                 geom = torch.empty(max(gs.value, 256), device=dev, dtype=torch.uint8)
                 binw = torch.empty(max(bs.value, 256), device=dev, dtype=torch.uint8)
                 imgw = torch.empty(max(is_.value, 256), device=dev, dtype=torch.uint8)
-                with _pinned_lock:
+                try:
                     L.check(lib.texgs_forward(C.byref(a), _ptr(geom), _ptr(binw), cap, _ptr(imgw), _ptr(image), _ptr(depth),
                                               _ptr(norm), _ptr(alpha), _ptr(radii), _ptr(extra) if ex is not None else None,
                                               C.c_void_p(pinned.data_ptr()), C.c_void_p(event.cuda_event), C.c_void_p(stream)),
@@ -297,11 +313,16 @@ class _RasterizeGaussians(torch.autograd.Function):
                     # waits only until the tile scan is done (early in the stream), not for the render
                     event.synchronize()
                     K, V, overflow, maxlen, blo, bhi = (int(x) & 0xFFFFFFFF for x in pinned[:6].tolist())
+                except BaseException:
+                    ent = None           # state of the pair unknown: drop it instead of returning it to the free list
+                    raise
                 if not overflow:
                     break
                 cap = int(K * 1.25) + 4096
             else:
                 raise L.TexgsError("pair capacity kept overflowing")
+            if ent is not None:
+                _release_counters(dev.index, ent)
             _capacity_hint[key] = max(cap, _capacity_hint.get(key, 0)) if not overflow else cap
             _last_stats.v = RasterStats(K, V, maxlen, blo | (bhi << 32), cap)
 
