@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--workload", default="cfg2_500k_1080p")
     ap.add_argument("--views", type=int, default=VIEWS_PER_STEP)
     ap.add_argument("--streams", type=int, default=DEFAULT_STREAMS,
-                    help="CUDA streams per rank that render alternate views concurrently (one gradient-bucket replica each)")
+                    help="CUDA streams per rank that render alternate views concurrently (they share the gradient bucket: atomic adds)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-pass", action="store_true", help="skip the single-stream per-kernel timing pass (roofline.per_kernel)")
@@ -335,7 +335,7 @@ def main():
     bg = torch.zeros(3, device=dev)
     # retexture.py renders every view twice (with SH, then active_sh_degree = 0): one dual render here
     render_fn = uv_tex_render_dual if (not bwd and wl.renders_per_view == 2) else uv_tex_render
-    bucket = GradBucket({k: v for k, v in g.tensors().items()}, replicas=streams) if bwd else None
+    bucket = GradBucket({k: v for k, v in g.tensors().items()}) if bwd else None
     views = shard_views(args.views, world, rank)
 
     def sync_all():

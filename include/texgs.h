@@ -36,6 +36,14 @@ extern "C" {
 
 #define TEXGS_FLAG_PREFILTERED 1u   /* GaussianRasterizationSettings.prefiltered (uv_tex_render.py:36) */
 #define TEXGS_FLAG_DEBUG       2u   /* GaussianRasterizationSettings.debug       (uv_tex_render.py:37) */
+/* Spec switches for the conventions the reference tree does not pin: the
+ * defaults are the flags cleared. Set, the textured render takes a cold instantiation of the render kernels that
+ * evaluates the alternative; needs the packed texel copy (texture_rgba) and, in the backward, dL_dtexture_rgba.      */
+#define TEXGS_FLAG_SEAMLESS_CUBE      4u   /* E11-alt: bilinear taps beyond a face edge come from the adjacent face (GL seamless /
+                                              nvdiffrast boundary_mode='cube', models/uv_map_gaussian3d.py:259) instead of clamp-to-edge */
+#define TEXGS_FLAG_DEPTH_INTERSECTION 8u   /* E7-alt: the depth output blends z of the ray-disc intersection instead of z of the centre */
+#define TEXGS_FLAG_STOPGRAD_DELTA     16u  /* E13-alt: no gradient through the intersection offset Delta (to means3D / rotations) */
+#define TEXGS_FLAG_SPEC_MASK          28u
 
 /* colour source of a splat */
 #define TEXGS_MODE_TEXTURE 0   /* diff_gauss_uv_tex: C0*cube(uv + J*delta) + SH_rest + 0.5, clamped at 0 */

@@ -87,7 +87,7 @@ class RasterSettings(NamedTuple):
 class Switches(NamedTuple):
     """Named spec choices that the reference does not pin (SURVEY §8c [EXT])."""
     depth_of_intersection: bool = False   # E7: False -> z of the Gaussian centre
-    seamless_cube: bool = False           # E11: False -> clamp-to-edge inside the face (only mode built)
+    seamless_cube: bool = False           # E11: False -> clamp-to-edge inside the face; True -> taps beyond a face edge come from the adjacent face
     stopgrad_delta: bool = False          # E13: False -> full derivative through the intersection
     normalize_quat: bool = False          # upstream CUDA uses the quaternion as given
 
@@ -282,8 +282,37 @@ def cube_face_coords(u: torch.Tensor):
     return face, sx_num * inv, sy_num * inv
 
 
-def cube_sample(texture: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
-    """Bilinear fetch with clamp-to-edge inside the face. texture (6,R,R,C), u (...,3)."""
+# E11-alt (seamless): which texel lies one step beyond an edge of a face. CUBE_WRAP[f][side] = (f', xcode, ycode), side
+# 0: x < 0, 1: x >= R, 2: y < 0, 3: y >= R; codes 0 -> 0, 1 -> R-1, 2 -> k, 3 -> R-1-k with k the position along the edge.
+# Derived from the reference's face table (NVDIFFREC/util.py:94-101) by tools/gen_cube_wrap.py; re-derived in the tests.
+CUBE_WRAP = [[(4, 1, 2), (5, 0, 2), (2, 1, 3), (3, 1, 2)], [(5, 1, 2), (4, 0, 2), (2, 0, 2), (3, 0, 3)],
+             [(1, 2, 0), (0, 3, 0), (5, 3, 0), (4, 2, 0)], [(1, 3, 1), (0, 2, 1), (4, 2, 1), (5, 3, 1)],
+             [(1, 1, 2), (0, 0, 2), (2, 2, 1), (3, 2, 0)], [(0, 1, 2), (1, 0, 2), (2, 3, 0), (3, 3, 1)]]
+
+
+def cube_wrap_tap(face: torch.Tensor, x: torch.Tensor, y: torch.Tensor, R: int):
+    """Texel (face, y, x) with x, y in [-1, R] -> the texel that holds it under seamless filtering: itself inside the
+    face, else the texel of the adjacent face across that edge at the same place along the edge. A tap beyond a CORNER
+    (x and y both outside) is first clamped in y, i.e. it takes the x-neighbour's corner texel."""
+    tab = torch.tensor(CUBE_WRAP, dtype=torch.int64, device=face.device)          # (6,4,3)
+    xo = (x < 0) | (x >= R)
+    yo = (y < 0) | (y >= R)
+    y = torch.where(xo & yo, y.clamp(0, R - 1), y)
+    yo = yo & ~xo
+    side = torch.where(xo, torch.where(x < 0, 0, 1), torch.where(y < 0, 2, 3))
+    k = torch.where(xo, y, x).clamp(0, R - 1)
+    ent = tab[face, side]                                                          # (...,3)
+    vals = torch.stack([torch.zeros_like(k), torch.full_like(k, R - 1), k, R - 1 - k], dim=-1)
+    xn = torch.gather(vals, -1, ent[..., 1:2]).squeeze(-1)
+    yn = torch.gather(vals, -1, ent[..., 2:3]).squeeze(-1)
+    out = xo | yo
+    return torch.where(out, ent[..., 0], face), torch.where(out, yn, y), torch.where(out, xn, x)
+
+
+def cube_sample(texture: torch.Tensor, u: torch.Tensor, seamless: bool = False) -> torch.Tensor:
+    """Bilinear fetch, texture (6,R,R,C), u (...,3). ``seamless=False`` (E11): clamp-to-edge inside the face.
+    ``seamless=True`` (E11-alt, what nvdiffrast's boundary_mode='cube' does for the reference's visuals,
+    models/uv_map_gaussian3d.py:259): taps beyond an edge are fetched from the adjacent face (``cube_wrap_tap``)."""
     R = texture.shape[1]
     face, sx, sy = cube_face_coords(u)
     fx = (sx + 1.0) * (0.5 * R) - 0.5
@@ -292,14 +321,18 @@ def cube_sample(texture: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
     y0f = torch.floor(fy.detach())
     wx = fx - x0f
     wy = fy - y0f
-    x0 = x0f.to(torch.int64)
-    y0 = y0f.to(torch.int64)
-    x0c, x1c = x0.clamp(0, R - 1), (x0 + 1).clamp(0, R - 1)
-    y0c, y1c = y0.clamp(0, R - 1), (y0 + 1).clamp(0, R - 1)
-    t00 = texture[face, y0c, x0c]
-    t01 = texture[face, y0c, x1c]
-    t10 = texture[face, y1c, x0c]
-    t11 = texture[face, y1c, x1c]
+    x0 = x0f.to(torch.int64).clamp(-1, R - 1)
+    y0 = y0f.to(torch.int64).clamp(-1, R - 1)
+    if seamless:
+        taps = [texture[cube_wrap_tap(face, x0 + dx, y0 + dy, R)] for dy in (0, 1) for dx in (0, 1)]
+        t00, t01, t10, t11 = taps
+    else:
+        x0c, x1c = x0.clamp(0, R - 1), (x0 + 1).clamp(0, R - 1)
+        y0c, y1c = y0.clamp(0, R - 1), (y0 + 1).clamp(0, R - 1)
+        t00 = texture[face, y0c, x0c]
+        t01 = texture[face, y0c, x1c]
+        t10 = texture[face, y1c, x0c]
+        t11 = texture[face, y1c, x1c]
     wx, wy = wx[..., None], wy[..., None]
     top = t00 + wx * (t01 - t00)
     bot = t10 + wx * (t11 - t10)
@@ -325,7 +358,6 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
     ``sh_degree = 0`` — max(0, C0*tex + 0.5) — into a second image, returned as
     ``aux["image_no_sh"]``; identical to a second call with ``sh_degree=0`` (what the reference does
     at models/texture_gaussian3d.py:375-389,505-511)."""
-    assert not sw.seamless_cube, "only clamp-to-edge is implemented"
     st = settings
     dt, dev = means3D.dtype, means3D.device
     H, W = int(st.image_height), int(st.image_width)
@@ -495,7 +527,7 @@ def rasterize(means3D, means2D, shs, opacities, scales, rotations, uvs, gradient
                     # the intersection amplifies rounding by 1 / cos(angle(n, d)): so does the margin
                     near = torch.minimum((fxd - fxd.round()).abs(), (fyd - fyd.round()).abs()) * cosang.clamp_min(GRAZING_COS) < TEXEL_TIE * Rt
                     texel_edge[pix[near]] = True
-                tex = cube_sample(texture, u)                                 # E11
+                tex = cube_sample(texture, u, sw.seamless_cube)               # E11
                 col_pre = C0 * tex + pre["csh"][g] + 0.5
                 with torch.no_grad():
                     texel_edge[pix[(col_pre.abs() < CLAMP_TIE).any(dim=-1)]] = True   # clamp mask decided by rounding

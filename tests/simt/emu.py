@@ -24,7 +24,7 @@ HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
 CSRC = ROOT / "texture_gs_b200" / "csrc"
 BUILD = HERE / "_build"
-DYN_SMEM = (("unsigned char", "smem_raw"), ("float", "prebwd_smem"))     # every `extern __shared__` array of the sources
+DYN_SMEM = (("unsigned char", "smem_raw"), ("float", "prebwd_smem"), ("float", "prefwd_smem"))     # every `extern __shared__` array of the sources
 GXX_FLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes",
              "-fno-extern-tls-init",     # `extern __shared__` arrays are plain extern thread_local arrays: no init wrapper
              "-fno-gnu-unique", "-Wl,-Bsymbolic"]   # two builds (different -D flags) loaded into one process keep their own state
@@ -203,7 +203,7 @@ def rasterize(*, means3D, opacities, scales=None, rotations=None, shs=None, colo
               texture=None, extra_attrs=None, cov3Ds_precomp=None, H, W, tanfovx, tanfovy, bg, scale_modifier=1.0,
               viewmatrix, projmatrix, campos, sh_degree, cotangents=None, dual_no_sh=False, packed_texture=True,
               packed_texture_grad=True, debug=False, cot_nosh=None, cot_extra=None, pair_capacity=None, lib=None,
-              accumulate_onto=None):
+              accumulate_onto=None, spec_flags=0):
     """Forward (+ backward when ``cotangents`` = (dL/dimage, dL/ddepth, dL/dnorm, dL/dalpha) is given) of the emulated
     library on CPU tensors; the call sequence is the one of texture_gs_b200/rasterizer.py.
 
@@ -217,7 +217,7 @@ def rasterize(*, means3D, opacities, scales=None, rotations=None, shs=None, colo
     a = L.TexgsFwdArgs()
     a.P, a.M, a.sh_degree, a.E = P, (0 if sh is None else sh.shape[1]), int(sh_degree), (0 if ex is None else ex.shape[1])
     a.H, a.W, a.R, a.mode = int(H), int(W), (0 if tex is None else tex.shape[1]), mode
-    a.flags = (L.FLAG_DEBUG if debug else 0)
+    a.flags = (L.FLAG_DEBUG if debug else 0) | int(spec_flags)
     a.tanfovx, a.tanfovy, a.scale_modifier = float(tanfovx), float(tanfovy), float(scale_modifier)
     a.viewmatrix = (C.c_float * 16)(*viewmatrix.reshape(-1).tolist())
     a.projmatrix = (C.c_float * 16)(*projmatrix.reshape(-1).tolist())

@@ -118,7 +118,7 @@ inline void make_context(Context* c, char* stack, size_t bytes, void (*entry)())
 constexpr size_t kStackBytes = 160 * 1024;
 constexpr size_t kDynSmemMax = 232448;      // 227 KB, the sm_100 opt-in maximum
 
-struct PendingCopy { void* dst; const void* src; unsigned bytes; };
+struct PendingCopy { void* dst; const void* src; unsigned bytes; int op = 0; };   // op 0: copy, 1: add.f32 (bulk reduction)
 
 struct Fiber {
     Context ctx;
@@ -132,6 +132,9 @@ struct Fiber {
     // cp.async (LDGSTS): copies of the group being built and the committed groups still in flight, oldest first
     std::vector<PendingCopy> cp_open;
     std::deque<std::vector<PendingCopy>> cp_groups;
+    // cp.async.bulk shared -> global (bulk_group completion): same bookkeeping
+    std::vector<PendingCopy> bulk_open;
+    std::deque<std::vector<PendingCopy>> bulk_groups;
 };
 
 struct Warp {
@@ -223,6 +226,7 @@ inline void fiber_main() {
     Fiber* f = g.cur;
     f->done = true;
     if (!f->cp_open.empty() || !f->cp_groups.empty()) fail("a thread exited with cp.async copies in flight (no cp.async.wait_group covered them)");
+    if (!f->bulk_open.empty() || !f->bulk_groups.empty()) fail("a thread exited with bulk stores in flight (no cp.async.bulk.wait_group covered them): their shared-memory source dies with the block");
     Warp& w = g.warps[f->warp];
     w.exited |= 1u << f->lane;
     if (w.arrived && (w.mask_in & (1u << f->lane))) fail("a lane exited while its warp waits for it in a *_sync collective");
@@ -502,6 +506,36 @@ template <int N> inline void cp_async_wait() {
         f->cp_groups.pop_front();
     }
 }
+// cp.async.bulk shared::cta -> global and its reducing form (cp.reduce.async.bulk ... .add.f32), bulk_group completion.
+// Late as legal: the data leaves shared memory at the wait that covers the group; eager: at issue.
+inline void simt_apply_bulk(const simt::PendingCopy& c) {
+    if (c.op == 0) { memcpy(c.dst, c.src, c.bytes); return; }
+    float* d = static_cast<float*>(c.dst);
+    const float* s = static_cast<const float*>(c.src);
+    for (unsigned i = 0; i < c.bytes / 4; ++i) d[i] += s[i];
+}
+inline void simt_bulk_issue(void* gdst, const void* ssrc, unsigned bytes, int op) {
+    if ((bytes & 15u) || ((uintptr_t)gdst & 15u) || ((uintptr_t)ssrc & 15u)) simt::fail("cp.async.bulk (shared -> global): size / addresses must be multiples of 16");
+    simt::Global& g = simt::G();
+    const simt::PendingCopy c{gdst, ssrc, bytes, op};
+    if (g.eager_copies) simt_apply_bulk(c);
+    else g.cur->bulk_open.push_back(c);
+}
+inline void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) { simt_bulk_issue(gdst, ssrc, bytes, 0); }
+inline void bulk_reduce_add_f32(float* gdst, const float* ssrc, uint32_t bytes) { simt_bulk_issue(gdst, ssrc, bytes, 1); }
+inline void bulk_commit() {
+    simt::Fiber* f = simt::G().cur;
+    f->bulk_groups.push_back(std::move(f->bulk_open));
+    f->bulk_open.clear();
+}
+template <int N> inline void bulk_wait() {
+    simt::Fiber* f = simt::G().cur;
+    while ((int)f->bulk_groups.size() > N) {
+        for (const simt::PendingCopy& c : f->bulk_groups.front()) simt_apply_bulk(c);
+        f->bulk_groups.pop_front();
+    }
+}
+inline void fence_proxy_async_smem() {}
 template <class T> inline void ldg256(const T* p, float (&o)[8]) {
     if ((uintptr_t)p & 31u) simt::fail("256-bit load: address must be 32-byte aligned");
     memcpy(o, p, 32);
@@ -551,7 +585,7 @@ inline void run_block() {
         Fiber& f = g.fibers[t];
         f.lin = (int)t; f.lane = (int)(t & 31); f.warp = (int)(t >> 5);
         f.tid = uint3{t % g.bdim.x, (t / g.bdim.x) % g.bdim.y, t / (g.bdim.x * g.bdim.y)};
-        f.done = false; f.wait_addr = nullptr; f.cp_open.clear(); f.cp_groups.clear();
+        f.done = false; f.wait_addr = nullptr; f.cp_open.clear(); f.cp_groups.clear(); f.bulk_open.clear(); f.bulk_groups.clear();
         g.warps[f.warp].exist |= 1u << f.lane;
         make_context(&f.ctx, g.stacks[t], kStackBytes, &fiber_main);
     }

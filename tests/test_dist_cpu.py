@@ -36,49 +36,38 @@ def test_bucket_slices_are_the_grads_and_accumulate_in_place():
     assert float(bk.flat.abs().sum()) == 0 and a.grad.data_ptr() == ptr_a
 
 
-def test_bucket_replicas_are_private_buffers_folded_into_the_grad_storage():
-    """One replica per CUDA stream of render_views_accumulate(..., streams=n): ``storage_for`` hands out the buffer of the
-    replica named by the enclosing ``fused(replica=r)``, ``reduce_replicas`` / ``all_reduce`` fold them into replica 0."""
+def test_fused_block_hands_out_the_bucket_storage_of_exact_leaves_only():
+    """Inside ``bucket.fused()`` the rasterizer asks ``storage_for`` where to accumulate: the padded (6,R,R,4) storage for
+    the texture, plain storage for the others, nothing for tensors that are not the bucket's leaves. One buffer for every
+    stream (the kernels' accumulations are atomic), so there is nothing to fold before the all-reduce."""
     from texture_gs_b200.dist import current_fused_bucket
     tex = torch.randn(6, 4, 4, 3, requires_grad=True)
     x = torch.randn(9, 3, requires_grad=True)
     other = torch.randn(9, 3, requires_grad=True)
-    bk = GradBucket({"texture": tex, "xyz": x}, replicas=3)
-    assert len(bk.flats) == 3 and bk.flats[0] is bk.flat and tex.grad.shape == tex.shape
-    ptrs = set()
-    for r in range(3):
-        with bk.fused(replica=r):
-            assert current_fused_bucket() is bk
-            buf, padded = bk.storage_for(tex)
-            assert padded and buf.shape == (6, 4, 4, 4)
-            buf[..., :3] += float(r + 1)
-            bx, px = bk.storage_for(x)
-            assert not px
-            bx += 10.0 * (r + 1)
-            ptrs.add(buf.data_ptr())
-            assert bk.storage_for(other) is None and bk.storage_for(x.detach()) is None       # only the exact leaf tensors
-    assert len(ptrs) == 3 and current_fused_bucket() is None
-    assert bk.storage_for(tex)[0].data_ptr() == bk.flat.data_ptr() + 4 * bk.offsets["texture"][0]   # outside fused(): replica 0
-    assert torch.allclose(tex.grad, torch.full_like(tex, 1.0))                                  # .grad is replica 0 only so far
-    bk.all_reduce()                                                                             # no process group: just folds
-    assert torch.allclose(tex.grad, torch.full_like(tex, 6.0)) and torch.allclose(x.grad, torch.full_like(x, 60.0))
-    assert all(float(f.abs().max()) == 0.0 for f in bk.flats[1:])
+    bk = GradBucket({"texture": tex, "xyz": x})
+    assert tex.grad.shape == tex.shape and current_fused_bucket() is None
+    with bk.fused():
+        assert current_fused_bucket() is bk
+        buf, padded = bk.storage_for(tex)
+        assert padded and buf.shape == (6, 4, 4, 4)
+        buf[..., :3] += 2.0
+        bx, px = bk.storage_for(x)
+        assert not px
+        bx += 10.0
+        assert bk.storage_for(other) is None and bk.storage_for(x.detach()) is None       # only the exact leaf tensors
+    assert current_fused_bucket() is None
+    assert bk.storage_for(tex)[0].data_ptr() == bk.flat.data_ptr() + 4 * bk.offsets["texture"][0]
+    assert bk.all_reduce() is None                                                              # no process group
+    assert torch.allclose(tex.grad, torch.full_like(tex, 2.0)) and torch.allclose(x.grad, torch.full_like(x, 10.0))
     pad = bk.flat[bk.offsets["texture"][0]: bk.offsets["texture"][0] + bk.offsets["texture"][1]].view(-1, 4)[:, 3]
     assert float(pad.abs().max()) == 0.0
     bk.zero()
-    assert all(float(f.abs().max()) == 0.0 for f in bk.flats)
-    with pytest.raises(ValueError):
-        with bk.fused(replica=3):
-            pass
+    assert float(bk.flat.abs().max()) == 0.0
 
 
-def test_multi_stream_rendering_needs_one_bucket_replica_per_stream():
+def test_multi_stream_rendering_needs_a_bucket():
     from texture_gs_b200.dist import render_views_accumulate
-    x = torch.randn(4, 3, requires_grad=True)
-    bk = GradBucket({"xyz": x}, replicas=1)
-    with pytest.raises(ValueError, match="replicas"):
-        render_views_accumulate(None, None, [None], None, [0, 1, 2], None, bucket=bk, streams=2)
-    with pytest.raises(ValueError, match="replicas"):
+    with pytest.raises(ValueError, match="GradBucket"):
         render_views_accumulate(None, None, [None], None, [0, 1, 2], None, bucket=None, streams=2)
 
 

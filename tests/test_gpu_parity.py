@@ -520,7 +520,11 @@ def test_heterogeneous_scales_with_very_large_splats():
     _check_forward(gg, cam, bg=(0.2, 0.2, 0.2), max_amb=0.6)
     # needle-shaped splats hundreds of pixels long: the conic-inverse backward (d conic -> d cov2D, divided by
     # det^2) cancels badly in fp32; the covariance gradients get 3e-3 here (measured 1.0e-3 / 6.9e-4), the rest 1e-3
-    _check_backward(gg, cam, bg=(0.2, 0.2, 0.2), max_flag=0.7, uv_tol=5e-3, tol_over={"rotation": 3e-3, "scaling": 3e-3})
+    # splats hundreds of pixels wide: their gradients are sums of ~1e5 per-pixel terms of both signs accumulated with fp32
+    # atomics, and the covariance chain amplifies the rounding (the max-norm tolerance of scale / rotation is 3e-3 here for the
+    # same reason): the per-row criterion is applied at 1e-2 on 99 % of the rows instead of 1e-3 on 99.9 %
+    _check_backward(gg, cam, bg=(0.2, 0.2, 0.2), max_flag=0.7, uv_tol=5e-3, tol_over={"rotation": 3e-3, "scaling": 3e-3}, rows_rtol=1e-2,
+                    rows_frac=1e-2)
 
 
 def test_capacity_overflow_retry_is_transparent():
@@ -586,3 +590,49 @@ def test_full_size_properties(n, w, h, r):
     # only approximately, so check the weaker bound image <= 0.6*alpha + bg*(1-alpha) + tol)
     bound = 0.6 * alpha + bg[:, None, None] * (1 - alpha) + 1e-3
     assert bool((img.detach() <= bound + 1e-3).all())
+
+
+@pytest.mark.parametrize("name", ["seamless_cube", "depth_of_intersection", "stopgrad_delta", "all"])
+def test_spec_switch_instantiations_match_the_oracle_with_the_same_switch(name):
+    """SURVEY §8c E11-alt / E7-alt / E13-alt on the GPU: ``with spec_switches(...)`` selects the cold ALT instantiations of
+    the render kernels (TEXGS_FLAG_SEAMLESS_CUBE / DEPTH_INTERSECTION / STOPGRAD_DELTA); each reproduces the oracle run
+    with the same switch, forward and backward (the backward runs OUTSIDE the with-block: it must remember the
+    forward's switches), and differs from the default convention."""
+    from oracle.raster_ref import Switches
+    sw = Switches(True, True, True) if name == "all" else Switches(**{name: True})
+    g = sphere_shell_scene(1200, 8, sh_degree=2, seed=21, tex_seed=22)
+    cam = orbit_cameras(1, 96, 64, seed=23)[0]
+    _check_forward(g, cam, bg=(0.1, 0.3, 0.2), max_amb=0.3, sw=sw)
+    _check_backward(g, cam, bg=(0.1, 0.3, 0.2), uv_tol=5e-3, max_flag=0.35, sw=sw)
+    cot = output_cotangents(64, 96, seed=3)
+    a, _, ga = run_cuda(g, cam, bg=(0.1, 0.3, 0.2), cot=cot)
+    b, _, gb = run_cuda(g, cam, bg=(0.1, 0.3, 0.2), cot=cot, sw=sw)
+    if sw.seamless_cube:
+        assert float((a[0] - b[0]).abs().max()) > 1e-3 and rel_err(gb["texture"], ga["texture"]) > 1e-3
+    if sw.depth_of_intersection:
+        assert float((a[1] - b[1]).abs().max()) > 1e-4
+    if sw.stopgrad_delta and not sw.depth_of_intersection:
+        assert torch.equal(a[0], b[0]) and rel_err(gb["xyz"], ga["xyz"]) > 1e-3 and rel_err(gb["uvs"], ga["uvs"]) < 1e-5
+
+
+def test_spec_switches_through_the_dual_render_and_a_larger_scene():
+    """The ALT instantiations with the dual image, at a size where most footprints are interior (the switch must not
+    disturb them): seamless + depth-of-intersection forward against the oracle run twice."""
+    from oracle.raster_ref import Switches
+    from texture_gs_b200 import spec_switches, uv_tex_render_dual
+    sw = Switches(depth_of_intersection=True, seamless_cube=True)
+    g = sphere_shell_scene(4000, 64, sh_degree=3, seed=31, tex_seed=32)
+    cam = orbit_cameras(1, 160, 96, seed=33)[0]
+    ref, aux, _ = run_oracle(g, cam, bg=(0.2, 0.1, 0.0), sw=sw)
+    gg = g.to(device="cuda", dtype=torch.float32)
+    with spec_switches(seamless_cube=True, depth_of_intersection=True):
+        pkg = uv_tex_render_dual(cam.to("cuda"), gg, None, torch.tensor([0.2, 0.1, 0.0], device="cuda"))
+    got = [pkg[k].detach().cpu() for k in ("render", "depth", "norm", "alpha")]
+    rep = compare_images(got, ref[:4], aux["ambiguous"])
+    for n in ("image", "depth", "norm", "alpha"):
+        assert rep[n]["max_clear"] <= ABS_TOL * (3.0 if n == "depth" else 1.0), (n, rep[n])
+    gz = g.to(device="cpu")
+    gz.active_sh_degree = 0
+    ref0, aux0, _ = run_oracle(gz, cam, bg=(0.2, 0.1, 0.0), sw=sw)
+    d = (pkg["render_no_sh"].detach().cpu() - ref0[0]).abs().amax(dim=0)
+    assert float(d[~(aux["ambiguous"] | aux0["ambiguous"])].max()) <= ABS_TOL

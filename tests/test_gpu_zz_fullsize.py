@@ -18,8 +18,9 @@ def test_full_size_forward_and_backward_against_the_c_oracle(n, w, h, r, view):
         pytest.fail("GPU tests selected (-m gpu) but no CUDA device is visible")
     g = sphere_shell_scene(n, r, sh_degree=3, seed=0)
     cam = orbit_cameras(32, w, h, seed=1)[view]
-    # R = 2048: a tap lands within TEXEL_TIE * R = 4e-3 texels of a texel boundary in a good part of the pixels
-    check_against_c_oracle(g, cam, bg=(0.1, 0.2, 0.3), max_flag=0.6)
+    # R = 2048: a tap lands within TEXEL_TIE * R = 4e-3 texels of a texel boundary in a good part of the pixels: the oracle
+    # flags 8.9 % of the pixels for values and 29.9 % for gradients (tests/golden/flag_fractions.json); caps = 1.2 x that
+    check_against_c_oracle(g, cam, bg=(0.1, 0.2, 0.3), max_flag=0.36, max_amb=0.11)
 
 
 @pytest.mark.parametrize("name,n,w,h,r", [("configs[1] stand-in", 300_000, 800, 600, 1024), ("configs[4]", 1_000_000, 3840, 2160, 4096)])
@@ -33,4 +34,5 @@ def test_forward_only_baseline_configs_against_the_c_oracle(name, n, w, h, r):
         pytest.fail("GPU tests selected (-m gpu) but no CUDA device is visible")
     g = sphere_shell_scene(n, r, sh_degree=3, seed=0)
     cam = orbit_cameras(32, w, h, seed=1)[3]
-    check_against_c_oracle(g, cam, bg=(0.0, 0.0, 0.0), max_flag=0.7, backward=False)
+    # observed: 13.0 % / 31.1 % (configs[1]) and 8.0 % / 38.2 % (configs[4]) of the pixels flagged for values / gradients
+    check_against_c_oracle(g, cam, bg=(0.0, 0.0, 0.0), max_flag=0.46, max_amb=0.16, backward=False)

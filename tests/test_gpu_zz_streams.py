@@ -20,15 +20,14 @@ def test_two_stream_accumulation_equals_single_stream():
     res = []
     for streams in (1, 2, 3):
         g = sphere_shell_scene(3000, 32, sh_degree=3, seed=10, device="cuda")
-        bk = GradBucket(g.tensors(), replicas=streams)
-        for _ in range(2):                           # second pass: replicas were cleared by the fold, caches are warm
+        bk = GradBucket(g.tensors())
+        for _ in range(2):                           # second pass: caches are warm
             invalidate_packed_cache()
             bk.zero()
             render_views_accumulate(uv_tex_render, g, cams, cot, range(5), bg, bucket=bk, streams=streams)
             bk.all_reduce()
         torch.cuda.synchronize()
         res.append({k: v.detach().clone() for k, v in bk.grads().items()})
-        assert all(float(f.abs().max()) == 0.0 for f in bk.flats[1:])
     for other in res[1:]:
         for k in res[0]:
             assert rel_err(other[k], res[0][k]) < 1e-5, k

@@ -422,3 +422,62 @@ def test_rotation_and_covariance_layout_equal_the_reference_code():
     So = Lo @ Lo.transpose(1, 2)
     ours = torch.stack([So[:, 0, 0], So[:, 0, 1], So[:, 0, 2], So[:, 1, 1], So[:, 1, 2], So[:, 2, 2]], dim=-1)
     assert torch.allclose(cov6.double(), ours, rtol=1e-5, atol=1e-7)
+
+
+def test_cube_wrap_table_is_derived_from_the_reference_face_table_and_is_the_same_in_the_kernels():
+    """E11-alt (seamless cube filtering): the neighbour table is re-derived with exact rational arithmetic from the face
+    table of NVDIFFREC/util.py:94-101 (tools/gen_cube_wrap.py) and must equal the oracle's constant and the one compiled
+    into the kernels (texgs_common.cuh); crossing an edge and coming back lands on the edge texel one started from."""
+    import re
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root / "tools"))
+    import gen_cube_wrap
+    from oracle.raster_ref import CUBE_WRAP, cube_wrap_tap
+    derived = gen_cube_wrap.derive(16)
+    assert [[tuple(e) for e in row] for row in CUBE_WRAP] == derived
+    src = (root / "texture_gs_b200" / "csrc" / "texgs_common.cuh").read_text()
+    body = src[src.index("CUBE_WRAP_TABLE[6][4][3] = {"):]
+    nums = [int(x) for x in re.findall(r"\d+", body[body.index("= {"):body.index("};")])]
+    assert nums == [v for row in derived for e in row for v in e]
+    R = 8
+    for f in range(6):
+        for side in range(4):
+            for k in range(R):
+                x, y = {0: (-1, k), 1: (R, k), 2: (k, -1), 3: (k, R)}[side]
+                nf, ny, nx = (int(v) for v in cube_wrap_tap(torch.tensor(f), torch.tensor(x), torch.tensor(y), R))
+                assert nf != f and 0 <= nx < R and 0 <= ny < R and (nx in (0, R - 1) or ny in (0, R - 1))
+                # step back over the same edge from the neighbour: the original face's edge texel
+                found = False
+                for bx, by in ((nx - 1, ny), (nx + 1, ny), (nx, ny - 1), (nx, ny + 1)):
+                    if 0 <= bx < R and 0 <= by < R:
+                        continue
+                    bf, byy, bxx = (int(v) for v in cube_wrap_tap(torch.tensor(nf), torch.tensor(bx), torch.tensor(by), R))
+                    ex, ey = {0: (0, k), 1: (R - 1, k), 2: (k, 0), 3: (k, R - 1)}[side]
+                    found = found or (bf, bxx, byy) == (f, ex, ey)
+                assert found, (f, side, k)
+
+
+def test_seamless_cube_sampling_is_continuous_across_face_edges_where_clamping_jumps():
+    """Directions a hair on either side of a face edge: clamp-to-edge (E11) samples two unrelated edge texels, seamless
+    filtering (E11-alt) blends the same two texels from both sides."""
+    from oracle.raster_ref import cube_sample
+    gen = torch.Generator().manual_seed(0)
+    tex = torch.rand(6, 8, 8, 3, generator=gen, dtype=torch.float64)
+    eps = 1e-7
+    jumps_clamp, jumps_seam = [], []
+    for t in torch.linspace(-0.8, 0.8, 13, dtype=torch.float64):     # away from the corners (there a tap is clamped in y first)
+        for a, b in ((torch.stack([torch.tensor(1.0, dtype=torch.float64), t, torch.tensor(1.0 - eps, dtype=torch.float64)]),
+                      torch.stack([torch.tensor(1.0 - eps, dtype=torch.float64), t, torch.tensor(1.0, dtype=torch.float64)])),
+                     (torch.stack([t, torch.tensor(1.0, dtype=torch.float64), torch.tensor(-1.0 + eps, dtype=torch.float64)]),
+                      torch.stack([t, torch.tensor(1.0 - eps, dtype=torch.float64), torch.tensor(-1.0, dtype=torch.float64)]))):
+            jumps_clamp.append(float((cube_sample(tex, a[None]) - cube_sample(tex, b[None])).abs().max()))
+            jumps_seam.append(float((cube_sample(tex, a[None], True) - cube_sample(tex, b[None], True)).abs().max()))
+    assert max(jumps_seam) < 1e-5 and max(jumps_clamp) > 0.1
+    # inside a face both conventions agree exactly
+    u = torch.nn.functional.normalize(torch.randn(2000, 3, generator=gen, dtype=torch.float64), dim=1)
+    from oracle.raster_ref import cube_face_coords
+    _, sx, sy = cube_face_coords(u)
+    inner = (sx.abs() < 1 - 1.01 / 8) & (sy.abs() < 1 - 1.01 / 8)
+    assert torch.equal(cube_sample(tex, u[inner]), cube_sample(tex, u[inner], True)) and int(inner.sum()) > 500

@@ -551,3 +551,39 @@ def test_emulated_kernels_under_random_warp_interleavings(emu, seed):
         assert torch.equal(x, y)
     for k in a.grads:
         assert rel_err(b.grads[k], a.grads[k]) < 1e-5, k
+
+
+@pytest.mark.parametrize("name", ["seamless_cube", "depth_of_intersection", "stopgrad_delta", "all"])
+def test_emulated_spec_switch_instantiations_match_the_oracle_with_the_same_switch(emu, name):
+    """the conventions the reference tree does not pin are run-time flags of the
+    library (TEXGS_FLAG_SEAMLESS_CUBE / DEPTH_INTERSECTION / STOPGRAD_DELTA -> cold ALT instantiations of the render
+    kernels); each must reproduce the oracle run with the same switch, forward and backward, and must actually change
+    the result against the default (a switch that does nothing would pass the parity test vacuously). Low texture
+    resolution on purpose: many bilinear footprints straddle a face edge."""
+    from oracle.raster_ref import Switches
+    sw = Switches(True, True, True) if name == "all" else Switches(**{name: True})
+    g = sphere_shell_scene(1200, 8, sh_degree=2, seed=21, tex_seed=22)
+    cam = orbit_cameras(1, 96, 64, seed=23)[0]
+    check_forward(g, cam, bg=(0.1, 0.3, 0.2), runner=run_emu, max_amb=0.3, sw=sw)
+    errs = check_backward(g, cam, bg=(0.1, 0.3, 0.2), runner=run_emu, uv_tol=5e-3, max_flag=0.35, sw=sw)
+    assert set(errs) >= {"xyz", "rotation", "uvs", "texture"}
+    # non-vacuous: the default convention gives a different picture / different gradients
+    cot = output_cotangents(64, 96, seed=3)
+    a, _, ga = run_emu(g, cam, bg=(0.1, 0.3, 0.2), cot=cot)
+    b, _, gb = run_emu(g, cam, bg=(0.1, 0.3, 0.2), cot=cot, sw=sw)
+    if sw.seamless_cube:
+        assert float((a[0] - b[0]).abs().max()) > 1e-3 and rel_err(gb["texture"], ga["texture"]) > 1e-3
+    if sw.depth_of_intersection:
+        assert float((a[1] - b[1]).abs().max()) > 1e-4
+    if sw.stopgrad_delta and not sw.depth_of_intersection:
+        assert torch.equal(a[0], b[0]) and rel_err(gb["xyz"], ga["xyz"]) > 1e-3 and rel_err(gb["uvs"], ga["uvs"]) < 1e-6
+
+
+def test_spec_switches_need_the_packed_texel_paths(emu):
+    """The ALT instantiations exist for the packed texel copy / padded texel gradient only; the plain layouts refuse."""
+    g = sphere_shell_scene(50, 8, sh_degree=0, seed=1)
+    cam = orbit_cameras(1, 32, 32, seed=2)[0]
+    t = g.tensors()
+    with pytest.raises(Exception, match="packed texel copy"):
+        emu.rasterize(means3D=t["xyz"], opacities=t["opacity"], scales=t["scaling"], rotations=t["rotation"], shs=t["shs"], uvs=t["uvs"],
+                      gradient_uvs=t["grad_uvs"], texture=t["texture"], packed_texture=False, spec_flags=4, **_cam_kw(cam, (0, 0, 0), 0))

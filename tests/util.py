@@ -12,6 +12,53 @@ from texture_gs_b200.scene import SyntheticGaussians, orbit_cameras, output_cota
 ABS_TOL = 1e-4      # BASELINE.json north_star: 1e-4 abs fp32 per pixel
 GRAD_RTOL = 1e-3    # BASELINE.json north_star: grads within 1e-3 rel
 
+# ---------------------------------------------------------------------------------------------
+# Budget of flagged pixels. The oracle flags pixels whose value / gradient fp32 arithmetic cannot pin;
+# how many it flags depends on the scene and the oracle alone, so the fraction every test observes is recorded once
+# (tests/golden/flag_fractions.json, written by tools/record_flag_fractions.py) and a test fails when its fraction
+# grows beyond 1.2 x the recorded one (+ 0.5 % of the pixels): a change that makes more of the image "ill-conditioned"
+# cannot hide behind a generous fixed cap.
+# ---------------------------------------------------------------------------------------------
+import json as _json
+import os as _os
+from pathlib import Path as _Path
+
+_FLAG_FILE = _Path(__file__).resolve().parent / "golden" / "flag_fractions.json"
+_FLAG_TABLE = _json.loads(_FLAG_FILE.read_text()) if _FLAG_FILE.exists() else {}
+_FLAG_RECORD = _os.environ.get("TEXGS_RECORD_FLAGS")          # path: record instead of checking
+_flag_seen: dict = {}
+
+
+def flag_budget(kind: str, value: float, hard_cap: float) -> bool:
+    """Assert ``value`` (a flagged-pixel fraction) against its recorded budget; ``hard_cap`` applies as well. In record
+    mode the value is stored and True is returned: the calling helper then returns without running any kernels."""
+    test = _os.environ.get("PYTEST_CURRENT_TEST", "?").split(" (")[0].replace("tests/", "")
+    n = _flag_seen.get((test, kind), 0)
+    _flag_seen[(test, kind)] = n + 1
+    key = f"{test}|{kind}|{n}"
+    if _FLAG_RECORD:
+        tab = _json.loads(_Path(_FLAG_RECORD).read_text()) if _Path(_FLAG_RECORD).exists() else {}
+        tab[key] = round(float(value), 5)
+        _Path(_FLAG_RECORD).write_text(_json.dumps(tab, indent=0, sort_keys=True))
+        return True
+    assert value <= hard_cap, (key, value, hard_cap)
+    rec = _FLAG_TABLE.get(key)
+    if rec is not None:
+        assert value <= 1.2 * rec + 0.005, f"{key}: flagged fraction {value:.4f} exceeds 1.2 x the recorded {rec:.4f}"
+    return False
+
+
+def rows_within(a: torch.Tensor, b: torch.Tensor, rtol: float = GRAD_RTOL) -> float:
+    """Per-element criterion next to the max-norm one: the fraction of ROWS (one row per Gaussian / texel) all of whose
+    entries satisfy |a - b| <= rtol * |b| + rtol * median|b| (median over the non-zero entries of b). The max-norm error
+    is set by the largest entry of half a million rows; this one also looks at the small ones."""
+    rows = (-1, b.shape[-1]) if b.dim() == 4 else (b.shape[0], -1)        # (6,R,R,3) texture: a row is a texel
+    a, b = a.double().reshape(*rows), b.double().reshape(*rows)
+    nz = b.abs()[b != 0]
+    med = float(nz.median()) if nz.numel() else 0.0
+    ok = ((a - b).abs() <= rtol * b.abs() + rtol * med).all(dim=1)
+    return float(ok.double().mean())
+
 
 def oracle_settings(cam, sh_degree, dtype=torch.float32, bg=(0.0, 0.0, 0.0), device="cpu", scale_modifier=1.0):
     return RasterSettings(
@@ -44,18 +91,25 @@ def run_oracle(g: SyntheticGaussians, cam, bg=(0.0, 0.0, 0.0), cot=None, dtype=t
     return (image.detach(), depth.detach(), norm.detach(), alpha.detach(), radii), aux, grads
 
 
-def run_cuda(g: SyntheticGaussians, cam, bg=(0.0, 0.0, 0.0), cot=None, debug=False, device="cuda", scale_modifier=1.0):
-    """Forward (+ backward) through the product operator ``uv_tex_render`` (-> C-ABI)."""
-    from texture_gs_b200 import uv_tex_render, last_stats
+def _spec_kw(sw):
+    """oracle Switches -> keyword arguments of texture_gs_b200.spec_switches (same names)."""
+    return {} if sw is None else dict(seamless_cube=sw.seamless_cube, depth_of_intersection=sw.depth_of_intersection,
+                                      stopgrad_delta=sw.stopgrad_delta)
+
+
+def run_cuda(g: SyntheticGaussians, cam, bg=(0.0, 0.0, 0.0), cot=None, debug=False, device="cuda", scale_modifier=1.0, sw=None):
+    """Forward (+ backward) through the product operator ``uv_tex_render`` (-> C-ABI); ``sw``: spec switches."""
+    from texture_gs_b200 import uv_tex_render, last_stats, spec_switches
     gg = g.to(device=device, dtype=torch.float32, requires_grad=cot is not None)
     cam_d = cam.to(device)
     bg_t = torch.tensor(bg, dtype=torch.float32, device=device)
-    pkg = uv_tex_render(cam_d, gg, None, bg_t, scaling_modifier=scale_modifier, debug=debug)
+    with spec_switches(**_spec_kw(sw)):
+        pkg = uv_tex_render(cam_d, gg, None, bg_t, scaling_modifier=scale_modifier, debug=debug)
     grads = None
     if cot is not None:
         c = [x.to(device) for x in cot]
         L = (pkg["render"] * c[0]).sum() + (pkg["depth"] * c[1]).sum() + (pkg["norm"] * c[2]).sum() + (pkg["alpha"] * c[3]).sum()
-        L.backward()
+        L.backward()                 # outside the block on purpose: the backward must remember the forward's switches
         t = gg.tensors()
         grads = {k: (v.grad.detach().cpu() if v is not None and v.grad is not None else None) for k, v in t.items()}
         grads["means2D"] = pkg["viewspace_points"].grad.detach().cpu()
@@ -85,13 +139,16 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return float((a - b).abs().max()) / den
 
 
-def run_emu(g: SyntheticGaussians, cam, bg=(0.0, 0.0, 0.0), cot=None, debug=False, scale_modifier=1.0, **kw):
+def run_emu(g: SyntheticGaussians, cam, bg=(0.0, 0.0, 0.0), cot=None, debug=False, scale_modifier=1.0, sw=None, **kw):
     """Same contract as ``run_cuda``, but the kernels run on the HOST: the CUDA sources compiled with g++ on top of
     the SIMT emulator of tests/simt (test infrastructure; lets the CPU-only suite execute the real kernel source)."""
     from collections import namedtuple
     from simt import emu
     gg = g.to(device="cpu", dtype=torch.float32)
     t = gg.tensors()
+    if sw is not None:
+        from texture_gs_b200.rasterizer import SpecSwitches
+        kw = dict(kw, spec_flags=SpecSwitches(**_spec_kw(sw)).flags())
     res = emu.rasterize(means3D=t["xyz"], opacities=t["opacity"], scales=t["scaling"], rotations=t["rotation"], shs=t["shs"],
                         uvs=t["uvs"], gradient_uvs=t["grad_uvs"], texture=t["texture"], H=cam.image_height, W=cam.image_width,
                         tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5), bg=bg, scale_modifier=scale_modifier,
@@ -109,12 +166,15 @@ def run_emu(g: SyntheticGaussians, cam, bg=(0.0, 0.0, 0.0), cot=None, debug=Fals
     return (res.image, res.depth, res.norm, res.alpha, res.radii), stats, grads
 
 
-def check_forward(g, cam, bg=(0.0, 0.0, 0.0), max_amb=0.15, scale_modifier=1.0, runner=None):
+def check_forward(g, cam, bg=(0.0, 0.0, 0.0), max_amb=0.15, scale_modifier=1.0, runner=None, sw=None):
     """Outputs of ``runner`` (run_cuda by default) against the fp32 oracle: BASELINE's 1e-4 abs on the pixels the oracle
     does not flag, radii and visible count exact, pair count between the contributing and the spec's pairs."""
     runner = runner or run_cuda
-    ref, aux, _ = run_oracle(g, cam, bg=bg, scale_modifier=scale_modifier)
-    got, stats, _ = runner(g, cam, bg=bg, scale_modifier=scale_modifier)
+    skw = {} if sw is None else {"sw": sw}
+    ref, aux, _ = run_oracle(g, cam, bg=bg, scale_modifier=scale_modifier, **skw)
+    if flag_budget("ambiguous", float(aux["ambiguous"].double().mean()), max_amb):
+        return {}
+    got, stats, _ = runner(g, cam, bg=bg, scale_modifier=scale_modifier, **skw)
     rep = compare_images(got[:4], ref[:4], aux["ambiguous"])
     print(rep, stats)
     # the binning drops (tile, Gaussian) pairs that provably cannot reach alpha >= 1/255 on the tile:
@@ -122,7 +182,6 @@ def check_forward(g, cam, bg=(0.0, 0.0, 0.0), max_amb=0.15, scale_modifier=1.0, 
     assert int(aux["pair_contributes"].sum()) <= stats.num_pairs <= aux["num_pairs"], (stats, aux["num_pairs"])
     assert stats.num_visible == aux["num_visible"]
     assert (got[4] != ref[4]).sum() == 0, "radii differ"
-    assert rep["ambiguous_frac"] <= max_amb
     for n in ("image", "depth", "norm", "alpha"):
         assert rep[n]["max_clear"] <= ABS_TOL * (3.0 if n == "depth" else 1.0), (n, rep[n])   # depth is O(2.5)-scaled
         assert rep[n]["frac_over"] <= 2e-3, (n, rep[n])
@@ -131,7 +190,7 @@ def check_forward(g, cam, bg=(0.0, 0.0, 0.0), max_amb=0.15, scale_modifier=1.0, 
 
 
 def check_backward(g, cam, bg=(0.0, 0.0, 0.0), seed=3, uv_tol=GRAD_RTOL, max_flag=0.2, scale_modifier=1.0, tol_over=None,
-                   runner=None):
+                   runner=None, sw=None, rows_rtol=GRAD_RTOL, rows_frac=1e-3):
     """Gradients of L = sum(out * cot) with the cotangents zeroed on the pixels the oracle flags as
     ill-conditioned in fp32 (a blend decision within a few ulp of its threshold, a ray grazing a
     disc: t = n.m/n.d with |cos| < GRAZING_COS — there the fp32 ORACLE differs from the fp64 oracle
@@ -144,14 +203,17 @@ def check_backward(g, cam, bg=(0.0, 0.0, 0.0), seed=3, uv_tol=GRAD_RTOL, max_fla
     error the reference fp32 arithmetic (the oracle run in fp32) itself shows."""
     runner = runner or run_cuda
     kw = dict(scale_modifier=scale_modifier)
+    if sw is not None:
+        kw["sw"] = sw
     _, aux, _ = run_oracle(g, cam, bg=bg, **kw)
     keep = (~aux["grad_ambiguous"]).float()       # + texel-boundary ties: the bilinear derivative jumps there
-    assert float(1 - keep.mean()) <= max_flag     # low-res scenes: big discs near the silhouette cover many pixels
+    if flag_budget("grad_flagged", float(1 - keep.mean()), max_flag):     # low-res scenes: big discs near the silhouette cover many pixels
+        return {}
     cot = [c * keep for c in output_cotangents(cam.image_height, cam.image_width, seed=seed)]
     _, _, g64 = run_oracle(g, cam, bg=bg, cot=cot, dtype=torch.float64, **kw)
     _, _, g32 = run_oracle(g, cam, bg=bg, cot=cot, **kw)
     _, _, ggot = runner(g, cam, bg=bg, cot=cot, **kw)
-    errs = {}
+    errs, rows = {}, {}
     for k, r in g64.items():
         if r is None:
             continue
@@ -160,10 +222,15 @@ def check_backward(g, cam, bg=(0.0, 0.0, 0.0), seed=3, uv_tol=GRAD_RTOL, max_fla
         if k == "means2D":
             c, r, o = c[:, :2], r[:, :2], o[:, :2]
         errs[k] = (rel_err(c.reshape(r.shape), r), rel_err(o.reshape(r.shape), r))
+        rows[k] = (rows_within(c.reshape(r.shape), r, rows_rtol), rows_within(o.reshape(r.shape), r, rows_rtol))
     print({k: ("%.2e" % a, "%.2e" % b) for k, (a, b) in errs.items()})
+    print("rows within %.0e (kernels, fp32 oracle):" % rows_rtol, {k: ("%.5f" % a, "%.5f" % b) for k, (a, b) in rows.items()})
     for k, (e_got, e_o32) in errs.items():
         tol = uv_tol if k == "uvs" else (tol_over or {}).get(k, GRAD_RTOL)
         assert e_got <= max(tol, 3.0 * e_o32), (k, e_got, e_o32)
+        # per-element: at most 0.1 % of the rows off, or no more than 3 x as many as the fp32 oracle itself has off
+        bad, bad32 = 1.0 - rows[k][0], 1.0 - rows[k][1]
+        assert bad <= max(rows_frac, 3.0 * bad32), (k, "rows off", bad, bad32)
     return errs
 
 
@@ -179,7 +246,7 @@ def run_c_oracle(g: SyntheticGaussians, cam, bg=(0.0, 0.0, 0.0), cot=None, dtype
 
 
 def check_against_c_oracle(g, cam, bg=(0.0, 0.0, 0.0), runner=None, seed=3, max_flag=0.5, scale_modifier=1.0, uv_tol=GRAD_RTOL,
-                           backward=True):
+                           backward=True, max_amb=0.2):
     """Forward and backward of ``runner`` (run_cuda by default) against the C oracle — the direct comparison that the
     torch oracle is too slow for at full size. Truth = the float64 build; the float32 build measures what fp32
     arithmetic can deliver:  outputs 1e-4 abs on the pixels the oracle does not flag (3e-4 for the O(2.5) depth),
@@ -195,7 +262,8 @@ def check_against_c_oracle(g, cam, bg=(0.0, 0.0, 0.0), runner=None, seed=3, max_
     aux = dict(aux, ambiguous=aux["ambiguous"] | aux32["ambiguous"], grad_ambiguous=aux["grad_ambiguous"] | aux32["grad_ambiguous"])
     keep = (~aux["grad_ambiguous"]).double()
     flagged = float(1 - keep.mean())
-    assert flagged <= max_flag, flagged
+    if flag_budget("ambiguous", float(aux["ambiguous"].double().mean()), max_amb) | flag_budget("grad_flagged", flagged, max_flag):
+        return {}, {}
     cot = [c.double() * keep for c in output_cotangents(H, W, seed=seed)] if backward else None
     if backward:
         _, _, g64 = run_c_oracle(g, cam, bg=bg, cot=cot, scale_modifier=scale_modifier)
@@ -223,7 +291,7 @@ def check_against_c_oracle(g, cam, bg=(0.0, 0.0, 0.0), runner=None, seed=3, max_
         assert rep[n]["max_clear"] <= max(tol, FP32_SLACK * rep32[n]["max_clear"]), (n, rep[n], rep32[n])
         assert n_over <= FP32_SLACK * n_over32 + int(5e-5 * npix) + 0.5, (n, n_over, n_over32)
         assert rep[n]["frac_over"] <= max(5e-3, 3.0 * rep32[n]["frac_over"]), (n, rep[n], rep32[n])   # flagged pixels included
-    errs = {}
+    errs, rows = {}, {}
     if not backward:
         return rep, errs
     for k, r in g64.items():
@@ -233,7 +301,11 @@ def check_against_c_oracle(g, cam, bg=(0.0, 0.0, 0.0), runner=None, seed=3, max_
         if k == "means2D":
             c, r, o = c[:, :2], r[:, :2], o[:, :2]
         errs[k] = (rel_err(c.reshape(r.shape), r), rel_err(o.reshape(r.shape), r))
+        rows[k] = (rows_within(c.reshape(r.shape), r), rows_within(o.reshape(r.shape), r))
     print({k: ("%.2e" % a, "%.2e" % b) for k, (a, b) in errs.items()})
+    print("rows within 1e-3 (kernels, c32):", {k: ("%.5f" % a, "%.5f" % b) for k, (a, b) in rows.items()})
     for k, (e_got, e_c32) in errs.items():
         assert e_got <= max(uv_tol if k == "uvs" else GRAD_RTOL, FP32_SLACK * e_c32), (k, e_got, e_c32)
+        bad, bad32 = 1.0 - rows[k][0], 1.0 - rows[k][1]
+        assert bad <= max(1e-3, FP32_SLACK * bad32), (k, "rows off", bad, bad32)
     return rep, errs

@@ -4,8 +4,8 @@ Public surface (mirrors what reference render/uv_tex_render.py and render/render
     GaussianRasterizationSettings, GaussianRasterizer, uv_tex_render, render
 """
 from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, invalidate_packed_cache, invalidate_settings_cache,  # noqa: F401
-                         last_stats)
+                         last_stats, SpecSwitches, spec_switches)
 from .render import render, uv_tex_render, uv_tex_render_dual, type2render_func  # noqa: F401
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "uv_tex_render", "uv_tex_render_dual", "render", "type2render_func",
-           "last_stats"]
+           "last_stats", "SpecSwitches", "spec_switches"]

@@ -16,6 +16,9 @@ LIB_PATH = Path(os.environ["TEXGS_LIB"]).resolve() if os.environ.get("TEXGS_LIB"
 TEXGS_ABI_VERSION = 2
 FLAG_PREFILTERED = 1
 FLAG_DEBUG = 2
+FLAG_SEAMLESS_CUBE = 4        # spec switches (include/texgs.h): E11-alt, E7-alt, E13-alt
+FLAG_DEPTH_INTERSECTION = 8
+FLAG_STOPGRAD_DELTA = 16
 MODE_TEXTURE, MODE_SH, MODE_PRECOMP = 0, 1, 2
 BWD_ACC_FLOATS = 24
 ACC_MEANS3D, ACC_MEANS2D, ACC_OPACITY, ACC_SCALES, ACC_ROTATIONS, ACC_SHS, ACC_COLORS, ACC_UVS = 1, 2, 4, 8, 16, 32, 64, 128

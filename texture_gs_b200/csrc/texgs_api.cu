@@ -156,20 +156,24 @@ int ensure_render_smem() {
     if (done_for_device == dev) return 0;
     const int bytes = (int)TEXGS_RENDER_SMEM;
 #define TEXGS_SET_SMEM(k) TEXGS_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
-    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, true, false>));
-    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, false, false>));
-    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, true, true>));
-    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, false, true>));
-    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_SH, false, false>));
-    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, true, false>));
-    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, false, false>));
-    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, true, false>));
-    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, false, false>));
-    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, true, true>));
-    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, false, true>));
-    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, true, true>));
-    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, false, true>));
-    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_SH, false, false, false>));
+    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, true, false, false>));
+    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, false, false, false>));
+    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, true, true, false>));
+    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, false, true, false>));
+    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_SH, false, false, false>));
+    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, true, false, true>));      // spec-switch (ALT) instantiations
+    TEXGS_SET_SMEM((texgs_render_fwd<TEXGS_MODE_TEXTURE, true, true, true>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, true, false, true>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, true, true, true>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, true, false, false>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, false, false, false>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, true, false, false>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, false, false, false>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, true, true, false>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, true, false, true, false>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, true, true, false>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_TEXTURE, false, false, true, false>));
+    TEXGS_SET_SMEM((texgs_render_bwd<TEXGS_MODE_SH, false, false, false, false>));
 #undef TEXGS_SET_SMEM
     done_for_device = dev;
     return 0;
@@ -225,7 +229,11 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
     TEXGS_CUDA_TRY(cudaMemsetAsync((char*)bin_ws + L.l.bin_counters, 0, L.bin_zero_bytes, stream));
     const int gblocks = (p.P + 255) / 256;
     if (p.P > 0) {
-        texgs_preprocess_fwd<<<gblocks, 256, 0, stream>>>(p, out_radii);
+        const size_t smem = prefwd_smem_bytes(p.M, p.mode, p.shs);      // SH rows of every warp staged by one bulk copy each
+        if (smem > 200 * 1024) return fail(TEXGS_E_INVALID, "too many SH coefficients per Gaussian for the staged forward");
+        if (smem > 48 * 1024)
+            TEXGS_CUDA_TRY(cudaFuncSetAttribute(texgs_preprocess_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        texgs_preprocess_fwd<<<gblocks, 256, smem, stream>>>(p, out_radii);
         TEXGS_KERNEL_CHECK("texgs_preprocess_fwd", debug, stream);
     }
     TEXGS_EV(a, TEXGS_EV_FWD_PREPROCESS, stream);
@@ -249,12 +257,16 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
     if (int rc = ensure_render_smem()) return rc;
     {
         const bool t4 = p.texture_rgba != nullptr, dual = p.out_image_nosh != nullptr;
-#define TEXGS_LAUNCH_FWD(M, T4, DU) texgs_render_fwd<M, T4, DU><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha)
-        if (p.mode != TEXGS_MODE_TEXTURE) TEXGS_LAUNCH_FWD(TEXGS_MODE_SH, false, false);
-        else if (t4 && dual)  TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, true, true);
-        else if (t4)          TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, true, false);
-        else if (dual)        TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, false, true);
-        else                  TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, false, false);
+#define TEXGS_LAUNCH_FWD(M, T4, DU, AL) texgs_render_fwd<M, T4, DU, AL><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha)
+        const bool alt = p.mode == TEXGS_MODE_TEXTURE && (p.flags & TEXGS_FLAG_SPEC_MASK) != 0u;
+        if (alt && !t4) return fail(TEXGS_E_INVALID, "the spec-switch flags need the packed texel copy (texture_rgba)");
+        if (p.mode != TEXGS_MODE_TEXTURE) TEXGS_LAUNCH_FWD(TEXGS_MODE_SH, false, false, false);
+        else if (alt && dual) TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, true, true, true);
+        else if (alt)         TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, true, false, true);
+        else if (t4 && dual)  TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, true, true, false);
+        else if (t4)          TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, true, false, false);
+        else if (dual)        TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, false, true, false);
+        else                  TEXGS_LAUNCH_FWD(TEXGS_MODE_TEXTURE, false, false, false);
 #undef TEXGS_LAUNCH_FWD
     }
     TEXGS_KERNEL_CHECK("texgs_render_fwd", debug, stream);
@@ -300,17 +312,21 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
     if (p.mode == TEXGS_MODE_TEXTURE) {
         const bool rd4 = p.texture_rgba != nullptr, wr4 = b->dL_dtexture_rgba != nullptr, dual = p.out_image_nosh != nullptr;
         float* dt = wr4 ? b->dL_dtexture_rgba : b->dL_dtexture;
-#define TEXGS_LAUNCH_BWD(R4, W4, DU) texgs_render_bwd<TEXGS_MODE_TEXTURE, R4, W4, DU><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, dt)
-        if (dual) {
-            if (rd4 && wr4) TEXGS_LAUNCH_BWD(true, true, true); else if (rd4) TEXGS_LAUNCH_BWD(true, false, true);
-            else if (wr4) TEXGS_LAUNCH_BWD(false, true, true); else TEXGS_LAUNCH_BWD(false, false, true);
+#define TEXGS_LAUNCH_BWD(R4, W4, DU, AL) texgs_render_bwd<TEXGS_MODE_TEXTURE, R4, W4, DU, AL><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, dt)
+        const bool alt = (p.flags & TEXGS_FLAG_SPEC_MASK) != 0u;
+        if (alt && (!rd4 || (dt && !wr4))) return fail(TEXGS_E_INVALID, "the spec-switch flags need texture_rgba and the padded texel gradient (dL_dtexture_rgba)");
+        if (alt) {
+            if (dual) TEXGS_LAUNCH_BWD(true, true, true, true); else TEXGS_LAUNCH_BWD(true, true, false, true);
+        } else if (dual) {
+            if (rd4 && wr4) TEXGS_LAUNCH_BWD(true, true, true, false); else if (rd4) TEXGS_LAUNCH_BWD(true, false, true, false);
+            else if (wr4) TEXGS_LAUNCH_BWD(false, true, true, false); else TEXGS_LAUNCH_BWD(false, false, true, false);
         } else {
-            if (rd4 && wr4) TEXGS_LAUNCH_BWD(true, true, false); else if (rd4) TEXGS_LAUNCH_BWD(true, false, false);
-            else if (wr4) TEXGS_LAUNCH_BWD(false, true, false); else TEXGS_LAUNCH_BWD(false, false, false);
+            if (rd4 && wr4) TEXGS_LAUNCH_BWD(true, true, false, false); else if (rd4) TEXGS_LAUNCH_BWD(true, false, false, false);
+            else if (wr4) TEXGS_LAUNCH_BWD(false, true, false, false); else TEXGS_LAUNCH_BWD(false, false, false, false);
         }
 #undef TEXGS_LAUNCH_BWD
     } else {
-        texgs_render_bwd<TEXGS_MODE_SH, false, false, false><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, nullptr);
+        texgs_render_bwd<TEXGS_MODE_SH, false, false, false, false><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, nullptr);
     }
     TEXGS_KERNEL_CHECK("texgs_render_bwd", debug, stream);
     if (p.E > 0 && p.P > 0) {

@@ -221,6 +221,54 @@ __device__ __forceinline__ Bilerp cube_bilerp(const CubeCoord& c, int R) {
     return b;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Spec switch E11-alt (TEXGS_FLAG_SEAMLESS_CUBE): seamless filtering. A tap one texel beyond an edge of the face is the
+// texel of the adjacent face that touches the same edge at the same place — what GL_TEXTURE_CUBE_MAP_SEAMLESS /
+// nvdiffrast boundary_mode='cube' (the reference's own visuals, models/uv_map_gaussian3d.py:259) fetch there.
+// CUBE_WRAP_TABLE[f][side] = {f', xcode, ycode}; side 0: x < 0, 1: x >= R, 2: y < 0, 3: y >= R; codes 0 -> 0, 1 -> R-1,
+// 2 -> k, 3 -> R-1-k (k = position along the edge). Derived from the reference's face table by tools/gen_cube_wrap.py.
+// Cold path: only the kernels' ALT instantiations reference it.
+// ---------------------------------------------------------------------------------------------
+__device__ __constant__ unsigned char CUBE_WRAP_TABLE[6][4][3] = {
+    {{4, 1, 2}, {5, 0, 2}, {2, 1, 3}, {3, 1, 2}}, {{5, 1, 2}, {4, 0, 2}, {2, 0, 2}, {3, 0, 3}},
+    {{1, 2, 0}, {0, 3, 0}, {5, 3, 0}, {4, 2, 0}}, {{1, 3, 1}, {0, 2, 1}, {4, 2, 1}, {5, 3, 1}},
+    {{1, 1, 2}, {0, 0, 2}, {2, 2, 1}, {3, 2, 0}}, {{0, 1, 2}, {1, 0, 2}, {2, 3, 0}, {3, 3, 1}}};
+
+// texel index of tap (face, x, y), x and y in [-1, R]; a tap beyond a corner is clamped in y first
+__device__ __noinline__ int cube_wrap_tap(int face, int x, int y, int R) {
+    const bool xo = (x < 0) || (x >= R);
+    bool yo = (y < 0) || (y >= R);
+    if (xo && yo) { y = min(max(y, 0), R - 1); yo = false; }
+    if (xo || yo) {
+        const int side = xo ? (x < 0 ? 0 : 1) : (y < 0 ? 2 : 3);
+        const int k = min(max(xo ? y : x, 0), R - 1);
+        const unsigned char* e = CUBE_WRAP_TABLE[face][side];
+        const int vals[4] = {0, R - 1, k, R - 1 - k};
+        face = e[0]; x = vals[e[1]]; y = vals[e[2]];
+    }
+    return (face * R + y) * R + x;
+}
+
+__device__ __forceinline__ Bilerp cube_bilerp_seamless(const CubeCoord& c, int R) {
+    Bilerp b;
+    const float halfR = 0.5f * (float)R;
+    const float sx = fminf(fmaxf(c.sx, -1.0f), 1.0f), sy = fminf(fmaxf(c.sy, -1.0f), 1.0f);
+    const float fx = (sx + 1.0f) * halfR - 0.5f;
+    const float fy = (sy + 1.0f) * halfR - 0.5f;
+    const float x0f = floorf(fx), y0f = floorf(fy);
+    b.wx = fx - x0f;
+    b.wy = fy - y0f;
+    const int x0 = (int)x0f, y0 = (int)y0f;          // in [-1, R-1]
+    if (x0 >= 0 && y0 >= 0 && x0 + 1 < R && y0 + 1 < R) {
+        const int row0 = (c.face * R + y0) * R;
+        b.i00 = row0 + x0; b.i01 = b.i00 + 1; b.i10 = b.i00 + R; b.i11 = b.i10 + 1;
+    } else {
+        b.i00 = cube_wrap_tap(c.face, x0, y0, R);     b.i01 = cube_wrap_tap(c.face, x0 + 1, y0, R);
+        b.i10 = cube_wrap_tap(c.face, x0, y0 + 1, R); b.i11 = cube_wrap_tap(c.face, x0 + 1, y0 + 1, R);
+    }
+    return b;
+}
+
 // Can  q(d) = a dx^2 + 2 b dx dy + c dy^2  (d = p - mu) drop to <= tau somewhere on the rectangle
 // [x0,x1] x [y0,y1]?  q is convex with its minimum at mu, so the constrained minimum is either mu
 // itself (inside) or lies on an edge that FACES mu; at most two 1-D clamped minimisations.
@@ -288,6 +336,18 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// shared -> global bulk copy / bulk reduction (TMA 1-D, bulk_group completion). The shared-memory source was written with
+// ordinary stores: fence_proxy_async_smem() first; the issuing thread commits and waits before the block may end.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+// global[i] += shared[i] for bytes/4 floats, done by the L2 (no read of the destination by the SM): SASS UBLKRED
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gmem_dst, const float* smem_src, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
 
 

@@ -141,11 +141,53 @@ __device__ __forceinline__ void project_gaussian(const RasterParams& p, int idx,
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+// TEXGS_PREFWD_STAGE_SH: as in the backward, the SH rows of the 32 Gaussians of a warp are one contiguous block of global
+// memory (128 * 3M bytes) that a thread owning one Gaussian would walk with a 12 M-byte stride (45 scalar loads, each
+// touching 32 lines per warp). One bulk copy (TMA 1-D) per warp stages the block in shared memory while the lanes
+// project their Gaussians; the SH evaluation then reads its row there (odd row stride: conflict-free).
+#ifndef TEXGS_PREFWD_STAGE_SH
+#define TEXGS_PREFWD_STAGE_SH 1
+#endif
+__host__ __forceinline__ size_t prefwd_smem_bytes(int M, int mode, const void* shs) {
+#if TEXGS_PREFWD_STAGE_SH
+    return (shs && mode != TEXGS_MODE_PRECOMP && M > 0 && ((3 * M) & 1)) ? (size_t)8 * 32 * 3 * M * sizeof(float) + 8 * sizeof(uint64_t) : 0;
+#else
+    (void)M; (void)mode; (void)shs;
+    return 0;
+#endif
+}
+
 __global__ void __launch_bounds__(256) texgs_preprocess_fwd(const RasterParams p, int* __restrict__ radii) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const float* sh_row = (p.shs != nullptr && idx < p.P) ? p.shs + (size_t)idx * p.M * 3 : nullptr;
+#if TEXGS_PREFWD_STAGE_SH
+    extern __shared__ __align__(128) float prefwd_smem[];
+    const int nsh = p.M * 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // warp-uniform: a full warp of Gaussians, odd row stride, 16-byte aligned coefficient tensor
+    const bool bulk = (p.shs != nullptr) && (p.mode != TEXGS_MODE_PRECOMP) && (nsh & 1) && (idx - lane + 32 <= p.P) &&
+                      (((uintptr_t)p.shs & 15) == 0);
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(prefwd_smem + (size_t)8 * 32 * nsh);
+    if (bulk) {
+        float* const wrows = prefwd_smem + (size_t)warp * 32 * nsh;
+        if (lane == 0) {
+            mbar_init(&bars[warp], 1);
+            mbar_fence_init();
+            mbar_arrive_expect_tx(&bars[warp], 128u * (unsigned)nsh);
+            bulk_g2s(wrows, p.shs + (size_t)(idx - lane) * nsh, 128u * (unsigned)nsh, &bars[warp]);
+        }
+        sh_row = wrows + lane * nsh;
+        __syncwarp();
+    }
+    if (idx >= p.P) return;                    // never taken by a lane of a warp with a copy in flight (full warps only)
+    Proj o;
+    project_gaussian(p, idx, o);               // overlaps the copy
+    if (bulk) mbar_wait(&bars[warp], 0u);      // every lane waits before it may leave: the copy must not outlive the block
+#else
     if (idx >= p.P) return;
     Proj o;
     project_gaussian(p, idx, o);
+#endif
     if (!o.visible) {
         radii[idx] = 0;
         p.rects[idx] = make_uint2(0u, 0u);
@@ -162,10 +204,9 @@ __global__ void __launch_bounds__(256) texgs_preprocess_fwd(const RasterParams p
         const float inv_len = rsqrtf(dot3(o.m, o.m));
         const float3 dir = f3(o.m.x * inv_len, o.m.y * inv_len, o.m.z * inv_len);
         if (p.mode == TEXGS_MODE_TEXTURE) {
-            col = (p.shs != nullptr) ? sh_rest_eval(min(p.sh_degree, 3), p.shs + (size_t)idx * p.M * 3, dir)
-                                     : f3(0.f, 0.f, 0.f);
+            col = (sh_row != nullptr) ? sh_rest_eval(min(p.sh_degree, 3), sh_row, dir) : f3(0.f, 0.f, 0.f);
         } else {  // full SH: DC + rest
-            const float* sh = p.shs + (size_t)idx * p.M * 3;
+            const float* sh = sh_row;
             col = sh_rest_eval(min(p.sh_degree, 3), sh + 3, dir);
             col.x += SH_C0 * sh[0]; col.y += SH_C0 * sh[1]; col.z += SH_C0 * sh[2];
         }
@@ -212,7 +253,9 @@ __global__ void __launch_bounds__(256) texgs_preprocess_fwd(const RasterParams p
 //   acc[13..15] dL/d uv                   acc[16] S0 = sum s, acc[17..19] sum s*Delta_v (intersection path,
 //                                          s = (J'^T gu . v)/(n_v . v))
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void put(float* p, float v, bool acc) { if (acc) *p += v; else *p = v; }
+// accumulate mode adds ATOMICALLY (fire-and-forget RED, no read of the destination): views rendered concurrently on
+// several CUDA streams accumulate into one gradient buffer (texture_gs_b200.dist.render_views_accumulate(streams=n))
+__device__ __forceinline__ void put(float* p, float v, bool acc) { if (acc) atomicAdd(p, v); else *p = v; }
 
 // ``sh`` and ``dsh`` may be the SAME row (staged path: the gradient replaces the coefficients in shared memory; each
 // coefficient is read before it is overwritten), hence no __restrict__.
@@ -327,15 +370,17 @@ __device__ __forceinline__ void prebwd_one(const RasterParams& p, const float* _
     if (p.mode == TEXGS_MODE_TEXTURE) {
         const float3 duv = f3(acc[13], acc[14], acc[15]);
         if (g.duvs) { put(g.duvs + 3 * idx, duv.x, a_uv); put(g.duvs + 3 * idx + 1, duv.y, a_uv); put(g.duvs + 3 * idx + 2, duv.z, a_uv); }
-        const float S0 = acc[16], S1 = acc[17], S2 = acc[18], S3 = acc[19];
-        // J'^T duv, J'[i][c] = sum_r J[i][r] V[r][c]
-        const float* J = p.gradient_uvs + (size_t)9 * idx;
-        float jtw[3];  // world: J^T duv
+        if (!(p.flags & TEXGS_FLAG_STOPGRAD_DELTA)) {      // E13-alt: nothing flows through Delta = t v - p_v
+            const float S0 = acc[16], S1 = acc[17], S2 = acc[18], S3 = acc[19];
+            // J'^T duv, J'[i][c] = sum_r J[i][r] V[r][c]
+            const float* J = p.gradient_uvs + (size_t)9 * idx;
+            float jtw[3];  // world: J^T duv
 #pragma unroll
-        for (int r = 0; r < 3; ++r) jtw[r] = J[r] * duv.x + J[3 + r] * duv.y + J[6 + r] * duv.z;
-        const float3 jtv = rot_w2v(p.view, f3(jtw[0], jtw[1], jtw[2]));   // view: J'^T duv
-        dpv.x += o.nv.x * S0 - jtv.x; dpv.y += o.nv.y * S0 - jtv.y; dpv.z += o.nv.z * S0 - jtv.z;
-        dnv.x -= S1; dnv.y -= S2; dnv.z -= S3;      // dL/dn_v = -sum s*Delta_v
+            for (int r = 0; r < 3; ++r) jtw[r] = J[r] * duv.x + J[3 + r] * duv.y + J[6 + r] * duv.z;
+            const float3 jtv = rot_w2v(p.view, f3(jtw[0], jtw[1], jtw[2]));   // view: J'^T duv
+            dpv.x += o.nv.x * S0 - jtv.x; dpv.y += o.nv.y * S0 - jtv.y; dpv.z += o.nv.z * S0 - jtv.z;
+            dnv.x -= S1; dnv.y -= S2; dnv.z -= S3;      // dL/dn_v = -sum s*Delta_v
+        }
     }
 
     // ---- 2-D mean -> clip -> world -----------------------------------------------------------
@@ -445,9 +490,8 @@ __device__ __forceinline__ void prebwd_one(const RasterParams& p, const float* _
         dq.y = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]);
         dq.z = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]);
         dq.w = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]);
-        float4* dst = reinterpret_cast<float4*>(g.drotations + 4 * idx);
-        if (a_ro) { const float4 o4 = *dst; dq.x += o4.x; dq.y += o4.y; dq.z += o4.z; dq.w += o4.w; }
-        *dst = dq;
+        if (a_ro) red_add_v4(g.drotations + 4 * idx, dq.x, dq.y, dq.z, dq.w);
+        else *reinterpret_cast<float4*>(g.drotations + 4 * idx) = dq;
     }
 }
 
@@ -464,7 +508,7 @@ __device__ __forceinline__ void prebwd_one(const RasterParams& p, const float* _
 __host__ __device__ __forceinline__ bool prebwd_stageable(int M) { return M > 0 && ((3 * M) & 1) != 0; }
 __host__ __forceinline__ size_t prebwd_smem_bytes(int M) {
 #if TEXGS_PREBWD_STAGE_SH
-    return prebwd_stageable(M) ? (size_t)8 * 32 * 3 * M * sizeof(float) : 0;
+    return prebwd_stageable(M) ? (size_t)8 * 32 * 3 * M * sizeof(float) + 8 * sizeof(uint64_t) : 0;     // rows + one mbarrier per warp
 #else
     (void)M;
     return 0;
@@ -476,30 +520,44 @@ __global__ void __launch_bounds__(256, TEXGS_PREBWD_MIN_CTAS) texgs_preprocess_b
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int nsh = p.M * 3;
 #if TEXGS_PREBWD_STAGE_SH
-    extern __shared__ float prebwd_smem[];
+    extern __shared__ __align__(128) float prebwd_smem[];
     const bool staged = (p.shs != nullptr) && prebwd_stageable(p.M) && p.mode != TEXGS_MODE_PRECOMP;
     if (staged) {
         const bool a_sh = g.acc & TEXGS_ACC_SHS;
-        const int lane = threadIdx.x & 31;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         // the warp's 32 rows, in the layout they have in global memory (row stride nsh: odd -> conflict-free)
-        float* const wrows = prebwd_smem + (size_t)(threadIdx.x >> 5) * 32 * nsh;
+        float* const wrows = prebwd_smem + (size_t)warp * 32 * nsh;
+        uint64_t* const bars = reinterpret_cast<uint64_t*>(prebwd_smem + (size_t)8 * 32 * nsh);
         float* const myrow = wrows + lane * nsh;
         const int g0 = idx - lane;                                                // first Gaussian of the warp
         const int wcnt = max(0, min(32, p.P - g0)) * nsh;                         // floats in the warp's block
         const float* __restrict__ src = p.shs + (size_t)g0 * nsh;
-        for (int i0 = lane; i0 < wcnt; i0 += 32 * 8) {                            // 8 independent loads in flight per lane
-            float t[8];
+        // a full warp's block is 128 * nsh bytes of contiguous global memory: ONE bulk copy (TMA 1-D) brings it in and
+        // one bulk copy / bulk reduction (the L2 adds, the SM never reads the destination) takes the gradient out
+        const bool bulk = (wcnt == 32 * nsh) && (((uintptr_t)p.shs | (uintptr_t)g.dshs) & 15) == 0;
+        if (bulk) {
+            if (lane == 0) {
+                mbar_init(&bars[warp], 1);
+                mbar_fence_init();
+                mbar_arrive_expect_tx(&bars[warp], (unsigned)wcnt * 4u);
+                bulk_g2s(wrows, src, (unsigned)wcnt * 4u, &bars[warp]);
+            }
+        } else {
+            for (int i0 = lane; i0 < wcnt; i0 += 32 * 8) {                        // 8 independent loads in flight per lane
+                float t[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) t[j] = (i0 + 32 * j < wcnt) ? __ldg(src + i0 + 32 * j) : 0.f;
+                for (int j = 0; j < 8; ++j) t[j] = (i0 + 32 * j < wcnt) ? __ldg(src + i0 + 32 * j) : 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) if (i0 + 32 * j < wcnt) wrows[i0 + 32 * j] = t[j];
+                for (int j = 0; j < 8; ++j) if (i0 + 32 * j < wcnt) wrows[i0 + 32 * j] = t[j];
+            }
         }
-        __syncwarp();
         // every lane stays until the cooperative store at the end: ``live`` replaces the early returns
         const bool live = idx < p.P;
         bool visible = false;
         Proj o;
-        if (live) { project_gaussian(p, idx, o); visible = o.visible; }
+        if (live) { project_gaussian(p, idx, o); visible = o.visible; }       // overlaps the copy
+        __syncwarp();
+        if (bulk) mbar_wait(&bars[warp], 0u);
         if (live && visible) {
             prebwd_one(p, acc_all, g, idx, o, myrow, myrow);
         } else {
@@ -509,12 +567,19 @@ __global__ void __launch_bounds__(256, TEXGS_PREBWD_MIN_CTAS) texgs_preprocess_b
         __syncwarp();
         if (g.dshs) {
             float* __restrict__ dst = g.dshs + (size_t)g0 * nsh;
-            for (int i0 = lane; i0 < wcnt; i0 += 32 * 8) {
-                float t[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) t[j] = (a_sh && i0 + 32 * j < wcnt) ? dst[i0 + 32 * j] : 0.f;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) if (i0 + 32 * j < wcnt) dst[i0 + 32 * j] = t[j] + wrows[i0 + 32 * j];
+            if (bulk) {
+                fence_proxy_async_smem();          // the rows were written with ordinary stores
+                __syncwarp();
+                if (lane == 0) {
+                    if (a_sh) bulk_reduce_add_f32(dst, wrows, (unsigned)wcnt * 4u);
+                    else bulk_s2g(dst, wrows, (unsigned)wcnt * 4u);
+                    bulk_commit();
+                    bulk_wait<0>();                // the shared-memory source must outlive the copy
+                }
+            } else {
+                for (int i0 = lane; i0 < wcnt; i0 += 32) {
+                    if (a_sh) atomicAdd(dst + i0, wrows[i0]); else dst[i0] = wrows[i0];
+                }
             }
         }
         return;

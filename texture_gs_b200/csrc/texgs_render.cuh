@@ -142,7 +142,9 @@ __device__ __forceinline__ UvEval eval_uv(const float4& g1, const float4& g2, co
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-template <int MODE, bool TEX4, bool DUAL>
+// ALT = true: cold instantiation that honours the spec switches of p.flags (TEXGS_FLAG_SEAMLESS_CUBE,
+// TEXGS_FLAG_DEPTH_INTERSECTION; include/texgs.h) — the default instantiations never test them.
+template <int MODE, bool TEX4, bool DUAL, bool ALT>
 __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(const RasterParams p, float* __restrict__ out_image,
                                                       float* __restrict__ out_depth, float* __restrict__ out_norm,
                                                       float* __restrict__ out_alpha) {
@@ -162,6 +164,8 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
     const float pxf = (float)g.px, pyf = (float)g.py;
     const float* __restrict__ tex = p.texture;
     const int R = p.R;
+    const bool seamless = ALT && (p.flags & TEXGS_FLAG_SEAMLESS_CUBE) != 0u;
+    const bool zalt = ALT && (p.flags & TEXGS_FLAG_DEPTH_INTERSECTION) != 0u;
 
     // a warp whose block lies completely outside the image has nothing to do
     if (nchunks > 0 && !__all_sync(0xffffffffu, done)) {
@@ -222,11 +226,13 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
                 if (cand) {
                     const float4 g2 = rec.q[2], g3 = rec.q[3];
                     float cr = g3.y, cg = g3.z, cb = g3.w;
+                    float zc = g1.z;                                  // E7: z of the centre
                     if (MODE == TEXGS_MODE_TEXTURE && !TEXGS_ABLATE_HEAVY) {
                         const float4 g4 = rec.q[4], g5 = rec.q[5], g6 = rec.q[6];
                         const UvEval e = eval_uv(g1, g2, g3, g4, g5, g6, g.vx, g.vy);
+                        if (ALT && zalt && e.safe) zc = e.t;          // E7-alt: z of the intersection (the view ray is (vx, vy, 1))
                         const CubeCoord cc = cube_coord(e.ux, e.uy, e.uz);
-                        const Bilerp bl = cube_bilerp(cc, R);
+                        const Bilerp bl = (ALT && seamless) ? cube_bilerp_seamless(cc, R) : cube_bilerp(cc, R);
                         float tx3[3], t00[3], t01[3], t10[3], t11[3];
                         fetch_taps<TEX4>(tex, p.texture_rgba, bl, t00, t01, t10, t11);
 #pragma unroll
@@ -247,7 +253,7 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
                     }
                     const float w = alpha * T;
                     Cr += w * cr; Cg += w * cg; Cb += w * cb;
-                    D += w * g1.z;
+                    D += w * zc;
                     Nx += w * g2.x; Ny += w * g2.y; Nz += w * g2.z;
                     A += w;
                     T = test_T;
@@ -303,7 +309,9 @@ struct BwdIn {
     const float *dL_dimage, *dL_ddepth, *dL_dnorm, *dL_dalpha, *dL_dimage_nosh;
 };
 
-template <int MODE, bool TEX4, bool GRAD4, bool DUAL>
+// ALT = true: cold instantiation for the spec switches of p.flags (E11-alt seamless taps, E7-alt depth of the
+// intersection, E13-alt no gradient through Delta), as in the forward.
+template <int MODE, bool TEX4, bool GRAD4, bool DUAL, bool ALT>
 __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(const RasterParams p, const BwdIn in, float* __restrict__ acc,
                                                       float* __restrict__ dtex) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -343,6 +351,9 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
     const float* __restrict__ tex = p.texture;
     const int R = p.R;
     const float halfR = 0.5f * (float)R;
+    const bool seamless = ALT && (p.flags & TEXGS_FLAG_SEAMLESS_CUBE) != 0u;
+    const bool zalt = ALT && (p.flags & TEXGS_FLAG_DEPTH_INTERSECTION) != 0u;
+    const bool stopgrad = ALT && (p.flags & TEXGS_FLAG_STOPGRAD_DELTA) != 0u;
 
     float T = T_final, acc_rec = 0.f, last_alpha = 0.f, last_X = 0.f;
 
@@ -420,7 +431,7 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
                     g4 = rec.q[4]; g5 = rec.q[5]; g6 = rec.q[6];
                     e = eval_uv(g1, g2, g3, g4, g5, g6, g.vx, g.vy);
                     cc = cube_coord(e.ux, e.uy, e.uz);
-                    bl = cube_bilerp(cc, R);
+                    bl = (ALT && seamless) ? cube_bilerp_seamless(cc, R) : cube_bilerp(cc, R);
                     float tx3[3];
                     fetch_taps<TEX4>(tex, p.texture_rgba, bl, t00, t01, t10, t11);
 #pragma unroll
@@ -439,7 +450,9 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
                         kr = (er < 0.f) ? 0.f : hr; kg = (eg < 0.f) ? 0.f : hg; kb = (eb < 0.f) ? 0.f : hb;
                     }
                 }
-                const float X = gr * cr + gg * cg + gb * cb + gd * g1.z + gnv.x * g2.x + gnv.y * g2.y + gnv.z * g2.z + ga + xdual;
+                // E7-alt: the depth term is z of the intersection = t; its gradient then goes to t (below) instead of the centre
+                const bool zint = ALT && zalt && MODE == TEXGS_MODE_TEXTURE && e.safe;
+                const float X = gr * cr + gg * cg + gb * cb + gd * (zint ? e.t : g1.z) + gnv.x * g2.x + gnv.y * g2.y + gnv.z * g2.z + ga + xdual;
                 acc_rec = last_alpha * last_X + (1.0f - last_alpha) * acc_rec;
                 const float dL_dalpha = (X - acc_rec) * T - (T_final * inv_1ma) * bgdot;
                 last_alpha = alpha;
@@ -456,7 +469,7 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
                 v[4] = -0.5f * GdG * dy * dy;
                 const float wr = w * gr * mr, wg = w * gg * mg, wb = w * gb * mb;   // dL/d col (masked)
                 v[6] = wr; v[7] = wg; v[8] = wb;
-                v[9] = w * gd;
+                v[9] = (zint && !stopgrad) ? 0.f : w * gd;
                 v[10] = w * gnv.x; v[11] = w * gnv.y; v[12] = w * gnv.z;
                 if (MODE == TEXGS_MODE_TEXTURE && !TEXGS_ABLATE_HEAVY) {
                     const float gt[3] = {SH_C0 * (wr + w * kr), SH_C0 * (wg + w * kg), SH_C0 * (wb + w * kb)};
@@ -486,12 +499,12 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
                     float gu[3];
                     cube_coord_bwd(cc, dwx * halfR * cc.inv_m, dwy * halfR * cc.inv_m, gu);
                     v[13] = gu[0]; v[14] = gu[1]; v[15] = gu[2];
-                    if (e.safe) {
-                        // g_v = J'^T gu ; s = (g_v . v) / nd
+                    if (e.safe && !(ALT && stopgrad)) {
+                        // g_v = J'^T gu ; s = dL/dt / nd,  dL/dt = g_v . v  (+ w gd when the depth output is t: E7-alt)
                         const float gvx = g4.w * gu[0] + g5.z * gu[1] + g6.y * gu[2];
                         const float gvy = g5.x * gu[0] + g5.w * gu[1] + g6.z * gu[2];
                         const float gvz = g5.y * gu[0] + g6.x * gu[1] + g6.w * gu[2];
-                        const float sden = __fdividef(gvx * g.vx + gvy * g.vy + gvz, e.nd);
+                        const float sden = __fdividef(gvx * g.vx + gvy * g.vy + gvz + (zint ? w * gd : 0.f), e.nd);
                         v[16] = sden;
                         v[17] = sden * e.dx;
                         v[18] = sden * e.dy;

@@ -68,11 +68,10 @@ class GradBucket:
     the all-reduce runs on — and autograd's separate ``AccumulateGrad`` pass (a zero-fill, a dense
     gradient tensor and an add kernel per input per view) disappears."""
 
-    def __init__(self, params: Dict[str, torch.Tensor], pad_texture: bool = True, replicas: int = 1):
-        """``replicas`` > 1 adds private copies of the flat buffer, one per CUDA stream of
-        ``render_views_accumulate(..., streams=replicas)``: views rendered concurrently on different streams must
-        not share an accumulation buffer (the per-Gaussian backward accumulates with plain read-modify-writes);
-        ``reduce_replicas()`` — called by ``all_reduce()`` — folds them into replica 0, the ``.grad`` storage."""
+    def __init__(self, params: Dict[str, torch.Tensor], pad_texture: bool = True):
+        """One flat buffer for all streams: every accumulation the backward kernels do into it is atomic (vector
+        ``red`` for texels, ``red`` / TMA bulk reductions for the per-Gaussian gradients), so views rendered
+        concurrently on several CUDA streams (``render_views_accumulate(..., streams=n)``) share it."""
         self.params = {k: v for k, v in params.items() if v is not None and v.requires_grad}
         if not self.params:
             raise ValueError("no tensor requires grad")
@@ -86,7 +85,6 @@ class GradBucket:
             self.padded[k] = pad
             off += (n + 63) // 64 * 64          # keep every slice 256-byte aligned
         self.flat = torch.zeros(off, dtype=torch.float32, device=first.device)
-        self.flats = [self.flat] + [torch.zeros_like(self.flat) for _ in range(max(1, int(replicas)) - 1)]
         self._by_id = {id(v): k for k, v in self.params.items()}
         self.install()
 
@@ -98,15 +96,13 @@ class GradBucket:
         return self.flat[o:o + n].view_as(v)
 
     def storage_for(self, tensor: torch.Tensor):
-        """(buffer, padded) the rasterizer may accumulate into for this exact leaf tensor, else None. Inside
-        ``fused(replica=r)`` the buffer is replica ``r``'s."""
+        """(buffer, padded) the rasterizer may accumulate into for this exact leaf tensor, else None."""
         k = self._by_id.get(id(tensor))
         if k is None or self.params[k] is not tensor:
             return None
         o, n = self.offsets[k]
         v = self.params[k]
-        r = getattr(_fused, "replica", 0) if getattr(_fused, "bucket", None) is self else 0
-        flat = self.flats[r]
+        flat = self.flat
         if self.padded[k]:
             return flat[o:o + n].view(*v.shape[:-1], 4), True
         return flat[o:o + n].view_as(v), False
@@ -116,8 +112,7 @@ class GradBucket:
             v.grad = self._view(k)
 
     def zero(self):
-        for f in self.flats:
-            f.zero_()
+        self.flat.zero_()
         for k, v in self.params.items():       # autograd keeps a defined .grad in place; re-check cheaply
             o, _ = self.offsets[k]
             if v.grad is None or v.grad.data_ptr() != self.flat.data_ptr() + 4 * o:
@@ -127,28 +122,18 @@ class GradBucket:
         return {k: self._view(k) for k in self.params}
 
     @contextmanager
-    def fused(self, replica: int = 0):
-        """Rasterizer calls made inside this block accumulate their gradients into the bucket (its replica
-        ``replica``) from within the backward kernels (for inputs that ARE bucket leaves; others go through autograd)."""
-        if not 0 <= replica < len(self.flats):
-            raise ValueError(f"replica {replica} of a bucket with {len(self.flats)}")
-        prev = getattr(_fused, "bucket", None), getattr(_fused, "replica", 0)
-        _fused.bucket, _fused.replica = self, replica
+    def fused(self):
+        """Rasterizer calls made inside this block accumulate their gradients into the bucket from within the backward
+        kernels (for inputs that ARE bucket leaves; others go through autograd)."""
+        prev = getattr(_fused, "bucket", None)
+        _fused.bucket = self
         try:
             yield self
         finally:
-            _fused.bucket, _fused.replica = prev
-
-    def reduce_replicas(self):
-        """Fold the per-stream replicas into replica 0 (the ``.grad`` storage) and clear them; call on a stream that
-        has waited for every stream that wrote a replica."""
-        for f in self.flats[1:]:
-            self.flat.add_(f)
-            f.zero_()
+            _fused.bucket = prev
 
     def all_reduce(self, group=None, async_op: bool = False):
         """Sum over ranks (one NCCL all-reduce per step over the flat bucket)."""
-        self.reduce_replicas()
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
             return None
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
@@ -181,12 +166,11 @@ def render_views_accumulate(render_fn, gaussians, cameras: Sequence, cotangents,
     (``retexture.py:18-37``). ``before_view(view, slot)`` / ``after_view(view, slot)`` run on the stream that renders
     the view (stream waits / event records of a host-fed input pipeline); ``slot`` counts the views of this call.
 
-    ``streams`` > 1 (needs a bucket with as many replicas whose leaves are ALL the differentiable inputs when
-    ``backward``): view i runs on CUDA stream i mod ``streams`` and accumulates into that stream's replica, so the
-    latency-bound small kernels of one view (tile scan, scatter, sort) and the tails of its render kernels overlap the
-    render kernels of the next one (+9 % views/s at the headline size, profiles/r2_variants.md). The packed texel copy is
-    built once before the fork; the calling stream joins all streams before returning, the replicas are folded by
-    ``bucket.all_reduce()`` / ``reduce_replicas()``."""
+    ``streams`` > 1 (needs a bucket whose leaves are ALL the differentiable inputs when ``backward``): view i runs on
+    CUDA stream i mod ``streams``, so the latency-bound small kernels of one view (tile scan, scatter, sort) and the
+    tails of its render kernels overlap the render kernels of the next one (+9 % views/s at the headline size,
+    profiles/r2_variants.md). All streams accumulate into the one bucket (atomic adds). The packed texel copy is built
+    once before the fork; the calling stream joins all streams before returning."""
     view_ids = list(view_ids)
 
     def one_view(slot, v, fused_ctx):
@@ -213,8 +197,8 @@ def render_views_accumulate(render_fn, gaussians, cameras: Sequence, cotangents,
             one_view(i, v, bucket.fused() if (bucket is not None and backward) else _null())
         return len(view_ids)
     if backward:
-        if bucket is None or len(bucket.flats) < streams:
-            raise ValueError("streams > 1 needs a GradBucket(..., replicas=streams): concurrent views must not share gradient buffers")
+        if bucket is None:
+            raise ValueError("streams > 1 needs a GradBucket: autograd would add the views' gradients into one .grad from several streams at once")
         # autograd would add the gradients of non-bucket leaves into ONE .grad tensor from several streams at once
         for t in _differentiable_inputs(gaussians):
             if t.requires_grad and (not t.is_leaf or bucket.storage_for(t) is None):
@@ -232,7 +216,7 @@ def render_views_accumulate(render_fn, gaussians, cameras: Sequence, cotangents,
     for i, v in enumerate(view_ids):
         r = i % streams
         with torch.cuda.stream(pool[r]):
-            one_view(i, v, bucket.fused(replica=r) if (bucket is not None and backward) else _null())
+            one_view(i, v, bucket.fused() if (bucket is not None and backward) else _null())
     for s in pool:
         main.wait_stream(s)
     return len(view_ids)

@@ -18,6 +18,7 @@ import ctypes as C
 import os
 import threading
 import weakref
+from contextlib import contextmanager
 from typing import NamedTuple, Optional
 
 import torch
@@ -202,6 +203,37 @@ class RasterStats(NamedTuple):
 
 
 _last_stats = threading.local()
+_spec = threading.local()
+
+
+class SpecSwitches(NamedTuple):
+    """The conventions of the path that the reference tree does not pin (its rasterizer source is not in
+    the tree). Defaults = what the library computes unless told otherwise; each alternative is a cold instantiation of
+    the render kernels with an oracle parity test (tests/test_gpu_parity.py), so the library can be re-pointed the day
+    the upstream source says which one it is."""
+    seamless_cube: bool = False           # E11-alt: taps beyond a face edge from the adjacent face (nvdiffrast 'cube' / GL seamless)
+    depth_of_intersection: bool = False   # E7-alt: depth output = z of the ray-disc intersection, not of the centre
+    stopgrad_delta: bool = False          # E13-alt: no gradient through the intersection offset
+
+    def flags(self) -> int:
+        return ((L.FLAG_SEAMLESS_CUBE if self.seamless_cube else 0) | (L.FLAG_DEPTH_INTERSECTION if self.depth_of_intersection else 0)
+                | (L.FLAG_STOPGRAD_DELTA if self.stopgrad_delta else 0))
+
+
+@contextmanager
+def spec_switches(**kw):
+    """``with spec_switches(seamless_cube=True): uv_tex_render(...)`` — rasterizer calls of this thread made inside the
+    block use the given conventions (forward and its backward)."""
+    prev = getattr(_spec, "v", SpecSwitches())
+    _spec.v = prev._replace(**kw)
+    try:
+        yield _spec.v
+    finally:
+        _spec.v = prev
+
+
+def current_spec() -> SpecSwitches:
+    return getattr(_spec, "v", SpecSwitches())
 
 
 def last_stats() -> Optional[RasterStats]:
@@ -211,7 +243,7 @@ def last_stats() -> Optional[RasterStats]:
 
 
 def _build_args(st: GaussianRasterizationSettings, mode: int, means3D, shs, colors_precomp, opacities, scales,
-                rotations, uvs, gradient_uvs, texture, profile_arr=None, extra_attrs=None, cov3Ds_precomp=None) -> L.TexgsFwdArgs:
+                rotations, uvs, gradient_uvs, texture, profile_arr=None, extra_attrs=None, cov3Ds_precomp=None, spec_flags: int = 0) -> L.TexgsFwdArgs:
     a = L.TexgsFwdArgs()
     a.P = means3D.shape[0]
     a.M = 0 if shs is None else shs.shape[1]
@@ -220,7 +252,7 @@ def _build_args(st: GaussianRasterizationSettings, mode: int, means3D, shs, colo
     a.H, a.W = int(st.image_height), int(st.image_width)
     a.R = 0 if texture is None else texture.shape[1]
     a.mode = mode
-    a.flags = (L.FLAG_PREFILTERED if st.prefiltered else 0) | (L.FLAG_DEBUG if st.debug else 0)
+    a.flags = (L.FLAG_PREFILTERED if st.prefiltered else 0) | (L.FLAG_DEBUG if st.debug else 0) | (spec_flags if mode == L.MODE_TEXTURE else 0)
     a.tanfovx, a.tanfovy, a.scale_modifier = float(st.tanfovx), float(st.tanfovy), float(st.scale_modifier)
     a.viewmatrix = (C.c_float * 16)(*_host_floats(st.viewmatrix, 16))
     a.projmatrix = (C.c_float * 16)(*_host_floats(st.projmatrix, 16))
@@ -281,7 +313,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             stream = torch.cuda.current_stream(dev).cuda_stream
             from .profiling import current_event_array
             prof = current_event_array()      # captured here: backward runs on autograd's thread
-            a = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex, prof, ex, cov)
+            spec_flags = current_spec().flags()      # captured here: backward runs on autograd's thread
+            a = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex, prof, ex, cov, spec_flags)
             tex4 = None
             if mode == L.MODE_TEXTURE and USE_PACKED_TEXTURE:
                 tex4 = _packed_texture(lib, texture, tex, stream)
@@ -326,7 +359,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             _capacity_hint[key] = max(cap, _capacity_hint.get(key, 0)) if not overflow else cap
             _last_stats.v = RasterStats(K, V, maxlen, blo | (bhi << 32), cap)
 
-        ctx.st, ctx.mode, ctx.cap, ctx.prof, ctx.tex4, ctx.dual = st, mode, cap, prof, tex4, dual
+        ctx.st, ctx.mode, ctx.cap, ctx.prof, ctx.tex4, ctx.dual, ctx.spec_flags = st, mode, cap, prof, tex4, dual, spec_flags
         # fused gradient accumulation (texture_gs_b200.dist.GradBucket.fused): resolved now because
         # backward runs on autograd's thread. Only inputs that ARE bucket leaves qualify.
         ctx.fuse = None
@@ -363,7 +396,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             b = L.TexgsBwdArgs()
-            b.fwd = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex, ctx.prof, ex, cov)
+            b.fwd = _build_args(st, mode, m3, sh, cp, op, sc, ro, uv, guv, tex, ctx.prof, ex, cov, ctx.spec_flags)
             if ctx.tex4 is not None:
                 b.fwd.texture_rgba = _ptr(ctx.tex4)
             b.geom_ws, b.bin_ws, b.img_ws, b.pair_capacity = _ptr(geom), _ptr(binw), _ptr(imgw), ctx.cap
