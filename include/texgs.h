@@ -43,7 +43,9 @@ extern "C" {
                                               nvdiffrast boundary_mode='cube', models/uv_map_gaussian3d.py:259) instead of clamp-to-edge */
 #define TEXGS_FLAG_DEPTH_INTERSECTION 8u   /* E7-alt: the depth output blends z of the ray-disc intersection instead of z of the centre */
 #define TEXGS_FLAG_STOPGRAD_DELTA     16u  /* E13-alt: no gradient through the intersection offset Delta (to means3D / rotations) */
-#define TEXGS_FLAG_SPEC_MASK          28u
+#define TEXGS_FLAG_SPEC_MASK          28u  /* the three above: they select the ALT render kernels */
+#define TEXGS_FLAG_CLAMP_GRAD_3DGS    32u  /* E2-alt (preprocess backward only): a clamped x/z, y/z of the EWA projection passes no gradient, as the
+                                              3DGS lineage does; default = exact derivative of t.x = clamp(x/z) * z                       */
 
 /* colour source of a splat */
 #define TEXGS_MODE_TEXTURE 0   /* diff_gauss_uv_tex: C0*cube(uv + J*delta) + SH_rest + 0.5, clamped at 0 */

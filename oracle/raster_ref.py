@@ -90,6 +90,8 @@ class Switches(NamedTuple):
     seamless_cube: bool = False           # E11: False -> clamp-to-edge inside the face; True -> taps beyond a face edge come from the adjacent face
     stopgrad_delta: bool = False          # E13: False -> full derivative through the intersection
     normalize_quat: bool = False          # upstream CUDA uses the quaternion as given
+    upstream_clamp_grad: bool = False     # E2-alt: a view-space x/z (y/z) clamped at 1.3 tan(fov/2) passes NO gradient (the 3DGS lineage
+                                          # zeroes it: `x_grad_mul`); False -> exact derivative of t.x = clamp(x/z) * z, i.e. lim * dz
 
 
 # ---------------------------------------------------------------------------------------------
@@ -167,6 +169,10 @@ def preprocess(means3D, means2D, scales, rotations, opacities, shs, st: RasterSe
     tz_safe = torch.where(in_front, tz, torch.ones_like(tz))
     tx = torch.clamp(p_view[:, 0] / tz_safe, -limx, limx) * tz_safe
     ty = torch.clamp(p_view[:, 1] / tz_safe, -limy, limy) * tz_safe
+    if sw.upstream_clamp_grad:
+        qx, qy = (p_view[:, 0] / tz_safe).detach(), (p_view[:, 1] / tz_safe).detach()
+        tx = torch.where((qx < -limx) | (qx > limx), tx.detach(), tx)
+        ty = torch.where((qy < -limy) | (qy > limy), ty.detach(), ty)
     fx = W / (2.0 * st.tanfovx)
     fy = H / (2.0 * st.tanfovy)
     zero = torch.zeros_like(tz)

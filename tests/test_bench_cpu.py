@@ -105,7 +105,8 @@ def test_roofline_report_from_round1_measurements():
     assert abs(r["frac"] - r["algorithmic_bytes_per_launch"] / (stage_ms["render_bwd"] * 1e-3) / 1e9 / peak) < 1e-3
     assert r["traffic"] == json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())["render_bwd"]
     iss = r["issue"]
-    assert iss["warp_instructions_per_launch"] == 989917246 and 0.5 < iss["frac"] < 0.65      # ncu measured 61 % issue-slot use
+    want = json.loads((ROOT / "profiles" / "ncu_issue.json").read_text())["render_bwd"]["warp_instructions"]
+    assert iss["warp_instructions_per_launch"] == want and 0.5 < iss["frac"] < 0.65      # ncu measured 59-61 % issue-slot use
     assert abs(iss["peak_ginst_s"] - 148 * 4 * 1.965) < 0.1
     json.dumps(r)
     r0 = bench.roofline_report(wl, 32, 1, ref["value"], {}, stats, c["U"], None, 148)

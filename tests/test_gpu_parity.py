@@ -636,3 +636,27 @@ def test_spec_switches_through_the_dual_render_and_a_larger_scene():
     ref0, aux0, _ = run_oracle(gz, cam, bg=(0.2, 0.1, 0.0), sw=sw)
     d = (pkg["render_no_sh"].detach().cpu() - ref0[0]).abs().amax(dim=0)
     assert float(d[~(aux["ambiguous"] | aux0["ambiguous"])].max()) <= ABS_TOL
+
+
+def _clamping_camera():
+    from texture_gs_b200.scene import SyntheticCamera, look_at_w2c
+    c = torch.tensor([0.0, 0.3, 0.55], dtype=torch.float64)
+    w2c = look_at_w2c(c, torch.tensor([0.2, 0.1, -1.0], dtype=torch.float64), torch.tensor([0.0, -1.0, 0.0], dtype=torch.float64))
+    return SyntheticCamera(120, 90, math.radians(60.0), w2c)
+
+
+def test_upstream_clamp_gradient_convention_is_a_switch():
+    """E2-alt (TEXGS_FLAG_CLAMP_GRAD_3DGS): where x/z or y/z of a splat hits the 1.3 tan(fov/2) clamp of the EWA Jacobian the
+    3DGS lineage passes no gradient through that coordinate; the default is the exact derivative of t.x = clamp(x/z) z.
+    Camera inside the shell so that the clamp is active for many visible splats: both conventions match the oracle run
+    with the same switch, and they differ from each other in the position gradient only."""
+    from oracle.raster_ref import Switches
+    g = _variant_scene(3000, 32, seed=45, deg=2, coverage=6.0)
+    cam = _clamping_camera()
+    sw = Switches(upstream_clamp_grad=True)
+    _check_backward(g, cam, bg=(0.1, 0.2, 0.3), max_flag=0.6, uv_tol=5e-3, sw=sw)
+    cot = output_cotangents(90, 120, seed=3)
+    a, _, ga = run_cuda(g, cam, bg=(0.1, 0.2, 0.3), cot=cot)
+    b, _, gb = run_cuda(g, cam, bg=(0.1, 0.2, 0.3), cot=cot, sw=sw)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    assert rel_err(gb["xyz"], ga["xyz"]) > 1e-4 and rel_err(gb["scaling"], ga["scaling"]) < 1e-6 and rel_err(gb["texture"], ga["texture"]) < 1e-6

@@ -3,6 +3,7 @@
 from pathlib import Path
 
 import numpy as np
+import pytest
 import torch
 
 from texture_gs_b200 import texture_io as TIO
@@ -84,3 +85,44 @@ def test_tcnn_flat_parameter_split():
     assert torch.equal(a, w_in[:, :3]) and torch.equal(b, w_hid) and torch.equal(c, w_out[:3])
     a, b = TIO.tcnn_mlp_weights(torch.cat([w_in.reshape(-1), w_hid.reshape(-1)]), 3, 128, n_hidden=1)
     assert torch.equal(a, w_in[:, :3]) and torch.equal(b, w_hid)
+
+
+def test_tcnn_checkpoint_uses_its_padded_input_columns_as_a_bias(tmp_path):
+    """The shipped config trains the UV network with tiny-cuda-nn (use_tcnn: True, configs/texture_gaussian3d.yaml:20-27):
+    bias-free FullyFusedMLPs whose 3 -> 128 layer has its input padded to 16 columns fed with the constant 1 — 13 columns
+    that act as a learned bias. A stand-in of that network (bias-free matrices of models/modules/utils.py:29-41's shapes
+    applied to the one-padded input) and the FusedUVNet loaded from the same flat parameter vectors must give the same uv
+    and Jacobian; dropping the padded columns (what the loader did before) must NOT."""
+    from oracle import uvnet_ref
+    from texture_gs_b200.uvnet import FusedUVNet
+    g = torch.Generator().manual_seed(5)
+    w1p, w2 = torch.randn(128, 16, generator=g) * 0.3, torch.randn(128, 128, generator=g) * 0.1
+    w3, w4, w5p = torch.randn(128, 128, generator=g) * 0.1, torch.randn(128, 128, generator=g) * 0.1, torch.randn(16, 128, generator=g) * 0.1
+    emb = torch.randn(128, generator=g) * 0.1
+    xyz = torch.randn(64, 3, generator=g)
+
+    def tcnn_stand_in(x):
+        xp = torch.cat([x, torch.ones(x.shape[0], 13)], dim=1)          # identity encoding: padded columns = 1
+        h = torch.relu(xp @ w1p.T) @ w2.T
+        h = torch.relu(h + emb[None])
+        h = torch.relu(torch.relu(h @ w3.T) @ w4.T)
+        return torch.nn.functional.normalize((h @ w5p.T)[:, :3], dim=-1)
+
+    sd = dict(hyperparams=(3, 1.0), optim_state=(), params=(xyz, xyz, torch.randn(64, 4), torch.randn(64, 1), None, torch.randn(6, 2, 2, 3)),
+              net_state=({"pre_mlp.params": torch.cat([w1p.reshape(-1), w2.reshape(-1)]).half(),
+                          "mlp.params": torch.cat([w3.reshape(-1), w4.reshape(-1), w5p.reshape(-1)]).half()}, {}, {"weight": emb[None]}))
+    net = FusedUVNet(bias=True)
+    TIO.CheckpointGaussians(sd, uv_net=net)
+    p = {k: v.detach() for k, v in net.state_dict().items()}
+    w1h, w2h, w3h, w4h, w5h = (t.half().float() for t in (w1p, w2, w3, w4, w5p))       # the checkpoint stores halves
+    w1p, w2, w3, w4, w5p = w1h, w2h, w3h, w4h, w5h
+    want = tcnn_stand_in(xyz)
+    got = uvnet_ref.uv_net_forward(xyz, emb, p)
+    assert torch.allclose(got, want, atol=1e-5)
+    jw = torch.autograd.functional.jacobian(lambda q: tcnn_stand_in(q).sum(dim=0), xyz).permute(1, 0, 2).reshape(-1, 9)
+    assert torch.allclose(uvnet_ref.grad_uvs(xyz, emb, p), jw, atol=1e-4)
+    assert torch.equal(p["pre_mlp.0.bias"], w1p[:, 3:].sum(dim=1)) and float(p["pre_mlp.2.bias"].abs().max()) == 0.0
+    p_old = dict(p, **{"pre_mlp.0.bias": torch.zeros(128)})
+    assert not torch.allclose(uvnet_ref.uv_net_forward(xyz, emb, p_old), want, atol=1e-2)
+    with pytest.raises(ValueError, match="bias=True"):
+        TIO.CheckpointGaussians(sd, uv_net=FusedUVNet(bias=False))

@@ -94,7 +94,7 @@ def run_oracle(g: SyntheticGaussians, cam, bg=(0.0, 0.0, 0.0), cot=None, dtype=t
 def _spec_kw(sw):
     """oracle Switches -> keyword arguments of texture_gs_b200.spec_switches (same names)."""
     return {} if sw is None else dict(seamless_cube=sw.seamless_cube, depth_of_intersection=sw.depth_of_intersection,
-                                      stopgrad_delta=sw.stopgrad_delta)
+                                      stopgrad_delta=sw.stopgrad_delta, upstream_clamp_grad=sw.upstream_clamp_grad)
 
 
 def run_cuda(g: SyntheticGaussians, cam, bg=(0.0, 0.0, 0.0), cot=None, debug=False, device="cuda", scale_modifier=1.0, sw=None):

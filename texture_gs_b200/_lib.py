@@ -19,6 +19,7 @@ FLAG_DEBUG = 2
 FLAG_SEAMLESS_CUBE = 4        # spec switches (include/texgs.h): E11-alt, E7-alt, E13-alt
 FLAG_DEPTH_INTERSECTION = 8
 FLAG_STOPGRAD_DELTA = 16
+FLAG_CLAMP_GRAD_3DGS = 32
 MODE_TEXTURE, MODE_SH, MODE_PRECOMP = 0, 1, 2
 BWD_ACC_FLOATS = 24
 ACC_MEANS3D, ACC_MEANS2D, ACC_OPACITY, ACC_SCALES, ACC_ROTATIONS, ACC_SHS, ACC_COLORS, ACC_UVS = 1, 2, 4, 8, 16, 32, 64, 128

@@ -5,6 +5,15 @@
 #include <cstring>
 #include <string>
 
+#ifndef TEXGS_HOST_EMU
+#include <nvtx3/nvToolsExt.h>      // header-only; a no-op unless a profiler (nsys / ncu --nvtx) is attached
+#define TEXGS_NVTX_PUSH(name) nvtxRangePushA(name)
+#define TEXGS_NVTX_POP() nvtxRangePop()
+#else
+#define TEXGS_NVTX_PUSH(name) ((void)0)
+#define TEXGS_NVTX_POP() ((void)0)
+#endif
+
 #include "texgs_binning.cuh"
 #include "texgs_common.cuh"
 #include "texgs_loss.cuh"
@@ -44,6 +53,13 @@ int fail(int code, const std::string& msg) {
     } while (0)
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// NVTX range over the enqueue of one stage of the path (reference train.py:124-125 brackets the whole iteration with
+// CUDA events; these name the pieces): texgs/forward{/preprocess,/binning,/render}, texgs/backward{/render,/preprocess}
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { TEXGS_NVTX_PUSH(name); }
+    ~NvtxRange() { TEXGS_NVTX_POP(); }
+};
 
 struct Layout {
     TexgsLayout l;
@@ -225,10 +241,12 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
     if (a->E > 0 && !out_extra) return fail(TEXGS_E_INVALID, "E > 0 needs out_extra (E,H,W)");
     const bool debug = (a->flags & TEXGS_FLAG_DEBUG) != 0;
 
+    NvtxRange nvtx_fwd("texgs/forward");
     TEXGS_EV(a, TEXGS_EV_FWD_START, stream);
     TEXGS_CUDA_TRY(cudaMemsetAsync((char*)bin_ws + L.l.bin_counters, 0, L.bin_zero_bytes, stream));
     const int gblocks = (p.P + 255) / 256;
     if (p.P > 0) {
+        NvtxRange r("texgs/forward/preprocess");
         const size_t smem = prefwd_smem_bytes(p.M, p.mode, p.shs);      // SH rows of every warp staged by one bulk copy each
         if (smem > 200 * 1024) return fail(TEXGS_E_INVALID, "too many SH coefficients per Gaussian for the staged forward");
         if (smem > 48 * 1024)
@@ -237,6 +255,8 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
         TEXGS_KERNEL_CHECK("texgs_preprocess_fwd", debug, stream);
     }
     TEXGS_EV(a, TEXGS_EV_FWD_PREPROCESS, stream);
+    {
+    NvtxRange r("texgs/forward/binning");
     texgs_scan_tiles<<<1, TEXGS_SCAN_THREADS, 0, stream>>>(p);
     TEXGS_KERNEL_CHECK("texgs_scan_tiles", debug, stream);
     TEXGS_EV(a, TEXGS_EV_FWD_SCAN, stream);
@@ -254,8 +274,10 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
     texgs_sort_tiles<<<p.num_tiles, TEXGS_SORT_THREADS, 0, stream>>>(p);
     TEXGS_KERNEL_CHECK("texgs_sort_tiles", debug, stream);
     TEXGS_EV(a, TEXGS_EV_FWD_SORT, stream);
+    }
     if (int rc = ensure_render_smem()) return rc;
     {
+        NvtxRange r("texgs/forward/render");
         const bool t4 = p.texture_rgba != nullptr, dual = p.out_image_nosh != nullptr;
 #define TEXGS_LAUNCH_FWD(M, T4, DU, AL) texgs_render_fwd<M, T4, DU, AL><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha)
         const bool alt = p.mode == TEXGS_MODE_TEXTURE && (p.flags & TEXGS_FLAG_SPEC_MASK) != 0u;
@@ -296,6 +318,7 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
     if ((uintptr_t)b->acc_ws & 15) return fail(TEXGS_E_WORKSPACE, "acc_ws must be 16-byte aligned");
     const bool debug = (a->flags & TEXGS_FLAG_DEBUG) != 0;
 
+    NvtxRange nvtx_bwd("texgs/backward");
     TEXGS_EV(a, TEXGS_EV_BWD_START, stream);
     TEXGS_CUDA_TRY(cudaMemsetAsync(b->acc_ws, 0, (size_t)p.P * TEXGS_BWD_ACC_FLOATS * sizeof(float), stream));
     if (b->dL_dtexture && b->dL_dtexture_rgba) return fail(TEXGS_E_INVALID, "give dL_dtexture or dL_dtexture_rgba, not both");
@@ -338,6 +361,7 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
     }
     TEXGS_EV(a, TEXGS_EV_BWD_RENDER, stream);
     if (p.P > 0) {
+        NvtxRange r("texgs/backward/preprocess");
         BwdOut g{b->dL_dmeans3D, b->dL_dmeans2D, b->dL_dopacity, b->dL_dscales, b->dL_drotations,
                  b->dL_dshs, b->dL_dcolors_precomp, b->dL_duvs, a->cov3Ds_precomp ? b->dL_dcov3Ds : nullptr, b->accumulate_mask};
         const size_t smem = prebwd_smem_bytes(p.M);

@@ -456,8 +456,10 @@ __device__ __forceinline__ void prebwd_one(const RasterParams& p, const float* _
     const float dtz = -p.focal_x * itz2 * dJ00 - p.focal_y * itz2 * dJ11 + 2.f * p.focal_x * o.tx * itz3 * dJ02 +
                       2.f * p.focal_y * o.ty * itz3 * dJ12;
     // tx = clamp(x/z) * z : unclamped -> tx = x ; clamped -> tx = lim * z
-    if (!o.clampx) dpv.x += dtx; else dpv.z += dtx * (o.tx * itz);
-    if (!o.clampy) dpv.y += dty; else dpv.z += dty * (o.ty * itz);
+    // E2-alt (TEXGS_FLAG_CLAMP_GRAD_3DGS): the 3DGS lineage passes no gradient through a clamped coordinate
+    const bool drop = (p.flags & TEXGS_FLAG_CLAMP_GRAD_3DGS) != 0u;
+    if (!o.clampx) dpv.x += dtx; else if (!drop) dpv.z += dtx * (o.tx * itz);
+    if (!o.clampy) dpv.y += dty; else if (!drop) dpv.z += dty * (o.ty * itz);
     dpv.z += dtz;
 
     // ---- view -> world -----------------------------------------------------------------------

@@ -214,10 +214,11 @@ class SpecSwitches(NamedTuple):
     seamless_cube: bool = False           # E11-alt: taps beyond a face edge from the adjacent face (nvdiffrast 'cube' / GL seamless)
     depth_of_intersection: bool = False   # E7-alt: depth output = z of the ray-disc intersection, not of the centre
     stopgrad_delta: bool = False          # E13-alt: no gradient through the intersection offset
+    upstream_clamp_grad: bool = False     # E2-alt: no gradient through a clamped x/z, y/z of the EWA projection (3DGS lineage)
 
     def flags(self) -> int:
         return ((L.FLAG_SEAMLESS_CUBE if self.seamless_cube else 0) | (L.FLAG_DEPTH_INTERSECTION if self.depth_of_intersection else 0)
-                | (L.FLAG_STOPGRAD_DELTA if self.stopgrad_delta else 0))
+                | (L.FLAG_STOPGRAD_DELTA if self.stopgrad_delta else 0) | (L.FLAG_CLAMP_GRAD_3DGS if self.upstream_clamp_grad else 0))
 
 
 @contextmanager
@@ -252,7 +253,7 @@ def _build_args(st: GaussianRasterizationSettings, mode: int, means3D, shs, colo
     a.H, a.W = int(st.image_height), int(st.image_width)
     a.R = 0 if texture is None else texture.shape[1]
     a.mode = mode
-    a.flags = (L.FLAG_PREFILTERED if st.prefiltered else 0) | (L.FLAG_DEBUG if st.debug else 0) | (spec_flags if mode == L.MODE_TEXTURE else 0)
+    a.flags = (L.FLAG_PREFILTERED if st.prefiltered else 0) | (L.FLAG_DEBUG if st.debug else 0) | (spec_flags if mode == L.MODE_TEXTURE else (spec_flags & L.FLAG_CLAMP_GRAD_3DGS))
     a.tanfovx, a.tanfovy, a.scale_modifier = float(st.tanfovx), float(st.tanfovy), float(st.scale_modifier)
     a.viewmatrix = (C.c_float * 16)(*_host_floats(st.viewmatrix, 16))
     a.projmatrix = (C.c_float * 16)(*_host_floats(st.projmatrix, 16))

@@ -145,13 +145,19 @@ def sphere_map(texture: torch.Tensor, resolution: Sequence[int] = (512, 1024)) -
 # checkpoint tuple
 # ---------------------------------------------------------------------------------------------------------------
 
-def tcnn_mlp_weights(params: torch.Tensor, n_in: int, n_out: int, width: int = 128, n_hidden: int = 1):
+TCNN_INPUT_PAD_VALUE = 1.0     # [EXT] what tiny-cuda-nn feeds the padded input columns of a bare ``tcnn.Network`` (see tcnn_mlp_weights)
+
+
+def tcnn_mlp_weights(params: torch.Tensor, n_in: int, n_out: int, width: int = 128, n_hidden: int = 1, return_input_pad: bool = False):
     """Split the flat ``params`` vector of a tiny-cuda-nn ``FullyFusedMLP`` (``models/modules/utils.py:29-41``) into
     ``nn.Linear``-style weights ``[(width, n_in), (width, width) * (n_hidden-1), (n_out, width)]``.
 
-    [EXT: tiny-cuda-nn is not in the reference tree] layout assumed from its published source: row-major (out, in)
-    matrices in layer order, input width padded up to a multiple of 16, output width padded up to a multiple of 16,
-    no biases. The padding rows / columns are dropped."""
+    [EXT: tiny-cuda-nn is not in the reference tree] layout from its published source: row-major (out, in) matrices in
+    layer order, input width padded up to a multiple of 16, output width padded up to a multiple of 16, no biases.
+    The padded OUTPUT rows are dropped (their outputs are never read). The padded INPUT columns are not dead: a bare
+    ``tcnn.Network`` runs behind an identity encoding that fills the columns it pads with the constant 1, so the sum of
+    those columns acts as a learned bias of the first layer. ``return_input_pad=True`` also returns that ``(width,
+    pad_in - n_in)`` block so the caller can fold it into a bias (``CheckpointGaussians._load_uv_net``)."""
     pad_in, pad_out = -(-n_in // 16) * 16, -(-n_out // 16) * 16
     sizes = [(width, pad_in)] + [(width, width)] * (n_hidden - 1) + [(pad_out, width)]
     need = sum(a * b for a, b in sizes)
@@ -162,9 +168,10 @@ def tcnn_mlp_weights(params: torch.Tensor, n_in: int, n_out: int, width: int = 1
     for a, b in sizes:
         out.append(flat[o:o + a * b].reshape(a, b))
         o += a * b
+    pad_cols = out[0][:, n_in:].contiguous()
     out[0] = out[0][:, :n_in].contiguous()
     out[-1] = out[-1][:n_out].contiguous()
-    return out
+    return (out, pad_cols) if return_input_pad else out
 
 
 class CheckpointGaussians:
@@ -199,14 +206,21 @@ class CheckpointGaussians:
 
     def _load_uv_net(self, sd: Dict):
         if "pre_mlp.params" in sd and "mlp.params" in sd:            # tiny-cuda-nn networks (use_tcnn: True)
-            w1, w2 = tcnn_mlp_weights(sd["pre_mlp.params"], 3, 128, n_hidden=1)
-            w3, w4, w5 = tcnn_mlp_weights(sd["mlp.params"], 128, 3, n_hidden=2)
+            (w1, w2), pad1 = tcnn_mlp_weights(sd["pre_mlp.params"], 3, 128, n_hidden=1, return_input_pad=True)
+            w3, w4, w5 = tcnn_mlp_weights(sd["mlp.params"], 128, 3, n_hidden=2)       # 128 inputs: nothing padded
             layers = (self.uv_net.pre_mlp[0], self.uv_net.pre_mlp[2], self.uv_net.mlp[0], self.uv_net.mlp[2], self.uv_net.mlp[4])
+            # the 13 padded input columns of the 3 -> 128 layer see the constant TCNN_INPUT_PAD_VALUE: a learned bias
+            bias1 = TCNN_INPUT_PAD_VALUE * pad1.sum(dim=1)
+            if layers[0].bias is None and float(bias1.abs().max()) > 0.0:
+                raise ValueError("this tiny-cuda-nn checkpoint uses its padded input columns as a bias: build FusedUVNet(bias=True)")
             with torch.no_grad():
-                for lin, w in zip(layers, (w1, w2, w3, w4, w5)):
+                for i, (lin, w) in enumerate(zip(layers, (w1, w2, w3, w4, w5))):
                     lin.weight.copy_(w.to(lin.weight.device))
                     if lin.bias is not None:
-                        lin.bias.zero_()
+                        if i == 0:
+                            lin.bias.copy_(bias1.to(lin.bias.device))
+                        else:
+                            lin.bias.zero_()
         else:                                                        # nn.Linear networks: same keys as FusedUVNet
             self.uv_net.load_state_dict(sd)
 

@@ -30,7 +30,8 @@ else:
     util.run_cuda = util.run_emu
 torch.cuda.is_available = lambda: True
 SEL = ("test_golden_tiny_scene or test_forward_parity_small or test_backward_parity_small or test_clamp_paths or test_saturating "
-       "or test_camera_inside or test_heterogeneous or test_long_tile_lists or test_forward_is_deterministic")
+       "or test_camera_inside or test_heterogeneous or test_long_tile_lists or test_forward_is_deterministic or test_spec_switch_inst "
+       "or test_upstream_clamp")
 if "config0" in sys.argv[1:]:
     SEL += " or test_config0_10k_256_forward_and_backward"
 sys.exit(pytest.main([str(ROOT / "tests" / "test_gpu_parity.py"), "-m", "gpu", "-q", "--tb=short", "-k", SEL, "-p", "no:cacheprovider",
