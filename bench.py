@@ -41,7 +41,8 @@ KERNELS_PER_VIEW = 8   # (+1 texgs_pack_texture_kernel per step) preprocess_fwd,
                        # sort_tiles, render_fwd, render_bwd, preprocess_bwd
 
 
-DEFAULT_STREAMS = 3    # views in flight per rank (profiles/r2_variants.md: 1 -> 371, 2 -> 396, 3 -> 405 views/s)
+DEFAULT_STREAMS = 4    # views in flight per rank (profiles/r2_variants.md: 1 -> 371, 2 -> 396, 3 -> 405 views/s; 4 = 3 at one GPU and
+                       # divides the 4 views a rank renders at 8 GPUs: no straggler view running alone)
 
 
 def parse():
@@ -54,6 +55,10 @@ def parse():
     ap.add_argument("--views", type=int, default=VIEWS_PER_STEP)
     ap.add_argument("--streams", type=int, default=DEFAULT_STREAMS,
                     help="CUDA streams per rank that render alternate views concurrently (they share the gradient bucket: atomic adds)")
+    ap.add_argument("--no-optimizer", action="store_true",
+                    help="leave the texture's Adam step out of the step and (N > 1) all-reduce the whole bucket with NCCL instead of "
+                         "the fused reduce + Adam + broadcast kernel (the round-1 definition of the step)")
+    ap.add_argument("--no-multicast", action="store_true", help="N > 1: peer loads / stores instead of NVSwitch multimem in the fused texture step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-pass", action="store_true", help="skip the single-stream per-kernel timing pass (roofline.per_kernel)")
@@ -335,8 +340,23 @@ def main():
     bg = torch.zeros(3, device=dev)
     # retexture.py renders every view twice (with SH, then active_sh_degree = 0): one dual render here
     render_fn = uv_tex_render_dual if (not bwd and wl.renders_per_view == 2) else uv_tex_render
-    bucket = GradBucket({k: v for k, v in g.tensors().items()}) if bwd else None
+    use_opt = bwd and not args.no_optimizer
+    bucket = GradBucket({k: v for k, v in g.tensors().items()},
+                        symmetric_group=dist.group.WORLD if (use_opt and world > 1) else None) if bwd else None
     views = shard_views(args.views, world, rank)
+    # the texture's optimizer (models/texture_gaussian3d.py:139-143: Adam, lr = tex_lr 0.0025, eps 1e-15) is part of the step:
+    # one GPU runs the fused TextureAdam kernel; N GPUs run ONE kernel each that pulls + adds the ranks' partial texture gradients
+    # over NVLink (multimem through the NVSwitch when available), updates the owned 1/N of the texels and pushes them to every rank —
+    # instead of all-reducing 403 MB and repeating the same update N times. The per-Gaussian gradients (118 MB) go through NCCL.
+    opt = None
+    if use_opt:
+        if world > 1:
+            from texture_gs_b200.dist import DistTextureAdam
+            opt = DistTextureAdam(g.get_texture, bucket, lr=0.0025, eps=1e-15, use_multicast=False if args.no_multicast else None)
+        else:
+            from texture_gs_b200.optim import TextureAdam
+            opt = TextureAdam([g.get_texture], lr=0.0025, eps=1e-15)
+    tex0_l1 = float(g.get_texture.detach().abs().sum().item())
 
     def sync_all():
         if world > 1:
@@ -345,14 +365,38 @@ def main():
 
     from texture_gs_b200 import invalidate_packed_cache
 
-    def step(tm=None, nstreams=streams):
-        # one texture update per step: the packed (6,R,R,4) copy is rebuilt once per 32-view batch
-        invalidate_packed_cache()
+    def finish_step():
+        """What follows the last view of a step: reduce the gradients over the ranks and (unless --no-optimizer) update the texture."""
+        if not bwd:
+            return
+        if opt is None:
+            bucket.all_reduce()
+        elif world > 1:
+            works = bucket.all_reduce(exclude=("texture",), async_op=True)      # per-Gaussian gradients: NCCL, concurrently
+            opt.step()
+            for w in works or []:
+                w.wait()
+        else:
+            opt.step()
+
+    fin_ev = []            # (start, end) CUDA events around finish_step() of the timed steps
+
+    def step(tm=None, nstreams=streams, record=False):
+        # one texture update per step: the packed (6,R,R,4) copy is rebuilt once per 32-view batch (by the optimizer
+        # kernel itself on one GPU, by the pack kernel after the fused multi-GPU step)
+        if opt is None:
+            invalidate_packed_cache()
         if bwd:
             bucket.zero()
         render_views_accumulate(render_fn, g, cams, cot, views, bg, timer=tm, bucket=bucket, streams=nstreams, backward=bwd)
-        if bwd:
-            bucket.all_reduce()
+        if record:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+            finish_step()
+            ev[1].record()
+            fin_ev.append(ev)
+        else:
+            finish_step()
 
     for _ in range(args.warmup):
         step()
@@ -367,11 +411,12 @@ def main():
     t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        step()
+        step(record=True)
     e1.record()
     sync_all()
     wall_ms = (time.perf_counter() - t0) * 1e3
     ms = e0.elapsed_time(e1)
+    finish_ms = sum(a.elapsed_time(b) for a, b in fin_ev) / max(1, len(fin_ev))
     if world > 1:
         tms = torch.tensor([ms, wall_ms], device=dev)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -382,9 +427,19 @@ def main():
     # ---- checksum of the all-reduced gradient bucket: the same number at every N (up to the order of the atomics) ----
     checksum = None
     if bwd:
-        fl = bucket.flat.double()
-        checksum = {"l1": float(fl.abs().sum().item()), "sum": float(fl.sum().item()), "numel": bucket.flat.numel(),
-                    "what": f"all-reduced gradient bucket after the last timed step ({args.views} views)"}
+        rest = [bucket.flat[a:b].double() for a, b in bucket.ranges_without(("texture",))]
+        checksum = {"gaussian_grads_l1": float(sum(r.abs().sum() for r in rest).item()),
+                    "gaussian_grads_sum": float(sum(r.sum() for r in rest).item()),
+                    "what": f"all-reduced per-Gaussian gradients of the last timed step ({args.views} views)"}
+        if opt is None:
+            tg = bucket.grads()["texture"].double()
+            checksum.update(texture_grad_l1=float(tg.abs().sum().item()), texture_grad_sum=float(tg.sum().item()))
+        else:
+            tx = g.get_texture.detach().double()
+            checksum.update(texture_l1=float(tx.abs().sum().item()), texture_sum=float(tx.sum().item()), texture_l1_initial=tex0_l1,
+                            optimizer_steps=args.warmup + args.steps,
+                            texture_what="the texture after warmup + steps Adam updates: the same on every rank and for every N "
+                                         "(up to the order of the gradient atomics)")
 
     # ---- per-kernel durations: ONE stream, so that no other view's kernels share the SMs with the kernel being timed ----
     stage_ms, timing_note = {}, None
@@ -402,7 +457,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         try:
-            e2e = run_e2e(args, wl, g, cams, bg, bucket, views, dev, world, sync_all, render_fn, streams)
+            e2e = run_e2e(args, wl, g, cams, bg, bucket, views, dev, world, sync_all, render_fn, streams, finish_step, opt is None)
         except Exception as e:              # keep the device-resident measurement; the line then says why e2e is missing
             if world > 1:
                 raise                       # a rank that drops out of the collectives would hang the others
@@ -444,11 +499,16 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(wl, args.views),
             "impl_notes": {"streams_per_rank": streams,
-                           "parallelism": (f"dp{world} (views sharded, 1 all-reduce of {bucket.nbytes / 1e6:.0f} MB/step)" if (world > 1 and bwd)
-                                           else (f"dp{world} (views sharded)" if world > 1 else "single GPU")),
+                           "parallelism": ((f"dp{world} (views sharded; per step: fused texture-gradient reduce + Adam + broadcast kernel over NVLink "
+                                            f"[{'multimem / NVLS' if opt.multicast else 'peer loads / stores'}], NCCL all-reduce of the other "
+                                            f"{sum(b - a for a, b in bucket.ranges_without(('texture',))) * 4 / 1e6:.0f} MB)") if (world > 1 and opt is not None)
+                                           else (f"dp{world} (views sharded, 1 all-reduce of {bucket.nbytes / 1e6:.0f} MB/step)" if (world > 1 and bwd)
+                                                 else (f"dp{world} (views sharded)" if world > 1 else "single GPU"))),
+                           "optimizer_in_step": (None if not bwd else ("none (--no-optimizer)" if opt is None else "texture Adam (lr 0.0025, eps 1e-15)")),
                            "l2_policy": "inputs larger than L2 (texture %d MB + records %d MB, a different camera every view)"
                                         % (6 * wl.tex_res ** 2 * 12 // 1000000, wl.n_gaussians * 128 // 1000000),
-                           "render_fn": render_fn.__name__, "host_wall_ms_per_step": wall_ms / args.steps, "numa_node": numa_node},
+                           "render_fn": render_fn.__name__, "host_wall_ms_per_step": wall_ms / args.steps, "numa_node": numa_node,
+                           "reduce_and_optimizer_ms_per_step": finish_ms},
             "clocks": clock_rec, "e2e": e2e, "gpu_launches": (kernels_per_view * len(views) + 1) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "grad_checksum": checksum}
     print(json.dumps(line), flush=True)
@@ -475,7 +535,7 @@ def make_supervision(wl, n_views: int, seed: int = 5):
     return out
 
 
-def run_e2e(args, wl, g, cams, bg, bucket, views, dev, world, sync_all, render_fn, streams):
+def run_e2e(args, wl, g, cams, bg, bucket, views, dev, world, sync_all, render_fn, streams, finish_step, invalidate):
     """The step a user of the reference runs, through the public operators, with HOST inputs (train.py:147-149,
     models/texture_gaussian3d.py:315-368 with the losses configs/texture_gaussian3d.yaml:77-88 enables): per view the
     ground-truth image (uint8), the alpha mask (uint8) and the normal prior (int8) are copied from pinned host memory on
@@ -554,7 +614,8 @@ def run_e2e(args, wl, g, cams, bg, bucket, views, dev, world, sync_all, render_f
             free[i % nslots].record(torch.cuda.current_stream(dev))
 
         def step():
-            invalidate_packed_cache()
+            if invalidate:
+                invalidate_packed_cache()
             bucket.zero()
             total.zero_()
             for s in range(nslots):
@@ -562,7 +623,7 @@ def run_e2e(args, wl, g, cams, bg, bucket, views, dev, world, sync_all, render_f
             upload(0)
             render_views_accumulate(render_fn, g, cams, None, views, bg, bucket=bucket, streams=streams, loss_fn=loss_fn,
                                     before_view=before_view, after_view=after_view)
-            bucket.all_reduce()
+            finish_step()
             result_host.copy_(total.sum().reshape(1), non_blocking=True)
 
     for _ in range(max(3, args.warmup)):
@@ -587,7 +648,7 @@ def run_e2e(args, wl, g, cams, bg, bucket, views, dev, world, sync_all, render_f
             "result": float(result_host.item()),
             "what": ("render + uint8 frame(s) read back per view (retexture.py)" if not bwd else
                      "uint8 image + uint8 mask + int8 normals H2D per view -> render -> fused losses (photometric, alpha, normal, "
-                     "normal smoothness) -> backward -> bucket all-reduce -> loss D2H per step")}
+                     "normal smoothness) -> backward -> gradient reduction (+ texture Adam) -> loss D2H per step")}
 
 
 if __name__ == "__main__":

@@ -240,6 +240,30 @@ int texgs_texture_adam_step(float* param, float* exp_avg, float* exp_avg_sq, con
                             float* param_rgba, uint64_t n_texels, double lr, double beta1, double beta2, double eps,
                             int32_t step, int32_t zero_grad, void* stream);
 
+/* ---- data-parallel texture step — gradient reduction + Adam + parameter broadcast in one kernel ----------
+ * One process per GPU, ``world`` ranks, the texture gradient of every rank in a symmetric buffer (padded (n,4) layout) and the
+ * texture parameter (n,3) in another. Rank ``rank`` owns the texels of tiles [tile_lo, tile_hi) (1024 texels per tile;
+ * texgs_dp_shard gives the canonical split), pulls and adds the ``world`` partial gradients of its tiles over NVLink
+ * (multimem.ld_reduce through ``grad_mc`` / ``param_mc``, the NVSwitch multicast mappings, when both are non-NULL; plain peer
+ * loads / stores through ``grad_ptrs`` / ``param_ptrs`` otherwise), applies texgs_texture_adam_step's update to its shard
+ * (``exp_avg`` / ``exp_avg_sq`` hold the owned texels only) and writes the updated texels into every rank's parameter.
+ * Replaces the NCCL all-reduce of the texture gradient + ``world`` identical optimizer steps. The caller synchronises the
+ * ranks before (all backward passes complete) and after (all owners done) the call; the gradients are left untouched. */
+typedef struct TexgsDpAdamArgs {
+    int32_t world, rank;
+    const float* grad_ptrs[16];
+    float* param_ptrs[16];
+    const float* grad_mc;
+    float* param_mc;
+    float* exp_avg;
+    float* exp_avg_sq;
+    uint64_t n_texels, tile_lo, tile_hi;
+    double lr, beta1, beta2, eps;
+    int32_t step, reserved;
+} TexgsDpAdamArgs;
+int texgs_dp_shard(uint64_t n_texels, int32_t world, int32_t rank, uint64_t* tile_lo, uint64_t* tile_hi);
+int texgs_texture_adam_dp_step(const TexgsDpAdamArgs* args, void* stream);
+
 /* ---- UV + Jacobian producer --------------------------------------------------------------
  * uv = normalize(mlp(relu(pre_mlp((xyz - offset) / scale) + emb)))   (models/modules/uv_net.py:19-36) and
  * J[n, 3i+j] = d uv_i / d xyz_j  (TextureGaussian3D.get_grad_uvs, models/texture_gaussian3d.py:217-227) in ONE

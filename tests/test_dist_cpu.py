@@ -137,3 +137,40 @@ def test_quiet_init_restores_stdout_and_the_group_works(tmp_path):
     for r, (p, (so, se)) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, se
         assert so.splitlines() == ["before", '{"rank": %d, "sum": 3}' % r], (so, se)
+
+
+def test_all_reduce_ranges_leave_the_excluded_parameters_alone():
+    """bucket.all_reduce(exclude=("texture",)): the texture slice is reduced by DistTextureAdam's own kernel; everything
+    else goes out as the contiguous ranges around it."""
+    tex = torch.randn(6, 4, 4, 3, requires_grad=True)
+    a = torch.randn(9, 3, requires_grad=True)
+    b = torch.randn(5, requires_grad=True)
+    bk = GradBucket({"a": a, "texture": tex, "b": b})
+    r = bk.ranges_without(("texture",))
+    o, n = bk.offsets["texture"]
+    assert r == [(0, o), ((o + n + 63) // 64 * 64, bk.flat.numel())]
+    assert bk.ranges_without(()) == [(0, bk.flat.numel())]
+    covered = torch.zeros(bk.flat.numel(), dtype=torch.bool)
+    for x, y in r:
+        covered[x:y] = True
+    for k in ("a", "b"):
+        ko, kn = bk.offsets[k]
+        assert bool(covered[ko:ko + kn].all())
+    assert not bool(covered[o:o + n].any())
+
+
+def test_dp_shard_partitions_the_texture_tiles():
+    """texgs_dp_shard: contiguous tile ranges (1024 texels per tile) that cover every tile exactly once, sizes within one."""
+    import ctypes as C
+    from texture_gs_b200 import _lib as L
+    lib = L.load()
+    for n, world in ((6 * 2048 * 2048, 8), (6 * 96 * 96, 3), (1000, 4), (1024 * 7 + 5, 2)):
+        tiles = (n + 1023) // 1024
+        prev = 0
+        for r in range(world):
+            lo, hi = C.c_uint64(), C.c_uint64()
+            assert lib.texgs_dp_shard(n, world, r, C.byref(lo), C.byref(hi)) == 0
+            assert lo.value == prev and hi.value >= lo.value and hi.value - lo.value <= tiles // world + 1
+            prev = hi.value
+        assert prev == tiles
+    assert lib.texgs_dp_shard(10, 2, 2, C.byref(lo), C.byref(hi)) != 0

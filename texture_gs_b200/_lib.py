@@ -79,6 +79,14 @@ class TexgsUvMlpArgs(C.Structure):
                 ("stash", C.c_void_p * 4), ("stash_inv_len", C.c_void_p), ("debug_accumulators", C.c_void_p)]
 
 
+class TexgsDpAdamArgs(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("grad_ptrs", C.c_void_p * 16), ("param_ptrs", C.c_void_p * 16),
+                ("grad_mc", C.c_void_p), ("param_mc", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("n_texels", C.c_uint64), ("tile_lo", C.c_uint64), ("tile_hi", C.c_uint64),
+                ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("step", C.c_int32), ("reserved", C.c_int32)]
+
+
 # every symbol include/texgs.h declares: (name, restype, argtypes)
 SYMBOLS = {
     "texgs_abi_version": (C.c_int, []),
@@ -99,6 +107,8 @@ SYMBOLS = {
     "texgs_geometry_loss_backward": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_float, _fp, _fp, _fp, _fp, C.c_void_p]),
     "texgs_texture_adam_step": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double,
                                           C.c_int32, C.c_int32, C.c_void_p]),
+    "texgs_dp_shard": (C.c_int, [C.c_uint64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "texgs_texture_adam_dp_step": (C.c_int, [C.POINTER(TexgsDpAdamArgs), C.c_void_p]),
     "texgs_uvmlp_forward": (C.c_int, [C.POINTER(TexgsUvMlpArgs), C.c_void_p]),
     "texgs_uvmlp_backward_head": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
     "texgs_uvmlp_backward_mask": (C.c_int, [C.c_int32, _fp, _fp, _fp, C.c_void_p]),

@@ -207,7 +207,7 @@ const char* texgs_kernel_names(void) {
     return "texgs_preprocess_fwd,texgs_scan_tiles,texgs_scatter_pairs,texgs_sort_tiles_small,texgs_sort_tiles,texgs_render_fwd,"
            "texgs_render_bwd,texgs_extra_fwd,texgs_extra_bwd,texgs_preprocess_bwd,texgs_mark_visible_kernel,texgs_pack_texture_kernel,"
            "texgs_photometric_fwd_kernel,texgs_photometric_finalize_kernel,texgs_photometric_bwd_kernel,"
-           "texgs_geometry_loss_fwd_kernel,texgs_geometry_loss_finalize_kernel,texgs_geometry_loss_bwd_kernel,texgs_texture_adam_kernel,texgs_uvmlp_fwd_kernel,"
+           "texgs_geometry_loss_fwd_kernel,texgs_geometry_loss_finalize_kernel,texgs_geometry_loss_bwd_kernel,texgs_texture_adam_kernel,texgs_texture_adam_dp_kernel,texgs_uvmlp_fwd_kernel,"
            "texgs_uvmlp_bwd_amax_kernel,texgs_uvmlp_bwd_head_kernel,texgs_uvmlp_bwd_mask_kernel,texgs_uvmlp_bwd_tail_kernel";
 }
 
@@ -510,6 +510,47 @@ int texgs_texture_adam_step(float* param, float* exp_avg, float* exp_avg_sq, con
     texgs_texture_adam_kernel<<<(unsigned)ctas, TEXGS_ADAM_THREADS, 0, stream>>>(a);
     TEXGS_KERNEL_CHECK("texgs_texture_adam_kernel", false, stream);
     return 0;
+}
+
+int texgs_dp_shard(uint64_t n_texels, int32_t world, int32_t rank, uint64_t* tile_lo, uint64_t* tile_hi) {
+    if (world < 1 || rank < 0 || rank >= world || !tile_lo || !tile_hi) return fail(TEXGS_E_INVALID, "bad arguments");
+    const uint64_t tiles = (n_texels + TEXGS_ADAM_TEXELS - 1) / TEXGS_ADAM_TEXELS;
+    *tile_lo = tiles * (uint64_t)rank / (uint64_t)world;
+    *tile_hi = tiles * (uint64_t)(rank + 1) / (uint64_t)world;
+    return 0;
+}
+
+int texgs_texture_adam_dp_step(const TexgsDpAdamArgs* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!a || a->world < 1 || a->world > TEXGS_DP_MAX_RANKS || a->rank < 0 || a->rank >= a->world || a->step < 1 || !a->exp_avg || !a->exp_avg_sq ||
+        !(a->beta1 >= 0.0 && a->beta1 < 1.0) || !(a->beta2 >= 0.0 && a->beta2 < 1.0) || a->tile_hi < a->tile_lo ||
+        a->tile_hi * TEXGS_ADAM_TEXELS >= a->n_texels + TEXGS_ADAM_TEXELS)
+        return fail(TEXGS_E_INVALID, "bad arguments (1 <= world <= 16, step >= 1, betas in [0,1), tile range inside the texture)");
+    uintptr_t al = (uintptr_t)a->exp_avg | (uintptr_t)a->exp_avg_sq | (uintptr_t)a->grad_mc | (uintptr_t)a->param_mc;
+    for (int r = 0; r < a->world; ++r) {
+        if (!a->grad_ptrs[r] || !a->param_ptrs[r]) return fail(TEXGS_E_INVALID, "a peer pointer is NULL");
+        al |= (uintptr_t)a->grad_ptrs[r] | (uintptr_t)a->param_ptrs[r];
+    }
+    if (al & 15) return fail(TEXGS_E_INVALID, "all buffers must be 16-byte aligned");
+    if ((a->grad_mc == nullptr) != (a->param_mc == nullptr)) return fail(TEXGS_E_INVALID, "give both multicast mappings or neither");
+#ifdef TEXGS_HOST_EMU
+    return fail(TEXGS_E_INVALID, "the data-parallel texture step needs NVLink peers (no host emulation)");
+#else
+    if (a->tile_hi == a->tile_lo) return 0;
+    DpAdamArgs k;
+    k.world = a->world; k.rank = a->rank;
+    for (int r = 0; r < TEXGS_DP_MAX_RANKS; ++r) { k.grad[r] = r < a->world ? a->grad_ptrs[r] : nullptr; k.param[r] = r < a->world ? a->param_ptrs[r] : nullptr; }
+    k.grad_mc = a->grad_mc; k.param_mc = a->param_mc; k.m = a->exp_avg; k.v = a->exp_avg_sq;
+    k.n = a->n_texels; k.tile_lo = a->tile_lo; k.tile_hi = a->tile_hi;
+    const double bc1 = 1.0 - pow(a->beta1, (double)a->step), bc2 = 1.0 - pow(a->beta2, (double)a->step);
+    k.one_minus_b1 = (float)(1.0 - a->beta1); k.b2 = (float)a->beta2; k.one_minus_b2 = (float)(1.0 - a->beta2);
+    k.step_size = (float)(a->lr / bc1); k.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2)); k.eps = (float)a->eps;
+    const unsigned ctas = (unsigned)(a->tile_hi - a->tile_lo);
+    if (a->grad_mc) texgs_texture_adam_dp_kernel<true><<<ctas, TEXGS_ADAM_THREADS, 0, stream>>>(k);
+    else texgs_texture_adam_dp_kernel<false><<<ctas, TEXGS_ADAM_THREADS, 0, stream>>>(k);
+    TEXGS_KERNEL_CHECK("texgs_texture_adam_dp_kernel", false, stream);
+    return 0;
+#endif
 }
 
 int texgs_uvmlp_forward(const TexgsUvMlpArgs* a, void* stream_) {

@@ -140,3 +140,125 @@ __global__ void __launch_bounds__(TEXGS_ADAM_THREADS, TEXGS_ADAM_MIN_CTAS) texgs
         }
     }
 }
+
+// =============================================================================================================
+// Data-parallel texture step: gradient reduction + Adam + parameter broadcast in ONE kernel over NVLink.
+//
+// With the view batch sharded over N GPUs every rank holds a dense partial gradient of the whole texture. Instead of
+// all-reducing it (2 (N-1)/N x 403 MB over the links) and then running the same Adam step on every rank, rank r owns the
+// texels of tile range [tile_lo, tile_hi) (1/N of the texture) and, for each of its tiles,
+//   1. PULLS the N partial gradients of the tile out of the ranks' symmetric buffers and adds them
+//        - multicast path: one multimem.ld_reduce per 16 bytes, the NVSwitch adds the N copies in the fabric (NVLS)
+//        - peer path: N plain 128-bit loads through the peer mappings (NVLink P2P)
+//   2. updates its shard of the Adam moments (kept only for the owned texels: the optimizer state is sharded)
+//   3. PUSHES the updated parameter texels into every rank's copy of the texture
+//        - multicast path: multimem.st (the switch replicates), peer path: N stores.
+// Links carry (N-1)/N x (403 + 302) MB per rank and direction (peer path) or 403 (N-1)/N out + 302 (N-1)/N in (multicast)
+// instead of 2 (N-1)/N x 403 MB each way, the optimizer arithmetic and its 24 B/texel of state traffic divide by N, and
+// no gradient is written back. Callers bracket the launch with device-side barriers over the symmetric-memory signal
+// pads (every rank's backward is complete before anyone pulls; nobody clears its gradient or samples the texture before
+// every owner is done) — texture_gs_b200/dist.py DistTextureAdam.
+// =============================================================================================================
+#define TEXGS_DP_MAX_RANKS 16
+
+struct DpAdamArgs {
+    int world, rank;
+    const float* grad[TEXGS_DP_MAX_RANKS];     // every rank's padded (n,4) gradient (peer mappings; [rank] is local)
+    float* param[TEXGS_DP_MAX_RANKS];          // every rank's (n,3) parameter
+    const float* grad_mc;                      // multicast mappings of the same two buffers, or NULL (peer path)
+    float* param_mc;
+    float* m; float* v;                        // moments of the OWNED texels only: ((tile_hi - tile_lo) * 1024 * 3) floats
+    unsigned long long n;                      // texels of the whole texture
+    unsigned long long tile_lo, tile_hi;       // owned tiles of TEXGS_ADAM_TEXELS texels
+    float one_minus_b1, b2, one_minus_b2, step_size, inv_sqrt_bc2, eps;
+};
+
+#ifndef TEXGS_HOST_EMU
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float4* mc) {
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+    return r;
+}
+__device__ __forceinline__ void multimem_st(float4* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <bool MC>
+__global__ void __launch_bounds__(TEXGS_ADAM_THREADS, 2) texgs_texture_adam_dp_kernel(const DpAdamArgs a) {
+    __shared__ __align__(16) float sg[TEXGS_ADAM_TEXELS * 3];
+    const unsigned long long tile = a.tile_lo + blockIdx.x;
+    const unsigned long long t0 = tile * TEXGS_ADAM_TEXELS;                      // first texel of the tile (global numbering)
+    const unsigned long long l0 = (unsigned long long)blockIdx.x * TEXGS_ADAM_TEXELS;   // ... in the owned shard (moments)
+    const int tid = threadIdx.x;
+    constexpr int KT = TEXGS_ADAM_TEXELS / TEXGS_ADAM_THREADS;           // texel float4s per thread (4)
+    constexpr int KF = 3 * TEXGS_ADAM_TEXELS / 4 / TEXGS_ADAM_THREADS;   // flat float4s per thread (3)
+    AdamArgs e;                                                          // the elementwise update shares adam_elem()
+    e.one_minus_b1 = a.one_minus_b1; e.b2 = a.b2; e.one_minus_b2 = a.one_minus_b2;
+    e.step_size = a.step_size; e.inv_sqrt_bc2 = a.inv_sqrt_bc2; e.eps = a.eps;
+    if (t0 + TEXGS_ADAM_TEXELS <= a.n) {
+        // 1. pull + add the N partial gradients of the tile; the local parameter / moment loads fly with them
+        float4 G[KT];
+        if (MC) {
+            const float4* g = reinterpret_cast<const float4*>(a.grad_mc) + t0;
+#pragma unroll
+            for (int k = 0; k < KT; ++k) G[k] = multimem_ld_reduce_add(g + tid + k * TEXGS_ADAM_THREADS);
+        } else {
+#pragma unroll
+            for (int k = 0; k < KT; ++k) G[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < a.world; ++r) {
+                const float4* g = reinterpret_cast<const float4*>(a.grad[(a.rank + r) % a.world]) + t0;   // start at home: spreads the peers
+#pragma unroll
+                for (int k = 0; k < KT; ++k) {
+                    const float4 x = __ldcs(g + tid + k * TEXGS_ADAM_THREADS);
+                    G[k].x += x.x; G[k].y += x.y; G[k].z += x.z;
+                }
+            }
+        }
+        float4* p4 = reinterpret_cast<float4*>(a.param[a.rank] + t0 * 3);
+        float4* m4 = reinterpret_cast<float4*>(a.m + l0 * 3);
+        float4* v4 = reinterpret_cast<float4*>(a.v + l0 * 3);
+        float4 P[KF], M[KF], V[KF];
+#pragma unroll
+        for (int k = 0; k < KF; ++k) {
+            const int f = tid + k * TEXGS_ADAM_THREADS;
+            P[k] = p4[f]; M[k] = m4[f]; V[k] = v4[f];
+        }
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            const int t = tid + k * TEXGS_ADAM_THREADS;
+            sg[3 * t] = G[k].x; sg[3 * t + 1] = G[k].y; sg[3 * t + 2] = G[k].z;
+        }
+        __syncthreads();
+        // 2. Adam on flat float4s, 3. push the updated parameters to every rank
+#pragma unroll
+        for (int k = 0; k < KF; ++k) {
+            const int f = tid + k * TEXGS_ADAM_THREADS;
+            const float4 g = reinterpret_cast<float4*>(sg)[f];
+            adam_elem(P[k].x, M[k].x, V[k].x, g.x, e); adam_elem(P[k].y, M[k].y, V[k].y, g.y, e);
+            adam_elem(P[k].z, M[k].z, V[k].z, g.z, e); adam_elem(P[k].w, M[k].w, V[k].w, g.w, e);
+            m4[f] = M[k]; v4[f] = V[k];
+            if (MC) {
+                multimem_st(reinterpret_cast<float4*>(a.param_mc + t0 * 3) + f, P[k]);
+            } else {
+                for (int r = 0; r < a.world; ++r)
+                    reinterpret_cast<float4*>(a.param[(a.rank + r) % a.world] + t0 * 3)[f] = P[k];
+            }
+        }
+    } else {
+        // tail tile (n % 1024 texels): scalar, peer path on both variants (a handful of texels)
+        for (unsigned long long t = t0 + tid; t < a.n; t += TEXGS_ADAM_THREADS) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float g = 0.f;
+                for (int r = 0; r < a.world; ++r) g += a.grad[r][t * 4 + c];
+                const unsigned long long el = (t - a.tile_lo * TEXGS_ADAM_TEXELS) * 3 + c;
+                float p = a.param[a.rank][t * 3 + c], m = a.m[el], v = a.v[el];
+                adam_elem(p, m, v, g, e);
+                a.m[el] = m; a.v[el] = v;
+                for (int r = 0; r < a.world; ++r) a.param[r][t * 3 + c] = p;
+            }
+        }
+    }
+}
+#endif

@@ -68,10 +68,14 @@ class GradBucket:
     the all-reduce runs on — and autograd's separate ``AccumulateGrad`` pass (a zero-fill, a dense
     gradient tensor and an add kernel per input per view) disappears."""
 
-    def __init__(self, params: Dict[str, torch.Tensor], pad_texture: bool = True):
+    def __init__(self, params: Dict[str, torch.Tensor], pad_texture: bool = True, symmetric_group=None):
         """One flat buffer for all streams: every accumulation the backward kernels do into it is atomic (vector
         ``red`` for texels, ``red`` / TMA bulk reductions for the per-Gaussian gradients), so views rendered
-        concurrently on several CUDA streams (``render_views_accumulate(..., streams=n)``) share it."""
+        concurrently on several CUDA streams (``render_views_accumulate(..., streams=n)``) share it.
+
+        ``symmetric_group`` (a process group, CUDA + NCCL only): the buffer is allocated as symmetric memory and
+        exchanged with the group's ranks, so that their kernels can read it over NVLink (``DistTextureAdam``: the
+        texture gradient is then reduced by the owner ranks instead of being all-reduced)."""
         self.params = {k: v for k, v in params.items() if v is not None and v.requires_grad}
         if not self.params:
             raise ValueError("no tensor requires grad")
@@ -84,7 +88,14 @@ class GradBucket:
             self.offsets[k] = (off, n)
             self.padded[k] = pad
             off += (n + 63) // 64 * 64          # keep every slice 256-byte aligned
-        self.flat = torch.zeros(off, dtype=torch.float32, device=first.device)
+        self.symm = None
+        if symmetric_group is not None:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.flat = symm_mem.empty(off, dtype=torch.float32, device=first.device)
+            self.flat.zero_()
+            self.symm = symm_mem.rendezvous(self.flat, symmetric_group.group_name)
+        else:
+            self.flat = torch.zeros(off, dtype=torch.float32, device=first.device)
         self._by_id = {id(v): k for k, v in self.params.items()}
         self.install()
 
@@ -132,15 +143,111 @@ class GradBucket:
         finally:
             _fused.bucket = prev
 
-    def all_reduce(self, group=None, async_op: bool = False):
-        """Sum over ranks (one NCCL all-reduce per step over the flat bucket)."""
+    def all_reduce(self, group=None, async_op: bool = False, exclude: Sequence[str] = ()):
+        """Sum over ranks (one NCCL all-reduce per step over the flat bucket). ``exclude``: parameter names
+        whose slices are left alone (the texture when ``DistTextureAdam`` reduces it itself); the rest goes out as the
+        contiguous ranges around them. Returns the work handle(s) with ``async_op``."""
         if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
             return None
-        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        if not exclude:
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        works = [dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+                 for a, b in self.ranges_without(exclude)]
+        return works if async_op else None
+
+    def ranges_without(self, exclude: Sequence[str]):
+        """Contiguous [a, b) element ranges of the flat buffer that do not belong to the named parameters."""
+        cuts = sorted((self.offsets[k][0], self.offsets[k][0] + (self.offsets[k][1] + 63) // 64 * 64) for k in exclude if k in self.offsets)
+        out, pos = [], 0
+        for a, b in cuts:
+            if a > pos:
+                out.append((pos, a))
+            pos = max(pos, b)
+        if pos < self.flat.numel():
+            out.append((pos, self.flat.numel()))
+        return out
 
     @property
     def nbytes(self) -> int:
         return self.flat.numel() * 4
+
+
+class DistTextureAdam:
+    """The texture's optimizer step across ``world`` GPUs without an all-reduce of its gradient.
+
+    Every rank accumulates the texture gradient of its views into a symmetric ``GradBucket``. ``step()`` then runs ONE
+    kernel per rank (``texgs_texture_adam_dp_step``): the rank owns 1/world of the texels, pulls the ``world`` partial
+    gradients of those texels over NVLink — ``multimem.ld_reduce`` through the NVSwitch multicast mapping when the
+    fabric offers one, plain peer loads otherwise —, applies ``torch.optim.Adam``'s update (the reference's optimizer,
+    ``models/texture_gaussian3d.py:139-143``) to its shard of the moments and pushes the updated texels into every
+    rank's copy of the texture (``multimem.st`` / peer stores). Device-side barriers over the symmetric-memory signal
+    pads bracket the kernel. The texture's storage is moved into symmetric memory at construction (same tensor object);
+    the Adam moments exist for the owned shard only (``state_shard()``).
+
+    Same hyper-parameter semantics as ``TextureAdam`` / ``torch.optim.Adam``; ``param_groups[0]['lr']`` may be changed
+    between steps (schedulers)."""
+
+    def __init__(self, texture: torch.Tensor, bucket: "GradBucket", lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 group=None, name: str = "texture", use_multicast: Optional[bool] = None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib as L
+        if bucket.symm is None:
+            raise ValueError("DistTextureAdam needs a GradBucket(..., symmetric_group=group)")
+        if not (texture.is_cuda and texture.dtype == torch.float32 and texture.is_contiguous() and texture.numel() % 3 == 0):
+            raise L.TexgsError("DistTextureAdam: the texture must be a contiguous fp32 CUDA tensor with numel % 3 == 0")
+        if bucket.storage_for(texture) is None or not bucket.padded[name]:
+            raise ValueError("the texture must be a (padded) leaf of the bucket")
+        group = group or dist.group.WORLD
+        self.group, self.bucket, self.texture, self.name = group, bucket, texture, name
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.param_groups = [dict(lr=lr, betas=tuple(betas), eps=eps)]
+        self.n_texels = texture.numel() // 3
+        # the parameter moves into symmetric memory: peers write their shards of the update into it
+        buf = symm_mem.empty(texture.numel(), dtype=torch.float32, device=texture.device)
+        buf.copy_(texture.detach().reshape(-1))
+        texture.data = buf.view(texture.shape)
+        self.param_symm = symm_mem.rendezvous(buf, group.group_name)
+        lo, hi = C.c_uint64(), C.c_uint64()
+        L.check(L.load().texgs_dp_shard(self.n_texels, self.world, self.rank, C.byref(lo), C.byref(hi)), "texgs_dp_shard")
+        self.tile_lo, self.tile_hi = lo.value, hi.value
+        own = max(1, (self.tile_hi - self.tile_lo) * 1024 * 3)
+        self.exp_avg = torch.zeros(own, dtype=torch.float32, device=texture.device)
+        self.exp_avg_sq = torch.zeros(own, dtype=torch.float32, device=texture.device)
+        self.step_count = 0
+        g_mc, p_mc = int(getattr(bucket.symm, "multicast_ptr", 0) or 0), int(getattr(self.param_symm, "multicast_ptr", 0) or 0)
+        self.multicast = bool(g_mc and p_mc) if use_multicast is None else bool(use_multicast and g_mc and p_mc)
+        self._mc = (g_mc, p_mc)
+
+    def state_shard(self):
+        """(first owned texel, exp_avg, exp_avg_sq) — the moments of texels [tile_lo*1024, min(tile_hi*1024, n))."""
+        return self.tile_lo * 1024, self.exp_avg, self.exp_avg_sq
+
+    @torch.no_grad()
+    def step(self):
+        import ctypes as C
+        from . import _lib as L
+        lib = L.load()
+        dev = self.texture.device
+        self.step_count += 1
+        pg = self.param_groups[0]
+        a = L.TexgsDpAdamArgs()
+        a.world, a.rank = self.world, self.rank
+        off = 4 * self.bucket.offsets[self.name][0]
+        for r in range(self.world):
+            a.grad_ptrs[r] = int(self.bucket.symm.buffer_ptrs[r]) + off
+            a.param_ptrs[r] = int(self.param_symm.buffer_ptrs[r])
+        if self.multicast:
+            a.grad_mc, a.param_mc = self._mc[0] + off, self._mc[1]
+        a.exp_avg, a.exp_avg_sq = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+        a.n_texels, a.tile_lo, a.tile_hi = self.n_texels, self.tile_lo, self.tile_hi
+        a.lr, (a.beta1, a.beta2), a.eps, a.step = float(pg["lr"]), pg["betas"], float(pg["eps"]), self.step_count
+        with torch.cuda.device(dev):
+            self.bucket.symm.barrier(channel=0)            # every rank's backward has landed in its gradient buffer
+            L.check(lib.texgs_texture_adam_dp_step(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
+                    "texgs_texture_adam_dp_step")
+            self.bucket.symm.barrier(channel=1)            # every owner is done reading gradients / writing texels
+        torch.autograd.graph.increment_version(self.texture)   # written through raw pointers (the packed copy is rebuilt)
 
 
 _stream_pools: dict = {}
