@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TEXGS_ABI_VERSION 2
+#define TEXGS_ABI_VERSION 3
 
 #define TEXGS_E_INVALID   1001   /* bad argument */
 #define TEXGS_E_WORKSPACE 1002   /* workspace too small */
@@ -323,6 +323,8 @@ typedef struct TexgsLayout {
     uint64_t bin_tile_cursor;  /* T x uint32                                                   */
     uint64_t bin_pairs;        /* capacity x 8 B  {gaussian id, depth bits} unsorted->sorted   */
     uint64_t bin_sorted_ids;   /* capacity x uint32 gaussian ids in (tile, depth, id) order    */
+    uint64_t bin_cull_masks;   /* (pair_capacity/32 + tiles + 1) * 8 uint2: per warp and list chunk, which entries can touch
+                                  its left / right 4x4 block (written by the forward render, re-used by the backward)  */
     uint64_t img_final_T;      /* H*W floats                                                   */
     uint64_t img_n_contrib;    /* H*W uint32                                                   */
     uint64_t num_tiles;

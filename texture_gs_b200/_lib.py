@@ -13,7 +13,7 @@ _PKG = Path(__file__).resolve().parent
 # TEXGS_LIB selects an alternative build of the same ABI (kernel-tuning experiments, tools/build_variants.py)
 LIB_PATH = Path(os.environ["TEXGS_LIB"]).resolve() if os.environ.get("TEXGS_LIB") else _PKG / "libtexgs.so"
 
-TEXGS_ABI_VERSION = 2
+TEXGS_ABI_VERSION = 3
 FLAG_PREFILTERED = 1
 FLAG_DEBUG = 2
 FLAG_SEAMLESS_CUBE = 4        # spec switches (include/texgs.h): E11-alt, E7-alt, E13-alt
@@ -69,7 +69,7 @@ class TexgsBwdArgs(C.Structure):
 class TexgsLayout(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "geom_records", "geom_rects", "bin_counters", "bin_tile_count", "bin_tile_offset", "bin_tile_cursor",
-        "bin_pairs", "bin_sorted_ids", "img_final_T", "img_n_contrib", "num_tiles", "record_bytes")]
+        "bin_pairs", "bin_sorted_ids", "bin_cull_masks", "img_final_T", "img_n_contrib", "num_tiles", "record_bytes")]
 
 
 class TexgsUvMlpArgs(C.Structure):

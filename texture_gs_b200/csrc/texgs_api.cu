@@ -87,6 +87,7 @@ int make_layout(const TexgsFwdArgs* a, uint64_t cap, Layout& L) {
     L.l.bin_tile_offset = o; o = align_up(o + (T + 1) * 4, 256);
     L.l.bin_pairs = o;       o = align_up(o + cap * 8, 256);
     L.l.bin_sorted_ids = o;  o = align_up(o + cap * 4, 256);
+    L.l.bin_cull_masks = o;  o = align_up(o + (cap / TEXGS_CHUNK + T + 1) * 8 * sizeof(uint2), 256);
     L.bin_bytes = o;
     o = 0;
     L.l.img_final_T = o;   o = align_up(o + HW * 4, 256);
@@ -156,6 +157,7 @@ int fill_params(const TexgsFwdArgs* a, void* geom, void* bin, uint64_t cap, void
     p.tile_offset = (unsigned*)(b + L.l.bin_tile_offset);
     p.pairs = (uint2*)(b + L.l.bin_pairs);
     p.sorted_ids = (unsigned*)(b + L.l.bin_sorted_ids);
+    p.cull_masks = (uint2*)(b + L.l.bin_cull_masks);
     p.pair_capacity = cap;
     p.out_image_nosh = (a->mode == TEXGS_MODE_TEXTURE) ? a->out_image_nosh : nullptr;
     p.final_T = (float*)(im + L.l.img_final_T);

@@ -62,6 +62,7 @@ struct RasterParams {
     unsigned* tile_cursor;
     uint2* pairs;            // .x = gaussian id, .y = depth bits  (as u64: depth in the high word)
     unsigned* sorted_ids;
+    uint2* cull_masks;       // per (list chunk, warp): entries of the chunk that can touch the warp's left (.x) / right (.y) 4x4 block
     unsigned long long pair_capacity;
     float* final_T;
     unsigned* n_contrib;

@@ -95,23 +95,44 @@ __device__ __forceinline__ unsigned stream_load_id(const RasterParams& p, unsign
     return valid ? __ldg(p.sorted_ids + start + e) : 0u;
 }
 
-// ballot the cull test of one chunk and gather the survivors into stage ``s``
-__device__ __forceinline__ void stream_issue(const RasterParams& p, WarpSmem& ws, int s, int lane, unsigned id, bool valid,
-                                             const float4& q0, const float4& q1, const PixelGeom& g) {
-    const float y0 = (float)g.by, y1 = (float)(g.by + 3);
-    const bool passL = valid && splat_hits_block(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, (float)g.bx, (float)(g.bx + 3), y0, y1);
-    const bool passR = valid && splat_hits_block(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, (float)(g.bx + 4), (float)(g.bx + 7), y0, y1);
-    const unsigned mL = __ballot_sync(0xffffffffu, passL), mR = __ballot_sync(0xffffffffu, passR);
+// gather the entries of a chunk whose masks say they can touch one of the warp's two blocks into stage ``s``
+__device__ __forceinline__ void stream_gather(const RasterParams& p, WarpSmem& ws, int s, int lane, unsigned id, unsigned mL, unsigned mR) {
     const unsigned m = mL | mR;
     if (lane == 0) {
         ws.maskL[s] = mL;
         ws.maskR[s] = mR;
         mbar_arrive_expect_tx(&ws.bar[s], (unsigned)__popc(m) * (unsigned)sizeof(GaussRec));
     }
-    if (passL || passR) {
+    if ((m >> lane) & 1u) {
         const int slot = __popc(m & ((1u << lane) - 1u));
         bulk_g2s(&ws.rec[s][slot], p.recs + id, (unsigned)sizeof(GaussRec), &ws.bar[s]);
     }
+}
+
+// where the masks of (tile, chunk, warp) live: chunk c of a list that starts at ``start`` gets slot (start / CHUNK) + tile + c
+// (the + tile keeps the slots of consecutive lists apart: a list of n entries has at most n / CHUNK + 1 chunks)
+__device__ __forceinline__ size_t cull_mask_slot(unsigned start, int tile, int chunk) {
+    return ((size_t)(start / TEXGS_CHUNK) + (size_t)tile + (size_t)chunk) * 8 + (threadIdx.x >> 5);
+}
+
+// forward: ballot the exact cull test of one chunk, keep the two masks for the backward, gather the survivors
+__device__ __forceinline__ void stream_issue(const RasterParams& p, WarpSmem& ws, int s, int lane, unsigned id, bool valid,
+                                             const float4& q0, const float4& q1, const PixelGeom& g, unsigned start, int chunk) {
+    const float y0 = (float)g.by, y1 = (float)(g.by + 3);
+    const bool passL = valid && splat_hits_block(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, (float)g.bx, (float)(g.bx + 3), y0, y1);
+    const bool passR = valid && splat_hits_block(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, (float)(g.bx + 4), (float)(g.bx + 7), y0, y1);
+    const unsigned mL = __ballot_sync(0xffffffffu, passL), mR = __ballot_sync(0xffffffffu, passR);
+    if (lane == 0) p.cull_masks[cull_mask_slot(start, g.tile, chunk)] = make_uint2(mL, mR);
+    stream_gather(p, ws, s, lane, id, mL, mR);
+}
+
+// backward: the forward decided already which entries of a chunk reach which block (the test depends on the record and
+// the block only); entries at or beyond ``limit`` (nothing blended behind the warp's last contribution) are dropped
+__device__ __forceinline__ void stream_issue_saved(const RasterParams& p, WarpSmem& ws, int s, int lane, unsigned id, uint2 m,
+                                                   int chunk, unsigned limit) {
+    const unsigned base = (unsigned)chunk * TEXGS_CHUNK;
+    const unsigned live = (limit >= base + TEXGS_CHUNK) ? 0xffffffffu : ((limit > base) ? ((1u << (limit - base)) - 1u) : 0u);
+    stream_gather(p, ws, s, lane, id, m.x & live, m.y & live);
 }
 
 // u' = uv + J' (t v - p_v)   (E9/E10, evaluated in view space)
@@ -183,11 +204,11 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
         {
             const float4* r0 = reinterpret_cast<const float4*>(p.recs + id0);
             const float4 a0 = v0 ? __ldg(r0) : make_float4(0.f, 0.f, 1.f, 0.f), a1 = v0 ? __ldg(r0 + 1) : make_float4(1.f, 0.f, 0.f, 0.f);
-            stream_issue(p, ws, 0, lane, id0, v0, a0, a1, g);
+            stream_issue(p, ws, 0, lane, id0, v0, a0, a1, g, start, 0);
             if (1 < nchunks) {
                 const float4* r1 = reinterpret_cast<const float4*>(p.recs + id1);
                 const float4 b0 = v1 ? __ldg(r1) : make_float4(0.f, 0.f, 1.f, 0.f), b1 = v1 ? __ldg(r1 + 1) : make_float4(1.f, 0.f, 0.f, 0.f);
-                stream_issue(p, ws, 1, lane, id1, v1, b0, b1, g);
+                stream_issue(p, ws, 1, lane, id1, v1, b0, b1, g, start, 1);
             }
         }
         for (int c = 0; c < nchunks; ++c) {
@@ -269,7 +290,7 @@ __global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(cons
                 break;
             }
             // stage s is free again: gather chunk c+2 into it
-            if (c + 2 < nchunks) stream_issue(p, ws, s, lane, idn, vn, q0n, q1n, g);
+            if (c + 2 < nchunks) stream_issue(p, ws, s, lane, idn, vn, q0n, q1n, g, start, c + 2);
         }
     }
 
@@ -363,34 +384,23 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
         mbar_fence_init();
     }
     __syncwarp();
-    // prologue: visits 0 and 1 gathered, id of visit 2 loaded. Entries at or beyond max_last can
-    // not contribute to this warp and are not gathered.
+    // prologue: visits 0 and 1 gathered, id + masks of visit 2 loaded. Which entries of a chunk reach the warp's blocks was
+    // decided (exactly) by the forward and is read back — two words per chunk instead of 32 record sectors and 64 ellipse
+    // tests. Entries at or beyond max_last can not contribute to this warp and are not gathered.
     bool v0, v1, v2;
     const unsigned id0 = stream_load_id(p, start, max_last, c_top, lane, v0);
     const unsigned id1 = stream_load_id(p, start, max_last, c_top - 1, lane, v1);
     unsigned id2 = stream_load_id(p, start, max_last, c_top - 2, lane, v2);
-    {
-        const float4* r0 = reinterpret_cast<const float4*>(p.recs + id0);
-        const float4 a0 = v0 ? __ldg(r0) : make_float4(0.f, 0.f, 1.f, 0.f), a1 = v0 ? __ldg(r0 + 1) : make_float4(1.f, 0.f, 0.f, 0.f);
-        stream_issue(p, ws, 0, lane, id0, v0, a0, a1, g);
-        if (c_top >= 1) {
-            const float4* r1 = reinterpret_cast<const float4*>(p.recs + id1);
-            const float4 b0 = v1 ? __ldg(r1) : make_float4(0.f, 0.f, 1.f, 0.f), b1 = v1 ? __ldg(r1 + 1) : make_float4(1.f, 0.f, 0.f, 0.f);
-            stream_issue(p, ws, 1, lane, id1, v1, b0, b1, g);
-        }
-    }
+    stream_issue_saved(p, ws, 0, lane, id0, __ldg(p.cull_masks + cull_mask_slot(start, g.tile, c_top)), c_top, max_last);
+    if (c_top >= 1) stream_issue_saved(p, ws, 1, lane, id1, __ldg(p.cull_masks + cull_mask_slot(start, g.tile, c_top - 1)), c_top - 1, max_last);
+    uint2 m2 = (c_top >= 2) ? __ldg(p.cull_masks + cull_mask_slot(start, g.tile, c_top - 2)) : make_uint2(0u, 0u);
     for (int k = 0; k <= c_top; ++k) {
         const int c = c_top - k;
         const int s = k & 1;
-        float4 q0n = make_float4(0.f, 0.f, 1.f, 0.f), q1n = make_float4(1.f, 0.f, 0.f, 0.f);
         const unsigned idn = id2;
-        const bool vn = v2;
-        if (vn) {
-            const float4* rn = reinterpret_cast<const float4*>(p.recs + idn);
-            q0n = __ldg(rn);
-            q1n = __ldg(rn + 1);
-        }
+        const uint2 mn = m2;
         id2 = stream_load_id(p, start, max_last, c - 3, lane, v2);
+        if (c >= 3) m2 = __ldg(p.cull_masks + cull_mask_slot(start, g.tile, c - 3));
 
         mbar_wait(&ws.bar[s], (unsigned)(k >> 1) & 1u);
         __syncwarp();
@@ -530,6 +540,6 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
             }
         }
         __syncwarp();
-        if (k + 2 <= c_top) stream_issue(p, ws, s, lane, idn, vn, q0n, q1n, g);
+        if (k + 2 <= c_top) stream_issue_saved(p, ws, s, lane, idn, mn, c - 2, max_last);
     }
 }
