@@ -372,8 +372,7 @@ def main():
         if opt is None:
             bucket.all_reduce()
         elif world > 1:
-            # per-Gaussian gradients: summed by the same call through the multicast mapping, else by NCCL next to it
-            works = None if opt.reduces_rest() else bucket.all_reduce(exclude=("texture",), async_op=True)
+            works = bucket.all_reduce(exclude=("texture",), async_op=True)      # per-Gaussian gradients: NCCL, concurrently
             opt.step()
             for w in works or []:
                 w.wait()
@@ -501,8 +500,7 @@ def main():
             "config": workload_config(wl, args.views),
             "impl_notes": {"streams_per_rank": streams,
                            "parallelism": ((f"dp{world} (views sharded; per step: fused texture-gradient reduce + Adam + broadcast kernel over NVLink "
-                                            f"[{'multimem / NVLS' if opt.multicast else 'peer loads / stores'}], "
-                                            f"{'multimem' if opt.reduces_rest() else 'NCCL'} all-reduce of the other "
+                                            f"[{'multimem / NVLS' if opt.multicast else 'peer loads / stores'}], NCCL all-reduce of the other "
                                             f"{sum(b - a for a, b in bucket.ranges_without(('texture',))) * 4 / 1e6:.0f} MB)") if (world > 1 and opt is not None)
                                            else (f"dp{world} (views sharded, 1 all-reduce of {bucket.nbytes / 1e6:.0f} MB/step)" if (world > 1 and bwd)
                                                  else (f"dp{world} (views sharded)" if world > 1 else "single GPU"))),

@@ -263,11 +263,6 @@ typedef struct TexgsDpAdamArgs {
 } TexgsDpAdamArgs;
 int texgs_dp_shard(uint64_t n_texels, int32_t world, int32_t rank, uint64_t* tile_lo, uint64_t* tile_hi);
 int texgs_texture_adam_dp_step(const TexgsDpAdamArgs* args, void* stream);
-/* In-place sum over ``world`` ranks of ``n_floats`` floats (multiple of 4, 16-byte aligned) of a symmetric buffer, through
- * its NVSwitch multicast mapping ``buffer_mc`` (multimem.ld_reduce + multimem.st; rank ``rank`` handles its 1/world of the
- * range). The per-Gaussian gradient slices of the bucket (dist.py GradBucket.ranges_without) next to the fused texture step;
- * same synchronisation contract as texgs_texture_adam_dp_step. */
-int texgs_allreduce_multimem(float* buffer_mc, uint64_t n_floats, int32_t world, int32_t rank, void* stream);
 
 /* ---- UV + Jacobian producer --------------------------------------------------------------
  * uv = normalize(mlp(relu(pre_mlp((xyz - offset) / scale) + emb)))   (models/modules/uv_net.py:19-36) and

@@ -44,7 +44,7 @@ for path in ("multicast", "peer"):
             invalidate_packed_cache()
             b.zero()
             render_views_accumulate(uv_tex_render, gg, cams, cot, views, bg, bucket=b, streams=2)
-        works = None if opt.reduces_rest() else bucket.all_reduce(exclude=("texture",), async_op=True)
+        works = bucket.all_reduce(exclude=("texture",), async_op=True)
         opt.step()
         for w in works or []:
             w.wait()

@@ -109,7 +109,6 @@ SYMBOLS = {
                                           C.c_int32, C.c_int32, C.c_void_p]),
     "texgs_dp_shard": (C.c_int, [C.c_uint64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "texgs_texture_adam_dp_step": (C.c_int, [C.POINTER(TexgsDpAdamArgs), C.c_void_p]),
-    "texgs_allreduce_multimem": (C.c_int, [_fp, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]),
     "texgs_uvmlp_forward": (C.c_int, [C.POINTER(TexgsUvMlpArgs), C.c_void_p]),
     "texgs_uvmlp_backward_head": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
     "texgs_uvmlp_backward_mask": (C.c_int, [C.c_int32, _fp, _fp, _fp, C.c_void_p]),

@@ -209,7 +209,7 @@ const char* texgs_kernel_names(void) {
     return "texgs_preprocess_fwd,texgs_scan_tiles,texgs_scatter_pairs,texgs_sort_tiles_small,texgs_sort_tiles,texgs_render_fwd,"
            "texgs_render_bwd,texgs_extra_fwd,texgs_extra_bwd,texgs_preprocess_bwd,texgs_mark_visible_kernel,texgs_pack_texture_kernel,"
            "texgs_photometric_fwd_kernel,texgs_photometric_finalize_kernel,texgs_photometric_bwd_kernel,"
-           "texgs_geometry_loss_fwd_kernel,texgs_geometry_loss_finalize_kernel,texgs_geometry_loss_bwd_kernel,texgs_texture_adam_kernel,texgs_texture_adam_dp_kernel,texgs_allreduce_multimem_kernel,texgs_uvmlp_fwd_kernel,"
+           "texgs_geometry_loss_fwd_kernel,texgs_geometry_loss_finalize_kernel,texgs_geometry_loss_bwd_kernel,texgs_texture_adam_kernel,texgs_texture_adam_dp_kernel,texgs_uvmlp_fwd_kernel,"
            "texgs_uvmlp_bwd_amax_kernel,texgs_uvmlp_bwd_head_kernel,texgs_uvmlp_bwd_mask_kernel,texgs_uvmlp_bwd_tail_kernel";
 }
 
@@ -551,22 +551,6 @@ int texgs_texture_adam_dp_step(const TexgsDpAdamArgs* a, void* stream_) {
     if (a->grad_mc) texgs_texture_adam_dp_kernel<true><<<ctas, TEXGS_ADAM_THREADS, 0, stream>>>(k);
     else texgs_texture_adam_dp_kernel<false><<<ctas, TEXGS_ADAM_THREADS, 0, stream>>>(k);
     TEXGS_KERNEL_CHECK("texgs_texture_adam_dp_kernel", false, stream);
-    return 0;
-#endif
-}
-
-int texgs_allreduce_multimem(float* buffer_mc, uint64_t n_floats, int32_t world, int32_t rank, void* stream_) {
-    if (!buffer_mc || world < 1 || rank < 0 || rank >= world || (n_floats & 3) || ((uintptr_t)buffer_mc & 15))
-        return fail(TEXGS_E_INVALID, "bad arguments (multicast pointer 16-byte aligned, n_floats a multiple of 4)");
-#ifdef TEXGS_HOST_EMU
-    return fail(TEXGS_E_INVALID, "multimem needs an NVSwitch fabric (no host emulation)");
-#else
-    const uint64_t n4 = n_floats / 4, lo = n4 * (uint64_t)rank / (uint64_t)world, hi = n4 * (uint64_t)(rank + 1) / (uint64_t)world;
-    if (hi == lo) return 0;
-    const uint64_t want = (hi - lo + 1023) / 1024;
-    const unsigned ctas = (unsigned)(want < 148 * 8 ? want : 148 * 8);
-    texgs_allreduce_multimem_kernel<<<ctas, 256, 0, (cudaStream_t)stream_>>>(reinterpret_cast<float4*>(buffer_mc), lo, hi);
-    TEXGS_KERNEL_CHECK("texgs_allreduce_multimem_kernel", false, (cudaStream_t)stream_);
     return 0;
 #endif
 }

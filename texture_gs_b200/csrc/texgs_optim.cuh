@@ -184,21 +184,6 @@ __device__ __forceinline__ void multimem_st(float4* mc, float4 v) {
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// In-place sum over the ranks of a symmetric buffer through its NVSwitch multicast mapping (one-shot NVLS all-reduce):
-// the rank that owns a 16-byte element pulls the fabric-reduced value (multimem.ld_reduce) and writes it back into every
-// rank's copy (multimem.st). Nobody else reads that element, so no staging buffer is needed. Used for the per-Gaussian
-// gradient slices of the bucket next to the fused texture step (one launch instead of a separate NCCL collective).
-__global__ void __launch_bounds__(256) texgs_allreduce_multimem_kernel(float4* __restrict__ mc, unsigned long long lo, unsigned long long hi) {
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x * 4;
-    for (unsigned long long i = lo + ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < hi; i += stride) {
-        float4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (i + k < hi) v[k] = multimem_ld_reduce_add(mc + i + k);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (i + k < hi) multimem_st(mc + i + k, v[k]);
-    }
-}
-
 template <bool MC>
 __global__ void __launch_bounds__(TEXGS_ADAM_THREADS, 2) texgs_texture_adam_dp_kernel(const DpAdamArgs a) {
     __shared__ __align__(16) float sg[TEXGS_ADAM_TEXELS * 3];

@@ -188,7 +188,7 @@ class DistTextureAdam:
     between steps (schedulers)."""
 
     def __init__(self, texture: torch.Tensor, bucket: "GradBucket", lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 group=None, name: str = "texture", use_multicast: Optional[bool] = None, reduce_rest: bool = True):
+                 group=None, name: str = "texture", use_multicast: Optional[bool] = None):
         import ctypes as C
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib as L
@@ -200,7 +200,6 @@ class DistTextureAdam:
             raise ValueError("the texture must be a (padded) leaf of the bucket")
         group = group or dist.group.WORLD
         self.group, self.bucket, self.texture, self.name = group, bucket, texture, name
-        self.reduce_rest = bool(reduce_rest)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.param_groups = [dict(lr=lr, betas=tuple(betas), eps=eps)]
         self.n_texels = texture.numel() // 3
@@ -219,11 +218,6 @@ class DistTextureAdam:
         g_mc, p_mc = int(getattr(bucket.symm, "multicast_ptr", 0) or 0), int(getattr(self.param_symm, "multicast_ptr", 0) or 0)
         self.multicast = bool(g_mc and p_mc) if use_multicast is None else bool(use_multicast and g_mc and p_mc)
         self._mc = (g_mc, p_mc)
-
-    def reduces_rest(self) -> bool:
-        """True when ``step()`` also sums the bucket's other slices over the ranks (multicast path); otherwise the caller
-        all-reduces them with NCCL (``bucket.all_reduce(exclude=(name,))``)."""
-        return self.multicast and self.reduce_rest
 
     def state_shard(self):
         """(first owned texel, exp_avg, exp_avg_sq) — the moments of texels [tile_lo*1024, min(tile_hi*1024, n))."""
@@ -252,10 +246,6 @@ class DistTextureAdam:
             self.bucket.symm.barrier(channel=0)            # every rank's backward has landed in its gradient buffer
             st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
             L.check(lib.texgs_texture_adam_dp_step(C.byref(a), st), "texgs_texture_adam_dp_step")
-            if self.reduces_rest():        # the per-Gaussian gradients: one-shot NVLS all-reduce in place, same barriers
-                for lo, hi in self.bucket.ranges_without((self.name,)):
-                    L.check(lib.texgs_allreduce_multimem(C.c_void_p(self._mc[0] + 4 * lo), hi - lo, self.world, self.rank, st),
-                            "texgs_allreduce_multimem")
             self.bucket.symm.barrier(channel=1)            # every owner is done reading gradients / writing texels
         torch.autograd.graph.increment_version(self.texture)   # written through raw pointers (the packed copy is rebuilt)
 
