@@ -304,7 +304,12 @@ int texgs_uvmlp_forward(const TexgsUvMlpArgs* a, void* stream);
  * Accumulated outputs must be zero-initialised by the caller. */
 int texgs_uvmlp_backward_head(int32_t N, const float* g_uv, const float* uv, const float* inv_len, const void* a4, const void* W5,
                               float* amax_scratch, float* scale, void* delta4, float* gW5, float* gb5, float* colsum, void* stream);
-int texgs_uvmlp_backward_mask(int32_t N, void* delta, const void* a, float* colsum, void* stream);
+/* One hidden layer of the backward on the tensor cores (tcgen05): gW[out][in] += delta^T a_prev, delta_out = (delta W) * (a_prev > 0)
+ * in fp16, colsum[in] += column sums of delta_out. ``Wt`` is the layer's weight TRANSPOSED ([in][out], fp16); ``gW`` and ``colsum``
+ * are accumulated into (clear them first); delta_out may not alias delta_in. Replaces torch.mm(delta.T, a), torch.mm(delta, W) and
+ * the ReLU-mask glue kernel of round 1. */
+int texgs_uvmlp_backward_layer(int32_t N, const void* delta_in, const void* a_prev, const void* Wt, void* delta_out, float* gW,
+                               float* colsum, void* stream);
 int texgs_uvmlp_backward_tail(int32_t N, const void* delta1, const float* xyz, const float* offset3_host, const float* inv_scale3_host,
                               const float* W1, const float* scale, float* gxyz, float* gW1, void* stream);
 

@@ -28,7 +28,7 @@ DYN_SMEM = (("unsigned char", "smem_raw"), ("float", "prebwd_smem"), ("float", "
 GXX_FLAGS = ["-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unknown-pragmas", "-Wno-attributes",
              "-fno-extern-tls-init",     # `extern __shared__` arrays are plain extern thread_local arrays: no init wrapper
              "-fno-gnu-unique", "-Wl,-Bsymbolic"]   # two builds (different -D flags) loaded into one process keep their own state
-SKIPPED_SYMBOLS = ("texgs_uvmlp_forward", "texgs_uvmlp_backward_head", "texgs_uvmlp_backward_mask", "texgs_uvmlp_backward_tail")
+SKIPPED_SYMBOLS = ("texgs_uvmlp_forward", "texgs_uvmlp_backward_head", "texgs_uvmlp_backward_layer", "texgs_uvmlp_backward_tail")
 
 
 def _split_top_level(s: str):

@@ -111,7 +111,7 @@ SYMBOLS = {
     "texgs_texture_adam_dp_step": (C.c_int, [C.POINTER(TexgsDpAdamArgs), C.c_void_p]),
     "texgs_uvmlp_forward": (C.c_int, [C.POINTER(TexgsUvMlpArgs), C.c_void_p]),
     "texgs_uvmlp_backward_head": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
-    "texgs_uvmlp_backward_mask": (C.c_int, [C.c_int32, _fp, _fp, _fp, C.c_void_p]),
+    "texgs_uvmlp_backward_layer": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
     "texgs_uvmlp_backward_tail": (C.c_int, [C.c_int32, _fp, _fp, C.POINTER(C.c_float), C.POINTER(C.c_float), _fp, _fp, _fp, _fp, C.c_void_p]),
     "texgs_mark_visible": (C.c_int, [C.c_int32, _fp, C.POINTER(C.c_float), C.POINTER(C.c_float), _fp, C.c_void_p]),
 }

@@ -210,7 +210,7 @@ const char* texgs_kernel_names(void) {
            "texgs_render_bwd,texgs_extra_fwd,texgs_extra_bwd,texgs_preprocess_bwd,texgs_mark_visible_kernel,texgs_pack_texture_kernel,"
            "texgs_photometric_fwd_kernel,texgs_photometric_finalize_kernel,texgs_photometric_bwd_kernel,"
            "texgs_geometry_loss_fwd_kernel,texgs_geometry_loss_finalize_kernel,texgs_geometry_loss_bwd_kernel,texgs_texture_adam_kernel,texgs_texture_adam_dp_kernel,texgs_uvmlp_fwd_kernel,"
-           "texgs_uvmlp_bwd_amax_kernel,texgs_uvmlp_bwd_head_kernel,texgs_uvmlp_bwd_mask_kernel,texgs_uvmlp_bwd_tail_kernel";
+           "texgs_uvmlp_bwd_amax_kernel,texgs_uvmlp_bwd_head_kernel,texgs_uvmlp_bwd_layer_kernel,texgs_uvmlp_bwd_tail_kernel";
 }
 
 int texgs_workspace_sizes(const TexgsFwdArgs* a, uint64_t pair_capacity, size_t* geom_bytes, size_t* bin_bytes,
@@ -607,13 +607,29 @@ int texgs_uvmlp_backward_head(int32_t N, const float* g_uv, const float* uv, con
     return 0;
 }
 
-int texgs_uvmlp_backward_mask(int32_t N, void* delta, const void* a, float* colsum, void* stream_) {
+int texgs_uvmlp_backward_layer(int32_t N, const void* delta_in, const void* a_prev, const void* Wt, void* delta_out, float* gW,
+                               float* colsum, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (N <= 0 || !delta || !a || !colsum) return fail(TEXGS_E_INVALID, "bad arguments");
-    if (((uintptr_t)delta | (uintptr_t)a) & 15) return fail(TEXGS_E_INVALID, "fp16 buffers must be 16-byte aligned");
-    texgs_uvmlp_bwd_mask_kernel<<<uvbwd_ctas(N), UVBWD_THREADS, 0, stream>>>(N, (__half*)delta, (const __half*)a, colsum);
-    TEXGS_KERNEL_CHECK("texgs_uvmlp_bwd_mask_kernel", false, stream);
+    if (N <= 0 || !delta_in || !a_prev || !Wt || !delta_out || !gW || !colsum || delta_in == delta_out) return fail(TEXGS_E_INVALID, "bad arguments");
+    if (((uintptr_t)delta_in | (uintptr_t)a_prev | (uintptr_t)Wt | (uintptr_t)delta_out) & 15) return fail(TEXGS_E_INVALID, "fp16 buffers must be 16-byte aligned");
+#ifdef TEXGS_HOST_EMU
+    return fail(TEXGS_E_INVALID, "tcgen05 kernels have no host emulation");
+#else
+    static thread_local int attr_set_for_device = -1;
+    int dev = 0, sms = 0;
+    TEXGS_CUDA_TRY(cudaGetDevice(&dev));
+    if (attr_set_for_device != dev) {
+        TEXGS_CUDA_TRY(cudaFuncSetAttribute(texgs_uvmlp_bwd_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UvBwdSmem::TOTAL));
+        attr_set_for_device = dev;
+    }
+    TEXGS_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int ntiles = (N + 127) / 128;
+    const int ctas = std::max(1, std::min(sms, (ntiles + UVBL_GROUPS - 1) / UVBL_GROUPS));
+    texgs_uvmlp_bwd_layer_kernel<<<ctas, UVBL_THREADS, UvBwdSmem::TOTAL, stream>>>(N, (const __half*)delta_in, (const __half*)a_prev, (const __half*)Wt,
+                                                                                 (__half*)delta_out, gW, colsum);
+    TEXGS_KERNEL_CHECK("texgs_uvmlp_bwd_layer_kernel", false, stream);
     return 0;
+#endif
 }
 
 int texgs_uvmlp_backward_tail(int32_t N, const void* delta1, const float* xyz, const float* offset3_host, const float* inv_scale3_host,

@@ -376,12 +376,10 @@ __global__ void __launch_bounds__(UVMLP_THREADS, 1) texgs_uvmlp_fwd_kernel(const
 
 // =====================================================================================================
 // Backward of uv w.r.t. xyz / emb / weights. The two 128x128 products per hidden layer (delta @ W and
-// delta^T @ a) are plain GEMMs and go to cuBLAS (host side: torch.mm on the fp16 stash); what surrounds them is
-// memory-bound glue, fused here into three streaming kernels so that every (N,128) fp16 tensor is read and
-// written once per layer:
+// delta^T @ a) run on the tensor cores in texgs_uvmlp_bwd_layer_kernel (end of this file); the K = 3 layers at both
+// ends and the normalisation are memory-bound glue, two streaming kernels:
 //   head : normalize backward + output layer (K = 3): d = (g - u (u.g)) / |out|;  gW5 += d^T a4, gb5 += sum d,
 //          delta4 = S * (d W5) * (a4 > 0) in fp16, column sums of delta4
-//   mask : delta <- delta_pre * (a > 0) in place + column sums (bias / embedding gradients)
 //   tail : input layer (K = 3): gxyz = delta1 W1 * inv_scale / S,  gW1 += delta1^T x' / S
 // S is one power of two taken from max|d| on the device (mixed-precision loss scaling, no host sync).
 // Thread layout everywhere: 16 lanes x 8 columns cover a row (one uint4 each), 16 rows per 256-thread pass.
@@ -482,33 +480,6 @@ __global__ void __launch_bounds__(UVBWD_THREADS) texgs_uvmlp_bwd_head_kernel(int
     }
 }
 
-__global__ void __launch_bounds__(UVBWD_THREADS) texgs_uvmlp_bwd_mask_kernel(int N, __half* __restrict__ delta, const __half* __restrict__ a,
-                                                                           float* __restrict__ colsum) {
-    __shared__ float sred[128];
-    const int tid = threadIdx.x, chunk = tid & 15, rl = tid >> 4;
-    float acc[1][8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc[0][c] = 0.f;
-    const int r0 = blockIdx.x * UVBWD_ROWS_PER_CTA;
-    for (int r = r0 + rl; r < min(N, r0 + UVBWD_ROWS_PER_CTA); r += 16) {
-        uint4* dp = reinterpret_cast<uint4*>(delta + (size_t)r * 128) + chunk;
-        uint4 dv = *dp;
-        const uint4 av = reinterpret_cast<const uint4*>(a + (size_t)r * 128)[chunk];
-        const __half2 zero2 = __float2half2_rn(0.f);
-        uint32_t* dw = reinterpret_cast<uint32_t*>(&dv);
-        const uint32_t* aw = reinterpret_cast<const uint32_t*>(&av);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            dw[k] &= __hgt2_mask(*reinterpret_cast<const __half2*>(&aw[k]), zero2);
-            const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&dw[k]));
-            acc[0][2 * k] += t.x; acc[0][2 * k + 1] += t.y;
-        }
-        *dp = dv;
-    }
-    float* const dst[1] = {colsum};
-    uvbwd_flush<1>(acc, sred, dst, 1.0f);
-}
-
 __global__ void __launch_bounds__(UVBWD_THREADS) texgs_uvmlp_bwd_tail_kernel(int N, const __half* __restrict__ delta, const float* __restrict__ xyz,
                                                                            float3 off, float3 isc, const float* __restrict__ W1,
                                                                            const float* __restrict__ scale, float* __restrict__ gxyz,
@@ -565,4 +536,178 @@ __global__ void __launch_bounds__(UVBWD_THREADS) texgs_uvmlp_bwd_tail_kernel(int
         }
     __syncthreads();
     for (int i = t; i < 3 * 128; i += UVBWD_THREADS) atomicAdd(&gW1[(i & 127) * 3 + (i >> 7)], sred[i] * invS);
+}
+
+// =====================================================================================================
+// Backward of ONE hidden layer on the tensor cores (round 2; replaces two cuBLAS GEMMs + the mask kernel per layer):
+//     gW        += delta^T @ a_prev                      (128 out x 128 in, K = points)
+//     delta_out  = (delta @ W) * (a_prev > 0)  in fp16   (points x 128 in)
+//     colsum    += column sums of delta_out              (bias / embedding gradient of the layer below)
+// A tile is 128 points; a 4-warp group owns a tile (thread = point), two groups per CTA interleave load / MMA / epilogue,
+// persistent grid. Both products are tcgen05.mma chains on fp16 operands with fp32 accumulators in TMEM:
+//   * delta @ W: A = the delta tile, K-major (16-byte chunk = 8 consecutive features of a point — the rows as they lie in
+//     global memory), B = W^T resident in shared memory, K-major (the host passes W transposed: [in][out]);
+//   * delta^T @ a_prev: K = the tile's 128 points. A = delta^T and B = a_prev^T as MN-MAJOR operands (UMMA instruction
+//     descriptor bits 15 / 16): the canonical no-swizzle MN-major layout is 8(K) x 8(MN) core matrices whose 16-byte rows are
+//     8 consecutive MN elements at one K — again a 16-byte row chunk of global memory, only PLACED differently:
+//     chunk (point k, feature group g) at (k / 8) * LBO + g * SBO + (k % 8) * 16. The K-major delta tile of the first product
+//     (chunk (point r, feature chunk kc) at kc * 2048 + r * 16) IS that layout with LBO = 128 and SBO = 2048, so one copy of the
+//     tile serves both products through two descriptors; a_prev is staged with SBO = 128, LBO = 2048. No element transposition. The accumulator stays in TMEM across all tiles of the group
+//     (split-K over CTAs; one fp32 red per element at the end).
+// The ReLU mask of the epilogue re-reads the a_prev chunk from the MN-major copy; column sums: transposing warp reduction
+// (31 shuffles per 32 columns) + shared-memory atomics.
+// =====================================================================================================
+#define UVBL_GROUPS 2
+#define UVBL_THREADS (UVBL_GROUPS * 128)
+struct UvBwdSmem {
+    static constexpr int WT = 0;                                           // 32768: W^T, K-major
+    static constexpr int GRP = WT + UVMLP_MAT_BYTES;                       // per group: the delta tile, the a_prev tile
+    static constexpr int GRP_BYTES = 2 * UVMLP_MAT_BYTES;
+    static constexpr int COLSUM = GRP + UVBL_GROUPS * GRP_BYTES;           // 128 floats
+    static constexpr int BAR = COLSUM + 512;                               // GROUPS x u64
+    static constexpr int TMEM = BAR + UVBL_GROUPS * 8;                     // u32
+    static constexpr int TOTAL = TMEM + 16;
+};
+static_assert(UvBwdSmem::TOTAL <= 227 * 1024, "shared memory budget");
+
+// sum over the warp's 32 lanes of 32 per-lane values; lane l returns the total of value l
+__device__ __forceinline__ float uv_warp_transpose_reduce32(const float (&v)[32], int lane) {
+    const unsigned full = 0xffffffffu;
+    float a16[16], a8[8], a4[4], a2[2];
+    const bool h4 = (lane & 16) != 0, h3 = (lane & 8) != 0, h2 = (lane & 4) != 0, h1 = (lane & 2) != 0, h0 = (lane & 1) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float send = h4 ? v[i] : v[i + 16], keep = h4 ? v[i + 16] : v[i]; a16[i] = keep + __shfl_xor_sync(full, send, 16); }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float send = h3 ? a16[i] : a16[i + 8], keep = h3 ? a16[i + 8] : a16[i]; a8[i] = keep + __shfl_xor_sync(full, send, 8); }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float send = h2 ? a8[i] : a8[i + 4], keep = h2 ? a8[i + 4] : a8[i]; a4[i] = keep + __shfl_xor_sync(full, send, 4); }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { const float send = h1 ? a4[i] : a4[i + 2], keep = h1 ? a4[i + 2] : a4[i]; a2[i] = keep + __shfl_xor_sync(full, send, 2); }
+    const float send = h0 ? a2[0] : a2[1], keep = h0 ? a2[1] : a2[0];
+    return keep + __shfl_xor_sync(full, send, 1);          // value index 16 h4 + 8 h3 + 4 h2 + 2 h1 + h0 = lane
+}
+
+__global__ void __launch_bounds__(UVBL_THREADS, 1) texgs_uvmlp_bwd_layer_kernel(int N, const __half* __restrict__ delta_in,
+                                                                              const __half* __restrict__ a_prev, const __half* __restrict__ Wt,
+                                                                              __half* __restrict__ delta_out, float* __restrict__ gW,
+                                                                              float* __restrict__ colsum) {
+    extern __shared__ __align__(1024) unsigned char uvb_smem[];
+    unsigned char* sWt = uvb_smem + UvBwdSmem::WT;
+    float* sCol = reinterpret_cast<float*>(uvb_smem + UvBwdSmem::COLSUM);
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(uvb_smem + UvBwdSmem::BAR);
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(uvb_smem + UvBwdSmem::TMEM);
+    const int tid = threadIdx.x, g = tid >> 7, gt = tid & 127, s = gt >> 5, lane = tid & 31;
+    unsigned char* sDK = uvb_smem + UvBwdSmem::GRP + g * UvBwdSmem::GRP_BYTES;
+    unsigned char* sAM = sDK + UVMLP_MAT_BYTES;
+
+    for (int q = tid; q < 2048; q += UVBL_THREADS) {          // W^T rows [in][out] -> K-major chunks (row n, k-chunk kc)
+        const int n = q >> 4, kc = q & 15;
+        *reinterpret_cast<uint4*>(sWt + kc * 2048 + n * 16) = reinterpret_cast<const uint4*>(Wt)[n * 16 + kc];
+    }
+    if (tid < 128) sCol[tid] = 0.f;
+    if (tid == 0) {
+        for (int i = 0; i < UVBL_GROUPS; ++i) mbar_init(&sBar[i], 1);
+        mbar_fence_init();
+    }
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    uv_fence_async_smem();
+    uv_tc_fence_before();
+    __syncthreads();
+    uv_tc_fence_after();
+    const uint32_t tmem_cta = *sTmem;
+    const uint32_t tmem_d1 = tmem_cta + (uint32_t)(g * 256), tmem_gw = tmem_d1 + 128u;
+    const uint32_t lane_off = (uint32_t)(s * 32) << 16;
+    const uint32_t idesc_k = uv_instr_desc(128, 128);                                   // both operands K-major
+    const uint32_t idesc_mn = uv_instr_desc(128, 128) | (1u << 15) | (1u << 16);        // both operands MN-major
+    const uint32_t aDK = smem_u32(sDK), aAM = smem_u32(sAM), aWt = smem_u32(sWt);
+    const int mn_off = (gt >> 3) * 2048 + (gt & 7) * 16;                                // this point's row inside an MN-major tile
+    const int ntiles = (N + 127) / 128;
+    uint32_t phase = 0;
+    bool first = true;
+
+    for (int tile = blockIdx.x * UVBL_GROUPS + g; tile < ntiles; tile += gridDim.x * UVBL_GROUPS) {
+        const int pt = tile * 128 + gt;
+        const bool valid = pt < N;
+        {   // rows of delta and a_prev -> the three operand tiles (rows beyond N are zero: they add nothing)
+            uint4 d[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) d[j] = valid ? reinterpret_cast<const uint4*>(delta_in + (size_t)pt * 128)[j] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) *reinterpret_cast<uint4*>(sDK + j * 2048 + gt * 16) = d[j];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) d[j] = valid ? reinterpret_cast<const uint4*>(a_prev + (size_t)pt * 128)[j] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) *reinterpret_cast<uint4*>(sAM + mn_off + j * 128) = d[j];
+        }
+        uv_fence_async_smem();
+        uv_group_bar(g);
+        if (gt == 0) {
+            uv_tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)        // delta @ W: K = 128 features in steps of 16
+                uv_umma(tmem_d1, uv_smem_desc(aDK + k * 4096, 2048u, 128u), uv_smem_desc(aWt + k * 4096, 2048u, 128u), idesc_k, k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)        // delta^T @ a_prev: K = 128 points in steps of 16 (two 8-point core-matrix rows)
+                uv_umma(tmem_gw, uv_smem_desc(aDK + k * 256, 128u, 2048u), uv_smem_desc(aAM + k * 4096, 2048u, 128u), idesc_mn,
+                        (first && k == 0) ? 0u : 1u);
+            uv_umma_commit(&sBar[g]);
+        }
+        first = false;
+        __syncwarp();
+        uv_mbar_wait(&sBar[g], phase);
+        phase ^= 1u;
+        uv_tc_fence_after();
+        // epilogue: this point's row of delta @ W, masked by a_prev > 0, to fp16; column sums of what is written
+        uint32_t r[2][32];
+        UV_TMEM_LD32(r[0], tmem_d1 + lane_off);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            uv_tmem_wait_ld();
+            if (cc < 3) UV_TMEM_LD32(r[(cc + 1) & 1], tmem_d1 + lane_off + (uint32_t)((cc + 1) * 32));
+            float csum[32];
+            const __half2 zero2 = __float2half2_rn(0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint4 av = *reinterpret_cast<const uint4*>(sAM + mn_off + (cc * 4 + q) * 128);
+                const uint32_t* aw = reinterpret_cast<const uint32_t*>(&av);
+                uint32_t h[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    h[k] = uv_pack_half2(__uint_as_float(r[cc & 1][8 * q + 2 * k]), __uint_as_float(r[cc & 1][8 * q + 2 * k + 1]));
+                    h[k] &= __hgt2_mask(*reinterpret_cast<const __half2*>(&aw[k]), zero2);
+                    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&h[k]));
+                    csum[8 * q + 2 * k] = valid ? t.x : 0.f; csum[8 * q + 2 * k + 1] = valid ? t.y : 0.f;
+                }
+                if (valid) reinterpret_cast<uint4*>(delta_out + (size_t)pt * 128)[cc * 4 + q] = make_uint4(h[0], h[1], h[2], h[3]);
+            }
+            const float tot = uv_warp_transpose_reduce32(csum, lane);
+            atomicAdd(&sCol[cc * 32 + lane], tot);
+        }
+        uv_tc_fence_before();
+        uv_group_bar(g);            // the tile's operand buffers are free again (all 16 MMAs completed before the epilogue)
+    }
+
+    // the group's weight-gradient accumulator: TMEM lane = out feature, 128 columns = in features
+    if (!first) {
+        uv_tc_fence_after();
+        const int m = gt;
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+            uint32_t r[32];
+            UV_TMEM_LD32(r, tmem_gw + lane_off + (uint32_t)(cc * 32));
+            uv_tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(gW + m * 128 + cc * 32 + i, __uint_as_float(r[i]));
+        }
+    }
+    uv_tc_fence_before();
+    __syncthreads();
+    if (tid < 128) atomicAdd(colsum + tid, sCol[tid]);
+    if (tid < 32) {
+        uv_tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_cta), "r"(512u) : "memory");
+    }
 }

@@ -90,10 +90,10 @@ class _UvMlp(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_uv, _g_jac):
-        """Per hidden layer two plain GEMMs (delta @ W and delta^T @ a: cuBLAS through torch.mm, fp16 operands on the
-        stash the forward kernel wrote, fp32 weight gradients) plus one streaming glue kernel of ours (ReLU mask + bias /
-        embedding column sums); the K = 3 input and output layers and the normalisation are handled entirely by the
-        ``head`` / ``tail`` kernels. The back-propagated signal stays in fp16 under one power-of-two scale chosen on
+        """Per hidden layer ONE tcgen05 kernel (``texgs_uvmlp_backward_layer``: delta^T @ a into TMEM across the CTA's tiles with
+        MN-major operands, delta @ W with K-major operands, ReLU mask and bias / embedding column sums in the epilogue; fp16
+        operands on the stash the forward kernel wrote, fp32 accumulation); the K = 3 input and output layers and the
+        normalisation are handled entirely by the ``head`` / ``tail`` kernels. No cuBLAS call is left on the path. The back-propagated signal stays in fp16 under one power-of-two scale chosen on
         the device from max|d loss / d out| (no host sync), as mixed-precision training does."""
         lib = L.load()
         saved = ctx.saved_tensors
@@ -119,15 +119,17 @@ class _UvMlp(torch.autograd.Function):
             L.check(lib.texgs_uvmlp_backward_head(N, _p(g), _p(uv), _p(inv_len), _p(a4), _p(w5h), _p(scratch), _p(scale), _p(d), _p(gW5),
                                                   _p(gb5), _p(cs[0]), st), "texgs_uvmlp_backward_head")
             inv = 1.0 / scale
-            gW4 = torch.mm(d.T, a3, out_dtype=f32) * inv
-            d = torch.mm(d, w4h)
-            L.check(lib.texgs_uvmlp_backward_mask(N, _p(d), _p(a3), _p(cs[1]), st), "texgs_uvmlp_backward_mask")
-            gW3 = torch.mm(d.T, a2, out_dtype=f32) * inv
-            d = torch.mm(d, w3h)
-            L.check(lib.texgs_uvmlp_backward_mask(N, _p(d), _p(a2), _p(cs[2]), st), "texgs_uvmlp_backward_mask")
-            gW2 = torch.mm(d.T, a1, out_dtype=f32) * inv
-            d = torch.mm(d, w2h)
-            L.check(lib.texgs_uvmlp_backward_mask(N, _p(d), _p(a1), _p(cs[3]), st), "texgs_uvmlp_backward_mask")
+            # hidden layers 4, 3, 2: one tcgen05 kernel each — gW += delta^T a (K = points, MN-major operands), delta <- (delta W) *
+            # (a > 0) (K-major operands, W^T resident in shared memory) and the column sums of the new delta
+            d2 = torch.empty_like(d)
+            gWs = []
+            for w, a_prev, k in ((w4h, a3, 1), (w3h, a2, 2), (w2h, a1, 3)):
+                gw = z(HIDDEN, HIDDEN)
+                L.check(lib.texgs_uvmlp_backward_layer(N, _p(d), _p(a_prev), _p(w.T.contiguous()), _p(d2), _p(gw), _p(cs[k]), st),
+                        "texgs_uvmlp_backward_layer")
+                gWs.append(gw * inv)
+                d, d2 = d2, d
+            gW4, gW3, gW2 = gWs
             off3, isc3 = (C.c_float * 3)(*ctx.offset), (C.c_float * 3)(*ctx.inv_scale)
             L.check(lib.texgs_uvmlp_backward_tail(N, _p(d), _p(x), off3, isc3, _p(w1), _p(scale), _p(gx), _p(gW1), st), "texgs_uvmlp_backward_tail")
             cs = cs * inv
