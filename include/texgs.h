@@ -121,7 +121,8 @@ typedef struct TexgsCounters {
     uint32_t max_tile_len;   /* longest per-tile list                                             */
     uint32_t num_blend_lo;   /* (pixel, Gaussian) contributions blended, low / high 32 bits       */
     uint32_t num_blend_hi;   /*   (only counted when TEXGS_FLAG_DEBUG is set)                     */
-    uint32_t reserved[2];
+    uint32_t num_long_tiles; /* tiles whose list is longer than the small-list sort handles (filled during the sort)   */
+    uint32_t reserved[1];
 } TexgsCounters;
 
 /* Sizes (bytes) of the three caller-owned workspaces for a given problem and pair capacity.

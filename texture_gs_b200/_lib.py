@@ -50,7 +50,7 @@ class TexgsFwdArgs(C.Structure):
 class TexgsCounters(C.Structure):
     _fields_ = [("num_pairs", C.c_uint32), ("num_visible", C.c_uint32), ("overflow", C.c_uint32),
                 ("max_tile_len", C.c_uint32), ("num_blend_lo", C.c_uint32), ("num_blend_hi", C.c_uint32),
-                ("reserved", C.c_uint32 * 2)]
+                ("num_long_tiles", C.c_uint32), ("reserved", C.c_uint32 * 1)]
 
 
 class TexgsBwdArgs(C.Structure):

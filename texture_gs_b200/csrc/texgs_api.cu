@@ -273,7 +273,7 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
     TEXGS_EV(a, TEXGS_EV_FWD_SCATTER, stream);
     texgs_sort_tiles_small<<<p.num_tiles, TEXGS_SORT_SMALL_THREADS, 0, stream>>>(p);
     TEXGS_KERNEL_CHECK("texgs_sort_tiles_small", debug, stream);
-    texgs_sort_tiles<<<p.num_tiles, TEXGS_SORT_THREADS, 0, stream>>>(p);
+    texgs_sort_tiles<<<TEXGS_SORT_LONG_CTAS, TEXGS_SORT_THREADS, 0, stream>>>(p);
     TEXGS_KERNEL_CHECK("texgs_sort_tiles", debug, stream);
     TEXGS_EV(a, TEXGS_EV_FWD_SORT, stream);
     }

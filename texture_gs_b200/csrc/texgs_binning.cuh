@@ -16,56 +16,64 @@
 
 #define TEXGS_SCAN_THREADS 1024
 
+// One CTA, ONE block-wide scan: every thread owns ceil(T / 1024) consecutive tiles, scans them serially, the 1024 thread
+// totals are scanned with shuffles (two barriers in all; the round-1 version ran 8 block-wide scans with 4 barriers each
+// for the 8160 tiles of a 1080p view: 13 us of pure latency).
 __global__ void __launch_bounds__(TEXGS_SCAN_THREADS) texgs_scan_tiles(const RasterParams p) {
     __shared__ unsigned warp_tot[32];
-    __shared__ unsigned carry;
     __shared__ unsigned smax[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) carry = 0;
-    unsigned vmax = 0;
-    __syncthreads();
-    for (int base = 0; base < p.num_tiles; base += TEXGS_SCAN_THREADS) {
-        const int i = base + tid;
-        const unsigned v = (i < p.num_tiles) ? p.tile_count[i] : 0u;
-        vmax = max(vmax, v);
-        unsigned x = v;
+    const int per = (p.num_tiles + TEXGS_SCAN_THREADS - 1) / TEXGS_SCAN_THREADS;
+    const int i0 = min(tid * per, p.num_tiles), i1 = min(i0 + per, p.num_tiles);
+    unsigned sum = 0, vmax = 0;
+    for (int b = i0; b < i1; b += 8) {                 // 8 independent loads in flight, not a chain of dependent ones
+        unsigned c[8];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) warp_tot[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            unsigned w = warp_tot[lane];
+        for (int j = 0; j < 8; ++j) c[j] = (b + j < i1) ? p.tile_count[b + j] : 0u;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
-            }
-            warp_tot[lane] = w;   // inclusive over warps
-        }
-        __syncthreads();
-        const unsigned warp_excl = (wid == 0) ? 0u : warp_tot[wid - 1];
-        const unsigned incl = carry + warp_excl + x;
-        if (i < p.num_tiles) p.tile_offset[i] = incl - v;
-        __syncthreads();
-        if (tid == TEXGS_SCAN_THREADS - 1) carry = incl;
-        __syncthreads();
+        for (int j = 0; j < 8; ++j) { sum += c[j]; vmax = max(vmax, c[j]); }
     }
-    // max tile length (statistics only)
+    unsigned x = sum;                                  // inclusive scan of the thread totals inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 31) warp_tot[wid] = x;
     if (lane == 0) smax[wid] = vmax;
     __syncthreads();
-    if (tid == 0) {
-        unsigned mm = 0;
-        for (int w = 0; w < TEXGS_SCAN_THREADS / 32; ++w) mm = max(mm, smax[w]);
-        const unsigned K = carry;
-        p.tile_offset[p.num_tiles] = K;
-        p.counters->num_pairs = K;
-        p.counters->max_tile_len = mm;
-        p.counters->overflow = ((unsigned long long)K > p.pair_capacity) ? 1u : 0u;
+    if (wid == 0) {
+        unsigned w = warp_tot[lane];
+        unsigned m = smax[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        warp_tot[lane] = w;                            // inclusive over warps
+        if (lane == 31) {
+            const unsigned K = w;
+            p.tile_offset[p.num_tiles] = K;
+            p.counters->num_pairs = K;
+            p.counters->max_tile_len = m;
+            p.counters->overflow = ((unsigned long long)K > p.pair_capacity) ? 1u : 0u;
+        }
+    }
+    __syncthreads();
+    unsigned run = ((wid == 0) ? 0u : warp_tot[wid - 1]) + x - sum;     // exclusive prefix of this thread's first tile
+    for (int b = i0; b < i1; b += 8) {
+        unsigned c[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = (b + j < i1) ? p.tile_count[b + j] : 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (b + j < i1) p.tile_offset[b + j] = run;
+            run += c[j];
+        }
     }
 }
 
@@ -102,7 +110,12 @@ __global__ void __launch_bounds__(TEXGS_SORT_SMALL_THREADS) texgs_sort_tiles_sma
     const int tile = blockIdx.x;
     const unsigned start = p.tile_offset[tile];
     const unsigned n = p.tile_offset[tile + 1] - start;
-    if (n == 0 || n > TEXGS_SORT_SMALL) return;             // long lists: texgs_sort_tiles
+    if (n > TEXGS_SORT_SMALL) {                             // long list: queued for texgs_sort_tiles (the cursors of the
+        if (threadIdx.x == 0)                               // scatter kernel are dead by now: they hold the queue)
+            p.tile_cursor[atomicAdd(&p.counters->num_long_tiles, 1u)] = (unsigned)tile;
+        return;
+    }
+    if (n == 0) return;
     unsigned long long* seg = reinterpret_cast<unsigned long long*>(p.pairs + start);
     const unsigned tid = threadIdx.x;
     unsigned npad = 2;
@@ -134,15 +147,19 @@ __global__ void __launch_bounds__(TEXGS_SORT_SMALL_THREADS) texgs_sort_tiles_sma
     }
 }
 
+// Long lists (> 512 entries; a handful of tiles per view): a small fixed grid walks the queue the small-list kernel filled.
+// (Round 1 launched one 256-thread CTA per tile here as well: 8160 CTAs of which a few had work, 26 us.)
+#define TEXGS_SORT_LONG_CTAS 296
 __global__ void __launch_bounds__(TEXGS_SORT_THREADS) texgs_sort_tiles(const RasterParams p) {
     __shared__ unsigned long long keys[TEXGS_SORT_SMEM_ELEMS];
     if (p.counters->overflow) return;
-    const int tile = blockIdx.x;
+    const unsigned nlong = p.counters->num_long_tiles;
+    const int tid = threadIdx.x;
+    for (unsigned q = blockIdx.x; q < nlong; q += gridDim.x) {
+    const int tile = (int)p.tile_cursor[q];
     const unsigned start = p.tile_offset[tile];
     const unsigned n = p.tile_offset[tile + 1] - start;
-    if (n <= TEXGS_SORT_SMALL) return;                      // short lists: texgs_sort_tiles_small
     unsigned long long* seg = reinterpret_cast<unsigned long long*>(p.pairs + start);
-    const int tid = threadIdx.x;
     unsigned npad = 2;
     while (npad < n) npad <<= 1;
     if (npad <= TEXGS_SORT_SMEM_ELEMS) {
@@ -197,5 +214,7 @@ __global__ void __launch_bounds__(TEXGS_SORT_THREADS) texgs_sort_tiles(const Ras
             }
         }
         for (unsigned i = tid; i < n; i += TEXGS_SORT_THREADS) p.sorted_ids[start + i] = (unsigned)(seg[i] & 0xffffffffull);
+    }
+    __syncthreads();                                        // ``keys`` is reused by the next queue entry
     }
 }
