@@ -129,10 +129,8 @@ struct Fiber {
     const volatile unsigned* wait_addr = nullptr;
     unsigned wait_val = 0;
     const char* wait_what = "";
-    // cp.async (LDGSTS): copies of the group being built and the committed groups still in flight, oldest first
-    std::vector<PendingCopy> cp_open;
-    std::deque<std::vector<PendingCopy>> cp_groups;
-    // cp.async.bulk shared -> global (bulk_group completion): same bookkeeping
+    // cp.async.bulk shared -> global (bulk_group completion): copies of the group being built and the committed groups
+    // still in flight, oldest first
     std::vector<PendingCopy> bulk_open;
     std::deque<std::vector<PendingCopy>> bulk_groups;
 };
@@ -225,7 +223,6 @@ inline void fiber_main() {
     g.entry(g.entry_arg);
     Fiber* f = g.cur;
     f->done = true;
-    if (!f->cp_open.empty() || !f->cp_groups.empty()) fail("a thread exited with cp.async copies in flight (no cp.async.wait_group covered them)");
     if (!f->bulk_open.empty() || !f->bulk_groups.empty()) fail("a thread exited with bulk stores in flight (no cp.async.bulk.wait_group covered them): their shared-memory source dies with the block");
     Warp& w = g.warps[f->warp];
     w.exited |= 1u << f->lane;
@@ -484,28 +481,6 @@ inline void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint6
     simt::G().copies[bar].push_back(simt::PendingCopy{smem_dst, gmem_src, bytes});
     if (simt::G().eager_copies) simt::mbar_flush(bar);
 }
-// cp.async (per-thread asynchronous copy, LDGSTS): lands as LATE as legal — at the cp.async.wait_group that covers its
-// group — or, with eager copies, at issue (as EARLY as legal: a slot still being read is overwritten)
-inline void cp_async_n(void* smem_dst, const void* gmem_src, unsigned bytes) {
-    if (((uintptr_t)smem_dst & (bytes - 1)) || ((uintptr_t)gmem_src & (bytes - 1))) simt::fail("cp.async: addresses must be aligned to the copy size");
-    simt::Global& g = simt::G();
-    if (g.eager_copies) memcpy(smem_dst, gmem_src, bytes);
-    else g.cur->cp_open.push_back(simt::PendingCopy{smem_dst, gmem_src, bytes});
-}
-inline void cp_async16(void* smem_dst, const void* gmem_src) { cp_async_n(smem_dst, gmem_src, 16); }
-inline void cp_async4(void* smem_dst, const void* gmem_src) { cp_async_n(smem_dst, gmem_src, 4); }
-inline void cp_async_commit() {
-    simt::Fiber* f = simt::G().cur;
-    f->cp_groups.push_back(std::move(f->cp_open));
-    f->cp_open.clear();
-}
-template <int N> inline void cp_async_wait() {
-    simt::Fiber* f = simt::G().cur;
-    while ((int)f->cp_groups.size() > N) {
-        for (const simt::PendingCopy& c : f->cp_groups.front()) memcpy(c.dst, c.src, c.bytes);
-        f->cp_groups.pop_front();
-    }
-}
 // cp.async.bulk shared::cta -> global and its reducing form (cp.reduce.async.bulk ... .add.f32), bulk_group completion.
 // Late as legal: the data leaves shared memory at the wait that covers the group; eager: at issue.
 inline void simt_apply_bulk(const simt::PendingCopy& c) {
@@ -536,10 +511,6 @@ template <int N> inline void bulk_wait() {
     }
 }
 inline void fence_proxy_async_smem() {}
-template <class T> inline void ldg256(const T* p, float (&o)[8]) {
-    if ((uintptr_t)p & 31u) simt::fail("256-bit load: address must be 32-byte aligned");
-    memcpy(o, p, 32);
-}
 inline void red_add_v4(float* addr, float a, float b, float c, float d) {
     if ((uintptr_t)addr & 15u) simt::fail("red.global.add.v4.f32: address must be 16-byte aligned");
     addr[0] += a; addr[1] += b; addr[2] += c; addr[3] += d;
@@ -585,7 +556,7 @@ inline void run_block() {
         Fiber& f = g.fibers[t];
         f.lin = (int)t; f.lane = (int)(t & 31); f.warp = (int)(t >> 5);
         f.tid = uint3{t % g.bdim.x, (t / g.bdim.x) % g.bdim.y, t / (g.bdim.x * g.bdim.y)};
-        f.done = false; f.wait_addr = nullptr; f.cp_open.clear(); f.cp_groups.clear(); f.bulk_open.clear(); f.bulk_groups.clear();
+        f.done = false; f.wait_addr = nullptr; f.bulk_open.clear(); f.bulk_groups.clear();
         g.warps[f.warp].exist |= 1u << f.lane;
         make_context(&f.ctx, g.stacks[t], kStackBytes, &fiber_main);
     }
