@@ -40,12 +40,13 @@ def test_abi_version_and_kernel_list():
 
 def test_struct_sizes_match_the_c_header(tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include "%s"\n#include <stdio.h>\nint main(){printf("%%zu %%zu %%zu %%zu\\n", sizeof(TexgsFwdArgs),'
-                   ' sizeof(TexgsBwdArgs), sizeof(TexgsCounters), sizeof(TexgsLayout));return 0;}\n' % HEADER)
+    src.write_text('#include "%s"\n#include <stdio.h>\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu\\n", sizeof(TexgsFwdArgs),'
+                   ' sizeof(TexgsBwdArgs), sizeof(TexgsCounters), sizeof(TexgsLayout), sizeof(TexgsDpAdamArgs), sizeof(TexgsUvMlpArgs));return 0;}\n' % HEADER)
     exe = tmp_path / "sz"
     subprocess.run(["gcc", str(src), "-o", str(exe)], check=True)   # plain C: the header must be C-clean
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    assert got == [C.sizeof(L.TexgsFwdArgs), C.sizeof(L.TexgsBwdArgs), C.sizeof(L.TexgsCounters), C.sizeof(L.TexgsLayout)]
+    assert got == [C.sizeof(L.TexgsFwdArgs), C.sizeof(L.TexgsBwdArgs), C.sizeof(L.TexgsCounters), C.sizeof(L.TexgsLayout),
+                   C.sizeof(L.TexgsDpAdamArgs), C.sizeof(L.TexgsUvMlpArgs)]
 
 
 def test_sass_is_sm100a_with_bulk_copy_and_mbarrier():
@@ -57,6 +58,11 @@ def test_sass_is_sm100a_with_bulk_copy_and_mbarrier():
     assert "sm_100a" in r.stdout
     assert "UBLKCP" in r.stdout
     assert "SYNCS" in r.stdout
+    # round 2: TMA bulk reduction of the SH gradient rows, tcgen05 MMAs of the UV network (forward and backward layers), and the
+    # multimem load of the fused multi-GPU texture step (multimem.ld_reduce.add.v4.f32: the NVSwitch adds the ranks' copies)
+    assert "UBLKRED" in r.stdout
+    assert r.stdout.count("UTCHMMA") >= 30 and "LDTM" in r.stdout
+    assert "LDGMC.E.ADD.F32x4" in r.stdout
 
 
 def _args(P=10, H=32, W=48, R=8, mode=L.MODE_TEXTURE):
