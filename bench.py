@@ -380,15 +380,29 @@ def main():
             opt.step()
 
     fin_ev = []            # (start, end) CUDA events around finish_step() of the timed steps
+    from texture_gs_b200.rasterizer import ensure_packed_texture
+    # The tail of a batch (gradient reduction, optimizer, repack of the new texels, clearing the bucket) runs on the main
+    # stream; the view streams of the NEXT batch fork from the moment this batch's views had joined (``joined``) and only
+    # their render kernels wait for the tail (``tail_done``): preprocess / scan / scatter / sort of the first views — which
+    # need neither the texture nor the bucket — run under it.
+    ev_state = {"joined": None, "tail_done": None}
 
-    def step(tm=None, nstreams=streams, record=False):
-        # one texture update per step: the packed (6,R,R,4) copy is rebuilt once per 32-view batch (by the optimizer
-        # kernel itself on one GPU, by the pack kernel after the fused multi-GPU step)
-        if opt is None:
-            invalidate_packed_cache()
+    def reset_pipeline():
+        """Plain state: the bucket is clear, the next batch forks from the main stream."""
+        ev_state["joined"] = ev_state["tail_done"] = None
         if bwd:
             bucket.zero()
-        render_views_accumulate(render_fn, g, cams, cot, views, bg, timer=tm, bucket=bucket, streams=nstreams, backward=bwd)
+
+    def run_batch(tm=None, nstreams=streams, record=False, final=False, tail_hook=None, **view_kw):
+        """One batch of this rank's views + what follows it. ``final``: leave the reduced gradients in the bucket (checksum)."""
+        if opt is None:
+            invalidate_packed_cache()          # one texture update per step: the packed (6,R,R,4) copy is rebuilt once per batch
+        render_views_accumulate(render_fn, g, cams, view_kw.pop("cotangents", cot), views, bg, timer=tm, bucket=bucket, streams=nstreams,
+                                backward=bwd, fork_event=ev_state["joined"], render_event=ev_state["tail_done"], **view_kw)
+        if not bwd:
+            return
+        joined = torch.cuda.Event()
+        joined.record()
         if record:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
@@ -397,7 +411,20 @@ def main():
             fin_ev.append(ev)
         else:
             finish_step()
+        if tail_hook is not None:
+            tail_hook()
+        if final:
+            ev_state["joined"] = ev_state["tail_done"] = None
+            return
+        if opt is not None:
+            ensure_packed_texture(g.get_texture)       # no-op on one GPU (TextureAdam emits the packed copy itself)
+        bucket.zero()                                  # for the next batch
+        tail = torch.cuda.Event()
+        tail.record()
+        ev_state["joined"], ev_state["tail_done"] = (joined, tail) if opt is not None else (None, None)
 
+    step = run_batch
+    reset_pipeline()
     for _ in range(args.warmup):
         step()
     sync_all()
@@ -410,8 +437,8 @@ def main():
     sync_all()
     t0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        step(record=True)
+    for i in range(args.steps):
+        step(record=True, final=(i == args.steps - 1))
     e1.record()
     sync_all()
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -446,6 +473,7 @@ def main():
     if not args.no_stage_pass:
         nsteps = max(1, min(args.steps, 4))
         timer = StageTimer(capacity=max(1, len(views)) * nsteps, device=dev)
+        reset_pipeline()
         for _ in range(nsteps):
             step(timer, 1)
         sync_all()
@@ -457,7 +485,8 @@ def main():
     e2e = None
     if not args.no_e2e:
         try:
-            e2e = run_e2e(args, wl, g, cams, bg, bucket, views, dev, world, sync_all, render_fn, streams, finish_step, opt is None)
+            reset_pipeline()
+            e2e = run_e2e(args, wl, g, cams, bg, bucket, views, dev, world, sync_all, render_fn, streams, run_batch)
         except Exception as e:              # keep the device-resident measurement; the line then says why e2e is missing
             if world > 1:
                 raise                       # a rank that drops out of the collectives would hang the others
@@ -465,6 +494,7 @@ def main():
 
     # ---- unique texels touched by one view (for the algorithmic byte count) ---------------------
     if bwd:
+        sync_all()
         bucket.zero()
         render_views_accumulate(uv_tex_render, g, cams, [torch.ones_like(c) for c in cot], views[:1] or [0], bg, bucket=bucket)
         U = int((bucket.grads()["texture"].abs().sum(dim=-1) > 0).sum().item())
@@ -535,7 +565,7 @@ def make_supervision(wl, n_views: int, seed: int = 5):
     return out
 
 
-def run_e2e(args, wl, g, cams, bg, bucket, views, dev, world, sync_all, render_fn, streams, finish_step, invalidate):
+def run_e2e(args, wl, g, cams, bg, bucket, views, dev, world, sync_all, render_fn, streams, run_batch):
     """The step a user of the reference runs, through the public operators, with HOST inputs (train.py:147-149,
     models/texture_gaussian3d.py:315-368 with the losses configs/texture_gaussian3d.yaml:77-88 enables): per view the
     ground-truth image (uint8), the alpha mask (uint8) and the normal prior (int8) are copied from pinned host memory on
@@ -613,18 +643,13 @@ def run_e2e(args, wl, g, cams, bg, bucket, views, dev, world, sync_all, render_f
         def after_view(v, i):
             free[i % nslots].record(torch.cuda.current_stream(dev))
 
-        def step():
-            if invalidate:
-                invalidate_packed_cache()
-            bucket.zero()
-            total.zero_()
-            for s in range(nslots):
-                free[s].record(main)
-            upload(0)
-            render_views_accumulate(render_fn, g, cams, None, views, bg, bucket=bucket, streams=streams, loss_fn=loss_fn,
-                                    before_view=before_view, after_view=after_view)
-            finish_step()
+        def read_back():                       # tail of the batch, before the next batch's renders may add to ``total`` again
             result_host.copy_(total.sum().reshape(1), non_blocking=True)
+            total.zero_()
+
+        def step():
+            upload(0)          # slot 0 was released by the last view that used it (after_view); nothing to wait for on main
+            run_batch(cotangents=None, loss_fn=loss_fn, before_view=before_view, after_view=after_view, tail_hook=read_back)
 
     for _ in range(max(3, args.warmup)):
         step()

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TEXGS_ABI_VERSION 3
+#define TEXGS_ABI_VERSION 4
 
 #define TEXGS_E_INVALID   1001   /* bad argument */
 #define TEXGS_E_WORKSPACE 1002   /* workspace too small */
@@ -99,6 +99,11 @@ typedef struct TexgsFwdArgs {
      * the stream at the stage boundaries below; NULL = off. Forward fills slots 0..5, backward
      * (through TexgsBwdArgs.fwd) slots 6..9. */
     void* const* profile_events;
+    /* optional: a cudaEvent_t (as void*) the stream waits for between binning and the render kernel (forward only). The
+     * per-Gaussian stages of a view need neither the texture nor the gradient buffers, so a caller whose previous optimizer
+     * step / gradient reduction is still running on another stream lets them start early and orders only the render
+     * (and everything behind it on the stream) after that work (dist.render_views_accumulate(render_event=...)). NULL = off. */
+    void* render_wait_event;
 } TexgsFwdArgs;
 
 #define TEXGS_EV_FWD_START      0

@@ -13,7 +13,7 @@ _PKG = Path(__file__).resolve().parent
 # TEXGS_LIB selects an alternative build of the same ABI (kernel-tuning experiments, tools/build_variants.py)
 LIB_PATH = Path(os.environ["TEXGS_LIB"]).resolve() if os.environ.get("TEXGS_LIB") else _PKG / "libtexgs.so"
 
-TEXGS_ABI_VERSION = 3
+TEXGS_ABI_VERSION = 4
 FLAG_PREFILTERED = 1
 FLAG_DEBUG = 2
 FLAG_SEAMLESS_CUBE = 4        # spec switches (include/texgs.h): E11-alt, E7-alt, E13-alt
@@ -44,6 +44,7 @@ class TexgsFwdArgs(C.Structure):
         ("texture_rgba", _fp),
         ("out_image_nosh", _fp),
         ("profile_events", C.POINTER(C.c_void_p)),
+        ("render_wait_event", C.c_void_p),
     ]
 
 

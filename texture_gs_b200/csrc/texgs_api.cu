@@ -278,6 +278,7 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
     TEXGS_EV(a, TEXGS_EV_FWD_SORT, stream);
     }
     if (int rc = ensure_render_smem()) return rc;
+    if (a->render_wait_event) TEXGS_CUDA_TRY(cudaStreamWaitEvent(stream, (cudaEvent_t)a->render_wait_event, 0));
     {
         NvtxRange r("texgs/forward/render");
         const bool t4 = p.texture_rgba != nullptr, dual = p.out_image_nosh != nullptr;

@@ -262,7 +262,7 @@ def _stream_pool(device: torch.device, n: int):
 
 def render_views_accumulate(render_fn, gaussians, cameras: Sequence, cotangents, view_ids: Iterable[int], bg,
                             timer=None, bucket: Optional["GradBucket"] = None, streams: int = 1, backward: bool = True,
-                            loss_fn=None, before_view=None, after_view=None):
+                            loss_fn=None, before_view=None, after_view=None, fork_event=None, render_event=None):
     """Forward (+ backward) of ``render_fn`` (``uv_tex_render``) for the given views; gradients accumulate into the
     leaves' ``.grad`` (i.e. the bucket) — from inside the backward kernels when ``bucket`` is given
     (``bucket.fused()``), through autograd otherwise.
@@ -277,13 +277,20 @@ def render_views_accumulate(render_fn, gaussians, cameras: Sequence, cotangents,
     CUDA stream i mod ``streams``, so the latency-bound small kernels of one view (tile scan, scatter, sort) and the
     tails of its render kernels overlap the render kernels of the next one (+9 % views/s at the headline size,
     profiles/r2_variants.md). All streams accumulate into the one bucket (atomic adds). The packed texel copy is built
-    once before the fork; the calling stream joins all streams before returning."""
+    once before the fork; the calling stream joins all streams before returning.
+
+    ``fork_event`` / ``render_event`` (``streams`` > 1) overlap the tail of the PREVIOUS batch with the head of this
+    one: the view streams start after ``fork_event`` (e.g. recorded when the previous batch's views had joined) instead
+    of after everything the calling stream has queued since (gradient reduction, optimizer step, repack, bucket clear),
+    and only the render kernel of each view — the first to touch the texture; the backward, the first to touch the
+    bucket, comes after it — waits for ``render_event``, recorded behind that work."""
     view_ids = list(view_ids)
+    from .rasterizer import wait_before_render
 
     def one_view(slot, v, fused_ctx):
         cam = cameras[v % len(cameras)]
         ctx = timer.view(backward=backward) if timer is not None else _null()
-        with ctx, fused_ctx:
+        with ctx, fused_ctx, wait_before_render(render_event):
             if before_view is not None:
                 before_view(v, slot)
             if not backward:
@@ -312,14 +319,20 @@ def render_views_accumulate(render_fn, gaussians, cameras: Sequence, cotangents,
                 raise ValueError("streams > 1: every differentiable input of the render must be a leaf of the bucket "
                                  "(activations computed outside it would be accumulated by autograd from several streams at once)")
     dev = bucket.flat.device if bucket is not None else torch.device("cuda", torch.cuda.current_device())
-    from .rasterizer import ensure_packed_texture
+    from .rasterizer import ensure_packed_texture, packed_is_current
     tex = getattr(gaussians, "get_texture", None)
+    early = fork_event is not None and render_event is not None
     if tex is not None:
+        if early and not packed_is_current(tex):
+            early = False                                # the repack below is newer than render_event: plain fork
         ensure_packed_texture(tex)                       # on the calling stream, before the fork
     main = torch.cuda.current_stream(dev)
     pool = _stream_pool(dev, streams)
     for s in pool:
-        s.wait_stream(main)
+        if early:
+            s.wait_event(fork_event)
+        else:
+            s.wait_stream(main)
     for i, v in enumerate(view_ids):
         r = i % streams
         with torch.cuda.stream(pool[r]):

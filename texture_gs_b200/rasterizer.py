@@ -157,6 +157,12 @@ def ensure_packed_texture(texture: torch.Tensor) -> Optional[torch.Tensor]:
         return _packed_texture(lib, texture, tex, torch.cuda.current_stream(texture.device).cuda_stream)
 
 
+def packed_is_current(texture: torch.Tensor) -> bool:
+    """True when the cached packed copy belongs to ``texture``'s current version (a forward would not repack)."""
+    hit = _packed_cache.get(id(texture))
+    return bool(hit is not None and hit[0]() is texture and hit[1] == texture._version and hit[2] == texture.data_ptr())
+
+
 def packed_texture_buffer(texture: torch.Tensor) -> torch.Tensor:
     """A (6,R,R,4) buffer for the packed copy of ``texture`` — the cached one if there is one (its content is about
     to be replaced by the caller, see ``adopt_packed_texture``), else a new one."""
@@ -237,6 +243,23 @@ def current_spec() -> SpecSwitches:
     return getattr(_spec, "v", SpecSwitches())
 
 
+_render_wait = threading.local()
+
+
+@contextmanager
+def wait_before_render(event: Optional["torch.cuda.Event"]):
+    """Forward calls of this thread made inside the block wait for ``event`` between binning and the render kernel
+    (``TexgsFwdArgs.render_wait_event``): preprocess, scan, scatter and sort of a view run while the optimizer step /
+    gradient reduction of the previous batch is still in flight on another stream; the render — the first kernel that
+    reads the texture — and the backward behind it are ordered after it."""
+    prev = getattr(_render_wait, "v", None)
+    _render_wait.v = event
+    try:
+        yield
+    finally:
+        _render_wait.v = prev
+
+
 def last_stats() -> Optional[RasterStats]:
     """Counters (V, K, longest tile list, [debug] blended contributions) of the calling thread's
     most recent forward — what bench.py needs for the algorithmic-byte count."""
@@ -272,6 +295,9 @@ def _build_args(st: GaussianRasterizationSettings, mode: int, means3D, shs, colo
     a.cov3Ds_precomp = _ptr(cov3Ds_precomp)
     if profile_arr is not None:
         a.profile_events = C.cast(profile_arr, C.POINTER(C.c_void_p))
+    ev = getattr(_render_wait, "v", None)
+    if ev is not None:
+        a.render_wait_event = C.c_void_p(ev.cuda_event)
     return a
 
 
