@@ -365,6 +365,8 @@ def main():
 
     from texture_gs_b200 import invalidate_packed_cache
 
+    from texture_gs_b200.rasterizer import ensure_packed_texture
+
     def finish_step():
         """What follows the last view of a step: reduce the gradients over the ranks and (unless --no-optimizer) update the texture."""
         if not bwd:
@@ -374,13 +376,13 @@ def main():
         elif world > 1:
             works = bucket.all_reduce(exclude=("texture",), async_op=True)      # per-Gaussian gradients: NCCL, concurrently
             opt.step()
+            ensure_packed_texture(g.get_texture)       # repack of the pushed texels: under the tail of the NCCL collective
             for w in works or []:
                 w.wait()
         else:
             opt.step()
 
     fin_ev = []            # (start, end) CUDA events around finish_step() of the timed steps
-    from texture_gs_b200.rasterizer import ensure_packed_texture
     # The tail of a batch (gradient reduction, optimizer, repack of the new texels, clearing the bucket) runs on the main
     # stream; the view streams of the NEXT batch fork from the moment this batch's views had joined (``joined``) and only
     # their render kernels wait for the tail (``tail_done``): preprocess / scan / scatter / sort of the first views — which
