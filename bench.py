@@ -541,7 +541,11 @@ def main():
                                         % (6 * wl.tex_res ** 2 * 12 // 1000000, wl.n_gaussians * 128 // 1000000),
                            "render_fn": render_fn.__name__, "host_wall_ms_per_step": wall_ms / args.steps, "numa_node": numa_node,
                            "reduce_and_optimizer_ms_per_step": finish_ms},
-            "clocks": clock_rec, "e2e": e2e, "gpu_launches": (kernels_per_view * len(views) + 1) * args.steps,
+            # our kernels in the timed region, per step: 8 (6 forward-only) per view + the texture step (one GPU: the fused Adam
+            # kernel, which also emits the packed copy; N GPUs: the fused reduce + Adam + broadcast kernel and the repack;
+            # --no-optimizer: the repack alone)
+            "clocks": clock_rec, "e2e": e2e,
+            "gpu_launches": (kernels_per_view * len(views) + (0 if not bwd else (2 if (opt is not None and world > 1) else 1))) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "grad_checksum": checksum}
     print(json.dumps(line), flush=True)
     if world > 1:
