@@ -341,21 +341,32 @@ def main():
     # retexture.py renders every view twice (with SH, then active_sh_degree = 0): one dual render here
     render_fn = uv_tex_render_dual if (not bwd and wl.renders_per_view == 2) else uv_tex_render
     use_opt = bwd and not args.no_optimizer
-    bucket = GradBucket({k: v for k, v in g.tensors().items()},
-                        symmetric_group=dist.group.WORLD if (use_opt and world > 1) else None) if bwd else None
     views = shard_views(args.views, world, rank)
     # the texture's optimizer (models/texture_gaussian3d.py:139-143: Adam, lr = tex_lr 0.0025, eps 1e-15) is part of the step:
     # one GPU runs the fused TextureAdam kernel; N GPUs run ONE kernel each that pulls + adds the ranks' partial texture gradients
     # over NVLink (multimem through the NVSwitch when available), updates the owned 1/N of the texels and pushes them to every rank —
     # instead of all-reducing 403 MB and repeating the same update N times. The per-Gaussian gradients (118 MB) go through NCCL.
-    opt = None
-    if use_opt:
-        if world > 1:
+    params = {k: v for k, v in g.tensors().items()}
+    bucket, opt, fused_note = None, None, None
+    if use_opt and world > 1:
+        ok = 1
+        try:
             from texture_gs_b200.dist import DistTextureAdam
+            bucket = GradBucket(params, symmetric_group=dist.group.WORLD)
             opt = DistTextureAdam(g.get_texture, bucket, lr=0.0025, eps=1e-15, use_multicast=False if args.no_multicast else None)
-        else:
-            from texture_gs_b200.optim import TextureAdam
-            opt = TextureAdam([g.get_texture], lr=0.0025, eps=1e-15)
+        except Exception as e:      # no symmetric memory / peer access on this box: every rank all-reduces and steps on its own
+            ok, fused_note = 0, "fused multi-GPU texture step unavailable (%s): NCCL all-reduce + TextureAdam on every rank" % repr(e)[:200]
+        agree = torch.tensor([ok], device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if int(agree.item()) == 0:
+            bucket, opt = None, None
+            fused_note = fused_note or "fused multi-GPU texture step unavailable on another rank: NCCL all-reduce + TextureAdam on every rank"
+    if bwd and bucket is None:
+        bucket = GradBucket(params)
+    if use_opt and opt is None:
+        from texture_gs_b200.optim import TextureAdam
+        opt = TextureAdam([g.get_texture], lr=0.0025, eps=1e-15)
+    fused_dp = opt is not None and hasattr(opt, "state_shard")
     tex0_l1 = float(g.get_texture.detach().abs().sum().item())
 
     def sync_all():
@@ -373,6 +384,9 @@ def main():
             return
         if opt is None:
             bucket.all_reduce()
+        elif world > 1 and not fused_dp:
+            bucket.all_reduce()                        # fallback: plain NCCL all-reduce, the same Adam step on every rank
+            opt.step()
         elif world > 1:
             works = bucket.all_reduce(exclude=("texture",), async_op=True)      # per-Gaussian gradients: NCCL, concurrently
             opt.step()
@@ -533,9 +547,10 @@ def main():
             "impl_notes": {"streams_per_rank": streams,
                            "parallelism": ((f"dp{world} (views sharded; per step: fused texture-gradient reduce + Adam + broadcast kernel over NVLink "
                                             f"[{'multimem / NVLS' if opt.multicast else 'peer loads / stores'}], NCCL all-reduce of the other "
-                                            f"{sum(b - a for a, b in bucket.ranges_without(('texture',))) * 4 / 1e6:.0f} MB)") if (world > 1 and opt is not None)
+                                            f"{sum(b - a for a, b in bucket.ranges_without(('texture',))) * 4 / 1e6:.0f} MB)") if (world > 1 and fused_dp)
                                            else (f"dp{world} (views sharded, 1 all-reduce of {bucket.nbytes / 1e6:.0f} MB/step)" if (world > 1 and bwd)
                                                  else (f"dp{world} (views sharded)" if world > 1 else "single GPU"))),
+                           "fallback": fused_note,
                            "optimizer_in_step": (None if not bwd else ("none (--no-optimizer)" if opt is None else "texture Adam (lr 0.0025, eps 1e-15)")),
                            "l2_policy": "inputs larger than L2 (texture %d MB + records %d MB, a different camera every view)"
                                         % (6 * wl.tex_res ** 2 * 12 // 1000000, wl.n_gaussians * 128 // 1000000),
@@ -545,7 +560,7 @@ def main():
             # kernel, which also emits the packed copy; N GPUs: the fused reduce + Adam + broadcast kernel and the repack;
             # --no-optimizer: the repack alone)
             "clocks": clock_rec, "e2e": e2e,
-            "gpu_launches": (kernels_per_view * len(views) + (0 if not bwd else (2 if (opt is not None and world > 1) else 1))) * args.steps,
+            "gpu_launches": (kernels_per_view * len(views) + (0 if not bwd else (2 if fused_dp else 1))) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "grad_checksum": checksum}
     print(json.dumps(line), flush=True)
     if world > 1:
