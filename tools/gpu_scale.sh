@@ -20,7 +20,7 @@ run 2 n2
 NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,COLL timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29977 \
    bench.py --gpus 8 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-stage-pass --no-optimizer 2>&1 | grep -iE "NVLS|algo|Connected|channels" | sort | uniq -c | sort -rn | head -12 > $O/${T}_nccl_info.txt
 nvidia-smi topo -m > $O/${T}_topo.txt 2>&1
-for f in n1 n8 n8_peer n8_allreduce n4 n2; do
+for f in n1 n8 n8_allreduce n4 n2; do
   python - "$O/${T}_$f.json" <<'PY'
 import json, sys
 try:
