@@ -631,16 +631,31 @@ __global__ void __launch_bounds__(UVBL_THREADS, 1) texgs_uvmlp_bwd_layer_kernel(
     for (int tile = blockIdx.x * UVBL_GROUPS + g; tile < ntiles; tile += gridDim.x * UVBL_GROUPS) {
         const int pt = tile * 128 + gt;
         const bool valid = pt < N;
-        {   // rows of delta and a_prev -> the three operand tiles (rows beyond N are zero: they add nothing)
+        {   // rows of delta and a_prev -> the two operand tiles (rows beyond N are zero: they add nothing). Coalesced: an
+            // instruction of a warp reads two whole 256-byte rows; the 16-byte chunks are scattered into the UMMA layouts
+            // (16-way bank conflicts on these stores, 0.3 us per tile — the thread-per-row loads they replace cost ten times that)
+            const int chunk = lane & 15;
             uint4 d[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) d[j] = valid ? reinterpret_cast<const uint4*>(delta_in + (size_t)pt * 128)[j] : make_uint4(0u, 0u, 0u, 0u);
+            for (int it = 0; it < 16; ++it) {
+                const int rl = s * 32 + 2 * it + (lane >> 4), row = tile * 128 + rl;
+                d[it] = (row < N) ? __ldg(reinterpret_cast<const uint4*>(delta_in + (size_t)row * 128) + chunk) : make_uint4(0u, 0u, 0u, 0u);
+            }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) *reinterpret_cast<uint4*>(sDK + j * 2048 + gt * 16) = d[j];
+            for (int it = 0; it < 16; ++it) {
+                const int rl = s * 32 + 2 * it + (lane >> 4);
+                *reinterpret_cast<uint4*>(sDK + chunk * 2048 + rl * 16) = d[it];
+            }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) d[j] = valid ? reinterpret_cast<const uint4*>(a_prev + (size_t)pt * 128)[j] : make_uint4(0u, 0u, 0u, 0u);
+            for (int it = 0; it < 16; ++it) {
+                const int rl = s * 32 + 2 * it + (lane >> 4), row = tile * 128 + rl;
+                d[it] = (row < N) ? __ldg(reinterpret_cast<const uint4*>(a_prev + (size_t)row * 128) + chunk) : make_uint4(0u, 0u, 0u, 0u);
+            }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) *reinterpret_cast<uint4*>(sAM + mn_off + j * 128) = d[j];
+            for (int it = 0; it < 16; ++it) {
+                const int rl = s * 32 + 2 * it + (lane >> 4);
+                *reinterpret_cast<uint4*>(sAM + (rl >> 3) * 2048 + chunk * 128 + (rl & 7) * 16) = d[it];
+            }
         }
         uv_fence_async_smem();
         uv_group_bar(g);
@@ -681,26 +696,45 @@ __global__ void __launch_bounds__(UVBL_THREADS, 1) texgs_uvmlp_bwd_layer_kernel(
                     const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&h[k]));
                     csum[8 * q + 2 * k] = valid ? t.x : 0.f; csum[8 * q + 2 * k + 1] = valid ? t.y : 0.f;
                 }
-                if (valid) reinterpret_cast<uint4*>(delta_out + (size_t)pt * 128)[cc * 4 + q] = make_uint4(h[0], h[1], h[2], h[3]);
+                // staged in the delta tile (its MMAs are complete) for a coalesced copy-out below; own row: conflict-free
+                *reinterpret_cast<uint4*>(sDK + (cc * 4 + q) * 2048 + gt * 16) = make_uint4(h[0], h[1], h[2], h[3]);
             }
             const float tot = uv_warp_transpose_reduce32(csum, lane);
             atomicAdd(&sCol[cc * 32 + lane], tot);
         }
         uv_tc_fence_before();
+        uv_group_bar(g);
+        {   // the new delta rows leave two whole rows per instruction
+            const int chunk = lane & 15;
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+                const int rl = s * 32 + 2 * it + (lane >> 4), row = tile * 128 + rl;
+                const uint4 v = *reinterpret_cast<const uint4*>(sDK + chunk * 2048 + rl * 16);
+                if (row < N) reinterpret_cast<uint4*>(delta_out + (size_t)row * 128)[chunk] = v;
+            }
+        }
         uv_group_bar(g);            // the tile's operand buffers are free again (all 16 MMAs completed before the epilogue)
     }
 
     // the group's weight-gradient accumulator: TMEM lane = out feature, 128 columns = in features
     if (!first) {
         uv_tc_fence_after();
+        // 148 CTAs x 2 groups add into the same 64 KB: 128-bit vector reductions (a quarter of the L2 operations of scalar
+        // ones) and a per-CTA rotation of the column order, so that the CTAs — which all arrive here at about the same time —
+        // are not queueing on the same addresses
         const int m = gt;
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int c4 = 0; c4 < 4; ++c4) {
+            const int cc = (c4 + (int)blockIdx.x + g) & 3;
             uint32_t r[32];
             UV_TMEM_LD32(r, tmem_gw + lane_off + (uint32_t)(cc * 32));
             uv_tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(gW + m * 128 + cc * 32 + i, __uint_as_float(r[i]));
+            for (int i4 = 0; i4 < 8; ++i4) {
+                const int j = (i4 + (int)(blockIdx.x >> 2)) & 7;
+                red_add_v4(gW + m * 128 + cc * 32 + 4 * j, __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            }
         }
     }
     uv_tc_fence_before();
