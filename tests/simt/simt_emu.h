@@ -365,6 +365,7 @@ inline void __threadfence_block() {}
 // scalar intrinsics
 // ---------------------------------------------------------------------------------------------
 template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T> inline T __ldcs(const T* p) { return *p; }
 namespace simt {
 inline float approx(float exact) {
     Global& g = G();

@@ -160,3 +160,63 @@ def test_emulated_mark_visible_matches_the_near_plane_rule(lib):
     z = pos @ cam.world_view_transform[:3, 2] + cam.world_view_transform[3, 2]
     clear = (z - 0.2).abs() > 1e-5
     assert torch.equal(present.bool()[clear], (z > 0.2)[clear]) and int(present.min()) >= 0
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_emulated_data_parallel_texture_step_equals_summed_gradient_adam(lib, world):
+    """The fused multi-GPU texture step (texgs_texture_adam_dp_step, peer path) with the ranks emulated as buffers of one
+    process: every "rank" holds a partial padded gradient and a copy of the texture; after each rank has run its launch
+    (it owns 1/world of the 1024-texel tiles, pulls and adds all partial gradients of those, updates its shard of the
+    moments, pushes the texels into every copy) all copies equal torch.optim.Adam(eps=1e-15) applied to the SUMMED gradient,
+    the gradients are untouched, and the concatenated moment shards are Adam's moments. Texel count not a multiple of the
+    tile (the tail tile belongs to the last rank), three steps."""
+    from simt.emu import _aligned_empty, check
+    from texture_gs_b200 import _lib as L
+    R = 23
+    ntex = 6 * R * R                                    # 3174 texels: 3 full tiles + a tail
+    gen = torch.Generator().manual_seed(11)
+    p_ref = torch.randn(6, R, R, 3, generator=gen).requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=2.5e-3, betas=(0.9, 0.999), eps=1e-15)
+    params = [_aligned_empty(ntex * 12).view(torch.float32) for _ in range(world)]
+    grads = [_aligned_empty(ntex * 16).view(torch.float32).view(ntex, 4) for _ in range(world)]
+    for p in params:
+        p.copy_(p_ref.detach().reshape(-1))
+    shards = []
+    for r in range(world):
+        lo, hi = C.c_uint64(), C.c_uint64()
+        check(lib, lib.texgs_dp_shard(ntex, world, r, C.byref(lo), C.byref(hi)), "shard")
+        n = max(1, (hi.value - lo.value) * 1024 * 3)
+        m, v = _aligned_empty(n * 4).view(torch.float32), _aligned_empty(n * 4).view(torch.float32)
+        m.zero_(); v.zero_()
+        shards.append((lo.value, hi.value, m, v))
+    assert shards[0][0] == 0 and shards[-1][1] == (ntex + 1023) // 1024 and all(shards[i][1] == shards[i + 1][0] for i in range(world - 1))
+    for step in range(1, 4):
+        parts = [torch.randn(ntex, 3, generator=gen) * (10.0 ** (step - 3)) for _ in range(world)]
+        for gbuf, part in zip(grads, parts):
+            gbuf[:, :3] = part
+            gbuf[:, 3] = 7.0                              # the pad float of a texel never reaches the update
+        p_ref.grad = sum(parts).reshape(6, R, R, 3).clone()
+        opt.step()
+        for r in range(world):
+            a = L.TexgsDpAdamArgs()
+            a.world, a.rank = world, r
+            for k in range(world):
+                a.grad_ptrs[k], a.param_ptrs[k] = grads[k].data_ptr(), params[k].data_ptr()
+            lo, hi, m, v = shards[r]
+            a.exp_avg, a.exp_avg_sq = m.data_ptr(), v.data_ptr()
+            a.n_texels, a.tile_lo, a.tile_hi = ntex, lo, hi
+            a.lr, a.beta1, a.beta2, a.eps, a.step = 2.5e-3, 0.9, 0.999, 1e-15, step
+            check(lib, lib.texgs_texture_adam_dp_step(C.byref(a), None), "dp_step")
+        for k in range(world):
+            assert float((params[k] - p_ref.detach().reshape(-1)).abs().max()) <= 2e-6, (step, k)
+            assert torch.equal(params[k], params[0])
+            assert torch.equal(grads[k][:, :3], parts[k]) and float((grads[k][:, 3] - 7.0).abs().max()) == 0.0
+    st = opt.state[p_ref]
+    for lo, hi, m, v in shards:
+        t0, t1 = lo * 1024, min(hi * 1024, ntex)
+        # the kernel adds the partial gradients rank by rank starting at its own: a different order than sum(parts)
+        np.testing.assert_allclose(m[:(t1 - t0) * 3].numpy(), st["exp_avg"].reshape(-1)[t0 * 3:t1 * 3].numpy(), rtol=2e-4, atol=1e-8)
+        np.testing.assert_allclose(v[:(t1 - t0) * 3].numpy(), st["exp_avg_sq"].reshape(-1)[t0 * 3:t1 * 3].numpy(), rtol=2e-4, atol=1e-11)
+    # the multicast variant needs the fabric: refused on the host
+    a.grad_mc, a.param_mc = grads[0].data_ptr(), params[0].data_ptr()
+    assert lib.texgs_texture_adam_dp_step(C.byref(a), None) != 0

@@ -537,8 +537,8 @@ int texgs_texture_adam_dp_step(const TexgsDpAdamArgs* a, void* stream_) {
     if (al & 15) return fail(TEXGS_E_INVALID, "all buffers must be 16-byte aligned");
     if ((a->grad_mc == nullptr) != (a->param_mc == nullptr)) return fail(TEXGS_E_INVALID, "give both multicast mappings or neither");
 #ifdef TEXGS_HOST_EMU
-    return fail(TEXGS_E_INVALID, "the data-parallel texture step needs NVLink peers (no host emulation)");
-#else
+    if (a->grad_mc) return fail(TEXGS_E_INVALID, "multimem needs an NVSwitch fabric (the host emulation runs the peer path only)");
+#endif
     if (a->tile_hi == a->tile_lo) return 0;
     DpAdamArgs k;
     k.world = a->world; k.rank = a->rank;
@@ -553,7 +553,6 @@ int texgs_texture_adam_dp_step(const TexgsDpAdamArgs* a, void* stream_) {
     else texgs_texture_adam_dp_kernel<false><<<ctas, TEXGS_ADAM_THREADS, 0, stream>>>(k);
     TEXGS_KERNEL_CHECK("texgs_texture_adam_dp_kernel", false, stream);
     return 0;
-#endif
 }
 
 int texgs_uvmlp_forward(const TexgsUvMlpArgs* a, void* stream_) {

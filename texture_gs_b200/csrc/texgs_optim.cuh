@@ -173,7 +173,10 @@ struct DpAdamArgs {
     float one_minus_b1, b2, one_minus_b2, step_size, inv_sqrt_bc2, eps;
 };
 
-#ifndef TEXGS_HOST_EMU
+#ifdef TEXGS_HOST_EMU      // the emulator (tests/simt) runs the PEER path of the kernel below: several "ranks" are buffers of one process
+inline float4 multimem_ld_reduce_add(const float4*) { simt::fail("multimem needs an NVSwitch fabric"); return make_float4(0.f, 0.f, 0.f, 0.f); }
+inline void multimem_st(float4*, float4) { simt::fail("multimem needs an NVSwitch fabric"); }
+#else
 __device__ __forceinline__ float4 multimem_ld_reduce_add(const float4* mc) {
     float4 r;
     asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -183,6 +186,7 @@ __device__ __forceinline__ float4 multimem_ld_reduce_add(const float4* mc) {
 __device__ __forceinline__ void multimem_st(float4* mc, float4 v) {
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+#endif
 
 template <bool MC>
 __global__ void __launch_bounds__(TEXGS_ADAM_THREADS, 2) texgs_texture_adam_dp_kernel(const DpAdamArgs a) {
@@ -261,4 +265,3 @@ __global__ void __launch_bounds__(TEXGS_ADAM_THREADS, 2) texgs_texture_adam_dp_k
         }
     }
 }
-#endif
