@@ -351,6 +351,8 @@ def main():
     if use_opt and world > 1:
         ok = 1
         try:
+            if os.environ.get("TEXGS_BENCH_NO_SYMM"):       # test hook: exercise the fallback on a box that has symmetric memory
+                raise RuntimeError("TEXGS_BENCH_NO_SYMM is set")
             from texture_gs_b200.dist import DistTextureAdam
             bucket = GradBucket(params, symmetric_group=dist.group.WORLD)
             opt = DistTextureAdam(g.get_texture, bucket, lr=0.0025, eps=1e-15, use_multicast=False if args.no_multicast else None)
