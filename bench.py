@@ -328,6 +328,10 @@ def main():
         raise SystemExit("bench.py (impl=ours) needs a CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    try:
+        full_affinity = os.sched_getaffinity(0)
+    except AttributeError:
+        full_affinity = None
     numa_node = bind_to_gpu_numa_node(dev)          # before any pinned allocation: host buffers land next to the GPU
     if world > 1:
         from texture_gs_b200.dist import init_process_group_quiet
@@ -534,6 +538,8 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
+        if full_affinity is not None:
+            os.sched_setaffinity(0, full_affinity)      # the CPU leg gets every core again, like the --impl reference run
         try:
             vs = [cpu_oracle_views_per_s(wl, args.cpu_threads) for _ in range(3)]       # a few seconds each; first call builds the scene
             v, desc, threads, _ = max(vs, key=lambda r: r[0])
