@@ -606,7 +606,7 @@ def run_e2e(args, wl, g, cams, bg, bucket, views, dev, world, sync_all, render_f
     import torch.distributed as dist
     from texture_gs_b200 import invalidate_packed_cache
     from texture_gs_b200.dist import render_views_accumulate
-    from texture_gs_b200.losses import geometry_losses, photometric_loss
+    from texture_gs_b200.losses import training_loss
     bwd = wl.backward
     H, W = wl.height, wl.width
     lam, lam_alpha, lam_norm, lam_nsm = 0.2, 1.0, 0.1, 0.5          # configs/texture_gaussian3d.yaml:77-88
@@ -660,12 +660,9 @@ def run_e2e(args, wl, g, cams, bg, bucket, views, dev, world, sync_all, render_f
         def loss_fn(pkg, v):
             k = cur[0]
             u8, m8, n8 = slots[k % nslots]
-            gt = u8.float().mul_(1.0 / 255.0)
-            gt_alpha = m8.float().mul_(1.0 / 255.0)
-            gt_norm = n8.float().mul_(1.0 / 127.0)
-            loss, _l1, _ls = photometric_loss(pkg["render"], gt, lam)
-            la, ln, lsm = geometry_losses(pkg["alpha"], pkg["norm"], gt_alpha, gt_norm, gt)
-            loss = loss + lam_alpha * la + lam_norm * ln + lam_nsm * lsm
+            gt, gt_alpha, gt_norm = u8 * (1.0 / 255.0), m8 * (1.0 / 255.0), n8 * (1.0 / 127.0)      # one decode kernel each
+            loss, _parts = training_loss(pkg["render"], pkg["alpha"], pkg["norm"], gt, gt_alpha, gt_norm,
+                                         lam, lam_alpha, lam_norm, lam_nsm)
             total[k % streams] += loss.detach()
             return loss
 
