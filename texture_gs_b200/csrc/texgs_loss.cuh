@@ -12,6 +12,9 @@
 #define TEXGS_LOSS_TILE 16
 #define TEXGS_LOSS_R 5
 #define TEXGS_LOSS_SPAN (TEXGS_LOSS_TILE + 2 * TEXGS_LOSS_R)   // 26
+// row stride of the halo tiles in shared memory: in the horizontal pass a warp reads 16 consecutive words of row r and 16 of
+// row r+1, so the stride must be 16 (mod 32) banks for the two half-warps not to collide (27 gave a 2-way conflict on 11 banks)
+#define TEXGS_LOSS_STRIDE 48
 #define TEXGS_SSIM_C1 0.0001f    // 0.01^2
 #define TEXGS_SSIM_C2 0.0009f    // 0.03^2
 
@@ -26,7 +29,7 @@ struct LossSums { double ssim, l1; };
 __global__ void __launch_bounds__(256) texgs_photometric_fwd_kernel(const float* __restrict__ img, const float* __restrict__ gt,
                                                                    int H, int W, float* __restrict__ d_mu1, float* __restrict__ d_e11,
                                                                    float* __restrict__ d_e12, LossSums* __restrict__ sums) {
-    __shared__ float sa[TEXGS_LOSS_SPAN][TEXGS_LOSS_SPAN + 1], sb[TEXGS_LOSS_SPAN][TEXGS_LOSS_SPAN + 1];
+    __shared__ float sa[TEXGS_LOSS_SPAN][TEXGS_LOSS_STRIDE], sb[TEXGS_LOSS_SPAN][TEXGS_LOSS_STRIDE];
     __shared__ float hq[5][TEXGS_LOSS_SPAN][TEXGS_LOSS_TILE];
     __shared__ double red[2][8];
     const int tid = threadIdx.y * TEXGS_LOSS_TILE + threadIdx.x;
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(256) texgs_photometric_bwd_kernel(const float*
                                                                    const float* __restrict__ d_mu1, const float* __restrict__ d_e11,
                                                                    const float* __restrict__ d_e12, const float* __restrict__ coef,
                                                                    float inv_n, float* __restrict__ dimg) {
-    __shared__ float sm[3][TEXGS_LOSS_SPAN][TEXGS_LOSS_SPAN + 1];
+    __shared__ float sm[3][TEXGS_LOSS_SPAN][TEXGS_LOSS_STRIDE];
     __shared__ float hq[3][TEXGS_LOSS_SPAN][TEXGS_LOSS_TILE];
     const int tid = threadIdx.y * TEXGS_LOSS_TILE + threadIdx.x;
     const size_t plane = (size_t)blockIdx.z * H * W;
