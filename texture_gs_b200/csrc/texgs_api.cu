@@ -406,7 +406,7 @@ int texgs_pack_texture(const float* texture, int32_t R, float* texture_rgba, voi
 }
 
 static size_t loss_parts_bytes(int C, int H, int W) {
-    const size_t nb = (size_t)((W + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE) * ((H + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE) * C;
+    const size_t nb = (size_t)((W + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE) * ((H + TEXGS_LOSS_TILE_H - 1) / TEXGS_LOSS_TILE_H) * C;
     return (nb * sizeof(LossSums) + 255) / 256 * 256;
 }
 
@@ -424,7 +424,7 @@ int texgs_photometric_forward(const float* image, const float* gt, int32_t C, in
     const size_t n = (size_t)C * H * W;
     LossSums* sums = (LossSums*)ws;
     float* maps = (float*)((char*)ws + loss_parts_bytes(C, H, W));
-    const dim3 grid((W + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE, (H + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE, C);
+    const dim3 grid((W + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE, (H + TEXGS_LOSS_TILE_H - 1) / TEXGS_LOSS_TILE_H, C);
     texgs_photometric_fwd_kernel<<<grid, dim3(TEXGS_LOSS_TILE, TEXGS_LOSS_TILE), 0, stream>>>(image, gt, H, W, maps, maps + n, maps + 2 * n, sums);
     TEXGS_KERNEL_CHECK("texgs_photometric_fwd_kernel", false, stream);
     texgs_photometric_finalize_kernel<<<1, 1024, 0, stream>>>(sums, (int)(grid.x * grid.y * grid.z), 1.0 / (double)n, lambda_dssim, out3);
@@ -438,7 +438,7 @@ int texgs_photometric_backward(const float* image, const float* gt, int32_t C, i
     if (!image || !gt || !ws || !coef2 || !dL_dimage || C <= 0 || H <= 0 || W <= 0 || C > 65535) return fail(TEXGS_E_INVALID, "bad arguments");
     const size_t n = (size_t)C * H * W;
     const float* maps = (const float*)((const char*)ws + loss_parts_bytes(C, H, W));
-    const dim3 grid((W + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE, (H + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE, C);
+    const dim3 grid((W + TEXGS_LOSS_TILE - 1) / TEXGS_LOSS_TILE, (H + TEXGS_LOSS_TILE_H - 1) / TEXGS_LOSS_TILE_H, C);
     texgs_photometric_bwd_kernel<<<grid, dim3(TEXGS_LOSS_TILE, TEXGS_LOSS_TILE), 0, stream>>>(image, gt, H, W, maps, maps + n, maps + 2 * n, coef2,
                                                                                              (float)(1.0 / (double)n), dL_dimage);
     TEXGS_KERNEL_CHECK("texgs_photometric_bwd_kernel", false, stream);

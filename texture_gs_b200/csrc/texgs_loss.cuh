@@ -9,12 +9,17 @@
 #pragma once
 #include "texgs_common.cuh"
 
-#define TEXGS_LOSS_TILE 16
+#define TEXGS_LOSS_TILE 16                                     // CTA = 16 x 16 threads
+#define TEXGS_LOSS_TILE_H 32                                   // ... for a 16 x 32 pixel tile: two vertically adjacent outputs per thread
 #define TEXGS_LOSS_R 5
-#define TEXGS_LOSS_SPAN (TEXGS_LOSS_TILE + 2 * TEXGS_LOSS_R)   // 26
-// row stride of the halo tiles in shared memory: in the horizontal pass a warp reads 16 consecutive words of row r and 16 of
-// row r+1, so the stride must be 16 (mod 32) banks for the two half-warps not to collide (27 gave a 2-way conflict on 11 banks)
-#define TEXGS_LOSS_STRIDE 48
+#define TEXGS_LOSS_SPAN (TEXGS_LOSS_TILE + 2 * TEXGS_LOSS_R)     // 26 halo columns
+#define TEXGS_LOSS_SPAN_H (TEXGS_LOSS_TILE_H + 2 * TEXGS_LOSS_R) // 42 halo rows
+// Shared-memory row strides (words). A warp = two half-warps of 16 consecutive columns; in both passes the halves work on rows
+// r and r+2 (the horizontal pass by its item order, the vertical pass because a thread owns rows 2*ly and 2*ly+1), so
+// 2 * stride = 16 (mod 32) keeps them on disjoint banks: 40 for the 26-wide halo tiles, 24 for the 16-wide row-filtered ones.
+// (Round 2 measured the 2-way conflict a stride of 27 gave: forward 0.158 -> 0.148 ms, backward 0.138 -> 0.107 ms at 1080p.)
+#define TEXGS_LOSS_STRIDE 40
+#define TEXGS_LOSS_HSTRIDE 24
 #define TEXGS_SSIM_C1 0.0001f    // 0.01^2
 #define TEXGS_SSIM_C2 0.0009f    // 0.03^2
 
@@ -25,17 +30,25 @@ __device__ __constant__ float TEXGS_WIN[11] = {0.00102838012f, 0.00759875821f, 0
 
 struct LossSums { double ssim, l1; };
 
+// item -> (row, column) of the horizontal pass: the two half-warps of a warp take rows r and r + 2
+__device__ __forceinline__ void loss_hpass_item(int i, int& r, int& c) {
+    const int q = i >> 5;
+    c = i & 15;
+    r = ((q >> 1) << 2) + (q & 1) + ((i >> 3) & 2);
+}
+#define TEXGS_LOSS_HITEMS (((TEXGS_LOSS_SPAN_H + 3) / 4) * 4 * TEXGS_LOSS_TILE)     // rows rounded up to whole groups of 4
+
 // grid (tiles_x, tiles_y, C), block 16x16
 __global__ void __launch_bounds__(256) texgs_photometric_fwd_kernel(const float* __restrict__ img, const float* __restrict__ gt,
                                                                    int H, int W, float* __restrict__ d_mu1, float* __restrict__ d_e11,
                                                                    float* __restrict__ d_e12, LossSums* __restrict__ sums) {
-    __shared__ float sa[TEXGS_LOSS_SPAN][TEXGS_LOSS_STRIDE], sb[TEXGS_LOSS_SPAN][TEXGS_LOSS_STRIDE];
-    __shared__ float hq[5][TEXGS_LOSS_SPAN][TEXGS_LOSS_TILE];
+    __shared__ float sa[TEXGS_LOSS_SPAN_H][TEXGS_LOSS_STRIDE], sb[TEXGS_LOSS_SPAN_H][TEXGS_LOSS_STRIDE];
+    __shared__ float hq[5][TEXGS_LOSS_SPAN_H][TEXGS_LOSS_HSTRIDE];
     __shared__ double red[2][8];
     const int tid = threadIdx.y * TEXGS_LOSS_TILE + threadIdx.x;
     const size_t plane = (size_t)blockIdx.z * H * W;
-    const int x0 = blockIdx.x * TEXGS_LOSS_TILE - TEXGS_LOSS_R, y0 = blockIdx.y * TEXGS_LOSS_TILE - TEXGS_LOSS_R;
-    for (int i = tid; i < TEXGS_LOSS_SPAN * TEXGS_LOSS_SPAN; i += 256) {
+    const int x0 = blockIdx.x * TEXGS_LOSS_TILE - TEXGS_LOSS_R, y0 = blockIdx.y * TEXGS_LOSS_TILE_H - TEXGS_LOSS_R;
+    for (int i = tid; i < TEXGS_LOSS_SPAN_H * TEXGS_LOSS_SPAN; i += 256) {
         const int r = i / TEXGS_LOSS_SPAN, c = i % TEXGS_LOSS_SPAN;
         const int gy = y0 + r, gx = x0 + c;
         const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;          // zero padding (conv2d padding=5)
@@ -43,8 +56,10 @@ __global__ void __launch_bounds__(256) texgs_photometric_fwd_kernel(const float*
         sb[r][c] = in ? gt[plane + (size_t)gy * W + gx] : 0.f;
     }
     __syncthreads();
-    for (int i = tid; i < TEXGS_LOSS_SPAN * TEXGS_LOSS_TILE; i += 256) {   // horizontal pass
-        const int r = i / TEXGS_LOSS_TILE, c = i % TEXGS_LOSS_TILE;
+    for (int i = tid; i < TEXGS_LOSS_HITEMS; i += 256) {                 // horizontal pass
+        int r, c;
+        loss_hpass_item(i, r, c);
+        if (r >= TEXGS_LOSS_SPAN_H) continue;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
 #pragma unroll
         for (int k = 0; k < 11; ++k) {
@@ -54,29 +69,40 @@ __global__ void __launch_bounds__(256) texgs_photometric_fwd_kernel(const float*
         hq[0][r][c] = s0; hq[1][r][c] = s1; hq[2][r][c] = s2; hq[3][r][c] = s3; hq[4][r][c] = s4;
     }
     __syncthreads();
-    const int lx = threadIdx.x, ly = threadIdx.y;
-    const int px = blockIdx.x * TEXGS_LOSS_TILE + lx, py = blockIdx.y * TEXGS_LOSS_TILE + ly;
+    const int lx = threadIdx.x, ly = 2 * threadIdx.y;                     // this thread: pixels (ly, lx) and (ly + 1, lx) of the tile
+    const int px = blockIdx.x * TEXGS_LOSS_TILE + lx, py = blockIdx.y * TEXGS_LOSS_TILE_H + ly;
     double my_ssim = 0.0, my_l1 = 0.0;
     if (px < W && py < H) {
-        float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+        float m1[2] = {0.f, 0.f}, m2[2] = {0.f, 0.f}, q11[2] = {0.f, 0.f}, q22[2] = {0.f, 0.f}, q12[2] = {0.f, 0.f};
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {                                        // vertical pass
-            const float w = TEXGS_WIN[k];
-            mu1 += w * hq[0][ly + k][lx]; mu2 += w * hq[1][ly + k][lx];
-            e11 += w * hq[2][ly + k][lx]; e22 += w * hq[3][ly + k][lx]; e12 += w * hq[4][ly + k][lx];
+        for (int k = 0; k < 12; ++k) {                                    // vertical pass: 12 rows serve both outputs
+            const float v0 = hq[0][ly + k][lx], v1 = hq[1][ly + k][lx], v2 = hq[2][ly + k][lx], v3 = hq[3][ly + k][lx], v4 = hq[4][ly + k][lx];
+            if (k < 11) {
+                const float w = TEXGS_WIN[k];
+                m1[0] += w * v0; m2[0] += w * v1; q11[0] += w * v2; q22[0] += w * v3; q12[0] += w * v4;
+            }
+            if (k > 0) {
+                const float w = TEXGS_WIN[k - 1];
+                m1[1] += w * v0; m2[1] += w * v1; q11[1] += w * v2; q22[1] += w * v3; q12[1] += w * v4;
+            }
         }
-        const float s11 = e11 - mu1 * mu1, s22 = e22 - mu2 * mu2, s12 = e12 - mu1 * mu2;
-        const float A = 2.f * mu1 * mu2 + TEXGS_SSIM_C1, B = 2.f * s12 + TEXGS_SSIM_C2;
-        const float Cc = mu1 * mu1 + mu2 * mu2 + TEXGS_SSIM_C1, D = s11 + s22 + TEXGS_SSIM_C2;
-        const float iCD = 1.0f / (Cc * D);
-        my_ssim = (double)(A * B * iCD);
-        // d ssim / d (mu1, E[x^2], E[xy]) with x = image (gt is a constant)
-        const float dE11 = -A * B * iCD / D;
-        const float dE12 = 2.f * A * iCD;
-        const float dmu1 = 2.f * mu2 * (B - A) * iCD - 2.f * mu1 * A * B * iCD / Cc - 2.f * mu1 * dE11;
-        const size_t o = plane + (size_t)py * W + px;
-        d_mu1[o] = dmu1; d_e11[o] = dE11; d_e12[o] = dE12;
-        my_l1 = (double)fabsf(sa[ly + TEXGS_LOSS_R][lx + TEXGS_LOSS_R] - sb[ly + TEXGS_LOSS_R][lx + TEXGS_LOSS_R]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (py + j >= H) break;
+            const float mu1 = m1[j], mu2 = m2[j], e11 = q11[j], e22 = q22[j], e12 = q12[j];
+            const float s11 = e11 - mu1 * mu1, s22 = e22 - mu2 * mu2, s12 = e12 - mu1 * mu2;
+            const float A = 2.f * mu1 * mu2 + TEXGS_SSIM_C1, B = 2.f * s12 + TEXGS_SSIM_C2;
+            const float Cc = mu1 * mu1 + mu2 * mu2 + TEXGS_SSIM_C1, D = s11 + s22 + TEXGS_SSIM_C2;
+            const float iCD = 1.0f / (Cc * D);
+            my_ssim += (double)(A * B * iCD);
+            // d ssim / d (mu1, E[x^2], E[xy]) with x = image (gt is a constant)
+            const float dE11 = -A * B * iCD / D;
+            const float dE12 = 2.f * A * iCD;
+            const float dmu1 = 2.f * mu2 * (B - A) * iCD - 2.f * mu1 * A * B * iCD / Cc - 2.f * mu1 * dE11;
+            const size_t o = plane + (size_t)(py + j) * W + px;
+            d_mu1[o] = dmu1; d_e11[o] = dE11; d_e12[o] = dE12;
+            my_l1 += (double)fabsf(sa[ly + j + TEXGS_LOSS_R][lx + TEXGS_LOSS_R] - sb[ly + j + TEXGS_LOSS_R][lx + TEXGS_LOSS_R]);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -119,12 +145,12 @@ __global__ void __launch_bounds__(256) texgs_photometric_bwd_kernel(const float*
                                                                    const float* __restrict__ d_mu1, const float* __restrict__ d_e11,
                                                                    const float* __restrict__ d_e12, const float* __restrict__ coef,
                                                                    float inv_n, float* __restrict__ dimg) {
-    __shared__ float sm[3][TEXGS_LOSS_SPAN][TEXGS_LOSS_STRIDE];
-    __shared__ float hq[3][TEXGS_LOSS_SPAN][TEXGS_LOSS_TILE];
+    __shared__ float sm[3][TEXGS_LOSS_SPAN_H][TEXGS_LOSS_STRIDE];
+    __shared__ float hq[3][TEXGS_LOSS_SPAN_H][TEXGS_LOSS_HSTRIDE];
     const int tid = threadIdx.y * TEXGS_LOSS_TILE + threadIdx.x;
     const size_t plane = (size_t)blockIdx.z * H * W;
-    const int x0 = blockIdx.x * TEXGS_LOSS_TILE - TEXGS_LOSS_R, y0 = blockIdx.y * TEXGS_LOSS_TILE - TEXGS_LOSS_R;
-    for (int i = tid; i < TEXGS_LOSS_SPAN * TEXGS_LOSS_SPAN; i += 256) {
+    const int x0 = blockIdx.x * TEXGS_LOSS_TILE - TEXGS_LOSS_R, y0 = blockIdx.y * TEXGS_LOSS_TILE_H - TEXGS_LOSS_R;
+    for (int i = tid; i < TEXGS_LOSS_SPAN_H * TEXGS_LOSS_SPAN; i += 256) {
         const int r = i / TEXGS_LOSS_SPAN, c = i % TEXGS_LOSS_SPAN;
         const int gy = y0 + r, gx = x0 + c;
         const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;          // derivative maps exist on image pixels only
@@ -134,8 +160,10 @@ __global__ void __launch_bounds__(256) texgs_photometric_bwd_kernel(const float*
         sm[2][r][c] = in ? d_e12[o] : 0.f;
     }
     __syncthreads();
-    for (int i = tid; i < TEXGS_LOSS_SPAN * TEXGS_LOSS_TILE; i += 256) {
-        const int r = i / TEXGS_LOSS_TILE, c = i % TEXGS_LOSS_TILE;
+    for (int i = tid; i < TEXGS_LOSS_HITEMS; i += 256) {
+        int r, c;
+        loss_hpass_item(i, r, c);
+        if (r >= TEXGS_LOSS_SPAN_H) continue;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int k = 0; k < 11; ++k) {
@@ -145,21 +173,27 @@ __global__ void __launch_bounds__(256) texgs_photometric_bwd_kernel(const float*
         hq[0][r][c] = s0; hq[1][r][c] = s1; hq[2][r][c] = s2;
     }
     __syncthreads();
-    const int lx = threadIdx.x, ly = threadIdx.y;
-    const int px = blockIdx.x * TEXGS_LOSS_TILE + lx, py = blockIdx.y * TEXGS_LOSS_TILE + ly;
+    const int lx = threadIdx.x, ly = 2 * threadIdx.y;
+    const int px = blockIdx.x * TEXGS_LOSS_TILE + lx, py = blockIdx.y * TEXGS_LOSS_TILE_H + ly;
     if (px < W && py < H) {
-        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        float c0[2] = {0.f, 0.f}, c1[2] = {0.f, 0.f}, c2[2] = {0.f, 0.f};
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
-            const float w = TEXGS_WIN[k];
-            c0 += w * hq[0][ly + k][lx]; c1 += w * hq[1][ly + k][lx]; c2 += w * hq[2][ly + k][lx];
+        for (int k = 0; k < 12; ++k) {
+            const float v0 = hq[0][ly + k][lx], v1 = hq[1][ly + k][lx], v2 = hq[2][ly + k][lx];
+            if (k < 11) { const float w = TEXGS_WIN[k]; c0[0] += w * v0; c1[0] += w * v1; c2[0] += w * v2; }
+            if (k > 0) { const float w = TEXGS_WIN[k - 1]; c0[1] += w * v0; c1[1] += w * v1; c2[1] += w * v2; }
         }
-        const size_t o = plane + (size_t)py * W + px;
-        const float a = img[o], b = gt[o];
-        const float dssim = c0 + 2.f * a * c1 + b * c2;                       // d(sum ssim)/d a
-        const float d = a - b;
-        const float sgn = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);          // torch.abs: gradient 0 at 0
-        dimg[o] = inv_n * (coef[0] * sgn - coef[1] * dssim);
+        const float k0 = coef[0], k1 = coef[1];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (py + j >= H) break;
+            const size_t o = plane + (size_t)(py + j) * W + px;
+            const float a = img[o], b = gt[o];
+            const float dssim = c0[j] + 2.f * a * c1[j] + b * c2[j];              // d(sum ssim)/d a
+            const float d = a - b;
+            const float sgn = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);          // torch.abs: gradient 0 at 0
+            dimg[o] = inv_n * (k0 * sgn - k1 * dssim);
+        }
     }
 }
 
