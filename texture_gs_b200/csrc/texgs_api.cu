@@ -282,7 +282,7 @@ int texgs_forward(const TexgsFwdArgs* a, void* geom_ws, void* bin_ws, uint64_t p
     {
         NvtxRange r("texgs/forward/render");
         const bool t4 = p.texture_rgba != nullptr, dual = p.out_image_nosh != nullptr;
-#define TEXGS_LAUNCH_FWD(M, T4, DU, AL) texgs_render_fwd<M, T4, DU, AL><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, out_image, out_depth, out_norm, out_alpha)
+#define TEXGS_LAUNCH_FWD(M, T4, DU, AL) texgs_render_fwd<M, T4, DU, AL><<<p.num_tiles * (8 / TEXGS_FWD_WARPS), 32 * TEXGS_FWD_WARPS, TEXGS_FWD_WARPS * sizeof(WarpSmem), stream>>>(p, out_image, out_depth, out_norm, out_alpha)
         const bool alt = p.mode == TEXGS_MODE_TEXTURE && (p.flags & TEXGS_FLAG_SPEC_MASK) != 0u;
         if (alt && !t4) return fail(TEXGS_E_INVALID, "the spec-switch flags need the packed texel copy (texture_rgba)");
         if (p.mode != TEXGS_MODE_TEXTURE) TEXGS_LAUNCH_FWD(TEXGS_MODE_SH, false, false, false);
@@ -338,7 +338,7 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
     if (p.mode == TEXGS_MODE_TEXTURE) {
         const bool rd4 = p.texture_rgba != nullptr, wr4 = b->dL_dtexture_rgba != nullptr, dual = p.out_image_nosh != nullptr;
         float* dt = wr4 ? b->dL_dtexture_rgba : b->dL_dtexture;
-#define TEXGS_LAUNCH_BWD(R4, W4, DU, AL) texgs_render_bwd<TEXGS_MODE_TEXTURE, R4, W4, DU, AL><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, dt)
+#define TEXGS_LAUNCH_BWD(R4, W4, DU, AL) texgs_render_bwd<TEXGS_MODE_TEXTURE, R4, W4, DU, AL><<<p.num_tiles * (8 / TEXGS_BWD_WARPS), 32 * TEXGS_BWD_WARPS, TEXGS_BWD_WARPS * sizeof(WarpSmem), stream>>>(p, in, b->acc_ws, dt)
         const bool alt = (p.flags & TEXGS_FLAG_SPEC_MASK) != 0u;
         if (alt && (!rd4 || (dt && !wr4))) return fail(TEXGS_E_INVALID, "the spec-switch flags need texture_rgba and the padded texel gradient (dL_dtexture_rgba)");
         if (alt) {
@@ -352,7 +352,7 @@ int texgs_backward(const TexgsBwdArgs* b, void* stream_) {
         }
 #undef TEXGS_LAUNCH_BWD
     } else {
-        texgs_render_bwd<TEXGS_MODE_SH, false, false, false, false><<<p.num_tiles, 256, TEXGS_RENDER_SMEM, stream>>>(p, in, b->acc_ws, nullptr);
+        texgs_render_bwd<TEXGS_MODE_SH, false, false, false, false><<<p.num_tiles * (8 / TEXGS_BWD_WARPS), 32 * TEXGS_BWD_WARPS, TEXGS_BWD_WARPS * sizeof(WarpSmem), stream>>>(p, in, b->acc_ws, nullptr);
     }
     TEXGS_KERNEL_CHECK("texgs_render_bwd", debug, stream);
     if (p.E > 0 && p.P > 0) {

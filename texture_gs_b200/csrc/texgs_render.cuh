@@ -9,11 +9,22 @@
 #include "texgs_common.cuh"
 
 
+// Warps per CTA of the two render kernels. The eight warps of a tile never talk to each other (no block barrier, private
+// rings), so a tile may be split over 8 / WARPS CTAs: with half-tile CTAs a finished warp's slot returns to the scheduler
+// when its three siblings are done instead of seven, and the backward fits 5 CTAs x 4 warps = 20 warps per SM at 96
+// registers (28 B of spills) where 2 x 8 warps at 122 registers gave 16. Measured on B200 (profiles/r2_experiments.md):
+// forward 0.776 -> 0.763 ms, backward 1.373 -> 1.323 ms; quarter-tile and single-warp CTAs lose the tile's L1 locality.
+#ifndef TEXGS_FWD_WARPS
+#define TEXGS_FWD_WARPS 4
+#endif
+#ifndef TEXGS_BWD_WARPS
+#define TEXGS_BWD_WARPS 4
+#endif
 #ifndef TEXGS_FWD_MIN_CTAS
-#define TEXGS_FWD_MIN_CTAS 3
+#define TEXGS_FWD_MIN_CTAS 6
 #endif
 #ifndef TEXGS_BWD_MIN_CTAS
-#define TEXGS_BWD_MIN_CTAS 2
+#define TEXGS_BWD_MIN_CTAS 5
 #endif
 #ifndef TEXGS_FAST_EXP
 #define TEXGS_FAST_EXP 1
@@ -38,17 +49,20 @@ __device__ __forceinline__ float texgs_exp(float x) {
 }
 
 struct PixelGeom {
-    int tile, px, py, pix;
+    int tile, warp, px, py, pix;   // warp = 0..7 inside the tile
     int bx, by;      // origin of this warp's 8x4 pixel block (= two 4x4 half-warp blocks side by side)
     bool inside;
     float vx, vy;    // view ray (vx, vy, 1)
 };
 
+// WPC = warps per CTA (8, 4, 2 or 1): a tile's eight warps never talk to each other, so a tile may be split over 8 / WPC CTAs
+template <int WPC>
 __device__ __forceinline__ PixelGeom pixel_geom(const RasterParams& p) {
     PixelGeom g;
-    g.tile = blockIdx.x;
+    g.tile = blockIdx.x / (8 / WPC);
     const int tx = g.tile % p.grid_x, ty = g.tile / p.grid_x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x % (8 / WPC)) * WPC + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    g.warp = warp;
     g.bx = tx * TEXGS_TILE + (warp & 1) * 8;
     g.by = ty * TEXGS_TILE + (warp >> 1) * 4;
     // half-warp h = lane >> 4 owns the 4x4 block at (bx + 4h, by): the two halves walk their own
@@ -111,8 +125,8 @@ __device__ __forceinline__ void stream_gather(const RasterParams& p, WarpSmem& w
 
 // where the masks of (tile, chunk, warp) live: chunk c of a list that starts at ``start`` gets slot (start / CHUNK) + tile + c
 // (the + tile keeps the slots of consecutive lists apart: a list of n entries has at most n / CHUNK + 1 chunks)
-__device__ __forceinline__ size_t cull_mask_slot(unsigned start, int tile, int chunk) {
-    return ((size_t)(start / TEXGS_CHUNK) + (size_t)tile + (size_t)chunk) * 8 + (threadIdx.x >> 5);
+__device__ __forceinline__ size_t cull_mask_slot(unsigned start, const PixelGeom& g, int chunk) {
+    return ((size_t)(start / TEXGS_CHUNK) + (size_t)g.tile + (size_t)chunk) * 8 + g.warp;
 }
 
 // forward: ballot the exact cull test of one chunk, keep the two masks for the backward, gather the survivors
@@ -122,7 +136,7 @@ __device__ __forceinline__ void stream_issue(const RasterParams& p, WarpSmem& ws
     const bool passL = valid && splat_hits_block(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, (float)g.bx, (float)(g.bx + 3), y0, y1);
     const bool passR = valid && splat_hits_block(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, (float)(g.bx + 4), (float)(g.bx + 7), y0, y1);
     const unsigned mL = __ballot_sync(0xffffffffu, passL), mR = __ballot_sync(0xffffffffu, passR);
-    if (lane == 0) p.cull_masks[cull_mask_slot(start, g.tile, chunk)] = make_uint2(mL, mR);
+    if (lane == 0) p.cull_masks[cull_mask_slot(start, g, chunk)] = make_uint2(mL, mR);
     stream_gather(p, ws, s, lane, id, mL, mR);
 }
 
@@ -166,12 +180,12 @@ __device__ __forceinline__ UvEval eval_uv(const float4& g1, const float4& g2, co
 // ALT = true: cold instantiation that honours the spec switches of p.flags (TEXGS_FLAG_SEAMLESS_CUBE,
 // TEXGS_FLAG_DEPTH_INTERSECTION; include/texgs.h) — the default instantiations never test them.
 template <int MODE, bool TEX4, bool DUAL, bool ALT>
-__global__ void __launch_bounds__(256, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(const RasterParams p, float* __restrict__ out_image,
+__global__ void __launch_bounds__(32 * TEXGS_FWD_WARPS, TEXGS_FWD_MIN_CTAS) texgs_render_fwd(const RasterParams p, float* __restrict__ out_image,
                                                       float* __restrict__ out_depth, float* __restrict__ out_norm,
                                                       float* __restrict__ out_alpha) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     if (p.counters->overflow) return;
-    const PixelGeom g = pixel_geom(p);
+    const PixelGeom g = pixel_geom<TEXGS_FWD_WARPS>(p);
     const int lane = threadIdx.x & 31;
     WarpSmem& ws = reinterpret_cast<WarpSmem*>(smem_raw)[threadIdx.x >> 5];
     const unsigned start = p.tile_offset[g.tile];
@@ -333,11 +347,11 @@ struct BwdIn {
 // ALT = true: cold instantiation for the spec switches of p.flags (E11-alt seamless taps, E7-alt depth of the
 // intersection, E13-alt no gradient through Delta), as in the forward.
 template <int MODE, bool TEX4, bool GRAD4, bool DUAL, bool ALT>
-__global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(const RasterParams p, const BwdIn in, float* __restrict__ acc,
+__global__ void __launch_bounds__(32 * TEXGS_BWD_WARPS, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(const RasterParams p, const BwdIn in, float* __restrict__ acc,
                                                       float* __restrict__ dtex) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     if (p.counters->overflow) return;
-    const PixelGeom g = pixel_geom(p);
+    const PixelGeom g = pixel_geom<TEXGS_BWD_WARPS>(p);
     const int lane = threadIdx.x & 31;
     WarpSmem& ws = reinterpret_cast<WarpSmem*>(smem_raw)[threadIdx.x >> 5];
     const unsigned start = p.tile_offset[g.tile];
@@ -391,16 +405,16 @@ __global__ void __launch_bounds__(256, TEXGS_BWD_MIN_CTAS) texgs_render_bwd(cons
     const unsigned id0 = stream_load_id(p, start, max_last, c_top, lane, v0);
     const unsigned id1 = stream_load_id(p, start, max_last, c_top - 1, lane, v1);
     unsigned id2 = stream_load_id(p, start, max_last, c_top - 2, lane, v2);
-    stream_issue_saved(p, ws, 0, lane, id0, __ldg(p.cull_masks + cull_mask_slot(start, g.tile, c_top)), c_top, max_last);
-    if (c_top >= 1) stream_issue_saved(p, ws, 1, lane, id1, __ldg(p.cull_masks + cull_mask_slot(start, g.tile, c_top - 1)), c_top - 1, max_last);
-    uint2 m2 = (c_top >= 2) ? __ldg(p.cull_masks + cull_mask_slot(start, g.tile, c_top - 2)) : make_uint2(0u, 0u);
+    stream_issue_saved(p, ws, 0, lane, id0, __ldg(p.cull_masks + cull_mask_slot(start, g, c_top)), c_top, max_last);
+    if (c_top >= 1) stream_issue_saved(p, ws, 1, lane, id1, __ldg(p.cull_masks + cull_mask_slot(start, g, c_top - 1)), c_top - 1, max_last);
+    uint2 m2 = (c_top >= 2) ? __ldg(p.cull_masks + cull_mask_slot(start, g, c_top - 2)) : make_uint2(0u, 0u);
     for (int k = 0; k <= c_top; ++k) {
         const int c = c_top - k;
         const int s = k & 1;
         const unsigned idn = id2;
         const uint2 mn = m2;
         id2 = stream_load_id(p, start, max_last, c - 3, lane, v2);
-        if (c >= 3) m2 = __ldg(p.cull_masks + cull_mask_slot(start, g.tile, c - 3));
+        if (c >= 3) m2 = __ldg(p.cull_masks + cull_mask_slot(start, g, c - 3));
 
         mbar_wait(&ws.bar[s], (unsigned)(k >> 1) & 1u);
         __syncwarp();
